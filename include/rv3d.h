@@ -1,0 +1,238 @@
+/*
+ * rv3d.h -- C ABI of librv3d.so: the B200 (sm_100a) implementation of torchbox3d's
+ * rasterize -> decode -> rotated-IoU / NMS path.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - the caller owns every buffer, including scratch; the library never allocates
+ *     device memory behind the caller's back (the one exception is the sort's
+ *     temporary storage, which is carved out of the caller's scratch), never changes
+ *     the current device, and enqueues all work on the caller's stream;
+ *   - functions return RV3D_OK (0) or a negative rv3d_status; no exceptions, no aborts;
+ *   - counts that only the device knows are returned in device memory; the two
+ *     entry points that need one on the host (rv3d_nms_sorted_setup) say so;
+ *   - re-entrant, no global mutable state; one host thread per GPU.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference).  The third-party natives the reference binds
+ * (torch.ops.detectron2.nms_rotated, weighted_nms_ext.wnms_gpu,
+ * mmcv ext_module.box_iou_rotated) are un-vendored; their call sites are cited.
+ */
+#ifndef RV3D_H_
+#define RV3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RV3D_VERSION 100 /* 0.1.0 */
+
+typedef void *rv3d_stream_t; /* cudaStream_t */
+
+typedef enum {
+  RV3D_OK = 0,
+  RV3D_ERR_ARG = -1,         /* bad shape / null pointer / unsupported enum value */
+  RV3D_ERR_ALIGN = -2,       /* pointer not aligned as documented */
+  RV3D_ERR_SCRATCH = -3,     /* scratch_bytes smaller than rv3d_*_scratch_bytes() */
+  RV3D_ERR_CUDA = -4,        /* a CUDA runtime call / launch failed */
+  RV3D_ERR_KEYBITS = -5,     /* (sweep,class,score,candidate) does not fit a 64-bit sort key: split the batch */
+  RV3D_ERR_CAPACITY = -6     /* an output buffer's capacity was exceeded (device-side flag) */
+} rv3d_status;
+
+int rv3d_version(void);
+const char *rv3d_strerror(int status);
+
+/* ------------------------------------------------------------------------------------
+ * 1. Rasterization
+ * replaces: math/range_view.py:14-44 build_range_view
+ *           math/numpy/conversions.py:46-73 cart_to_sph, :9-43 build_range_view_coordinates,
+ *           :106-128 z_buffer (numba)            [and the copies in converters/av2/utils.py]
+ * ------------------------------------------------------------------------------------ */
+#define RV3D_COL_LIBRARY 0   /* col = rint(W - az' - 1)   numpy/conversions.py:35      */
+#define RV3D_COL_CONVERTER 1 /* col = W - rint(az')       converters/av2/utils.py:137  */
+
+typedef struct {
+  int32_t batch;        /* B sweeps in one launch                                        */
+  int32_t max_points;   /* stride, in points, between consecutive sweeps                 */
+  int32_t height;       /* H = n_inclination_bins                                        */
+  int32_t width;        /* W the z-buffer ravels with (z_buffer's `width`)               */
+  int32_t azimuth_bins; /* n_azimuth_bins of the column formula (the reference's library
+                           wrapper leaves this at 1800 whatever `width` is)              */
+  int32_t num_lasers;   /* points with laser >= num_lasers are dropped (range_view.py:23);
+                           also the length of laser_mapping                              */
+  int32_t col_mode;     /* RV3D_COL_*                                                    */
+  int32_t reserved;     /* must be 0.  (Arithmetic is always f64, the production configuration:
+                           converters/av2/export.py:77-81 casts to Float64 and
+                           datasets/argoverse/av2.py:162 passes an f64 offset.)            */
+  double lidar_offset[3];
+  double min_distance;  /* z_buffer's min_distance (1.0)                                 */
+} rv3d_raster_params;
+
+size_t rv3d_rasterize_scratch_bytes(const rv3d_raster_params *p);
+
+/* points: (B, max_points, 4) f32 [x, y, z, intensity], 16-byte aligned.
+ * laser: (B, max_points) u8.  n_points: (B,) i32.  laser_mapping: (num_lasers,) i32
+ * (row = H - laser_mapping[laser] - 1).
+ * image: (B, 7, H, W) f32 [azimuth, inclination, range, x, y, z, intensity]
+ * (range_view.py:33).  winner: (B, H, W) i32 index of the point that owns the pixel,
+ * -1 if empty; may be NULL. */
+int rv3d_rasterize(const rv3d_raster_params *p, const float *points, const uint8_t *laser,
+                   const int32_t *n_points, const int32_t *laser_mapping, float *image,
+                   int32_t *winner, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
+/* Generic nearest-return scatter == z_buffer(indices, distances, features, H, W, min_distance)
+ * (numpy/conversions.py:106-128).  rows/cols (N,) i64; dist (N,) f64 or f32; feat (C,N) f64
+ * or f32; image (C,H,W) f32; winner (H,W) i32 or NULL. */
+size_t rv3d_zbuffer_scratch_bytes(int32_t height, int32_t width);
+int rv3d_zbuffer(const int64_t *rows, const int64_t *cols, const void *dist, int32_t dist_is_f64,
+                 const void *feat, int32_t feat_is_f64, int32_t channels, int64_t n, int32_t height,
+                 int32_t width, double min_distance, float *image, int32_t *winner, void *scratch,
+                 size_t scratch_bytes, rv3d_stream_t stream);
+
+/* cart_to_sph (numpy/conversions.py:46-73): (N,3) f64 -> (N,3) f64 [az, inc, r]. */
+int rv3d_cart_to_sph(const double *cart, double *sph, int64_t n, rv3d_stream_t stream);
+/* build_range_view_coordinates (numpy/conversions.py:9-43 / converters/av2/utils.py:108-153):
+ * sph (N,3) f64 is MUTATED in place exactly like the reference (az' = (az+pi)*W/tau). */
+int rv3d_range_view_coordinates(double *sph, const int64_t *laser, const int64_t *laser_mapping,
+                                int32_t n_mapping, int64_t n, int32_t n_inclination_bins,
+                                int32_t n_azimuth_bins, int32_t col_mode, double *hybrid,
+                                rv3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 2. Decoding
+ * replaces: math/ops/coding.py:110-144 decode_range_view (+ :79-107 egovehicle_from_azimuth)
+ *           nn/decoders/range_decoder.py:127-156 sample_by_range, :49-77 the per-task body
+ *           of RangeDecoder.decode, math/linalg/lie/SO3.py:122-134 yaw_to_quat
+ * ------------------------------------------------------------------------------------ */
+#define RV3D_F32 0
+#define RV3D_F16 1
+#define RV3D_BF16 2
+#define RV3D_MAX_PARTITIONS 8
+
+/* decode_range_view: regressands (B,8,H,W), cart (B,3,H,W) -> out (B,7,H,W), all `dtype`;
+ * arithmetic in f64 (coding.py:126-128), one cast at the end (:144). */
+int rv3d_decode_range_view(const void *regressands, const void *cart, void *out, int32_t dtype,
+                           int32_t batch, int32_t height, int32_t width, int32_t azimuth_invariant,
+                           rv3d_stream_t stream);
+
+typedef struct {
+  int32_t n_partitions;                 /* 0 = sample_by_range disabled (BCHW_to_BKC) */
+  float lower[RV3D_MAX_PARTITIONS];
+  float upper[RV3D_MAX_PARTITIONS];
+  int32_t rate[RV3D_MAX_PARTITIONS];
+} rv3d_partitions;
+
+/* number of candidates per sweep: sum_i H*ceil(W/rate_i), or H*W when disabled */
+int64_t rv3d_num_candidates(const rv3d_partitions *parts, int32_t height, int32_t width);
+
+/* sample_by_range: scores (B,1,H,W) f32, categories (B,1,H,W) i64, cuboids (B,7,H,W) f32,
+ * cart (B,3,H,W) f32 -> out_scores (B,K) f32, out_categories (B,K) i64, out_cuboids (B,K,7) f32. */
+int rv3d_sample_by_range(const float *scores, const int64_t *categories, const float *cuboids,
+                         const float *cart, const rv3d_partitions *parts, int32_t batch, int32_t height,
+                         int32_t width, float *out_scores, int64_t *out_categories, float *out_cuboids,
+                         rv3d_stream_t stream);
+
+typedef struct {
+  int32_t batch, n_classes, height, width;
+  int32_t dtype;             /* RV3D_F32 / F16 / BF16 of logits, regressands, cart          */
+  int32_t azimuth_invariant; /* enable_azimuth_invariant_targets                            */
+  int32_t category_offset;   /* task_offset (range_decoder.py:77)                           */
+  int32_t candidate_offset;  /* index of this (stride, task)'s first candidate in the
+                                concatenated K axis (range_decoder.py:88-93)                */
+  int32_t total_candidates;  /* K of the concatenated axis (key packing)                    */
+  int32_t total_classes;     /* classes over all tasks (key packing)                        */
+  int32_t capacity;          /* rows available in out_keys / out_boxes                      */
+  float min_confidence;      /* compared as float32, like torch does                        */
+  rv3d_partitions parts;
+} rv3d_decode_params;
+
+/* Fused: sigmoid * mask, max over classes, threshold, decode of the survivors only,
+ * range-partition subsampling, warp-aggregated compaction.
+ * logits (B,C,H,W), regressands (B,8,H,W), cart (B,3,H,W) in `dtype`; mask (B,1,H,W) u8/bool.
+ * Survivor r gets: out_keys[r] = sort key (sweep, class | score desc | candidate asc),
+ * out_boxes[r] = 8 f32 [x,y,z,l,w,h,yaw,score].  *counter (device i32) is advanced
+ * atomically, so several (stride, task) calls append to the same arrays; rows past
+ * `capacity` are dropped and counted (the caller checks *counter <= capacity). */
+int rv3d_decode_compact(const rv3d_decode_params *p, const void *logits, const void *regressands,
+                        const void *cart, const uint8_t *mask, uint64_t *out_keys, float *out_boxes,
+                        int32_t *counter, rv3d_stream_t stream);
+
+/* Same compaction for already-dense candidates (the input of batched_multiclass_nms,
+ * math/ops/nms.py:181-190): cuboids (B,K,7) f32, scores (B,K) f32, categories (B,K) i64. */
+int rv3d_compact_candidates(const float *cuboids, const float *scores, const int64_t *categories,
+                            int32_t batch, int32_t k, int32_t total_classes, float min_confidence,
+                            int32_t apply_threshold, int32_t capacity, uint64_t *out_keys,
+                            float *out_boxes, int32_t *counter, rv3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 3. Suppression
+ * replaces: math/ops/nms.py:181-266 batched_multiclass_nms, :11-61 hard_multiclass_nms
+ *           (detectron2 nms_rotated, :41-45), :64-123 weighted_multiclass_nms,
+ *           :126-177 weighted_nms (TorchEx wnms_gpu, :161-170),
+ *           math/ops/iou.py:11-47 iou_3d_axis_aligned (mmcv box_iou_rotated, :15)
+ * ------------------------------------------------------------------------------------ */
+#define RV3D_NMS_HARD 0
+#define RV3D_NMS_WEIGHTED 1
+
+typedef struct {
+  int32_t batch, total_classes, total_candidates;
+  int32_t num_pre_nms, num_post_nms;
+  int32_t mode;              /* RV3D_NMS_*                                              */
+  float iou_threshold;       /* float32(iou_threshold): nms.py:44 passes an f32 tensor  */
+  float merge_threshold;     /* weighted only (0.5, nms.py:106)                         */
+  int32_t n_candidates;      /* HOST copy of the compaction counter                     */
+  int32_t out_capacity;      /* rows available in the out_* arrays                      */
+} rv3d_nms_params;
+
+size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);
+
+/* keys / boxes: the compaction output (keys are sorted in place -> clobbered).
+ * Outputs, in the reference's order (sweep asc, class asc, score desc):
+ *   out_params (out_capacity,10) f32 [x,y,z,l,w,h,qw,qx,qy,qz]   (range_decoder.py:122-123)
+ *   out_scores, out_categories, out_batch (out_capacity,) f32      (nms.py:51,113,242)
+ *   out_count device i32: rows written.
+ * stats (device, 8 x i64, may be NULL): [0] rotated-IoU evaluations, [1] kept,
+ * [2] frontier rounds, [3] circle tests. */
+int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys, const float *boxes, float *out_params,
+             float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
+             int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
+/* detectron2-style entry: boxes (N,5) f32 (xc,yc,w,h,angle_deg), scores (N,) f32 ->
+ * keep (N,) i64 original indices in score order, *n_keep device i32.
+ * replaces torch.ops.detectron2.nms_rotated (call site nms.py:41-45). */
+size_t rv3d_nms_rotated_scratch_bytes(int32_t n);
+int rv3d_nms_rotated(const float *boxes, const float *scores, int32_t n, float iou_threshold,
+                     int64_t *keep, int32_t *n_keep, void *scratch, size_t scratch_bytes,
+                     rv3d_stream_t stream);
+
+/* TorchEx-style entry: boxes (N,5) f32 (x1,y1,x2,y2,ry) and data (N,D) f32 (score LAST),
+ * both already sorted by score descending (nms.py:148-154).  output (N,D) f32, keep (N,) i64,
+ * count (N,) i64, *n_out device i32.  replaces weighted_nms_ext.wnms_gpu (nms.py:161-170). */
+size_t rv3d_wnms_scratch_bytes(int32_t n, int32_t d);
+int rv3d_wnms(const float *boxes, const float *data, int32_t n, int32_t d, float nms_threshold,
+              float merge_threshold, float *output, int64_t *keep, int64_t *count, int32_t *n_out,
+              void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
+/* Aligned rotated BEV IoU + axis-aligned 3D IoU of (N,7) f32 cuboids (iou.py:11-47).
+ * status (device i32): set to 1 if any 3D IoU is non-finite (the reference raises). */
+int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b, int64_t n, float *iou3d,
+                       float *iou_bev, int32_t *status, rv3d_stream_t stream);
+
+/* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
+int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);
+
+/* Threshold-only branch of RangeDecoder.decode (use_nms=False, range_decoder.py:110-120):
+ * compaction output -> rows ordered by (sweep, candidate). */
+size_t rv3d_pack_candidates_scratch_bytes(int32_t n_candidates);
+int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n_candidates, int32_t batch,
+                         int32_t total_classes, int32_t total_candidates, float *out_params,
+                         float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
+                         size_t scratch_bytes, rv3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RV3D_H_ */

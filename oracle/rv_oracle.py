@@ -131,7 +131,8 @@ def build_range_view(xyz, intensity, laser_number, laser_mapping, lidar_offset,
     out = z_buffer(indices, hybrid[:, 2], feats, num_lasers, width, return_winner=return_winner)
     if return_winner:
         img, win = out
-        win = np.where(win >= 0, keep[np.maximum(win, 0)], -1).astype(np.int32)
+        if len(keep):
+            win = np.where(win >= 0, keep[np.maximum(win, 0)], -1).astype(np.int32)
         return img, win
     return out
 

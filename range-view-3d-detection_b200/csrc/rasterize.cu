@@ -1,0 +1,285 @@
+// rasterize.cu -- range-image rasterization of raw sweeps (K1 scatter + K1b resolve).
+//
+// Replaces (paths relative to /root/reference):
+//   math/range_view.py:14-44            build_range_view
+//   math/numpy/conversions.py:46-73     cart_to_sph
+//   math/numpy/conversions.py:9-43      build_range_view_coordinates (library column formula)
+//   converters/av2/utils.py:108-153     build_range_view_coordinates (converter column formula)
+//   math/numpy/conversions.py:106-128   z_buffer (numba serial loop)
+//
+// Design: the reference's z-buffer is a serial, order-dependent loop with a float32 depth
+// buffer and float64 distances.  Its fixed point has a closed form (DESIGN.md "K1"):
+//   m      = min_i f32(d_i)                      (f32 = round-to-nearest)
+//   class0 = { i : f32(d_i) == m and d_i <  m }  (rounded up: always re-trigger the `<` test)
+//   class1 = { i : f32(d_i) == m and d_i >= m }
+//   winner = max index of class0 if class0 is non-empty, else min index of class1.
+// That is the minimum of one packed 64-bit key per point, so a single atomicMin per point
+// gives a deterministic, order-independent, bit-exact winner:
+//   key = f32bits(m) << 32 | class << 31 | (class ? i : ~i & 0x7fffffff)
+// K1  (scatter): 1 thread / point, float4 load, fp64 index math, atomicMin.u64 (REDG).
+// K1b (resolve): 1 thread / pixel, reads the key, gathers the winning point, recomputes its
+//                spherical coordinates and writes the 7 channel planes coalesced.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rv3d {
+
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ unsigned long long pack_key(double d, uint32_t i) {
+  const float m = __double2float_rn(d);
+  const uint32_t cls = (d < static_cast<double>(m)) ? 0u : 1u;
+  const uint32_t low = cls ? (0x80000000u | i) : (~i & 0x7fffffffu);
+  return (static_cast<unsigned long long>(__float_as_uint(m)) << 32) | low;
+}
+__device__ __forceinline__ uint32_t key_index(unsigned long long key) {
+  const uint32_t low = static_cast<uint32_t>(key);
+  return (low & 0x80000000u) ? (low & 0x7fffffffu) : (~low & 0x7fffffffu);
+}
+
+struct RasterArgs {
+  int32_t B, max_points, H, W, az_bins, num_lasers, col_mode;
+  double ox, oy, oz, min_distance, bin_scale;  // bin_scale = az_bins / tau (computed on the host in double)
+};
+
+// azimuth -> column, both formulas, in fp64 with round-half-even (np.round == rint)
+__device__ __forceinline__ double column_of(double az, const RasterArgs &a) {
+  double t = az + CUDART_PI;   // azimuth += math.pi
+  t = t * a.bin_scale;         // azimuth *= n_azimuth_bins / math.tau
+  const double nb = static_cast<double>(a.az_bins);
+  double c = (a.col_mode == RV3D_COL_LIBRARY) ? rint((nb - t) - 1.0) : (nb - rint(t));
+  return fmin(fmax(c, 0.0), nb - 1.0);  // np.clip(col, 0, W-1)
+}
+
+__global__ void __launch_bounds__(256)
+raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uint8_t *__restrict__ laser,
+                      const int32_t *__restrict__ n_points, const int32_t *__restrict__ laser_mapping,
+                      unsigned long long *__restrict__ keys) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points[b]) return;
+  const size_t gi = static_cast<size_t>(b) * a.max_points + i;
+  const int l = laser[gi];
+  if (l >= a.num_lasers) return;  // range_view.py:23-26
+  const float4 p = ldg_stream_f4(points + gi);
+  const double cx = static_cast<double>(p.x) - a.ox;  // range_view.py:29
+  const double cy = static_cast<double>(p.y) - a.oy;
+  const double cz = static_cast<double>(p.z) - a.oz;
+  const double hxy = hypot(cx, cy);
+  const double r = hypot(hxy, cz);
+  // z_buffer: `d < min_distance -> continue`, then `d < buffer` with buffer starting at +inf;
+  // NaN and +inf never write.
+  if (!(r >= a.min_distance) || !(r < CUDART_INF)) return;
+  const double col = column_of(atan2(cy, cx), a);
+  const int row = a.H - laser_mapping[l] - 1;  // conversions.py:37
+  const long long pix = static_cast<long long>(row) * a.W + static_cast<long long>(col);
+  if (pix < 0 || pix >= static_cast<long long>(a.H) * a.W) return;
+  atomicMin(keys + static_cast<size_t>(b) * a.H * a.W + pix, pack_key(r, static_cast<uint32_t>(i)));
+}
+
+__global__ void __launch_bounds__(256)
+raster_resolve_kernel(RasterArgs a, const float4 *__restrict__ points,
+                      const unsigned long long *__restrict__ keys, float *__restrict__ image,
+                      int32_t *__restrict__ winner) {
+  const int b = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const unsigned long long key = keys[static_cast<size_t>(b) * HW + pix];
+  float *out = image + static_cast<size_t>(b) * 7 * HW + pix;
+  float az = 0.f, inc = 0.f, rr = 0.f, x = 0.f, y = 0.f, z = 0.f, it = 0.f;
+  int32_t w = -1;
+  if (key != kEmptyKey) {
+    w = static_cast<int32_t>(key_index(key));
+    const float4 p = points[static_cast<size_t>(b) * a.max_points + w];
+    const double cx = static_cast<double>(p.x) - a.ox;
+    const double cy = static_cast<double>(p.y) - a.oy;
+    const double cz = static_cast<double>(p.z) - a.oz;
+    const double hxy = hypot(cx, cy);
+    // features are snapshotted BEFORE the in-place azimuth rescale (range_view.py:33, H3)
+    az = static_cast<float>(atan2(cy, cx));
+    inc = static_cast<float>(atan2(cz, hxy));
+    rr = static_cast<float>(hypot(hxy, cz));
+    x = p.x; y = p.y; z = p.z; it = p.w;
+  }
+  out[0 * HW] = az;
+  out[1 * HW] = inc;
+  out[2 * HW] = rr;
+  out[3 * HW] = x;
+  out[4 * HW] = y;
+  out[5 * HW] = z;
+  out[6 * HW] = it;
+  if (winner) winner[static_cast<size_t>(b) * HW + pix] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic z_buffer(indices, distances, features, H, W, min_distance)
+// ---------------------------------------------------------------------------------------------
+template <typename D>
+__global__ void __launch_bounds__(256)
+zbuffer_scatter_kernel(const int64_t *__restrict__ rows, const int64_t *__restrict__ cols,
+                       const D *__restrict__ dist, int64_t n, int H, int W, double min_distance,
+                       unsigned long long *__restrict__ keys) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double d = static_cast<double>(dist[i]);
+  if (!(d >= min_distance) || !(d < CUDART_INF)) return;
+  const int64_t pix = rows[i] * W + cols[i];
+  if (pix < 0 || pix >= static_cast<int64_t>(H) * W) return;
+  atomicMin(keys + pix, pack_key(d, static_cast<uint32_t>(i)));
+}
+
+template <typename F>
+__global__ void __launch_bounds__(256)
+zbuffer_resolve_kernel(const F *__restrict__ feat, int C, int64_t n, int HW,
+                       const unsigned long long *__restrict__ keys, float *__restrict__ image,
+                       int32_t *__restrict__ winner) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const unsigned long long key = keys[pix];
+  const int32_t w = (key == kEmptyKey) ? -1 : static_cast<int32_t>(key_index(key));
+  for (int c = 0; c < C; ++c)
+    image[static_cast<size_t>(c) * HW + pix] = (w < 0) ? 0.f : static_cast<float>(feat[static_cast<size_t>(c) * n + w]);
+  if (winner) winner[pix] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cart_to_sph / build_range_view_coordinates as free-standing operators
+// ---------------------------------------------------------------------------------------------
+__global__ void cart_to_sph_kernel(const double *__restrict__ cart, double *__restrict__ sph, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = cart[3 * i], y = cart[3 * i + 1], z = cart[3 * i + 2];
+  const double hxy = hypot(x, y);
+  sph[3 * i] = atan2(y, x);
+  sph[3 * i + 1] = atan2(z, hxy);
+  sph[3 * i + 2] = hypot(hxy, z);
+}
+
+__global__ void rv_coordinates_kernel(double *__restrict__ sph, const int64_t *__restrict__ laser,
+                                      const int64_t *__restrict__ mapping, int n_mapping, int64_t n,
+                                      int n_inc, RasterArgs a, double *__restrict__ hybrid) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = sph[3 * i] + CUDART_PI;
+  t = t * a.bin_scale;
+  sph[3 * i] = t;  // the reference mutates its input (conversions.py:33-34)
+  const double nb = static_cast<double>(a.az_bins);
+  double c = (a.col_mode == RV3D_COL_LIBRARY) ? rint((nb - t) - 1.0) : (nb - rint(t));
+  c = fmin(fmax(c, 0.0), nb - 1.0);
+  int64_t l = laser[i];
+  if (l < 0) l += n_mapping;  // numpy negative indexing
+  const double row = (l >= 0 && l < n_mapping) ? static_cast<double>(n_inc - mapping[l] - 1) : CUDART_NAN;
+  hybrid[3 * i] = row;
+  hybrid[3 * i + 1] = c;
+  hybrid[3 * i + 2] = sph[3 * i + 2];
+}
+
+static RasterArgs make_args(const rv3d_raster_params *p) {
+  RasterArgs a;
+  a.B = p->batch; a.max_points = p->max_points; a.H = p->height; a.W = p->width;
+  a.az_bins = p->azimuth_bins; a.num_lasers = p->num_lasers; a.col_mode = p->col_mode;
+  a.ox = p->lidar_offset[0]; a.oy = p->lidar_offset[1]; a.oz = p->lidar_offset[2];
+  a.min_distance = p->min_distance;
+  a.bin_scale = static_cast<double>(p->azimuth_bins) / 6.283185307179586;  // n_azimuth_bins / math.tau
+  return a;
+}
+
+}  // namespace rv3d
+
+using namespace rv3d;
+
+extern "C" size_t rv3d_rasterize_scratch_bytes(const rv3d_raster_params *p) {
+  if (!p) return 0;
+  return static_cast<size_t>(p->batch) * p->height * p->width * sizeof(unsigned long long);
+}
+
+extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, const uint8_t *laser,
+                              const int32_t *n_points, const int32_t *laser_mapping, float *image,
+                              int32_t *winner, void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && points && laser && n_points && laser_mapping && image && scratch);
+  RV3D_CHECK_ARG(p->batch > 0 && p->max_points > 0 && p->height > 0 && p->width > 0 && p->azimuth_bins > 0);
+  RV3D_CHECK_ARG(p->num_lasers > 0 && p->num_lasers <= 256 && p->reserved == 0);
+  RV3D_CHECK_ARG(p->col_mode == RV3D_COL_LIBRARY || p->col_mode == RV3D_COL_CONVERTER);
+  RV3D_CHECK_ARG(static_cast<int64_t>(p->height) * p->width < (int64_t(1) << 31));
+  if (!aligned(points, 16) || !aligned(scratch, 8)) return RV3D_ERR_ALIGN;
+  const size_t need = rv3d_rasterize_scratch_bytes(p);
+  if (scratch_bytes < need) return RV3D_ERR_SCRATCH;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const RasterArgs a = make_args(p);
+  auto *keys = static_cast<unsigned long long *>(scratch);
+  RV3D_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, need, s));
+  dim3 g1(ceil_div(p->max_points, 256), p->batch);
+  raster_scatter_kernel<<<g1, 256, 0, s>>>(a, reinterpret_cast<const float4 *>(points), laser, n_points,
+                                           laser_mapping, keys);
+  RV3D_CHECK_LAUNCH();
+  dim3 g2(ceil_div(static_cast<int64_t>(p->height) * p->width, 256), p->batch);
+  raster_resolve_kernel<<<g2, 256, 0, s>>>(a, reinterpret_cast<const float4 *>(points), keys, image, winner);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" size_t rv3d_zbuffer_scratch_bytes(int32_t height, int32_t width) {
+  return static_cast<size_t>(height) * width * sizeof(unsigned long long);
+}
+
+extern "C" int rv3d_zbuffer(const int64_t *rows, const int64_t *cols, const void *dist, int32_t dist_is_f64,
+                            const void *feat, int32_t feat_is_f64, int32_t channels, int64_t n,
+                            int32_t height, int32_t width, double min_distance, float *image,
+                            int32_t *winner, void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(image && scratch && height > 0 && width > 0 && channels >= 0 && n >= 0);
+  RV3D_CHECK_ARG(n == 0 || (rows && cols && dist && feat));
+  RV3D_CHECK_ARG(n < (int64_t(1) << 31) && static_cast<int64_t>(height) * width < (int64_t(1) << 31));
+  const size_t need = rv3d_zbuffer_scratch_bytes(height, width);
+  if (scratch_bytes < need) return RV3D_ERR_SCRATCH;
+  if (!aligned(scratch, 8)) return RV3D_ERR_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto *keys = static_cast<unsigned long long *>(scratch);
+  const int HW = height * width;
+  RV3D_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, need, s));
+  if (n > 0) {
+    const int g = ceil_div(n, 256);
+    if (dist_is_f64)
+      zbuffer_scatter_kernel<double><<<g, 256, 0, s>>>(rows, cols, static_cast<const double *>(dist), n, height,
+                                                       width, min_distance, keys);
+    else
+      zbuffer_scatter_kernel<float><<<g, 256, 0, s>>>(rows, cols, static_cast<const float *>(dist), n, height,
+                                                      width, min_distance, keys);
+    RV3D_CHECK_LAUNCH();
+  }
+  const int g2 = ceil_div(HW, 256);
+  if (feat_is_f64)
+    zbuffer_resolve_kernel<double><<<g2, 256, 0, s>>>(static_cast<const double *>(feat), channels, n, HW, keys,
+                                                      image, winner);
+  else
+    zbuffer_resolve_kernel<float><<<g2, 256, 0, s>>>(static_cast<const float *>(feat), channels, n, HW, keys,
+                                                     image, winner);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_cart_to_sph(const double *cart, double *sph, int64_t n, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && (n == 0 || (cart && sph)));
+  if (n == 0) return RV3D_OK;
+  cart_to_sph_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cart, sph, n);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_range_view_coordinates(double *sph, const int64_t *laser, const int64_t *laser_mapping,
+                                           int32_t n_mapping, int64_t n, int32_t n_inclination_bins,
+                                           int32_t n_azimuth_bins, int32_t col_mode, double *hybrid,
+                                           rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && n_mapping > 0 && n_azimuth_bins > 0 && (n == 0 || (sph && laser && laser_mapping && hybrid)));
+  RV3D_CHECK_ARG(col_mode == RV3D_COL_LIBRARY || col_mode == RV3D_COL_CONVERTER);
+  if (n == 0) return RV3D_OK;
+  RasterArgs a{};
+  a.az_bins = n_azimuth_bins;
+  a.col_mode = col_mode;
+  a.bin_scale = static_cast<double>(n_azimuth_bins) / 6.283185307179586;
+  rv_coordinates_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sph, laser, laser_mapping, n_mapping, n, n_inclination_bins, a, hybrid);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}

@@ -1,0 +1,110 @@
+"""Range-image rasterization.  Host-side mirror of ``torchbox3d/math/range_view.py``.
+
+``build_range_view`` keeps the reference signature (math/range_view.py:14-22) and semantics;
+``rasterize_sweeps`` is the batched tensor-in / tensor-out entry the hot path uses.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .._util import ptr, require_cuda, scratch, stream_ptr
+
+__all__ = ["build_range_view", "rasterize_sweeps", "pack_sweeps"]
+
+
+def rasterize_sweeps(points: torch.Tensor, laser: torch.Tensor, n_points: torch.Tensor,
+                     laser_mapping: torch.Tensor, lidar_offset: Sequence[float], height: int = 64,
+                     width: int = 1800, n_azimuth_bins: Optional[int] = None, num_lasers: Optional[int] = None,
+                     col_mode: str = "library", min_distance: float = 1.0, return_winner: bool = False,
+                     out: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None
+                     ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """Rasterize B raw sweeps in one launch pair.
+
+    points (B,Nmax,4) f32 [x,y,z,intensity] (ego frame), laser (B,Nmax) u8, n_points (B,) i32,
+    laser_mapping (num_lasers,) i32 -> image (B,7,H,W) f32 [az, inc, range, x, y, z, intensity]
+    (math/range_view.py:33), optionally the winner map (B,H,W) i32 (-1 = empty pixel).
+    ``n_azimuth_bins`` defaults to ``width`` (the reference's library wrapper always uses 1800,
+    see ``build_range_view``)."""
+    dev = require_cuda(points, laser, n_points, laser_mapping)
+    if points.dtype != torch.float32 or points.dim() != 3 or points.shape[-1] != 4:
+        raise ValueError("points must be (B,Nmax,4) float32")
+    if laser.dtype != torch.uint8 or n_points.dtype != torch.int32 or laser_mapping.dtype != torch.int32:
+        raise ValueError("laser must be uint8; n_points and laser_mapping int32")
+    points, laser = points.contiguous(), laser.contiguous()
+    B, nmax, _ = points.shape
+    p = N.RasterParams()
+    p.batch, p.max_points, p.height, p.width = B, nmax, height, width
+    p.azimuth_bins = width if n_azimuth_bins is None else n_azimuth_bins
+    p.num_lasers = laser_mapping.numel() if num_lasers is None else num_lasers
+    if p.num_lasers > laser_mapping.numel():
+        raise ValueError("laser_mapping is shorter than num_lasers")
+    p.col_mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
+    p.lidar_offset[:] = [float(v) for v in lidar_offset]
+    p.min_distance = float(min_distance)
+    lib = N.lib()
+    need = lib.rv3d_rasterize_scratch_bytes(p)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = scratch(need, dev)
+    image = out if out is not None else torch.empty((B, 7, height, width), dtype=torch.float32, device=dev)
+    winner = torch.empty((B, height, width), dtype=torch.int32, device=dev) if return_winner else None
+    N.check(lib.rv3d_rasterize(p, ptr(points), ptr(laser), ptr(n_points), ptr(laser_mapping), ptr(image),
+                               ptr(winner), ptr(workspace), workspace.numel() * workspace.element_size(),
+                               stream_ptr(dev)), "rv3d_rasterize")
+    return (image, winner) if return_winner else image
+
+
+def pack_sweeps(sweeps, device, pin: bool = False):
+    """[(xyz (n,3) f32, intensity (n,), laser (n,) u8), ...] -> padded host tensors
+    (points (B,Nmax,4) f32, laser (B,Nmax) u8, n_points (B,) i32)."""
+    B = len(sweeps)
+    nmax = max(len(s[0]) for s in sweeps)
+    nmax = (nmax + 63) // 64 * 64
+    pts = torch.zeros((B, nmax, 4), dtype=torch.float32, pin_memory=pin)
+    las = torch.full((B, nmax), 255, dtype=torch.uint8, pin_memory=pin)
+    cnt = torch.zeros((B,), dtype=torch.int32, pin_memory=pin)
+    for b, (xyz, inten, laser) in enumerate(sweeps):
+        n = len(xyz)
+        pts[b, :n, :3] = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float32))
+        pts[b, :n, 3] = torch.as_tensor(np.ascontiguousarray(inten, dtype=np.float32))
+        las[b, :n] = torch.as_tensor(np.ascontiguousarray(laser, dtype=np.uint8))
+        cnt[b] = n
+    return pts, las, cnt
+
+
+def _column(sweep, name: str) -> np.ndarray:
+    col = sweep[name]
+    if hasattr(col, "to_numpy"):
+        col = col.to_numpy()
+    return np.asarray(col)
+
+
+def build_range_view(sweep, laser_mapping: np.ndarray, lidar_offset: np.ndarray, timestamp_ns: Optional[int] = None,
+                     max_timestamp_ns: Optional[int] = None, num_lasers: int = 64, width: int = 1800,
+                     device: Union[str, torch.device] = "cuda") -> np.ndarray:
+    """Drop-in for ``torchbox3d.math.range_view.build_range_view`` (math/range_view.py:14-44).
+
+    ``sweep``: a polars DataFrame (as in the reference) or any mapping with columns
+    ``x, y, z, intensity, laser_number``.  Returns a (7, num_lasers, width) float32 numpy array.
+    Like the reference, the azimuth column is always computed for 1800 bins because the
+    reference never forwards ``width`` to build_range_view_coordinates (math/range_view.py:34-40)."""
+    del timestamp_ns, max_timestamp_ns  # unused upstream as well (range_view.py:25)
+    xyz = np.stack([_column(sweep, "x"), _column(sweep, "y"), _column(sweep, "z")], axis=1)
+    if xyz.dtype == np.float64:
+        raise TypeError("build_range_view: x/y/z must be float32 (or float16) storage; the f64 "
+                        "arithmetic happens on the device")
+    laser = _column(sweep, "laser_number")
+    if laser.max(initial=0) > 255:
+        raise ValueError("laser_number must fit uint8")
+    pts, las, cnt = pack_sweeps([(xyz.astype(np.float32), _column(sweep, "intensity").astype(np.float32),
+                                  laser.astype(np.uint8))], device)
+    dev = torch.device(device)
+    mapping = torch.as_tensor(np.asarray(laser_mapping)[:num_lasers].astype(np.int32), device=dev)
+    if mapping.numel() < num_lasers:
+        raise ValueError("laser_mapping is shorter than num_lasers")
+    image = rasterize_sweeps(pts.to(dev), las.to(dev), cnt.to(dev), mapping, np.asarray(lidar_offset, dtype=np.float64),
+                             height=num_lasers, width=width, n_azimuth_bins=1800, num_lasers=num_lasers)
+    return image[0].cpu().numpy()
