@@ -10,7 +10,7 @@
  *     the current device, and enqueues all work on the caller's stream;
  *   - functions return RV3D_OK (0) or a negative rv3d_status; no exceptions, no aborts;
  *   - counts that only the device knows are returned in device memory; the two
- *     entry points that need one on the host (rv3d_nms_sorted_setup) say so;
+ *     entry points that need one on the host (rv3d_nms: n_candidates) say so;
  *   - re-entrant, no global mutable state; one host thread per GPU.
  *
  * Each entry point names the reference interface it replaces (paths relative to
@@ -176,6 +176,8 @@ int rv3d_compact_candidates(const float *cuboids, const float *scores, const int
  * ------------------------------------------------------------------------------------ */
 #define RV3D_NMS_HARD 0
 #define RV3D_NMS_WEIGHTED 1
+#define RV3D_OUT_QUAT 0
+#define RV3D_OUT_YAW 1
 
 typedef struct {
   int32_t batch, total_classes, total_candidates;
@@ -185,13 +187,16 @@ typedef struct {
   float merge_threshold;     /* weighted only (0.5, nms.py:106)                         */
   int32_t n_candidates;      /* HOST copy of the compaction counter                     */
   int32_t out_capacity;      /* rows available in the out_* arrays                      */
+  int32_t out_layout;        /* RV3D_OUT_QUAT: out_params (cap,10) [x,y,z,l,w,h,qw,qx,qy,qz]
+                                (RangeDecoder.decode); RV3D_OUT_YAW: out_params (cap,7)
+                                [x,y,z,l,w,h,yaw] (batched_multiclass_nms)               */
 } rv3d_nms_params;
 
 size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);
 
 /* keys / boxes: the compaction output (keys are sorted in place -> clobbered).
  * Outputs, in the reference's order (sweep asc, class asc, score desc):
- *   out_params (out_capacity,10) f32 [x,y,z,l,w,h,qw,qx,qy,qz]   (range_decoder.py:122-123)
+ *   out_params (out_capacity,10|7) f32, see out_layout          (range_decoder.py:122-123)
  *   out_scores, out_categories, out_batch (out_capacity,) f32      (nms.py:51,113,242)
  *   out_count device i32: rows written.
  * stats (device, 8 x i64, may be NULL): [0] rotated-IoU evaluations, [1] kept,

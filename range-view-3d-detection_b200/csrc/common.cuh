@@ -28,6 +28,7 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74
 
 static inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ constexpr size_t align_up_c(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 static inline int bits_for(int64_t n) {  // bits needed to hold values 0..n-1
   int b = 0;

@@ -1,0 +1,588 @@
+// decode.cu -- dense per-pixel box decoding (K2) and its free-standing operator forms.
+//
+// Replaces (paths relative to /root/reference):
+//   math/ops/coding.py:110-144          decode_range_view  (+ :79-107 egovehicle_from_azimuth)
+//   nn/decoders/range_decoder.py:49-77  sigmoid*mask, max over classes, decode, sample_by_range
+//   nn/decoders/range_decoder.py:127-156 sample_by_range
+//   math/ops/nms.py:212-215             min-confidence gather
+//   math/linalg/lie/SO3.py:122-134      yaw_to_quat
+//
+// K2 (decode_compact) is one pass over the head outputs:
+//   phase A  every thread owns 4 consecutive pixels: float4 loads of the C logit planes + mask,
+//            running max (first index wins ties, NaN kills the pixel like torch.max would),
+//            correctly-rounded float32 sigmoid of the winner, threshold; for pixels that pass,
+//            the range-partition / column-stride test of sample_by_range on ||cart||.
+//   scan     block-wide exclusive scan of (live pixels, emitted candidates); ONE global atomicAdd
+//            per 1024 pixels reserves the output rows.
+//   phase B  live pixels are compacted into a shared-memory queue so the fp64 decode
+//            (3 exp, 2 atan2, sincos) runs with dense lanes instead of ~20 %-full warps;
+//            each live pixel writes 1..n_partitions (key, box) rows.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rv3d {
+
+// ------------------------------------------------------------------------------------------
+// typed loads: everything is widened to float on load (exact for f16 / bf16)
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Ld;
+template <> struct Ld<float> {
+  static __device__ __forceinline__ float one(const float *p) { return __ldg(p); }
+  static __device__ __forceinline__ void four(const float *p, float (&v)[4]) {
+    const float4 t = ldg_stream_f4(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ float cast(double x) { return static_cast<float>(x); }
+};
+template <> struct Ld<__half> {
+  static __device__ __forceinline__ float one(const __half *p) { return __half2float(*p); }
+  static __device__ __forceinline__ void four(const __half *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    const __half2 a = *reinterpret_cast<const __half2 *>(&t.x), b = *reinterpret_cast<const __half2 *>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ __half cast(double x) { return __double2half(x); }
+};
+template <> struct Ld<__nv_bfloat16> {
+  static __device__ __forceinline__ float one(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void four(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ __nv_bfloat16 cast(double x) { return __double2bfloat16(x); }
+};
+
+// sigmoid evaluated in fp64 and rounded ONCE to the tensor dtype (float32 scores for float32
+// logits; under fp16 autocast the reference's scores are fp16 too), returned widened to float
+template <typename T>
+__device__ __forceinline__ float sigmoid_t(float x) {
+  return static_cast<float>(Ld<T>::cast(1.0 / (1.0 + exp(-static_cast<double>(x)))));
+}
+
+// coding.py:110-144 in fp64.  reg[8], cart[3] -> out[7] (double)
+__device__ __forceinline__ void decode_box(const float (&reg)[8], const float (&cart)[3], bool az_inv,
+                                           double (&out)[7]) {
+  double ox = reg[0], oy = reg[1];
+  const double oz = reg[2];
+  double yaw = atan2(static_cast<double>(reg[6]), static_cast<double>(reg[7]));  // :136
+  const double cx = cart[0], cy = cart[1], cz = cart[2];
+  if (az_inv) {                                                                    // :79-107
+    const double phi = atan2(cy, cx);
+    double s, c;
+    sincos(phi, &s, &c);
+    const double x = c * ox - s * oy;
+    const double y = s * ox + c * oy;
+    ox = x; oy = y;
+    yaw += phi;
+  }
+  out[0] = cx + ox; out[1] = cy + oy; out[2] = cz + oz;                            // :142
+  out[3] = exp(static_cast<double>(reg[3]));                                       // :132
+  out[4] = exp(static_cast<double>(reg[4]));
+  out[5] = exp(static_cast<double>(reg[5]));
+  out[6] = yaw;
+}
+
+// ------------------------------------------------------------------------------------------
+// decode_range_view as a dense operator: (B,8,H,W) + (B,3,H,W) -> (B,7,H,W)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+decode_dense_kernel(const T *__restrict__ reg, const T *__restrict__ cart, T *__restrict__ out, int HW,
+                    int az_inv) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  float r[8], c[3];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(reg + (static_cast<size_t>(b) * 8 + k) * HW + p);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c[k] = Ld<T>::one(cart + (static_cast<size_t>(b) * 3 + k) * HW + p);
+  double o[7];
+  decode_box(r, c, az_inv != 0, o);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) out[(static_cast<size_t>(b) * 7 + k) * HW + p] = Ld<T>::cast(o[k]);
+}
+
+// ------------------------------------------------------------------------------------------
+// sample_by_range as a dense operator
+// ------------------------------------------------------------------------------------------
+struct PartArgs {
+  int n;
+  float lower[RV3D_MAX_PARTITIONS], upper[RV3D_MAX_PARTITIONS];
+  int rate[RV3D_MAX_PARTITIONS], wsub[RV3D_MAX_PARTITIONS], off[RV3D_MAX_PARTITIONS + 1];
+};
+
+static PartArgs make_parts(const rv3d_partitions *p, int H, int W) {
+  PartArgs a{};
+  a.n = p ? p->n_partitions : 0;
+  int off = 0;
+  for (int i = 0; i < a.n; ++i) {
+    a.lower[i] = p->lower[i]; a.upper[i] = p->upper[i]; a.rate[i] = p->rate[i];
+    a.wsub[i] = (W + p->rate[i] - 1) / p->rate[i];
+    a.off[i] = off;
+    off += H * a.wsub[i];
+  }
+  a.off[a.n] = off;
+  if (a.n == 0) a.off[0] = H * W;
+  return a;
+}
+
+// ||cart||_2 in float32, the way torch's CPU / CUDA vector_norm reduces three floats
+__device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
+
+__global__ void __launch_bounds__(256)
+sample_by_range_kernel(const float *__restrict__ scores, const int64_t *__restrict__ cats,
+                       const float *__restrict__ cub, const float *__restrict__ cart, PartArgs pa, int H, int W,
+                       float *__restrict__ o_scores, int64_t *__restrict__ o_cats, float *__restrict__ o_cub) {
+  const int b = blockIdx.y;
+  const int K = pa.off[pa.n];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int i = 0;
+  while (i + 1 < pa.n && k >= pa.off[i + 1]) ++i;
+  const int local = k - pa.off[i];
+  const int h = local / pa.wsub[i];
+  const int w = (local - h * pa.wsub[i]) * pa.rate[i];
+  const int HW = H * W, p = h * W + w;
+  const float *c = cart + static_cast<size_t>(b) * 3 * HW + p;
+  const float d = norm3(c[0], c[HW], c[2 * HW]);
+  const bool in = (d > pa.lower[i]) && (d <= pa.upper[i]);
+  const float s = scores[static_cast<size_t>(b) * HW + p];
+  o_scores[static_cast<size_t>(b) * K + k] = in ? s : s * 0.0f;  // scores * partition (NaN/inf semantics kept)
+  o_cats[static_cast<size_t>(b) * K + k] = cats[static_cast<size_t>(b) * HW + p];
+  float *oc = o_cub + (static_cast<size_t>(b) * K + k) * 7;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) oc[j] = cub[(static_cast<size_t>(b) * 7 + j) * HW + p];
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: fused decode + threshold + compaction
+// ------------------------------------------------------------------------------------------
+// 64-bit sort key: [ segment = sweep * total_classes + class | ~orderable(score) | candidate ].
+// Ascending key order == segment asc, score desc, candidate index asc: the total order the
+// suppression step works in (DESIGN.md "K3").
+struct KeyPack {
+  int idx_bits;  // width of the low field (candidate index)
+  __device__ __forceinline__ unsigned long long make(uint32_t seg, float score, uint32_t cand) const {
+    const uint32_t desc = ~orderable_f32(__float_as_uint(score));
+    return (static_cast<unsigned long long>(seg) << (32 + idx_bits)) |
+           (static_cast<unsigned long long>(desc) << idx_bits) | cand;
+  }
+};
+
+struct DecodeArgs {
+  int B, C, H, W, az_inv, cat_off, cand_off, total_classes, capacity;
+  float thr;
+  KeyPack kp;
+  PartArgs pa;
+};
+
+constexpr int kDecThreads = 256;
+constexpr int kPxPerThread = 4;
+constexpr int kPxPerBlock = kDecThreads * kPxPerThread;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kDecThreads)
+decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__restrict__ reg,
+                      const T *__restrict__ cart, const uint8_t *__restrict__ mask,
+                      unsigned long long *__restrict__ out_keys, float *__restrict__ out_boxes,
+                      int32_t *__restrict__ counter) {
+  __shared__ uint32_t s_scan[kDecThreads / 32];
+  __shared__ uint32_t s_base, s_total_live;
+  __shared__ uint16_t q_pix[kPxPerBlock];     // local pixel id of live pixel t
+  __shared__ uint16_t q_meta[kPxPerBlock];    // class index within the task
+  __shared__ uint8_t q_emit[kPxPerBlock];     // partition bit-mask
+  __shared__ float q_score[kPxPerBlock];
+  __shared__ uint32_t q_off[kPxPerBlock];     // exclusive emit offset inside the block
+
+  const int b = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int tid = threadIdx.x;
+  const int blk0 = blockIdx.x * kPxPerBlock;
+
+  int pix[kPxPerThread];
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) pix[j] = kVec ? blk0 + tid * 4 + j : blk0 + j * kDecThreads + tid;
+
+  // ---------------- phase A: class max ----------------
+  float best[kPxPerThread];
+  int cls[kPxPerThread];
+  bool bad[kPxPerThread];
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) { best[j] = -CUDART_INF_F; cls[j] = 0; bad[j] = false; }
+  const T *lg = logits + static_cast<size_t>(b) * a.C * HW;
+  const bool vec_ok = kVec && (pix[0] + 3 < HW);
+#pragma unroll 2
+  for (int c = 0; c < a.C; ++c) {
+    float v[4];
+    if (kVec) {
+      if (vec_ok) Ld<T>::four(lg + static_cast<size_t>(c) * HW + pix[0], v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = pix[j] < HW ? Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = pix[j] < HW ? Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bad[j] |= (v[j] != v[j]);
+      if (v[j] > best[j]) { best[j] = v[j]; cls[j] = c; }
+    }
+  }
+  uint32_t mbits = 0;
+  {
+    const uint8_t *mk = mask + static_cast<size_t>(b) * HW;
+    if (kVec && vec_ok) {
+      const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + pix[0]);
+      mbits = (m4.x ? 1u : 0u) | (m4.y ? 2u : 0u) | (m4.z ? 4u : 0u) | (m4.w ? 8u : 0u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (pix[j] < HW && mk[pix[j]]) mbits |= 1u << j;
+    }
+  }
+
+  // score + threshold + partition test
+  float score[kPxPerThread];
+  uint32_t emit[kPxPerThread];
+  uint32_t n_live = 0, n_emit = 0;
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) {
+    emit[j] = 0;
+    score[j] = 0.f;
+    if (pix[j] >= HW || bad[j]) continue;
+    if (mbits & (1u << j)) {
+      score[j] = sigmoid_t<T>(best[j]);
+      // torch.max returns the FIRST index attaining the max of the float32 scores: an earlier
+      // class with a smaller logit can round to the same float32 sigmoid (always when saturated)
+      if (cls[j] > 0 && score[j] >= a.thr) {
+        for (int c = 0; c < cls[j]; ++c) {
+          const float x = Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]);
+          if ((best[j] >= 15.f || x > best[j] - 1.0f) && sigmoid_t<T>(x) == score[j]) { cls[j] = c; break; }
+        }
+      }
+    } else {
+      cls[j] = 0;  // sigmoid * 0 == 0 for every class -> argmax 0
+    }
+  }
+  // range partitions (need ||cart|| only where something can pass)
+  const bool zero_passes = 0.0f >= a.thr;
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) any |= (pix[j] < HW && !bad[j] && (score[j] >= a.thr || zero_passes));
+  if (any) {
+    if (a.pa.n == 0) {
+#pragma unroll
+      for (int j = 0; j < kPxPerThread; ++j)
+        if (pix[j] < HW && !bad[j] && score[j] >= a.thr) emit[j] = 1u;
+    } else {
+      const T *ct = cart + static_cast<size_t>(b) * 3 * HW;
+      float cx[4], cy[4], cz[4];
+      if (kVec && vec_ok) {
+        Ld<T>::four(ct + pix[0], cx);
+        Ld<T>::four(ct + HW + pix[0], cy);
+        Ld<T>::four(ct + 2 * static_cast<size_t>(HW) + pix[0], cz);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = pix[j] < HW;
+          cx[j] = ok ? Ld<T>::one(ct + pix[j]) : 0.f;
+          cy[j] = ok ? Ld<T>::one(ct + HW + pix[j]) : 0.f;
+          cz[j] = ok ? Ld<T>::one(ct + 2 * static_cast<size_t>(HW) + pix[j]) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kPxPerThread; ++j) {
+        if (pix[j] >= HW || bad[j]) continue;
+        const float d = norm3(cx[j], cy[j], cz[j]);
+        const int w = pix[j] % a.W;
+        for (int i = 0; i < a.pa.n; ++i) {
+          if (w % a.pa.rate[i]) continue;
+          const bool in = (d > a.pa.lower[i]) && (d <= a.pa.upper[i]);
+          const float s = in ? score[j] : 0.0f;
+          if (s >= a.thr) emit[j] |= 1u << i;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) {
+    n_live += emit[j] ? 1u : 0u;
+    n_emit += __popc(emit[j]);
+  }
+
+  // ---------------- block scan of (live, emit) packed as hi16 | lo16 ----------------
+  // per block: live <= 1024, emit <= 1024 * 8 -> both fit 16 bits, no carry between the halves
+  const uint32_t mine = (n_live << 16) | n_emit;
+  uint32_t incl = mine;
+  const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_scan[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    constexpr int kWarps = kDecThreads / 32;
+    const uint32_t v = lane < kWarps ? s_scan[lane] : 0u;
+    uint32_t inc2 = v;
+#pragma unroll
+    for (int o = 1; o < kWarps; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+      if (lane >= o) inc2 += t;
+    }
+    if (lane < kWarps) s_scan[lane] = inc2 - v;  // exclusive warp offsets
+    if (lane == kWarps - 1) {
+      const uint32_t total_emit = inc2 & 0xffffu;
+      s_total_live = inc2 >> 16;
+      // ONE global atomic per 1024 pixels reserves the block's output rows
+      s_base = total_emit ? static_cast<uint32_t>(atomicAdd(counter, static_cast<int>(total_emit))) : 0u;
+    }
+  }
+  __syncthreads();
+  const uint32_t excl = s_scan[wid] + (incl - mine);
+  uint32_t live_pos = excl >> 16, emit_pos = excl & 0xffffu;
+#pragma unroll
+  for (int j = 0; j < kPxPerThread; ++j) {
+    if (!emit[j]) continue;
+    q_pix[live_pos] = static_cast<uint16_t>(kVec ? tid * 4 + j : j * kDecThreads + tid);
+    q_meta[live_pos] = static_cast<uint16_t>(cls[j]);
+    q_emit[live_pos] = static_cast<uint8_t>(emit[j]);
+    q_score[live_pos] = score[j];
+    q_off[live_pos] = emit_pos;
+    ++live_pos;
+    emit_pos += __popc(emit[j]);
+  }
+  __syncthreads();
+  const uint32_t total_live = s_total_live;
+  const uint32_t base = s_base;
+
+  // ---------------- phase B: dense-lane fp64 decode of the live pixels ----------------
+  for (uint32_t t = tid; t < total_live; t += kDecThreads) {
+    const int p = blk0 + q_pix[t];
+    float r[8], c[3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(reg + (static_cast<size_t>(b) * 8 + k) * HW + p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = Ld<T>::one(cart + (static_cast<size_t>(b) * 3 + k) * HW + p);
+    double o[7];
+    decode_box(r, c, a.az_inv != 0, o);
+    // decode_range_view casts back to the input dtype (coding.py:144); widen that to f32
+    float box[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) box[k] = static_cast<float>(Ld<T>::cast(o[k]));
+    const uint32_t seg = static_cast<uint32_t>(b) * a.total_classes + q_meta[t] + a.cat_off;
+    const int h = p / a.W, w = p - h * a.W;
+    uint32_t e = q_emit[t];
+    uint32_t row = base + q_off[t];
+    const float sc = q_score[t];
+    while (e) {
+      const int i = __ffs(e) - 1;
+      e &= e - 1;
+      float s_out = sc;
+      uint32_t cand;
+      if (a.pa.n == 0) {
+        cand = p;
+      } else {
+        cand = a.pa.off[i] + h * a.pa.wsub[i] + w / a.pa.rate[i];
+        // the partition that does not contain the pixel contributes score 0 (only when 0 >= thr)
+        const float d = norm3(c[0], c[1], c[2]);
+        if (!((d > a.pa.lower[i]) && (d <= a.pa.upper[i]))) s_out = 0.0f;
+      }
+      if (row < static_cast<uint32_t>(a.capacity)) {
+        out_keys[row] = a.kp.make(seg, s_out, cand + a.cand_off);
+        float4 *ob = reinterpret_cast<float4 *>(out_boxes + static_cast<size_t>(row) * 8);
+        ob[0] = make_float4(box[0], box[1], box[2], box[3]);
+        ob[1] = make_float4(box[4], box[5], box[6], s_out);
+      }
+      ++row;
+    }
+  }
+}
+
+// dense candidates -> (key, box) rows
+__global__ void __launch_bounds__(256)
+compact_candidates_kernel(const float *__restrict__ cub, const float *__restrict__ scores,
+                          const int64_t *__restrict__ cats, int K, int total_classes, float thr, int apply_thr,
+                          int capacity, KeyPack kp, unsigned long long *__restrict__ out_keys,
+                          float *__restrict__ out_boxes, int32_t *__restrict__ counter) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_base;
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool live = false;
+  float s = 0.f;
+  if (k < K) {
+    s = scores[static_cast<size_t>(b) * K + k];
+    live = apply_thr ? (s >= thr) : true;
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, live);
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int i = 0; i < 8; ++i) { const uint32_t c = s_warp[i]; s_warp[i] = tot; tot += c; }
+    s_base = tot ? static_cast<uint32_t>(atomicAdd(counter, static_cast<int>(tot))) : 0u;
+  }
+  __syncthreads();
+  if (!live) return;
+  const uint32_t row = s_base + s_warp[wid] + __popc(bal & ((1u << lane) - 1u));
+  if (row >= static_cast<uint32_t>(capacity)) return;
+  const float *c = cub + (static_cast<size_t>(b) * K + k) * 7;
+  const uint32_t seg = static_cast<uint32_t>(b) * total_classes + static_cast<uint32_t>(cats[static_cast<size_t>(b) * K + k]);
+  out_keys[row] = kp.make(seg, s, static_cast<uint32_t>(k));
+  float4 *ob = reinterpret_cast<float4 *>(out_boxes + static_cast<size_t>(row) * 8);
+  ob[0] = make_float4(c[0], c[1], c[2], c[3]);
+  ob[1] = make_float4(c[4], c[5], c[6], s);
+}
+
+__global__ void yaw_to_quat_kernel(const float *__restrict__ yaw, float *__restrict__ quat, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s, c;
+  sincos(static_cast<double>(yaw[i] * 0.5f), &s, &c);
+  reinterpret_cast<float4 *>(quat)[i] = make_float4(static_cast<float>(c), 0.f, 0.f, static_cast<float>(s));
+}
+
+template <typename T>
+static int launch_decode_compact(const DecodeArgs &a, const void *logits, const void *reg, const void *cart,
+                                 const uint8_t *mask, unsigned long long *keys, float *boxes, int32_t *counter,
+                                 cudaStream_t s) {
+  const int HW = a.H * a.W;
+  dim3 grid(ceil_div(HW, kPxPerBlock), a.B);
+  const bool vec = (HW % 4 == 0) && aligned(logits, 16) && aligned(cart, 16) && aligned(mask, 4);
+  if (vec)
+    decode_compact_kernel<T, true><<<grid, kDecThreads, 0, s>>>(a, static_cast<const T *>(logits),
+                                                                 static_cast<const T *>(reg),
+                                                                 static_cast<const T *>(cart), mask, keys, boxes, counter);
+  else
+    decode_compact_kernel<T, false><<<grid, kDecThreads, 0, s>>>(a, static_cast<const T *>(logits),
+                                                                  static_cast<const T *>(reg),
+                                                                  static_cast<const T *>(cart), mask, keys, boxes, counter);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+}  // namespace rv3d
+
+using namespace rv3d;
+
+extern "C" int rv3d_decode_range_view(const void *regressands, const void *cart, void *out, int32_t dtype,
+                                      int32_t batch, int32_t height, int32_t width, int32_t azimuth_invariant,
+                                      rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(regressands && cart && out && batch > 0 && height > 0 && width > 0);
+  const int HW = height * width;
+  dim3 grid(ceil_div(HW, 256), batch);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case RV3D_F32:
+      decode_dense_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(regressands),
+                                                      static_cast<const float *>(cart), static_cast<float *>(out), HW,
+                                                      azimuth_invariant);
+      break;
+    case RV3D_F16:
+      decode_dense_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(regressands),
+                                                       static_cast<const __half *>(cart), static_cast<__half *>(out),
+                                                       HW, azimuth_invariant);
+      break;
+    case RV3D_BF16:
+      decode_dense_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(regressands),
+                                                              static_cast<const __nv_bfloat16 *>(cart),
+                                                              static_cast<__nv_bfloat16 *>(out), HW, azimuth_invariant);
+      break;
+    default: return RV3D_ERR_ARG;
+  }
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+static bool parts_ok(const rv3d_partitions *p) {
+  if (!p) return true;
+  if (p->n_partitions < 0 || p->n_partitions > RV3D_MAX_PARTITIONS) return false;
+  for (int i = 0; i < p->n_partitions; ++i)
+    if (p->rate[i] <= 0) return false;
+  return true;
+}
+
+extern "C" int64_t rv3d_num_candidates(const rv3d_partitions *parts, int32_t height, int32_t width) {
+  if (!parts_ok(parts) || height <= 0 || width <= 0) return -1;
+  const PartArgs a = make_parts(parts, height, width);
+  return a.off[a.n];
+}
+
+extern "C" int rv3d_sample_by_range(const float *scores, const int64_t *categories, const float *cuboids,
+                                    const float *cart, const rv3d_partitions *parts, int32_t batch,
+                                    int32_t height, int32_t width, float *out_scores, int64_t *out_categories,
+                                    float *out_cuboids, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(scores && categories && cuboids && cart && parts && out_scores && out_categories && out_cuboids);
+  RV3D_CHECK_ARG(batch > 0 && height > 0 && width > 0 && parts_ok(parts) && parts->n_partitions > 0);
+  const PartArgs a = make_parts(parts, height, width);
+  dim3 grid(ceil_div(a.off[a.n], 256), batch);
+  sample_by_range_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, categories, cuboids, cart, a, height, width, out_scores, out_categories, out_cuboids);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_decode_compact(const rv3d_decode_params *p, const void *logits, const void *regressands,
+                                   const void *cart, const uint8_t *mask, uint64_t *out_keys, float *out_boxes,
+                                   int32_t *counter, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && logits && regressands && cart && mask && out_keys && out_boxes && counter);
+  RV3D_CHECK_ARG(p->batch > 0 && p->n_classes > 0 && p->height > 0 && p->width > 0 && p->capacity >= 0);
+  RV3D_CHECK_ARG(parts_ok(&p->parts) && p->total_classes >= p->category_offset + p->n_classes);
+  RV3D_CHECK_ARG(static_cast<int64_t>(p->height) * p->width < (int64_t(1) << 30));
+  if (!aligned(out_boxes, 16) || !aligned(out_keys, 8)) return RV3D_ERR_ALIGN;
+  DecodeArgs a;
+  a.B = p->batch; a.C = p->n_classes; a.H = p->height; a.W = p->width; a.az_inv = p->azimuth_invariant;
+  a.cat_off = p->category_offset; a.cand_off = p->candidate_offset; a.total_classes = p->total_classes;
+  a.capacity = p->capacity; a.thr = p->min_confidence;
+  a.pa = make_parts(&p->parts, p->height, p->width);
+  RV3D_CHECK_ARG(p->total_candidates >= p->candidate_offset + a.pa.off[a.pa.n]);
+  a.kp.idx_bits = bits_for(p->total_candidates);
+  if (bits_for(static_cast<int64_t>(p->batch) * p->total_classes) + 32 + a.kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto *keys = reinterpret_cast<unsigned long long *>(out_keys);
+  switch (p->dtype) {
+    case RV3D_F32: return launch_decode_compact<float>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
+    case RV3D_F16: return launch_decode_compact<__half>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
+    case RV3D_BF16:
+      return launch_decode_compact<__nv_bfloat16>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
+    default: return RV3D_ERR_ARG;
+  }
+}
+
+extern "C" int rv3d_compact_candidates(const float *cuboids, const float *scores, const int64_t *categories,
+                                       int32_t batch, int32_t k, int32_t total_classes, float min_confidence,
+                                       int32_t apply_threshold, int32_t capacity, uint64_t *out_keys,
+                                       float *out_boxes, int32_t *counter, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(batch > 0 && k >= 0 && total_classes > 0 && capacity >= 0 && out_keys && out_boxes && counter);
+  if (k == 0) return RV3D_OK;
+  RV3D_CHECK_ARG(cuboids && scores && categories);
+  if (!aligned(out_boxes, 16) || !aligned(out_keys, 8)) return RV3D_ERR_ALIGN;
+  KeyPack kp;
+  kp.idx_bits = bits_for(k);
+  if (bits_for(static_cast<int64_t>(batch) * total_classes) + 32 + kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
+  dim3 grid(ceil_div(k, 256), batch);
+  compact_candidates_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cuboids, scores, categories, k, total_classes, min_confidence, apply_threshold, capacity, kp,
+      reinterpret_cast<unsigned long long *>(out_keys), out_boxes, counter);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && (n == 0 || (yaw && quat)));
+  if (n == 0) return RV3D_OK;
+  if (!aligned(quat, 16)) return RV3D_ERR_ALIGN;
+  yaw_to_quat_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(yaw, quat, n);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}

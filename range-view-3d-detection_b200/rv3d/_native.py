@@ -16,6 +16,7 @@ ERR_KEYBITS = -5
 COL_LIBRARY, COL_CONVERTER = 0, 1
 F32, F16, BF16 = 0, 1, 2
 NMS_HARD, NMS_WEIGHTED = 0, 1
+OUT_QUAT, OUT_YAW = 0, 1
 
 
 class RasterParams(C.Structure):
@@ -40,7 +41,7 @@ class NmsParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("total_classes", C.c_int32), ("total_candidates", C.c_int32),
                 ("num_pre_nms", C.c_int32), ("num_post_nms", C.c_int32), ("mode", C.c_int32),
                 ("iou_threshold", C.c_float), ("merge_threshold", C.c_float), ("n_candidates", C.c_int32),
-                ("out_capacity", C.c_int32)]
+                ("out_capacity", C.c_int32), ("out_layout", C.c_int32)]
 
 
 class Rv3dError(RuntimeError):
@@ -76,11 +77,7 @@ _SIGNATURES = {
     "rv3d_pack_candidates": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
 }
 
-# dev scaffolding: entry points declared in rv3d.h whose kernels are still being written
-_NOT_YET_BUILT = {"rv3d_decode_range_view", "rv3d_num_candidates", "rv3d_sample_by_range", "rv3d_decode_compact",
-                  "rv3d_compact_candidates", "rv3d_nms_scratch_bytes", "rv3d_nms", "rv3d_nms_rotated_scratch_bytes",
-                  "rv3d_nms_rotated", "rv3d_wnms_scratch_bytes", "rv3d_wnms", "rv3d_iou3d_aligned",
-                  "rv3d_yaw_to_quat", "rv3d_pack_candidates_scratch_bytes", "rv3d_pack_candidates"}
+_NOT_YET_BUILT: set = set()
 _lib = None
 
 

@@ -1,0 +1,148 @@
+"""Host-side mirror of ``torchbox3d/nn/decoders/range_decoder.py``.
+
+``RangeDecoder`` keeps the reference's five dataclass fields and ``decode`` signature
+(nn/decoders/range_decoder.py:20-36), so a Hydra config swaps it in with
+``_decoder._target_: rv3d.nn.decoders.range_decoder.RangeDecoder``.  Behind it the dense head
+outputs go through ONE fused CUDA kernel per (stride, task) (sigmoid*mask, class max, threshold,
+range-partition subsampling, fp64 box decode, compaction), then segment sort + exact greedy
+rotated / weighted NMS, without the per-sweep / per-class Python loops and host syncs of the
+reference (math/ops/nms.py:210-242)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, Mapping, Sequence, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from ... import _native as N
+from ..._pipeline import Workspace, dtype_code, new_candidates, run_nms, threshold_as
+from ..._util import ptr, require_cuda, scratch, stream_ptr
+
+__all__ = ["RangeDecoder", "sample_by_range"]
+
+
+def _mask_u8(mask: Tensor) -> Tensor:
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    if mask.is_floating_point():
+        raise TypeError("rv3d: `mask` must be a bool / uint8 validity mask (the reference builds it as "
+                        "`range > 0`, prototype/loader.py:645-650)")
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
+@dataclass
+class RangeDecoder:
+    enable_azimuth_invariant_targets: bool
+    enable_sample_by_range: bool
+
+    lower_bounds: Sequence[float]
+    upper_bounds: Sequence[float]
+    subsampling_rates: Sequence[int]
+
+    _ws: Workspace = field(default_factory=Workspace, init=False, repr=False, compare=False)
+
+    def _partitions(self) -> N.Partitions:
+        if not self.enable_sample_by_range:
+            return N.make_partitions([], [], [])
+        return N.make_partitions(list(self.lower_bounds), list(self.upper_bounds), list(self.subsampling_rates))
+
+    def candidates(self, multiscale_outputs: Mapping[Union[int, str], Mapping[Any, Any]],
+                   post_processing_config: Mapping[str, Any], task_config: Mapping[Any, Sequence[str]]):
+        """Fused decode + threshold + compaction of every (stride, task).  Enqueues work only; no host sync."""
+        parts = self._partitions()
+        lib = N.lib()
+        total_classes = sum(len(g) for g in task_config.values())
+        plan, total_candidates = [], 0
+        for _stride, ms in multiscale_outputs.items():                     # range_decoder.py:39
+            cart, mask = ms["cart"], ms["mask"]
+            B, _, H, W = cart.shape
+            k = int(lib.rv3d_num_candidates(parts, H, W))
+            task_offset = 0
+            for task_id, group in task_config.items():                     # :45
+                plan.append((ms, task_id, task_offset, total_candidates, H, W, B))
+                task_offset += len(group)                                  # :78
+                total_candidates += k
+        if not plan:
+            raise ValueError("empty multiscale_outputs / task_config")
+        B = plan[0][6]
+        dev = require_cuda(plan[0][0]["cart"])
+        cand = new_candidates(self._ws, B, total_classes, total_candidates, dev)
+        for ms, task_id, task_offset, cand_offset, H, W, b in plan:
+            if b != B:
+                raise ValueError("all strides must share the batch size")
+            out = ms[task_id]
+            logits = out["logits"].contiguous()
+            dt = logits.dtype
+            reg = out["regressands"].to(dt).contiguous()
+            cart = ms["cart"].to(dt).contiguous()
+            mask = _mask_u8(ms["mask"])
+            require_cuda(logits, reg, cart, mask)
+            p = N.DecodeParams()
+            p.batch, p.n_classes, p.height, p.width = B, logits.shape[1], H, W
+            p.dtype = dtype_code(dt)
+            p.azimuth_invariant = int(bool(self.enable_azimuth_invariant_targets))
+            p.category_offset, p.candidate_offset = task_offset, cand_offset
+            p.total_candidates, p.total_classes = total_candidates, total_classes
+            p.capacity = cand.keys.numel()
+            p.min_confidence = threshold_as(dt, post_processing_config["min_confidence"])
+            p.parts = parts
+            N.check(lib.rv3d_decode_compact(p, ptr(logits), ptr(reg), ptr(cart), ptr(mask), ptr(cand.keys),
+                                            ptr(cand.boxes), ptr(cand.counter), stream_ptr(dev)),
+                    "rv3d_decode_compact")
+        return cand
+
+    def decode(self, multiscale_outputs: Dict[Union[int, str], Dict[Any, Any]],
+               post_processing_config: Mapping[str, Any], task_config: Mapping[Any, Sequence[str]],
+               use_nms: bool = True, **kwargs: Any) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        """Drop-in for RangeDecoder.decode (nn/decoders/range_decoder.py:29-124) ->
+        (params (K,10) [x,y,z,l,w,h,qw,qx,qy,qz], scores (K,), categories (K,), batch_index (K,)).
+        With NMS, categories / batch_index are float32 (math/ops/nms.py:51,242); without, int64."""
+        del kwargs                                                         # tools/benchmark.py passes data=
+        first = next(iter(multiscale_outputs.values()))
+        dt = first[next(iter(task_config.keys()))]["logits"].dtype
+        cand = self.candidates(multiscale_outputs, post_processing_config, task_config)
+        n = cand.count()
+        dev = cand.keys.device
+        if use_nms:
+            if n == 0:
+                mode = str(post_processing_config["nms_mode"]).upper()
+                if mode not in ("HARD", "WEIGHTED"):
+                    raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
+                e = torch.empty((0,), dtype=dt, device=dev)
+                return torch.empty((0, 10), dtype=dt, device=dev), e.view(0, 1), e.view(0, 1), e.view(0, 1)
+            params, scores, cats, bidx = run_nms(
+                self._ws, cand, n, post_processing_config["num_pre_nms"], post_processing_config["num_post_nms"],
+                post_processing_config["nms_threshold"], str(post_processing_config["nms_mode"]), N.OUT_QUAT)
+            return params.to(dt), scores.to(dt), cats.to(dt), bidx.to(dt)
+        params = torch.empty((n, 10), dtype=torch.float32, device=dev)
+        scores = torch.empty((n,), dtype=torch.float32, device=dev)
+        cats = torch.empty((n,), dtype=torch.int64, device=dev)
+        bidx = torch.empty((n,), dtype=torch.int64, device=dev)
+        lib = N.lib()
+        work = self._ws.bytes("pack_scratch", lib.rv3d_pack_candidates_scratch_bytes(n), dev)
+        N.check(lib.rv3d_pack_candidates(ptr(cand.keys), ptr(cand.boxes), n, cand.batch, cand.total_classes,
+                                         cand.total_candidates, ptr(params), ptr(scores), ptr(cats), ptr(bidx),
+                                         ptr(work), work.numel(), stream_ptr(dev)), "rv3d_pack_candidates")
+        return params.to(dt), scores.to(dt), cats, bidx
+
+
+def sample_by_range(scores: Tensor, categories: Tensor, cuboids: Tensor, cart: Tensor,
+                    lower_bounds: Tuple[float, ...], upper_bounds: Tuple[float, ...],
+                    subsampling_rates: Tuple[int, ...]) -> Tuple[Tensor, Tensor, Tensor]:
+    """Drop-in for nn/decoders/range_decoder.py:127-156: scores / categories (B,1,H,W), cuboids (B,7,H,W),
+    cart (B,3,H,W) -> scores (B,K), categories (B,K), cuboids (B,K,7)."""
+    dev = require_cuda(scores, categories, cuboids, cart)
+    B, _, H, W = cuboids.shape
+    parts = N.make_partitions(list(lower_bounds), list(upper_bounds), list(subsampling_rates))
+    lib = N.lib()
+    K = int(lib.rv3d_num_candidates(parts, H, W))
+    o_s = torch.empty((B, K), dtype=torch.float32, device=dev)
+    o_c = torch.empty((B, K), dtype=torch.int64, device=dev)
+    o_b = torch.empty((B, K, 7), dtype=torch.float32, device=dev)
+    N.check(lib.rv3d_sample_by_range(ptr(scores.float().contiguous()), ptr(categories.to(torch.int64).contiguous()),
+                                     ptr(cuboids.float().contiguous()), ptr(cart.float().contiguous()), parts, B, H, W,
+                                     ptr(o_s), ptr(o_c), ptr(o_b), stream_ptr(dev)), "rv3d_sample_by_range")
+    return o_s.to(scores.dtype), o_c.to(categories.dtype), o_b.to(cuboids.dtype)
