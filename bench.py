@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- sweeps/sec of the rasterize -> decode -> NMS path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nms-mode HARD|WEIGHTED]
+
+One "step" = one pass of the hot path over one batch of synthetic sweeps:
+rasterize B raw sweeps (N points each -> 64 x W range image), then RangeDecoder.decode of B sets of
+dense head outputs (sigmoid/max/threshold/sample_by_range/box decode/NMS).  Workload at N=1:
+BASELINE.json configs[1], Waymo shape, B=16.  With N>1 (torchrun, one rank per GPU) every rank runs
+its own B sweeps (weak scaling) and the step ends with the path's one collective, a gather of the
+detections.
+
+The JSON line's `value` is measured with inputs resident in HBM; `e2e` goes through the same public
+API from pinned HOST buffers (H2D of every input + D2H of the detections inside the timed region).
+`--impl reference` times the reference's CPU path (oracle port: /root/reference does not exist on the
+GPU box, and its third-party natives are not installable) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path[:0] = [str(ROOT), str(ROOT / "range-view-3d-detection_b200")]
+
+from tests import synth  # noqa: E402
+
+METRIC = "sweeps/sec (rasterize+decode+NMS)"
+WORKLOADS = {
+    # name: (points per sweep, H, W, classes, objects per sweep, identity row map?)
+    "waymo": (180_000, 64, 2650, 3, 96, True),
+    "av2": (100_000, 64, 1800, 26, 64, False),
+}
+PP = {"num_pre_nms": 50000, "num_post_nms": 1000, "nms_threshold": 0.3, "min_confidence": 0.1}  # range_view.yaml:43-47
+SBR = ([0, 15, 30], [15, 30, math.inf], [8, 2, 1])                                              # range_view.yaml:133-135
+FP_RATE = 0.95   # fraction of valid background pixels that fire (S ~ 20 % of K pass 0.1)
+
+
+def make_inputs(shape: str, batch: int, seed0: int):
+    n, H, W, C, M, ident = WORKLOADS[shape]
+    sweeps = [synth.make_points(n, H, seed0 + s) for s in range(batch)]
+    head = synth.make_head_outputs(batch, C, H, W, seed=seed0, n_objects=M, fp_rate=FP_RATE, distinct_scores=False)
+    mapping = np.arange(H) if ident else None
+    return sweeps, head, mapping
+
+
+def algorithmic_bytes(shape: str, batch: int, survivors: int):
+    """rasterize reads N*(16+1) B and writes 7*H*W*4 B per sweep; decode reads
+    H*W*(4*(C+8+3)+1) B per sweep (dense count: every input once) and writes 40 B per survivor."""
+    n, H, W, C, _, _ = WORKLOADS[shape]
+    raster = batch * (n * 17 + 7 * H * W * 4)
+    decode = batch * (H * W * (4 * (C + 8 + 3) + 1)) + 40 * survivors
+    return raster, decode
+
+
+# --------------------------------------------------------------------------------------- #
+# clocks                                                                                   #
+# --------------------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0])); mx = max(mx, int(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- #
+# the CPU arm (oracle port of the reference's CPU path)                                    #
+# --------------------------------------------------------------------------------------- #
+def cpu_step(sweep, head1, mapping, shape: str, nms_mode: str, pool: ThreadPoolExecutor):
+    """One sweep through the reference's CPU path, restated (oracle/): numpy rasterizer + serial z-buffer,
+    torch-CPU decode on all host threads, C rotated NMS with one host thread per class."""
+    import oracle
+    _, H, W, C, _, _ = WORKLOADS[shape]
+    t0 = time.perf_counter()
+    oracle.build_range_view(sweep[0], sweep[1], sweep[2], mapping if mapping is not None else oracle.ROW_MAPPING_64,
+                            synth.LIDAR_OFFSET, num_lasers=H, width=W, n_azimuth_bins=W)
+    t1 = time.perf_counter()
+    ms = {1: {"cart": head1["cart"], "mask": head1["mask"], 0: {"logits": head1["logits"], "regressands": head1["regressands"]}}}
+    tasks = {0: [f"c{i}" for i in range(C)]}
+    params, scores, cats = oracle.range_decoder_decode(ms, PP, tasks, True, True, *SBR, return_candidates=True)
+    t2 = time.perf_counter()
+    live = scores[0] >= PP["min_confidence"]
+    cu, sc, ca = params[0, live], scores[0, live], cats[0, live]
+    fn = oracle.hard_multiclass_nms if nms_mode == "HARD" else oracle.weighted_multiclass_nms
+
+    def one_class(j):
+        m = ca == j
+        return fn(cu[m], sc[m], ca[m], PP["nms_threshold"], PP["num_pre_nms"], PP["num_post_nms"])[1].shape[0]
+
+    kept = sum(pool.map(one_class, torch.unique(ca).tolist()))
+    t3 = time.perf_counter()
+    return {"rasterize_ms": (t1 - t0) * 1e3, "decode_ms": (t2 - t1) * 1e3, "nms_ms": (t3 - t2) * 1e3,
+            "total_s": t3 - t0, "kept": kept, "survivors": int(live.sum())}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle  # noqa: F401  (builds the C part)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sweeps, head, mapping = make_inputs(args.shape, 1, 1000)
+    pool = ThreadPoolExecutor(max_workers=cores)
+    for _ in range(args.warmup):
+        cpu_step(sweeps[0], head, mapping, args.shape, args.nms_mode, pool)
+    t0 = time.perf_counter()
+    stages = [cpu_step(sweeps[0], head, mapping, args.shape, args.nms_mode, pool) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = (f"1 {args.shape}-shaped sweep per step ({WORKLOADS[args.shape][0]} pts, 64x{WORKLOADS[args.shape][2]}, "
+              f"{stages[-1]['survivors']} candidates >= 0.1): numpy rasterize + serial z-buffer (1 thread), torch-CPU "
+              f"decode ({cores} threads), C rotated NMS (1 thread per class, greedy scan stopped at num_post_nms kept)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in ("rasterize_ms", "decode_ms", "nms_ms")}},
+            "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    n, H, W, C, M, _ = WORKLOADS[args.shape]
+    return {"workload": f"{args.shape}-shaped synthetic sweeps: rasterize ({n} pts -> {H}x{W}x7) + RangeDecoder.decode "
+                        f"({C} classes, sample_by_range [8,2,1], azimuth-invariant) + {args.nms_mode} rotated NMS "
+                        f"(pre {PP['num_pre_nms']}, post {PP['num_post_nms']}, iou {PP['nms_threshold']}, conf {PP['min_confidence']})",
+            "batch_per_gpu": batch, "points_per_sweep": n, "height": H, "width": W, "classes": C,
+            "objects_per_sweep": M, "fp_rate": FP_RATE, "nms_mode": args.nms_mode,
+            "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)"}
+
+
+# --------------------------------------------------------------------------------------- #
+# the CUDA arm                                                                             #
+# --------------------------------------------------------------------------------------- #
+def run_ours(args):
+    import torch.distributed as dist
+    from rv3d.distributed import gather_detections, pack_rows
+    from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
+    from rv3d.nn.decoders.range_decoder import RangeDecoder
+    from rv3d import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rv3d path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N.lib()
+
+    B = args.batch
+    n, H, W, C, M, ident = WORKLOADS[args.shape]
+    sweeps, head, mapping = make_inputs(args.shape, B, 1000 + 100 * rank)
+    pts_h, las_h, cnt_h = pack_sweeps(sweeps, dev, pin=True)
+    head_h = {k: v.pin_memory() for k, v in head.items()}
+    from rv3d.constants import ROW_MAPPING_64
+    row_map = torch.as_tensor((np.arange(H) if ident else ROW_MAPPING_64).astype(np.int32), device=dev)
+    pp = dict(PP, nms_mode=args.nms_mode)
+    tasks = {0: [f"c{i}" for i in range(C)]}
+    dec = RangeDecoder(True, True, *SBR)
+
+    # resident copies
+    pts, las, cnt = pts_h.to(dev), las_h.to(dev), cnt_h.to(dev)
+    hd = {k: v.to(dev) for k, v in head_h.items()}
+    image = torch.empty((B, 7, H, W), dtype=torch.float32, device=dev)
+    rws = torch.empty(B * H * W * 8, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def ms_of(h):
+        return {1: {"cart": h["cart"], "mask": h["mask"], 0: {"logits": h["logits"], "regressands": h["regressands"]}}}
+
+    def step(p, l, c, h, evs=None):
+        rasterize_sweeps(p, l, c, row_map, synth.LIDAR_OFFSET, H, W, out=image, workspace=rws)
+        if evs: evs[1].record()
+        cand = dec.candidates(ms_of(h), pp, tasks)
+        if evs: evs[2].record()
+        ncand = cand.count()
+        from rv3d._pipeline import run_nms
+        out = run_nms(dec._ws, cand, ncand, pp["num_pre_nms"], pp["num_post_nms"], pp["nms_threshold"], pp["nms_mode"],
+                      N.OUT_QUAT, stats=stats) if ncand else None
+        if out is None:
+            e = torch.empty((0,), device=dev)
+            out = (torch.empty((0, 10), device=dev), e, e, e)
+        if world > 1:
+            rows = gather_detections(pack_rows(*out, batch_offset=rank * B))
+        else:
+            rows = out
+        return ncand, out, rows
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(pts, las, cnt, hd)
+    barrier()
+
+    # ---------------- resident timing: K steps, per-step CUDA events, L2 flushed between steps -----------
+    stats.zero_()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ncand = ndet = 0
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall = time.perf_counter()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            ncand, out, _ = step(pts, las, cnt, hd, ev[k])
+            ev[k][3].record()
+            ndet = out[0].shape[0]
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    clocks = clk.summary()
+    t_step = np.array([e[0].elapsed_time(e[3]) for e in ev])
+    t_raster = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    t_decode = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    t_nms = np.array([e[2].elapsed_time(e[3]) for e in ev])
+    total_ms = torch.tensor([t_step.sum()], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+    st = (stats.cpu().numpy() / args.steps).tolist()
+
+    # ---------------- e2e: pinned host inputs -> H2D -> path -> D2H of the detections, every step --------
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [dict(pts=torch.empty_like(pts), las=torch.empty_like(las), cnt=torch.empty_like(cnt),
+                 head={k: torch.empty_like(v) for k, v in hd.items()}, ready=torch.cuda.Event(), free=torch.cuda.Event())
+            for _ in range(2)]
+    h2d = pts_h.numel() * 4 + las_h.numel() + cnt_h.numel() * 4 + sum(v.numel() * v.element_size() for v in head_h.values())
+    out_h = [torch.empty((B * C * PP["num_post_nms"], 13), dtype=torch.float32).pin_memory() for _ in range(1)]
+
+    def upload(slot):
+        b = bufs[slot]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b["free"])
+            b["pts"].copy_(pts_h, non_blocking=True); b["las"].copy_(las_h, non_blocking=True)
+            b["cnt"].copy_(cnt_h, non_blocking=True)
+            for k2, v in head_h.items():
+                b["head"][k2].copy_(v, non_blocking=True)
+            b["ready"].record(copy_stream)
+
+    def e2e_run(steps):
+        cur = torch.cuda.current_stream(dev)
+        for b in bufs:
+            b["free"].record(cur)
+        d2h = 0
+        upload(0)
+        for k in range(steps):
+            slot = k & 1
+            if k + 1 < steps:
+                upload(slot ^ 1)          # next step's inputs cross PCIe while this step computes
+            cur.wait_event(bufs[slot]["ready"])
+            b = bufs[slot]
+            # the calls a user makes: rv3d.math.range_view.rasterize_sweeps + RangeDecoder.decode
+            rasterize_sweeps(b["pts"], b["las"], b["cnt"], row_map, synth.LIDAR_OFFSET, H, W, out=image, workspace=rws)
+            out = dec.decode(ms_of(b["head"]), pp, tasks)
+            b["free"].record(cur)
+            rows = pack_rows(*out, batch_offset=rank * B)
+            if world > 1:
+                rows = gather_detections(rows)
+            out_h[0][: rows.shape[0]].copy_(rows, non_blocking=True)
+            d2h = rows.numel() * 4 + 8   # rows + the two device counters read by the host
+        return d2h
+
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = e2e_run(args.steps)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        raster_b, decode_b = algorithmic_bytes(args.shape, B, ncand)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        rd_ms = float(np.mean(t_raster) + np.mean(t_decode))
+        achieved = (raster_b + decode_b) / (rd_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, B),
+            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": 11 * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernels": "rasterize (scatter+resolve) + decode_compact", "achieved": achieved,
+                         "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes": {"rasterize": raster_b, "decode": decode_b},
+                         "rasterize_gbs": raster_b / (float(np.mean(t_raster)) * 1e-3) / 1e9,
+                         "decode_gbs": decode_b / (float(np.mean(t_decode)) * 1e-3) / 1e9},
+            "stage_ms": {"rasterize": float(np.mean(t_raster)), "decode_compact": float(np.mean(t_decode)),
+                         "sort+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": t_wall / args.steps * 1e3},
+            "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "iou_evals_per_step": st[0],
+                    "kept_per_step": st[1], "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3],
+                    "segments": B * C},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle  # noqa: F401
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            pool = ThreadPoolExecutor(max_workers=cores)
+            h1 = {k: v[:1] for k, v in head.items()}
+            cpu_step(sweeps[0], h1, mapping, args.shape, args.nms_mode, pool)        # JIT / page-in
+            r = cpu_step(sweeps[0], h1, mapping, args.shape, args.nms_mode, pool)
+            line["cpu_baseline"] = {
+                "value": 1.0 / r["total_s"], "unit": "sweeps/s", "cores": cores, "kind": "port",
+                "sample": f"1 sweep of the same workload ({r['survivors']} candidates): numpy rasterize + serial z-buffer "
+                          f"(1 thread), torch-CPU decode ({cores} threads), C rotated NMS (1 thread per class)",
+                "stage_ms": {k: r[k] for k in ("rasterize_ms", "decode_ms", "nms_ms")}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="waymo", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=16, help="sweeps per GPU per step")
+    ap.add_argument("--nms-mode", default="HARD", choices=["HARD", "WEIGHTED"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

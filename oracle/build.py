@@ -37,7 +37,7 @@ def lib() -> ctypes.CDLL:
         _lib.orc_rot_iou_aligned.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_double, c.c_void_p]
         _lib.orc_nms_rotated.restype = c.c_int64
         _lib.orc_nms_rotated.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_double, c.c_double,
-                                         c.c_void_p, c.c_void_p]
+                                         c.c_void_p, c.c_void_p, c.c_int64]
         _lib.orc_iou_bev.restype = c.c_float
         _lib.orc_iou_bev.argtypes = [c.c_void_p, c.c_void_p]
         _lib.orc_wnms.restype = c.c_int64

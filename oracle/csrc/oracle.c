@@ -218,11 +218,14 @@ void orc_rot_iou_aligned(const float *a, const float *b, int64_t n,
  * Returns the number kept; keep[] receives ORIGINAL indices in score order. */
 int64_t orc_nms_rotated(const float *boxes, const int64_t *order, int64_t n,
                         double thr, double angle_scale, int64_t *keep,
-                        int64_t *n_iou_evals) {
+                        int64_t *n_iou_evals, int64_t max_keep) {
   uint8_t *removed = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
   int64_t nk = 0, evals = 0;
   for (int64_t i = 0; i < n; ++i) {
     if (removed[i]) continue;
+    /* max_keep >= 0: stop once that many boxes are kept.  The caller only uses the
+     * first num_post_nms kept boxes (nms.py:53-56), so the output is unchanged. */
+    if (max_keep >= 0 && nk >= max_keep) break;
     keep[nk++] = order[i];
     const float *bi = boxes + 5 * order[i];
     for (int64_t j = i + 1; j < n; ++j) {

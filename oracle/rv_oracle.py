@@ -211,7 +211,8 @@ def _order_desc(scores: np.ndarray) -> np.ndarray:
     return np.argsort(-scores.astype(np.float64), kind="stable").astype(np.int64)
 
 
-def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold, return_evals: bool = False):
+def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold, return_evals: bool = False,
+                max_keep: int = -1):
     """Stand-in for detectron2.layers.nms.nms_rotated (call site math/ops/nms.py:41-45):
     (N,5) f32 (xc,yc,w,h,angle_deg), (N,) f32 -> kept ORIGINAL indices in score order."""
     b = np.ascontiguousarray(boxes.detach().cpu().numpy(), dtype=np.float32)
@@ -220,7 +221,7 @@ def nms_rotated(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold, return
     order = _order_desc(s)
     keep = np.empty(max(len(s), 1), dtype=np.int64)
     evals = ctypes.c_int64(0)
-    n = lib().orc_nms_rotated(_p(b), _p(order), len(s), thr, 0.01745329251, _p(keep), ctypes.byref(evals))
+    n = lib().orc_nms_rotated(_p(b), _p(order), len(s), thr, 0.01745329251, _p(keep), ctypes.byref(evals), max_keep)
     out = torch.from_numpy(keep[:n].copy())
     return (out, evals.value) if return_evals else out
 
@@ -268,7 +269,8 @@ def hard_multiclass_nms(cuboids_i, scores_i, categories_i, iou_threshold, num_pr
         cu = cu[rank]
         inp = cu[:, [0, 1, 3, 4, 6]].contiguous().float()
         inp[:, -1] = -inp[:, -1].rad2deg()                                           # :40 (f32)
-        keep = nms_rotated(inp, sc.float(), torch.as_tensor(iou_threshold))          # :41-45
+        # :41-45; max_keep: only the first num_post_nms kept boxes survive :53-56, so stopping there is exact
+        keep = nms_rotated(inp, sc.float(), torch.as_tensor(iou_threshold), max_keep=num_post_nms)
         cu, sc = cu[keep], sc[keep].flatten()
         sc, rank = _topk_stable(sc, min(len(cu), num_post_nms))                      # :53-56
         outs.append((cu[rank], sc, torch.full_like(sc, fill_value=float(j))))
