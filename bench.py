@@ -211,7 +211,7 @@ def run_ours(args):
     image = torch.empty((B, 7, H, W), dtype=torch.float32, device=dev)
     rws = torch.empty(B * H * W * 8, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    stats = torch.zeros(16, dtype=torch.int64, device=dev)
 
     def ms_of(h):
         return {1: {"cart": h["cart"], "mask": h["mask"], 0: {"logits": h["logits"], "regressands": h["regressands"]}}}
@@ -348,7 +348,7 @@ def run_ours(args):
             "stage_ms": {"rasterize": float(np.mean(t_raster)), "decode_compact": float(np.mean(t_decode)),
                          "sort+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": t_wall / args.steps * 1e3},
             "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "iou_evals_per_step": st[0],
-                    "kept_per_step": st[1], "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3],
+                    "kept_per_step": st[1], "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3], "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]],
                     "segments": B * C},
         }
         if world == 1 and not args.no_cpu_baseline:

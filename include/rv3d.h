@@ -199,8 +199,9 @@ size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);
  *   out_params (out_capacity,10|7) f32, see out_layout          (range_decoder.py:122-123)
  *   out_scores, out_categories, out_batch (out_capacity,) f32      (nms.py:51,113,242)
  *   out_count device i32: rows written.
- * stats (device, 8 x i64, may be NULL): [0] rotated-IoU evaluations, [1] kept,
- * [2] frontier rounds, [3] circle tests. */
+ * stats (device, 16 x i64, may be NULL): [0] rotated-IoU evaluations, [1] kept, [2] frontier rounds,
+ * [3] pair considerations, [4..9] SM cycles summed over segments per phase (frontier gather, grid
+ * build, frontier pairs, greedy, kill scan, kill drain). */
 int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys, const float *boxes, float *out_params,
              float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
              int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);

@@ -35,9 +35,6 @@ namespace rv3d {
 constexpr int kNmsThreads = 512;
 constexpr int kF = 256;                 // frontier size
 constexpr int kFW = kF / 32;            // words per bit-matrix row
-constexpr int kPairCap = 12288;         // frontier pair queue entries (u16 each)
-constexpr int kTile = 4096;             // candidates per kill-phase tile
-constexpr int kKillCap = 8192;          // kill-phase queue entries
 constexpr int kMaxD = 16;               // max data columns of the weighted merge
 
 // ------------------------------------------------------------------------------------------
@@ -111,8 +108,13 @@ struct NmsArgs {
   const int *seg_begin, *seg_end, *kept_base;
   int num_pre, num_post;
   float thr, mthr;
+  int prune;               // 0: thresholds < 0 make even disjoint boxes interact -> test every pair
   int *kept_pos;           // [kept_base[s] + i] = position inside the segment
   int *kept_count;         // [s]
+  // static candidate grid (scratch, per segment at 4*seg_begin / seg_begin)
+  void *grid_entries;      // GridEntry[4 * n_total]
+  uint32_t *oversize;      // [n_total] candidates that are not in the grid
+  int *firstsup;           // [n_total] weighted: first suppressor rank of a candidate in the current round
   // weighted merge
   const float *data;       // (n, D) rows in sorted order, score last
   int D;
@@ -121,31 +123,96 @@ struct NmsArgs {
   unsigned long long *stats;
 };
 
-template <typename Rec>
-struct Smem {
-  uint32_t *alive;                 // nwords
-  int *front_pos;                  // kF
-  Rec *frec;                       // kF
-  uint32_t *sup;                   // kF * kFW
-  uint32_t *mrg;                   // kF * kFW (weighted)
-  uint16_t *keptf;                 // kF
-  float *kx, *ky, *kr;             // kF each
-  uint32_t *queue;                 // max(kPairCap/2, kKillCap) words
-  float *qiou;                     // kKillCap (weighted)
-  uint8_t *firstsup;               // kTile (weighted)
+// ---- static spatial hash over a segment's candidates ----------------------------------------
+// Built once per segment.  Cells are `cell` metres wide, chosen from the segment's mean box radius
+// (classes have characteristic sizes) so that nearly every candidate's padded circle spans at most
+// 2x2 cells; such a candidate is registered in every cell its circle's bounding square touches.
+// Bigger / far-away / non-finite candidates go to an "oversize" list that every query scans.
+// Entries are counting-sorted by hash bucket, so one cell's entries are contiguous.
+//
+// Two boxes can only interact if their circle AABBs intersect, and then the cell holding the lower
+// corner of that intersection is registered by the candidate and visited by the query: a query
+// visiting cell c accepts an entry only if c is the FIRST cell of the query or the FIRST cell of the
+// entry on each axis, which finds every interacting pair exactly once.
+constexpr float kPosCap = 1.0e6f;
+constexpr int kNB = 1024;                // hash buckets (2 per thread in the scan)
+constexpr int kMaxQueryCells = 6;        // a query spanning more cells per axis scans everything
+constexpr int kQ2Cap = 8192;             // exact-IoU work queue (pairs that passed circle + bound)
+constexpr int kWBuf = 64;                // per-warp hit buffer
+static_assert(kNB == 2 * kNmsThreads, "two hash buckets per scan lane");
+
+// 16-byte grid entry: circle of the candidate + meta = idx (20 bits) | first_x << 20 | first_y << 21 |
+// cell key << 22.  The 10-bit cell key only filters hash collisions cheaply; a false match is still
+// rejected by the circle test, so aliasing cannot create or lose a pair.
+struct __align__(16) GridEntry { float x, y, r; uint32_t meta; };
+constexpr uint32_t kIdxMask = (1u << 20) - 1u;
+
+__device__ __forceinline__ uint32_t cell_key(int cx, int cy) {
+  return ((static_cast<uint32_t>(cx) & 31u) | ((static_cast<uint32_t>(cy) & 31u) << 5)) << 22;
+}
+__device__ __forceinline__ int bucket_of(int cx, int cy) {
+  return static_cast<int>((static_cast<uint32_t>(cx) * 73856093u) ^ (static_cast<uint32_t>(cy) * 19349663u)) & (kNB - 1);
+}
+
+struct BoxCells {
+  int cx0, cy0, cx1, cy1;
+  bool gridded;   // false: not representable in the grid -> handled by the "everything" paths
 };
+
+// cells overlapped by the circle's bounding square; at most `max_span` cells per axis
+__device__ __forceinline__ BoxCells cells_of(float x, float y, float r, float inv_cell, int max_span) {
+  BoxCells c;
+  c.gridded = (r == r) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap) && (r * inv_cell <= 0.49f * (max_span - 1));
+  if (c.gridded) {
+    c.cx0 = __float2int_rd((x - r) * inv_cell); c.cx1 = __float2int_rd((x + r) * inv_cell);
+    c.cy0 = __float2int_rd((y - r) * inv_cell); c.cy1 = __float2int_rd((y + r) * inv_cell);
+    c.gridded = (c.cx1 - c.cx0 < max_span) && (c.cy1 - c.cy0 < max_span);
+  }
+  if (!c.gridded) c.cx0 = c.cy0 = c.cx1 = c.cy1 = 0;
+  return c;
+}
+
+// ---- cheap, safe upper bound on the IoU (separating axes + projected overlap) -----------------
+// The intersection lies inside box A and inside B's bounding box in A's frame, so its area is at
+// most (overlap of the projections on A's two axes); same in B's frame.  Used only to SKIP the
+// exact routine when even the bound (inflated by 2 % + 1e-5) cannot exceed the threshold.
+struct Obb { float x, y, w, h, c, s; };  // centre, full extents, axis u = (c, s), v = (-s, c)
+__device__ __forceinline__ Obb obb_of(const HardRec &r) { return Obb{r.x, r.y, r.w, r.h, 2.f * r.c2, -2.f * r.s2}; }
+__device__ __forceinline__ Obb obb_of(const WRec &r) {
+  return Obb{(r.x1 + r.x2) * 0.5f, (r.y1 + r.y2) * 0.5f, r.x2 - r.x1, r.y2 - r.y1, r.ca, r.sa};
+}
+__device__ __forceinline__ float overlap_in_frame(const Obb &a, const Obb &b) {
+  const float dx = b.x - a.x, dy = b.y - a.y;
+  const float du = dx * a.c + dy * a.s, dv = -dx * a.s + dy * a.c;
+  const float cd = fabsf(a.c * b.c + a.s * b.s), sd = fabsf(a.c * b.s - a.s * b.c);
+  const float bw = fabsf(b.w) * 0.5f, bh = fabsf(b.h) * 0.5f, aw = fabsf(a.w) * 0.5f, ah = fabsf(a.h) * 0.5f;
+  const float eu = cd * bw + sd * bh, ev = sd * bw + cd * bh;
+  const float ou = fminf(aw, du + eu) - fmaxf(-aw, du - eu);
+  const float ov = fminf(ah, dv + ev) - fmaxf(-ah, dv - ev);
+  return fmaxf(ou, 0.f) * fmaxf(ov, 0.f);
+}
+template <typename Rec>
+__device__ __forceinline__ bool iou_may_exceed(const Rec &ra, const Rec &rb, float thr) {
+  const Obb a = obb_of(ra), b = obb_of(rb);
+  const float inter = fminf(overlap_in_frame(a, b), overlap_in_frame(b, a));
+  const float uni = fabsf(a.w * a.h) + fabsf(b.w * b.h) - inter;
+  if (!(uni > 0.f) || !(inter == inter)) return true;  // degenerate / NaN: let the exact routine decide
+  return (inter / uni) * 1.02f + 1e-5f >= thr;
+}
 
 template <typename Rec, bool kWeighted>
 __host__ __device__ inline size_t nms_smem_bytes(int nwords) {
   size_t b = 0;
-  b += align_up_c(sizeof(uint32_t) * nwords, 16);
-  b += sizeof(int) * kF;
-  b += sizeof(Rec) * kF;
-  b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);
-  b += align_up_c(sizeof(uint16_t) * kF, 16);
-  b += sizeof(float) * kF * 3;
-  b += sizeof(uint32_t) * (kKillCap > kPairCap / 2 ? kKillCap : kPairCap / 2);
-  if (kWeighted) b += sizeof(float) * kKillCap + kTile;
+  b += align_up_c(sizeof(uint32_t) * nwords, 16);                  // alive
+  b += sizeof(Rec) * kF;                                           // frec
+  b += sizeof(float) * kF * 3;                                     // fx, fy, fr
+  b += sizeof(int) * kF;                                           // front_pos
+  b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
+  b += sizeof(int) * (kNB + 1) * 2;                                // b_start, b_cursor
+  b += sizeof(uint32_t) * kQ2Cap;                                  // queue2
+  b += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;              // per-warp hit buffers
+  b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
+  if (kWeighted) b += sizeof(float) * kQ2Cap;                      // qiou
   return b;
 }
 
@@ -182,56 +249,159 @@ __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_segment_kernel(NmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsThreads / 32 + 1];
-  __shared__ int s_qn, s_nk;
+  __shared__ int s_qn, s_nk, s_nos, s_overflow;
+  __shared__ float s_red[kNmsThreads / 32 * 2];
+  __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
 
   const int seg = blockIdx.x;
   const int beg = a.seg_begin[seg];
   const int n = min(a.seg_end[seg] - beg, a.num_pre);  // top num_pre_nms by score (nms.py:29-32)
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (n <= 0) {
     if (tid == 0) a.kept_count[seg] = 0;
     return;
   }
   const int nwords = (n + 31) >> 5;
   const Rec *recs = static_cast<const Rec *>(a.recs) + beg;
+  GridEntry *entries = static_cast<GridEntry *>(a.grid_entries) + 4 * static_cast<size_t>(beg);
+  uint32_t *os_list = a.oversize + beg;
+  int *firstsup = kWeighted ? a.firstsup + beg : nullptr;
   const int kbase = a.kept_base[seg];
+  const float thr_any = kWeighted ? fminf(a.thr, a.mthr) : a.thr;  // smallest IoU that matters
+  const bool prune = a.prune != 0;
 
   // ---- carve shared memory
-  Smem<Rec> S;
-  {
-    unsigned char *p = smem_raw;
-    S.alive = reinterpret_cast<uint32_t *>(p); p += align_up_c(sizeof(uint32_t) * nwords, 16);
-    S.frec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;
-    S.front_pos = reinterpret_cast<int *>(p); p += sizeof(int) * kF;
-    S.sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
-    S.mrg = S.sup;
-    if (kWeighted) { S.mrg = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW; }
-    S.kx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-    S.ky = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-    S.kr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-    S.queue = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * (kKillCap > kPairCap / 2 ? kKillCap : kPairCap / 2);
-    S.keptf = reinterpret_cast<uint16_t *>(p); p += align_up_c(sizeof(uint16_t) * kF, 16);
-    S.qiou = nullptr; S.firstsup = nullptr;
-    if (kWeighted) {
-      S.qiou = reinterpret_cast<float *>(p); p += sizeof(float) * kKillCap;
-      S.firstsup = p;
-    }
-  }
-  for (int w = tid; w < nwords; w += kNmsThreads)
-    S.alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+  unsigned char *p = smem_raw;
+  uint32_t *alive = reinterpret_cast<uint32_t *>(p); p += align_up_c(sizeof(uint32_t) * nwords, 16);
+  Rec *frec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;
+  float *fx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  float *fy = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  float *fr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  int *front_pos = reinterpret_cast<int *>(p); p += sizeof(int) * kF;
+  uint32_t *sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
+  uint32_t *mrg = sup;
+  if (kWeighted) { mrg = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW; }
+  int *b_start = reinterpret_cast<int *>(p); p += sizeof(int) * (kNB + 1);
+  int *b_cursor = reinterpret_cast<int *>(p); p += sizeof(int) * (kNB + 1);
+  uint32_t *queue2 = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kQ2Cap;
+  uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;
+  uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
+  int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
+  p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
+  float *qiou = kWeighted ? reinterpret_cast<float *>(p) : nullptr;
 
   unsigned long long st_iou = 0, st_circle = 0;
+  // per-phase cycle counters (thread 0, only when stats are requested):
+  // [0] grid build + frontier gather, [1] frontier load, [2] frontier pairs, [3] greedy, [4] kill scan, [5] exact IoU
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long t_mark = clock64();
+  auto lap = [&](int k) {
+    if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
+  };
+
+  // ======================= 0. alive bitmap + static candidate grid =======================
+  for (int w = tid; w < nwords; w += kNmsThreads)
+    alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+  for (int b = tid; b <= kNB; b += kNmsThreads) b_cursor[b] = 0;
+  if (tid == 0) { s_nos = 0; s_overflow = 0; }
+  float inv_cell = 0.f;
+  {
+    // mean padded radius of the finite, sane candidates -> cell size = 4 * mean radius
+    float sum = 0.f, cnt = 0.f;
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const float r = recs[i].r;
+      if (r > 0.f && r < 1.0e4f) { sum += r; cnt += 1.f; }
+    }
+    for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if (lane == 0) { s_red[wid] = sum; s_red[kNmsThreads / 32 + wid] = cnt; }
+    __syncthreads();
+    float ts = 0.f, tc = 0.f;
+    for (int w = 0; w < kNmsThreads / 32; ++w) { ts += s_red[w]; tc += s_red[kNmsThreads / 32 + w]; }
+    const float cell = fminf(fmaxf(4.0f * (tc > 0.f ? ts / tc : 1.0f), 0.25f), 4.0e4f);
+    inv_cell = 1.0f / cell;
+  }
+  if (prune) {
+    for (int i = tid; i < n; i += kNmsThreads) {           // count
+      const Rec r = recs[i];
+      const BoxCells c = cells_of(rec_cx(r), rec_cy(r), r.r, inv_cell, 2);
+      if (c.gridded) {
+        for (int cy = c.cy0; cy <= c.cy1; ++cy)
+          for (int cx = c.cx0; cx <= c.cx1; ++cx) atomicAdd(&b_cursor[bucket_of(cx, cy)], 1);
+      } else {
+        os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
+      }
+    }
+  } else {
+    for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
+    if (tid == 0) s_nos = n;
+  }
+  __syncthreads();
+  {
+    int total;
+    const int c0 = b_cursor[2 * tid], c1 = b_cursor[2 * tid + 1];
+    const int off = block_exclusive_scan(c0 + c1, s_warp, total);
+    b_start[2 * tid] = off; b_start[2 * tid + 1] = off + c0;
+    b_cursor[2 * tid] = off; b_cursor[2 * tid + 1] = off + c0;
+    if (tid == 0) b_start[kNB] = total;
+  }
+  __syncthreads();
+  if (prune) {
+    for (int i = tid; i < n; i += kNmsThreads) {           // fill
+      const Rec r = recs[i];
+      const float x = rec_cx(r), y = rec_cy(r);
+      const BoxCells c = cells_of(x, y, r.r, inv_cell, 2);
+      if (!c.gridded) continue;
+      for (int cy = c.cy0; cy <= c.cy1; ++cy)
+        for (int cx = c.cx0; cx <= c.cx1; ++cx) {
+          const uint32_t meta = static_cast<uint32_t>(i) | (cx == c.cx0 ? (1u << 20) : 0u) |
+                                (cy == c.cy0 ? (1u << 21) : 0u) | cell_key(cx, cy);
+          entries[atomicAdd(&b_cursor[bucket_of(cx, cy)], 1)] = GridEntry{x, y, r.r, meta};
+        }
+    }
+  }
+  if (kWeighted)
+    for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
+  __syncthreads();
+  const int nos = s_nos;
+
   int kept_total = 0;
   int cursor_word = 0;
   int rounds = 0;
-  __syncthreads();
+
+  // record one evaluated pair in the frontier bit-matrices
+  auto mark_pair = [&](int i, int j, float iou) {
+    if (iou > a.thr) atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31));
+    if (kWeighted && iou > a.mthr) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
+  };
+  auto accumulate = [&](int slot, int row_in_seg) {  // merge candidate `row_in_seg` into kept slot
+    const size_t rowj = static_cast<size_t>(beg + row_in_seg) * a.D;
+    const double sj = a.data[rowj + a.D - 1];
+    double *acc = a.acc + static_cast<size_t>(kbase + slot) * a.D;
+    for (int c = 0; c < a.D - 1; ++c) atomicAdd(acc + c, sj * static_cast<double>(a.data[rowj + c]));
+    atomicAdd(acc + a.D - 1, sj);
+    atomicAdd(a.merge_count + kbase + slot, 1);
+  };
+  // warp-converged append of `item` (valid where `pred`) to the exact-IoU queue; returns false for the
+  // lanes whose item did not fit (caller handles them in place)
+  auto q2_push = [&](bool pred, uint32_t item) -> bool {
+    const uint32_t m = __ballot_sync(0xffffffffu, pred);
+    if (!m) return true;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!pred) return true;
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot >= kQ2Cap) return false;
+    queue2[slot] = item;
+    return true;
+  };
 
   while (true) {
     // ================= 1. frontier: first kF alive candidates =================
     int nf = 0;
     for (int base = cursor_word; base < nwords && nf < kF; base += kNmsThreads) {
       const int wi = base + tid;
-      const uint32_t word = wi < nwords ? S.alive[wi] : 0u;
+      const uint32_t word = wi < nwords ? alive[wi] : 0u;
       int total;
       const int off = block_exclusive_scan(__popc(word), s_warp, total);
       if (word && nf + off < kF) {
@@ -240,7 +410,7 @@ nms_segment_kernel(NmsArgs a) {
         while (m && r < kF) {
           const int bit = __ffs(m) - 1;
           m &= m - 1;
-          S.front_pos[r++] = (wi << 5) + bit;
+          front_pos[r++] = (wi << 5) + bit;
         }
       }
       nf = min(kF, nf + total);
@@ -248,241 +418,322 @@ nms_segment_kernel(NmsArgs a) {
     __syncthreads();
     if (nf == 0) break;
     ++rounds;
-    // the frontier is decided this round: clear its bits, load its records, zero the bit-matrices
+    lap(0);
+
+    // the frontier is decided this round: clear its bits, load its records, reset per-round state
     if (tid < nf) {
-      const int pos = S.front_pos[tid];
-      atomicAnd(&S.alive[pos >> 5], ~(1u << (pos & 31)));
-      S.frec[tid] = recs[pos];
+      const int pos = front_pos[tid];
+      atomicAnd(&alive[pos >> 5], ~(1u << (pos & 31)));
+      const Rec r = recs[pos];
+      frec[tid] = r;
+      fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
+      keptrank[tid] = -1;
     }
     for (int i = tid; i < kF * kFW; i += kNmsThreads) {
-      S.sup[i] = 0u;
-      if (kWeighted) S.mrg[i] = 0u;
+      sup[i] = 0u;
+      if (kWeighted) mrg[i] = 0u;
+    }
+    if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+    cursor_word = front_pos[0] >> 5;
+    lap(1);
+
+    // ================= 2. interacting pairs inside the frontier =================
+    // all nf*(nf-1)/2 circle tests (<= 32 k, shared-memory SoA, warp-converged), bound, queue, exact IoU
+    {
+      const int npairs = nf * nf;
+      for (int idx0 = 0; idx0 < npairs; idx0 += kNmsThreads) {
+        const int idx = idx0 + tid;
+        const int i = idx / nf, j = idx - i * nf;
+        bool hit = false;
+        if (idx < npairs && i < j) {
+          ++st_circle;
+          hit = true;
+          if (prune) {
+            const float dx = fx[i] - fx[j], dy = fy[i] - fy[j], rr = fr[i] + fr[j];
+            hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
+          }
+        }
+        if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
+          ++st_iou;
+          mark_pair(i, j, pair_iou(frec[i], frec[j]));
+        }
+      }
+      __syncthreads();
+      const int qn = min(s_qn, kQ2Cap);
+      for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
+        __syncwarp();
+        const int q = q0 + tid;
+        if (q >= qn) continue;
+        const int i = queue2[q] >> 8, j = queue2[q] & 255;
+        ++st_iou;
+        mark_pair(i, j, pair_iou(frec[i], frec[j]));
+      }
+      __syncthreads();
+    }
+    lap(2);
+
+    // ================= 3. greedy resolution of the frontier =================
+    // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
+    // parallel; only the rest needs the dependent scan, done by one warp.
+    {
+      const int w = tid & (kFW - 1);
+      uint32_t colbits = 0u;
+      for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
+      if (colbits) atomicOr(&s_haspred[w], colbits);
+    }
+    __syncthreads();
+    {
+      const int w = tid & (kFW - 1);
+      uint32_t rm = 0u;
+      for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW)
+        if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
+      if (rm) atomicOr(&s_removed[w], rm);
     }
     if (tid == 0) s_qn = 0;
     __syncthreads();
-    cursor_word = S.front_pos[0] >> 5;
-
-    // ================= 2. pairs inside the frontier =================
-    {
-      uint16_t *pq = reinterpret_cast<uint16_t *>(S.queue);
-      for (int idx = tid; idx < nf * nf; idx += kNmsThreads) {
-        const int i = idx / nf, j = idx - i * nf;
-        if (i >= j) continue;
-        const Rec &ri = S.frec[i];
-        const Rec &rj = S.frec[j];
-        const float dx = rec_cx(ri) - rec_cx(rj), dy = rec_cy(ri) - rec_cy(rj), rr = ri.r + rj.r;
-        ++st_circle;
-        if (!(dx * dx + dy * dy <= rr * rr)) continue;
-        const int slot = atomicAdd(&s_qn, 1);
-        if (slot < kPairCap) {
-          pq[slot] = static_cast<uint16_t>((i << 8) | j);
-        } else {  // queue full: evaluate in place (rare)
-          const float iou = pair_iou(ri, rj);
-          ++st_iou;
-          if (iou > a.thr) atomicOr(&S.sup[i * kFW + (j >> 5)], 1u << (j & 31));
-          if (kWeighted && iou > a.mthr) atomicOr(&S.mrg[i * kFW + (j >> 5)], 1u << (j & 31));
-        }
-      }
-      __syncthreads();
-      const int qn = min(s_qn, kPairCap);
-      for (int q = tid; q < qn; q += kNmsThreads) {
-        const int i = pq[q] >> 8, j = pq[q] & 255;
-        const float iou = pair_iou(S.frec[i], S.frec[j]);
-        ++st_iou;
-        if (iou > a.thr) atomicOr(&S.sup[i * kFW + (j >> 5)], 1u << (j & 31));
-        if (kWeighted && iou > a.mthr) atomicOr(&S.mrg[i * kFW + (j >> 5)], 1u << (j & 31));
-      }
-      __syncthreads();
-    }
-
-    // ================= 3. greedy resolution of the frontier (one warp) =================
     if (tid < 32) {
-      const int lane = tid;
-      // lane w < kFW owns word w of the `removed` set; bits >= nf are pre-removed
-      uint32_t removed = 0u;
+      // lane w < kFW owns word w.  valid = bits < nf; free = valid & ~haspred (kept for sure)
+      uint32_t valid = 0u, removed = 0u, pending = 0u, kept = 0u;
       if (lane < kFW) {
         const int lo = lane << 5;
-        removed = (nf >= lo + 32) ? 0u : (nf <= lo ? 0xffffffffu : ~((1u << (nf - lo)) - 1u));
+        valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
+        removed = s_removed[lane];
+        pending = valid & s_haspred[lane];       // must be visited in rank order
+        kept = valid & ~s_haspred[lane];
       }
-      int nk = 0;
-      const int room = a.num_post - kept_total;
-      int next = 0;
-      while (nk < room) {
-        uint32_t avail = 0u;
-        if (lane < kFW) {
-          avail = ~removed;
-          const int lo = lane << 5;
-          if (next >= lo + 32) avail = 0u;
-          else if (next > lo) avail &= ~((1u << (next - lo)) - 1u);
-        }
-        const uint32_t have = __ballot_sync(0xffffffffu, avail != 0u);
+      while (true) {
+        const uint32_t cand = pending & ~removed;
+        const uint32_t have = __ballot_sync(0xffffffffu, cand != 0u);
         if (!have) break;
         const int wsel = __ffs(have) - 1;
-        const uint32_t aw = __shfl_sync(0xffffffffu, avail, wsel);
-        const int i = (wsel << 5) + __ffs(aw) - 1;
-        if (lane == 0) S.keptf[nk] = static_cast<uint16_t>(i);
-        ++nk;
-        if (lane < kFW) removed |= S.sup[i * kFW + lane];
-        next = i + 1;
+        const uint32_t cw = __shfl_sync(0xffffffffu, cand, wsel);
+        const int bit = __ffs(cw) - 1;
+        const int i = (wsel << 5) + bit;
+        if (lane == wsel) kept |= 1u << bit;
+        if (lane < kFW) {
+          // everything up to and including i is decided now
+          const int lo = lane << 5;
+          if (i >= lo + 31) pending = 0u;
+          else if (i >= lo) pending &= ~((2u << (i - lo)) - 1u);
+          removed |= sup[i * kFW + lane];
+        }
       }
-      if (lane == 0) s_nk = nk;
+      // kept boxes in rank order, truncated to the room left under num_post_nms
+      const int room = a.num_post - kept_total;
+      const int cnt = lane < kFW ? __popc(kept) : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < kFW; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      int rank = incl - cnt;
+      if (lane < kFW) {
+        uint32_t m = kept;
+        while (m && rank < room) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          const int i = (lane << 5) + bit;
+          keptf[rank] = static_cast<uint16_t>(i);
+          keptrank[i] = static_cast<int16_t>(rank);
+          ++rank;
+        }
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, kFW - 1);
+      if (lane == 0) s_nk = min(total, room);
     }
     __syncthreads();
     const int nk = s_nk;
+    lap(3);
 
     // ================= 4. publish the newly kept boxes =================
-    if (tid < nk) {
-      const int fi = S.keptf[tid];
-      a.kept_pos[kbase + kept_total + tid] = S.front_pos[fi];
-      S.kx[tid] = rec_cx(S.frec[fi]);
-      S.ky[tid] = rec_cy(S.frec[fi]);
-      S.kr[tid] = S.frec[fi].r;
-    }
+    if (tid < nk) a.kept_pos[kbase + kept_total + tid] = front_pos[keptf[tid]];
     if (kWeighted) {
       // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr
       // that comes no later than its first suppressor; kept boxes join themselves.
       if (tid < nf) {
         const int j = tid;
-        const size_t rowj = static_cast<size_t>(beg + S.front_pos[j]) * a.D;
-        const double sj = a.data[rowj + a.D - 1];
         for (int t = 0; t < nk; ++t) {
-          const int i = S.keptf[t];
+          const int i = keptf[t];
           if (i > j) break;
           const bool self = (i == j);
-          const bool m = self || (S.mrg[i * kFW + (j >> 5)] >> (j & 31)) & 1u;
-          if (m) {
-            double *acc = a.acc + static_cast<size_t>(kbase + kept_total + t) * a.D;
-            for (int c = 0; c < a.D - 1; ++c) atomicAdd(acc + c, sj * static_cast<double>(a.data[rowj + c]));
-            atomicAdd(acc + a.D - 1, sj);
-            atomicAdd(a.merge_count + kbase + kept_total + t, 1);
-          }
-          if (self || ((S.sup[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) break;
+          if (self || ((mrg[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) accumulate(kept_total + t, front_pos[j]);
+          if (self || ((sup[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) break;
         }
       }
     }
     kept_total += nk;
-    __syncthreads();
     // nms.py:53-56: only the first num_post_nms kept survive, so the scan can stop there.  The
     // weighted mode still owes the last kept boxes their merge sets from the candidates behind
     // the frontier, so it runs one more kill phase before leaving.
     const bool last_round = kept_total >= a.num_post;
     if (last_round && !kWeighted) break;
 
-    // ================= 5. kill phase: alive candidates vs the newly kept boxes =================
-    for (int tile0 = cursor_word << 5; tile0 < n; tile0 += kTile) {
-      if (tid == 0) s_qn = 0;
-      if (kWeighted)
-        for (int i = tid; i < kTile; i += kNmsThreads) S.firstsup[i] = 255;
-      __syncthreads();
-      // 4 threads per bitmap word, 8 candidates each
-      for (int sub = tid; sub < (kTile >> 3); sub += kNmsThreads) {
-        const int wi = (tile0 >> 5) + (sub >> 2);
-        if (wi >= nwords) continue;
-        uint32_t bits = (S.alive[wi] >> ((sub & 3) << 3)) & 0xffu;
-        while (bits) {
-          const int bit = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int j = (wi << 5) + ((sub & 3) << 3) + bit;
-          const Rec &rj = recs[j];
-          const float jx = rec_cx(rj), jy = rec_cy(rj), jr = rj.r;
-          for (int t = 0; t < nk; ++t) {
-            const float dx = S.kx[t] - jx, dy = S.ky[t] - jy, rr = S.kr[t] + jr;
-            if (!(dx * dx + dy * dy <= rr * rr)) continue;
-            const int slot = atomicAdd(&s_qn, 1);
-            if (slot < kKillCap) {
-              S.queue[slot] = (static_cast<uint32_t>(j - tile0) << 8) | t;
-            } else if (!kWeighted) {  // queue full: evaluate in place (hard mode only needs ANY suppressor)
-              ++st_iou;
-              if (pair_iou(S.frec[S.keptf[t]], rj) > a.thr) {
-                atomicAnd(&S.alive[j >> 5], ~(1u << (j & 31)));
-                break;
-              }
+    // ================= 5. kill scan: one warp per newly kept box over the static grid ==============
+    // Lanes stride over the contiguous entries of each cell the kept box's circle touches (+ the
+    // oversize list): alive test, circle test, hits compacted per warp so the IoU bound runs on full
+    // warps; pairs that pass go to the exact-IoU queue.
+    for (int t = wid; t < nk; t += kNmsThreads / 32) {
+      const int fi = keptf[t];
+      const Rec &rk = frec[fi];
+      const float kx = fx[fi], ky = fy[fi], kr = fr[fi];
+      int nbuf = 0;  // warp-uniform count of buffered hits
+      auto flush = [&](int count) {   // run the bound on `count` (<= 32) buffered hits, lanes < count
+        __syncwarp();
+        bool pass = false;
+        uint32_t j = 0;
+        if (lane < count) {
+          j = wbuf[lane];
+          pass = !prune || iou_may_exceed(rk, recs[j], thr_any);
+        }
+        if (!q2_push(pass, (j << 8) | static_cast<uint32_t>(t))) {
+          if (kWeighted) {
+            s_overflow = 1;   // redo this round's kill phase with the exact serial fallback
+          } else {            // hard mode only needs ANY suppressor: evaluate in place
+            ++st_iou;
+            if (pair_iou(rk, recs[j]) > a.thr) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+          }
+        }
+        __syncwarp();
+      };
+      auto offer = [&](bool hit, uint32_t j) {  // warp-converged: buffer the hits, flush full warps
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (!m) return;
+        if (hit) wbuf[nbuf + __popc(m & ((1u << lane) - 1u))] = j;
+        nbuf += __popc(m);
+        if (nbuf >= 32) {
+          flush(32);
+          if (lane < nbuf - 32) wbuf[lane] = wbuf[32 + lane];   // disjoint halves: no hazard
+          nbuf -= 32;
+          __syncwarp();
+        }
+      };
+      auto scan_range = [&](const GridEntry *ents, int e0, int e1, uint32_t key, uint32_t need) {
+        for (int eb = e0; eb < e1; eb += 32) {
+          const int e = eb + lane;
+          bool hit = false;
+          uint32_t j = 0;
+          if (e < e1) {
+            const GridEntry ge = ents[e];
+            j = ge.meta & kIdxMask;
+            if ((ge.meta & 0xffc00000u) == key && (ge.meta & need) == need && ((alive[j >> 5] >> (j & 31)) & 1u)) {
+              ++st_circle;
+              const float dx = ge.x - kx, dy = ge.y - ky, rr = ge.r + kr;
+              hit = dx * dx + dy * dy <= rr * rr;
             }
           }
-          st_circle += nk;
+          offer(hit, j);
         }
-      }
-      __syncthreads();
-      int qn = s_qn;
-      if (kWeighted && qn > kKillCap) {
-        // (weighted) overflow: the dropped pairs are redone serially per candidate by thread 0..;
-        // keep it simple and exact: re-run this tile candidate-by-candidate without the queue
-        qn = -1;
-      }
-      if (!kWeighted) {
-        qn = min(qn, kKillCap);
-        for (int q = tid; q < qn; q += kNmsThreads) {
-          const uint32_t e = S.queue[q];
-          const int j = tile0 + (e >> 8), t = e & 255;
-          if (!((S.alive[j >> 5] >> (j & 31)) & 1u)) continue;  // already suppressed by another pair
-          ++st_iou;
-          if (pair_iou(S.frec[S.keptf[t]], recs[j]) > a.thr) atomicAnd(&S.alive[j >> 5], ~(1u << (j & 31)));
-        }
-      } else if (qn >= 0) {
-        // pass 1: IoU of every queued pair; remember each candidate's FIRST suppressor (rank order)
-        for (int q = tid; q < qn; q += kNmsThreads) {
-          const uint32_t e = S.queue[q];
-          const int jl = e >> 8, t = e & 255;
-          const float iou = pair_iou(S.frec[S.keptf[t]], recs[tile0 + jl]);
-          ++st_iou;
-          S.qiou[q] = iou;
-          if (iou > a.thr) {
-            // atomicMin on a byte: CAS on the containing word
-            uint32_t *wp = reinterpret_cast<uint32_t *>(S.firstsup + (jl & ~3));
-            const int sh = (jl & 3) << 3;
-            uint32_t old = *wp, assumed;
-            do {
-              assumed = old;
-              const uint32_t cur = (assumed >> sh) & 255u;
-              if (cur <= static_cast<uint32_t>(t)) break;
-              old = atomicCAS(wp, assumed, (assumed & ~(255u << sh)) | (static_cast<uint32_t>(t) << sh));
-            } while (old != assumed);
+      };
+      const BoxCells kc = cells_of(kx, ky, kr, inv_cell, kMaxQueryCells);
+      if (prune && kc.gridded) {
+        for (int cy = kc.cy0; cy <= kc.cy1; ++cy)
+          for (int cx = kc.cx0; cx <= kc.cx1; ++cx) {
+            const int b = bucket_of(cx, cy);
+            const uint32_t need = (cx == kc.cx0 ? 0u : (1u << 20)) | (cy == kc.cy0 ? 0u : (1u << 21));
+            scan_range(entries, b_start[b], b_start[b + 1], cell_key(cx, cy), need);
           }
+        for (int ob = 0; ob < nos; ob += 32) {               // oversize candidates
+          const int o = ob + lane;
+          bool hit = false;
+          uint32_t j = 0;
+          if (o < nos) {
+            j = os_list[o];
+            if ((alive[j >> 5] >> (j & 31)) & 1u) {
+              ++st_circle;
+              const Rec &rj = recs[j];
+              const float dx = rec_cx(rj) - kx, dy = rec_cy(rj) - ky, rr = rj.r + kr;
+              hit = dx * dx + dy * dy <= rr * rr;
+            }
+          }
+          offer(hit, j);
+        }
+      } else {
+        // kept box too big / far for the grid, or pruning disabled: every alive candidate
+        for (int jb = cursor_word << 5; jb < n; jb += 32) {
+          const int j = jb + lane;
+          bool hit = false;
+          if (j < n && ((alive[j >> 5] >> (j & 31)) & 1u)) {
+            ++st_circle;
+            hit = true;
+            if (prune) {
+              const Rec &rj = recs[j];
+              const float dx = rec_cx(rj) - kx, dy = rec_cy(rj) - ky, rr = rj.r + kr;
+              hit = dx * dx + dy * dy <= rr * rr;
+            }
+          }
+          offer(hit, static_cast<uint32_t>(j));
+        }
+      }
+      if (nbuf > 0) flush(nbuf);
+    }
+    __syncthreads();
+    lap(4);
+
+    // ================= 6. exact IoU of the queued (candidate, kept) pairs =================
+    {
+      const int qn = min(s_qn, kQ2Cap);
+      const int slot0 = kept_total - nk;
+      if (!kWeighted) {
+        for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
+          __syncwarp();
+          const int q = q0 + tid;
+          if (q >= qn) continue;
+          const uint32_t e = queue2[q];
+          const int j = e >> 8, t = e & 255;
+          if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;  // already suppressed by another pair
+          ++st_iou;
+          if (pair_iou(frec[keptf[t]], recs[j]) > a.thr) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+        }
+      } else if (!s_overflow) {
+        // pass 1: IoU of every queued pair; remember each candidate's FIRST suppressor (rank order)
+        for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
+          __syncwarp();
+          const int q = q0 + tid;
+          if (q >= qn) continue;
+          const uint32_t e = queue2[q];
+          const int j = e >> 8, t = e & 255;
+          const float iou = pair_iou(frec[keptf[t]], recs[j]);
+          ++st_iou;
+          qiou[q] = iou;
+          if (iou > a.thr) atomicMin(&firstsup[j], t);
         }
         __syncthreads();
         // pass 2: merges up to and including the first suppressor; the suppressor clears the bit
         for (int q = tid; q < qn; q += kNmsThreads) {
-          const uint32_t e = S.queue[q];
-          const int jl = e >> 8, t = e & 255;
-          const int fs = S.firstsup[jl];
+          const uint32_t e = queue2[q];
+          const int j = e >> 8, t = e & 255;
+          const int fs = firstsup[j];
           if (t > fs) continue;
-          const int j = tile0 + jl;
-          if (S.qiou[q] > a.mthr) {
-            const size_t rowj = static_cast<size_t>(beg + j) * a.D;
-            const double sj = a.data[rowj + a.D - 1];
-            double *acc = a.acc + static_cast<size_t>(kbase + kept_total - nk + t) * a.D;
-            for (int c = 0; c < a.D - 1; ++c) atomicAdd(acc + c, sj * static_cast<double>(a.data[rowj + c]));
-            atomicAdd(acc + a.D - 1, sj);
-            atomicAdd(a.merge_count + kbase + kept_total - nk + t, 1);
-          }
-          if (t == fs) atomicAnd(&S.alive[j >> 5], ~(1u << (j & 31)));
+          if (qiou[q] > a.mthr) accumulate(slot0 + t, j);
+          if (t == fs) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
         }
       } else {
-        // exact serial fallback for an overflowing weighted tile: one thread per candidate
-        for (int jl = tid; jl < kTile; jl += kNmsThreads) {
-          const int j = tile0 + jl;
-          if (j >= n || !((S.alive[j >> 5] >> (j & 31)) & 1u)) continue;
+        // exact serial fallback (queue overflow in weighted mode): one thread per alive candidate,
+        // kept boxes visited in rank order
+        for (int j = (cursor_word << 5) + tid; j < n; j += kNmsThreads) {
+          if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
           const Rec rj = recs[j];
           const float jx = rec_cx(rj), jy = rec_cy(rj);
           for (int t = 0; t < nk; ++t) {
-            const float dx = S.kx[t] - jx, dy = S.ky[t] - jy, rr = S.kr[t] + rj.r;
-            if (!(dx * dx + dy * dy <= rr * rr)) continue;
-            const float iou = pair_iou(S.frec[S.keptf[t]], rj);
-            ++st_iou;
-            if (iou > a.mthr) {
-              const size_t rowj = static_cast<size_t>(beg + j) * a.D;
-              const double sj = a.data[rowj + a.D - 1];
-              double *acc = a.acc + static_cast<size_t>(kbase + kept_total - nk + t) * a.D;
-              for (int c = 0; c < a.D - 1; ++c) atomicAdd(acc + c, sj * static_cast<double>(a.data[rowj + c]));
-              atomicAdd(acc + a.D - 1, sj);
-              atomicAdd(a.merge_count + kbase + kept_total - nk + t, 1);
+            const int fi = keptf[t];
+            if (prune) {
+              const float dx = fx[fi] - jx, dy = fy[fi] - jy, rr = fr[fi] + rj.r;
+              if (!(dx * dx + dy * dy <= rr * rr)) continue;
             }
-            if (iou > a.thr) { atomicAnd(&S.alive[j >> 5], ~(1u << (j & 31))); break; }
+            const float iou = pair_iou(frec[fi], rj);
+            ++st_iou;
+            if (iou > a.mthr) accumulate(slot0 + t, j);
+            if (iou > a.thr) { atomicAnd(&alive[j >> 5], ~(1u << (j & 31))); break; }
           }
         }
       }
       __syncthreads();
+      if (tid == 0) s_overflow = 0;
     }
+    lap(5);
     if (last_round) break;
   }
 
@@ -493,13 +744,14 @@ nms_segment_kernel(NmsArgs a) {
       st_iou += __shfl_xor_sync(0xffffffffu, st_iou, o);
       st_circle += __shfl_xor_sync(0xffffffffu, st_circle, o);
     }
-    if ((tid & 31) == 0) {
+    if (lane == 0) {
       atomicAdd(a.stats + 0, st_iou);
       atomicAdd(a.stats + 3, st_circle);
     }
     if (tid == 0) {
       atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept_total));
       atomicAdd(a.stats + 2, static_cast<unsigned long long>(rounds));
+      for (int k = 0; k < 6; ++k) atomicAdd(a.stats + 4 + k, static_cast<unsigned long long>(ph[k]));
     }
   }
 }
@@ -597,6 +849,9 @@ struct NmsLayout {
   void *recs;
   float *data;
   double *acc;
+  void *grid_entries;
+  uint32_t *oversize;
+  int *firstsup;
   void *cub_tmp;
   size_t cub_bytes, total;
 };
@@ -629,6 +884,9 @@ static NmsLayout nms_layout(void *scratch, int n, int S, bool weighted, int D, i
     L.acc = c.take<double>(static_cast<size_t>(nn) * D);   // acc + merge_count contiguous (one memset)
     L.merge_count = c.take<int>(nn);
   }
+  L.grid_entries = c.take<GridEntry>(4 * static_cast<size_t>(nn));
+  L.oversize = c.take<uint32_t>(nn);
+  L.firstsup = weighted ? c.take<int>(nn) : nullptr;
   L.cub_bytes = cub_sort_bytes(nn, end_bit);
   L.cub_tmp = c.take<unsigned char>(L.cub_bytes);
   L.total = align_up(c.used, 256);
@@ -639,7 +897,8 @@ template <typename Rec, bool kWeighted>
 static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStream_t s) {
   const int nwords = (max_seg_n + 31) / 32;
   const size_t smem = nms_smem_bytes<Rec, kWeighted>(nwords);
-  if (smem > 200 * 1024) return RV3D_ERR_ARG;  // num_pre_nms too large for the shared-memory bitmap
+  // the alive bitmap lives in shared memory and grid entries index candidates with 20 bits
+  if (smem > 200 * 1024 || max_seg_n >= (1 << 20)) return RV3D_ERR_ARG;
   RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   nms_segment_kernel<Rec, kWeighted><<<S, kNmsThreads, smem, s>>>(a);
@@ -702,8 +961,10 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   NmsArgs a{};
   a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
   a.num_pre = p->num_pre_nms; a.num_post = p->num_post_nms; a.thr = p->iou_threshold; a.mthr = p->merge_threshold;
+  a.prune = (p->iou_threshold >= 0.f && (p->mode != RV3D_NMS_WEIGHTED || p->merge_threshold >= 0.f)) ? 1 : 0;
   a.kept_pos = L.kept_pos; a.kept_count = L.kept_count; a.data = L.data; a.D = 9; a.acc = L.acc;
   a.merge_count = L.merge_count; a.stats = reinterpret_cast<unsigned long long *>(stats);
+  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
   const int max_seg_n = n < p->num_pre_nms ? n : p->num_pre_nms;
   int rc;
   if (weighted) {
@@ -867,6 +1128,9 @@ struct OpLayout {
   int *seg_begin, *seg_end, *kept_base, *kept_count, *kept_pos, *merge_count;
   void *recs;
   double *acc;
+  void *grid_entries;
+  uint32_t *oversize;
+  int *firstsup;
   void *cub_tmp;
   size_t cub_bytes, total;
 };
@@ -891,6 +1155,9 @@ static OpLayout op_layout(void *scratch, int n, bool weighted, int D, bool sort)
     L.acc = c.take<double>(static_cast<size_t>(nn) * D);
     L.merge_count = c.take<int>(nn);
   }
+  L.grid_entries = c.take<GridEntry>(4 * static_cast<size_t>(nn));
+  L.oversize = c.take<uint32_t>(nn);
+  L.firstsup = weighted ? c.take<int>(nn) : nullptr;
   L.cub_bytes = sort ? cub_sort_bytes(nn, 64) : 0;
   L.cub_tmp = c.take<unsigned char>(L.cub_bytes ? L.cub_bytes : 1);
   L.total = align_up(c.used, 256);
@@ -929,8 +1196,9 @@ extern "C" int rv3d_nms_rotated(const float *boxes, const float *scores, int32_t
   RV3D_CHECK_LAUNCH();
   NmsArgs a{};
   a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
-  a.num_pre = n; a.num_post = n; a.thr = iou_threshold; a.mthr = 0.f;
+  a.num_pre = n; a.num_post = n; a.thr = iou_threshold; a.mthr = 0.f; a.prune = iou_threshold >= 0.f ? 1 : 0;
   a.kept_pos = L.kept_pos; a.kept_count = L.kept_count;
+  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
   const int rc = launch_nms_segments<HardRec, false>(a, 1, n, s);
   if (rc != RV3D_OK) return rc;
   keep_indices_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.kept_pos, L.kept_count, order, keep, n_keep);
@@ -964,8 +1232,10 @@ extern "C" int rv3d_wnms(const float *boxes, const float *data, int32_t n, int32
   NmsArgs a{};
   a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
   a.num_pre = n; a.num_post = n; a.thr = nms_threshold; a.mthr = merge_threshold;
+  a.prune = (nms_threshold >= 0.f && merge_threshold >= 0.f) ? 1 : 0;
   a.kept_pos = L.kept_pos; a.kept_count = L.kept_count; a.data = data; a.D = d; a.acc = L.acc;
   a.merge_count = L.merge_count;
+  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
   const int rc = launch_nms_segments<WRec, true>(a, 1, n, s);
   if (rc != RV3D_OK) return rc;
   wnms_finalize_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.kept_pos, L.kept_count, L.acc, L.merge_count, data, d,
