@@ -442,22 +442,24 @@ nms_segment_kernel(NmsArgs a) {
     // ================= 2. interacting pairs inside the frontier =================
     // all nf*(nf-1)/2 circle tests (<= 32 k, shared-memory SoA, warp-converged), bound, queue, exact IoU
     {
-      const int npairs = nf * nf;
-      for (int idx0 = 0; idx0 < npairs; idx0 += kNmsThreads) {
-        const int idx = idx0 + tid;
-        const int i = idx / nf, j = idx - i * nf;
-        bool hit = false;
-        if (idx < npairs && i < j) {
-          ++st_circle;
-          hit = true;
-          if (prune) {
-            const float dx = fx[i] - fx[j], dy = fy[i] - fy[j], rr = fr[i] + fr[j];
-            hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
+      // warp per row i, lanes over the columns j > i: every tested pair is a useful one
+      for (int i = wid; i < nf - 1; i += kNmsThreads / 32) {
+        const float xi = fx[i], yi = fy[i], ri = fr[i];
+        for (int jb = i + 1; jb < nf; jb += 32) {
+          const int j = jb + lane;
+          bool hit = false;
+          if (j < nf) {
+            ++st_circle;
+            hit = true;
+            if (prune) {
+              const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
+              hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
+            }
           }
-        }
-        if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
-          ++st_iou;
-          mark_pair(i, j, pair_iou(frec[i], frec[j]));
+          if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
+            ++st_iou;
+            mark_pair(i, j, pair_iou(frec[i], frec[j]));
+          }
         }
       }
       __syncthreads();
@@ -611,20 +613,28 @@ nms_segment_kernel(NmsArgs a) {
         }
       };
       auto scan_range = [&](const GridEntry *ents, int e0, int e1, uint32_t key, uint32_t need) {
-        for (int eb = e0; eb < e1; eb += 32) {
-          const int e = eb + lane;
-          bool hit = false;
-          uint32_t j = 0;
-          if (e < e1) {
-            const GridEntry ge = ents[e];
-            j = ge.meta & kIdxMask;
-            if ((ge.meta & 0xffc00000u) == key && (ge.meta & need) == need && ((alive[j >> 5] >> (j & 31)) & 1u)) {
+        // kUnroll independent 16-byte loads in flight per lane: the scan is L2-latency bound otherwise
+        constexpr int kUnroll = 4;
+        for (int eb = e0; eb < e1; eb += 32 * kUnroll) {
+          GridEntry ge[kUnroll];
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const int e = eb + u * 32 + lane;
+            ge[u] = (e < e1) ? ents[e] : GridEntry{0.f, 0.f, 0.f, 0xffffffffu};
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            if (eb + u * 32 >= e1) break;   // warp-uniform
+            const uint32_t j = ge[u].meta & kIdxMask;
+            bool hit = false;
+            if (eb + u * 32 + lane < e1 && (ge[u].meta & 0xffc00000u) == key && (ge[u].meta & need) == need &&
+                ((alive[j >> 5] >> (j & 31)) & 1u)) {
               ++st_circle;
-              const float dx = ge.x - kx, dy = ge.y - ky, rr = ge.r + kr;
+              const float dx = ge[u].x - kx, dy = ge[u].y - ky, rr = ge[u].r + kr;
               hit = dx * dx + dy * dy <= rr * rr;
             }
+            offer(hit, j);
           }
-          offer(hit, j);
         }
       };
       const BoxCells kc = cells_of(kx, ky, kr, inv_cell, kMaxQueryCells);
