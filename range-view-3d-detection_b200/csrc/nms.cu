@@ -24,11 +24,14 @@
 // no earlier kept box suppressed it, the frontier is resolved in rank order, and pruned pairs
 // have IoU exactly 0 (iou.cuh padded_radius).  IoU evaluations drop from O(N * kept) on
 // every candidate to (alive candidates near a kept box).
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
 
 #include "common.cuh"
 #include "iou.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace rv3d {
 
@@ -204,8 +207,8 @@ template <typename Rec, bool kWeighted>
 __host__ __device__ inline size_t nms_smem_bytes(int nwords) {
   size_t b = 0;
   b += align_up_c(sizeof(uint32_t) * nwords, 16);                  // alive
-  b += sizeof(Rec) * kF;                                           // frec
-  b += sizeof(float) * kF * 3;                                     // fx, fy, fr
+  b += sizeof(Rec) * kF * 2;                                       // frec, krec
+  b += sizeof(float) * kF * 6;                                     // fx, fy, fr, kx, ky, kr
   b += sizeof(int) * kF;                                           // front_pos
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
   b += sizeof(int) * (kNB + 1) * 2;                                // b_start, b_cursor
@@ -250,15 +253,24 @@ nms_segment_kernel(NmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsThreads / 32 + 1];
   __shared__ int s_qn, s_nk, s_nos, s_overflow;
+  __shared__ int s_round[8];   // leader -> cluster: {nf, nk, cursor_word, -, n oversize, inv_cell bits}
   __shared__ float s_red[kNmsThreads / 32 * 2];
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
 
-  const int seg = blockIdx.x;
+  // A cluster of P CTAs works on one segment.  CTA 0 (the leader) owns the alive bitmap and runs the
+  // serial-ish phases (frontier, pairs, greedy); the kill scan and the exact IoU -- 80 % of the work --
+  // are split over all P CTAs, which read the leader's state and clear bits in its bitmap through
+  // distributed shared memory.  P = 1 degenerates to a plain CTA per segment.
+  cg::cluster_group cluster = cg::this_cluster();
+  const int P = static_cast<int>(cluster.num_blocks());
+  const int crank = static_cast<int>(cluster.block_rank());
+  const bool leader = crank == 0;
+  const int seg = blockIdx.x / P;
   const int beg = a.seg_begin[seg];
   const int n = min(a.seg_end[seg] - beg, a.num_pre);  // top num_pre_nms by score (nms.py:29-32)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (n <= 0) {
-    if (tid == 0) a.kept_count[seg] = 0;
+  if (n <= 0) {   // uniform over the cluster
+    if (tid == 0 && leader) a.kept_count[seg] = 0;
     return;
   }
   const int nwords = (n + 31) >> 5;
@@ -277,6 +289,10 @@ nms_segment_kernel(NmsArgs a) {
   float *fx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
   float *fy = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
   float *fr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  Rec *krec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;   // this round's kept boxes, rank order
+  float *kx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  float *ky = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  float *kr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
   int *front_pos = reinterpret_cast<int *>(p); p += sizeof(int) * kF;
   uint32_t *sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
   uint32_t *mrg = sup;
@@ -299,70 +315,82 @@ nms_segment_kernel(NmsArgs a) {
     if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
   };
 
-  // ======================= 0. alive bitmap + static candidate grid =======================
+  // ======================= 0. alive bitmap + static candidate grid (leader) =======================
   for (int w = tid; w < nwords; w += kNmsThreads)
     alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
-  for (int b = tid; b <= kNB; b += kNmsThreads) b_cursor[b] = 0;
-  if (tid == 0) { s_nos = 0; s_overflow = 0; }
+  if (tid == 0) { s_nos = 0; s_overflow = 0; s_qn = 0; }
   float inv_cell = 0.f;
-  {
-    // mean padded radius of the finite, sane candidates -> cell size = 4 * mean radius
-    float sum = 0.f, cnt = 0.f;
-    for (int i = tid; i < n; i += kNmsThreads) {
-      const float r = recs[i].r;
-      if (r > 0.f && r < 1.0e4f) { sum += r; cnt += 1.f; }
+  if (leader) {
+    for (int b = tid; b <= kNB; b += kNmsThreads) b_cursor[b] = 0;
+    {
+      // mean padded radius of the finite, sane candidates -> cell size = 4 * mean radius
+      float sum = 0.f, cnt = 0.f;
+      for (int i = tid; i < n; i += kNmsThreads) {
+        const float r = recs[i].r;
+        if (r > 0.f && r < 1.0e4f) { sum += r; cnt += 1.f; }
+      }
+      for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+      if (lane == 0) { s_red[wid] = sum; s_red[kNmsThreads / 32 + wid] = cnt; }
+      __syncthreads();
+      float ts = 0.f, tc = 0.f;
+      for (int w = 0; w < kNmsThreads / 32; ++w) { ts += s_red[w]; tc += s_red[kNmsThreads / 32 + w]; }
+      const float cell = fminf(fmaxf(4.0f * (tc > 0.f ? ts / tc : 1.0f), 0.25f), 4.0e4f);
+      inv_cell = 1.0f / cell;
     }
-    for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) { s_red[wid] = sum; s_red[kNmsThreads / 32 + wid] = cnt; }
+    if (prune) {
+      for (int i = tid; i < n; i += kNmsThreads) {           // count
+        const Rec r = recs[i];
+        const BoxCells c = cells_of(rec_cx(r), rec_cy(r), r.r, inv_cell, 2);
+        if (c.gridded) {
+          for (int cy = c.cy0; cy <= c.cy1; ++cy)
+            for (int cx = c.cx0; cx <= c.cx1; ++cx) atomicAdd(&b_cursor[bucket_of(cx, cy)], 1);
+        } else {
+          os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
+        }
+      }
+    } else {
+      for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
+      if (tid == 0) s_nos = n;
+    }
     __syncthreads();
-    float ts = 0.f, tc = 0.f;
-    for (int w = 0; w < kNmsThreads / 32; ++w) { ts += s_red[w]; tc += s_red[kNmsThreads / 32 + w]; }
-    const float cell = fminf(fmaxf(4.0f * (tc > 0.f ? ts / tc : 1.0f), 0.25f), 4.0e4f);
-    inv_cell = 1.0f / cell;
-  }
-  if (prune) {
-    for (int i = tid; i < n; i += kNmsThreads) {           // count
-      const Rec r = recs[i];
-      const BoxCells c = cells_of(rec_cx(r), rec_cy(r), r.r, inv_cell, 2);
-      if (c.gridded) {
+    {
+      int total;
+      const int c0 = b_cursor[2 * tid], c1 = b_cursor[2 * tid + 1];
+      const int off = block_exclusive_scan(c0 + c1, s_warp, total);
+      b_start[2 * tid] = off; b_start[2 * tid + 1] = off + c0;
+      b_cursor[2 * tid] = off; b_cursor[2 * tid + 1] = off + c0;
+      if (tid == 0) b_start[kNB] = total;
+    }
+    __syncthreads();
+    if (prune) {
+      for (int i = tid; i < n; i += kNmsThreads) {           // fill
+        const Rec r = recs[i];
+        const float x = rec_cx(r), y = rec_cy(r);
+        const BoxCells c = cells_of(x, y, r.r, inv_cell, 2);
+        if (!c.gridded) continue;
         for (int cy = c.cy0; cy <= c.cy1; ++cy)
-          for (int cx = c.cx0; cx <= c.cx1; ++cx) atomicAdd(&b_cursor[bucket_of(cx, cy)], 1);
-      } else {
-        os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
+          for (int cx = c.cx0; cx <= c.cx1; ++cx) {
+            const uint32_t meta = static_cast<uint32_t>(i) | (cx == c.cx0 ? (1u << 20) : 0u) |
+                                  (cy == c.cy0 ? (1u << 21) : 0u) | cell_key(cx, cy);
+            entries[atomicAdd(&b_cursor[bucket_of(cx, cy)], 1)] = GridEntry{x, y, r.r, meta};
+          }
       }
     }
-  } else {
-    for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
-    if (tid == 0) s_nos = n;
+    if (kWeighted)
+      for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
+    if (tid == 0) { s_round[4] = s_nos; s_round[5] = __float_as_int(inv_cell); }
+    __threadfence();
   }
-  __syncthreads();
-  {
-    int total;
-    const int c0 = b_cursor[2 * tid], c1 = b_cursor[2 * tid + 1];
-    const int off = block_exclusive_scan(c0 + c1, s_warp, total);
-    b_start[2 * tid] = off; b_start[2 * tid + 1] = off + c0;
-    b_cursor[2 * tid] = off; b_cursor[2 * tid + 1] = off + c0;
-    if (tid == 0) b_start[kNB] = total;
+  cluster.sync();   // grid (global) + bucket offsets (leader's shared memory) are ready
+  uint32_t *lead_alive = cluster.map_shared_rank(alive, 0);
+  const int *lead_round = cluster.map_shared_rank(s_round, 0);
+  if (!leader) {
+    const int *lead_bstart = cluster.map_shared_rank(b_start, 0);
+    for (int b = tid; b <= kNB; b += kNmsThreads) b_start[b] = lead_bstart[b];
   }
+  const int nos = lead_round[4];
+  inv_cell = __int_as_float(lead_round[5]);
   __syncthreads();
-  if (prune) {
-    for (int i = tid; i < n; i += kNmsThreads) {           // fill
-      const Rec r = recs[i];
-      const float x = rec_cx(r), y = rec_cy(r);
-      const BoxCells c = cells_of(x, y, r.r, inv_cell, 2);
-      if (!c.gridded) continue;
-      for (int cy = c.cy0; cy <= c.cy1; ++cy)
-        for (int cx = c.cx0; cx <= c.cx1; ++cx) {
-          const uint32_t meta = static_cast<uint32_t>(i) | (cx == c.cx0 ? (1u << 20) : 0u) |
-                                (cy == c.cy0 ? (1u << 21) : 0u) | cell_key(cx, cy);
-          entries[atomicAdd(&b_cursor[bucket_of(cx, cy)], 1)] = GridEntry{x, y, r.r, meta};
-        }
-    }
-  }
-  if (kWeighted)
-    for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
-  __syncthreads();
-  const int nos = s_nos;
 
   int kept_total = 0;
   int cursor_word = 0;
@@ -381,6 +409,12 @@ nms_segment_kernel(NmsArgs a) {
     atomicAdd(acc + a.D - 1, sj);
     atomicAdd(a.merge_count + kbase + slot, 1);
   };
+  // a candidate is suppressed: clear it in the leader's bitmap (the truth) and in the local snapshot
+  auto kill = [&](int j) {
+    const uint32_t m = ~(1u << (j & 31));
+    atomicAnd(&lead_alive[j >> 5], m);
+    if (!leader) atomicAnd(&alive[j >> 5], m);
+  };
   // warp-converged append of `item` (valid where `pred`) to the exact-IoU queue; returns false for the
   // lanes whose item did not fit (caller handles them in place)
   auto q2_push = [&](bool pred, uint32_t item) -> bool {
@@ -397,190 +431,212 @@ nms_segment_kernel(NmsArgs a) {
   };
 
   while (true) {
-    // ================= 1. frontier: first kF alive candidates =================
-    int nf = 0;
-    for (int base = cursor_word; base < nwords && nf < kF; base += kNmsThreads) {
-      const int wi = base + tid;
-      const uint32_t word = wi < nwords ? alive[wi] : 0u;
-      int total;
-      const int off = block_exclusive_scan(__popc(word), s_warp, total);
-      if (word && nf + off < kF) {
-        uint32_t m = word;
-        int r = nf + off;
-        while (m && r < kF) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          front_pos[r++] = (wi << 5) + bit;
+    int nf = 0, nk = 0;
+    if (leader) {
+      // ================= 1. frontier: first kF alive candidates =================
+      for (int base = cursor_word; base < nwords && nf < kF; base += kNmsThreads) {
+        const int wi = base + tid;
+        const uint32_t word = wi < nwords ? alive[wi] : 0u;
+        int total;
+        const int off = block_exclusive_scan(__popc(word), s_warp, total);
+        if (word && nf + off < kF) {
+          uint32_t m = word;
+          int r = nf + off;
+          while (m && r < kF) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            front_pos[r++] = (wi << 5) + bit;
+          }
         }
+        nf = min(kF, nf + total);
       }
-      nf = min(kF, nf + total);
-    }
-    __syncthreads();
-    if (nf == 0) break;
-    ++rounds;
-    lap(0);
+      __syncthreads();
+      lap(0);
+      if (nf > 0) {
+        ++rounds;
+        // the frontier is decided this round: clear its bits, load its records, reset per-round state
+        if (tid < nf) {
+          const int pos = front_pos[tid];
+          atomicAnd(&alive[pos >> 5], ~(1u << (pos & 31)));
+          const Rec r = recs[pos];
+          frec[tid] = r;
+          fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
+          keptrank[tid] = -1;
+        }
+        for (int i = tid; i < kF * kFW; i += kNmsThreads) {
+          sup[i] = 0u;
+          if (kWeighted) mrg[i] = 0u;
+        }
+        if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
+        if (tid == 0) s_qn = 0;
+        __syncthreads();
+        cursor_word = front_pos[0] >> 5;
+        lap(1);
 
-    // the frontier is decided this round: clear its bits, load its records, reset per-round state
-    if (tid < nf) {
-      const int pos = front_pos[tid];
-      atomicAnd(&alive[pos >> 5], ~(1u << (pos & 31)));
-      const Rec r = recs[pos];
-      frec[tid] = r;
-      fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
-      keptrank[tid] = -1;
-    }
-    for (int i = tid; i < kF * kFW; i += kNmsThreads) {
-      sup[i] = 0u;
-      if (kWeighted) mrg[i] = 0u;
-    }
-    if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
-    if (tid == 0) s_qn = 0;
-    __syncthreads();
-    cursor_word = front_pos[0] >> 5;
-    lap(1);
-
-    // ================= 2. interacting pairs inside the frontier =================
-    // all nf*(nf-1)/2 circle tests (<= 32 k, shared-memory SoA, warp-converged), bound, queue, exact IoU
-    {
-      // warp per row i, lanes over the columns j > i: every tested pair is a useful one
-      for (int i = wid; i < nf - 1; i += kNmsThreads / 32) {
-        const float xi = fx[i], yi = fy[i], ri = fr[i];
-        for (int jb = i + 1; jb < nf; jb += 32) {
-          const int j = jb + lane;
-          bool hit = false;
-          if (j < nf) {
-            ++st_circle;
-            hit = true;
-            if (prune) {
-              const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
-              hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
+        // ================= 2. interacting pairs inside the frontier =================
+        // warp per row i, lanes over the columns j > i: circle test, IoU bound, queue, exact IoU
+        for (int i = wid; i < nf - 1; i += kNmsThreads / 32) {
+          const float xi = fx[i], yi = fy[i], ri = fr[i];
+          for (int jb = i + 1; jb < nf; jb += 32) {
+            const int j = jb + lane;
+            bool hit = false;
+            if (j < nf) {
+              ++st_circle;
+              hit = true;
+              if (prune) {
+                const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
+                hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
+              }
+            }
+            if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
+              ++st_iou;
+              mark_pair(i, j, pair_iou(frec[i], frec[j]));
             }
           }
-          if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
+        }
+        __syncthreads();
+        {
+          const int qn = min(s_qn, kQ2Cap);
+          for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
+            __syncwarp();
+            const int q = q0 + tid;
+            if (q >= qn) continue;
+            const int i = queue2[q] >> 8, j = queue2[q] & 255;
             ++st_iou;
             mark_pair(i, j, pair_iou(frec[i], frec[j]));
           }
         }
-      }
-      __syncthreads();
-      const int qn = min(s_qn, kQ2Cap);
-      for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
-        __syncwarp();
-        const int q = q0 + tid;
-        if (q >= qn) continue;
-        const int i = queue2[q] >> 8, j = queue2[q] & 255;
-        ++st_iou;
-        mark_pair(i, j, pair_iou(frec[i], frec[j]));
-      }
-      __syncthreads();
-    }
-    lap(2);
+        __syncthreads();
+        lap(2);
 
-    // ================= 3. greedy resolution of the frontier =================
-    // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
-    // parallel; only the rest needs the dependent scan, done by one warp.
-    {
-      const int w = tid & (kFW - 1);
-      uint32_t colbits = 0u;
-      for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
-      if (colbits) atomicOr(&s_haspred[w], colbits);
-    }
-    __syncthreads();
-    {
-      const int w = tid & (kFW - 1);
-      uint32_t rm = 0u;
-      for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW)
-        if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
-      if (rm) atomicOr(&s_removed[w], rm);
-    }
-    if (tid == 0) s_qn = 0;
-    __syncthreads();
-    if (tid < 32) {
-      // lane w < kFW owns word w.  valid = bits < nf; free = valid & ~haspred (kept for sure)
-      uint32_t valid = 0u, removed = 0u, pending = 0u, kept = 0u;
-      if (lane < kFW) {
-        const int lo = lane << 5;
-        valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
-        removed = s_removed[lane];
-        pending = valid & s_haspred[lane];       // must be visited in rank order
-        kept = valid & ~s_haspred[lane];
-      }
-      while (true) {
-        const uint32_t cand = pending & ~removed;
-        const uint32_t have = __ballot_sync(0xffffffffu, cand != 0u);
-        if (!have) break;
-        const int wsel = __ffs(have) - 1;
-        const uint32_t cw = __shfl_sync(0xffffffffu, cand, wsel);
-        const int bit = __ffs(cw) - 1;
-        const int i = (wsel << 5) + bit;
-        if (lane == wsel) kept |= 1u << bit;
-        if (lane < kFW) {
-          // everything up to and including i is decided now
-          const int lo = lane << 5;
-          if (i >= lo + 31) pending = 0u;
-          else if (i >= lo) pending &= ~((2u << (i - lo)) - 1u);
-          removed |= sup[i * kFW + lane];
+        // ================= 3. greedy resolution of the frontier =================
+        // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
+        // parallel; only the rest needs the dependent scan, done by one warp.
+        {
+          const int w = tid & (kFW - 1);
+          uint32_t colbits = 0u;
+          for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
+          if (colbits) atomicOr(&s_haspred[w], colbits);
         }
-      }
-      // kept boxes in rank order, truncated to the room left under num_post_nms
-      const int room = a.num_post - kept_total;
-      const int cnt = lane < kFW ? __popc(kept) : 0;
-      int incl = cnt;
+        __syncthreads();
+        {
+          const int w = tid & (kFW - 1);
+          uint32_t rm = 0u;
+          for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW)
+            if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
+          if (rm) atomicOr(&s_removed[w], rm);
+        }
+        __syncthreads();
+        if (tid < 32) {
+          // lane w < kFW owns word w.  valid = bits < nf; free = valid & ~haspred (kept for sure)
+          uint32_t valid = 0u, removed = 0u, pending = 0u, kept = 0u;
+          if (lane < kFW) {
+            const int lo = lane << 5;
+            valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
+            removed = s_removed[lane];
+            pending = valid & s_haspred[lane];       // must be visited in rank order
+            kept = valid & ~s_haspred[lane];
+          }
+          while (true) {
+            const uint32_t cand = pending & ~removed;
+            const uint32_t have = __ballot_sync(0xffffffffu, cand != 0u);
+            if (!have) break;
+            const int wsel = __ffs(have) - 1;
+            const uint32_t cw = __shfl_sync(0xffffffffu, cand, wsel);
+            const int bit = __ffs(cw) - 1;
+            const int i = (wsel << 5) + bit;
+            if (lane == wsel) kept |= 1u << bit;
+            if (lane < kFW) {
+              // everything up to and including i is decided now
+              const int lo = lane << 5;
+              if (i >= lo + 31) pending = 0u;
+              else if (i >= lo) pending &= ~((2u << (i - lo)) - 1u);
+              removed |= sup[i * kFW + lane];
+            }
+          }
+          // kept boxes in rank order, truncated to the room left under num_post_nms
+          const int room = a.num_post - kept_total;
+          const int cnt = lane < kFW ? __popc(kept) : 0;
+          int incl = cnt;
 #pragma unroll
-      for (int o = 1; o < kFW; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      int rank = incl - cnt;
-      if (lane < kFW) {
-        uint32_t m = kept;
-        while (m && rank < room) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          const int i = (lane << 5) + bit;
-          keptf[rank] = static_cast<uint16_t>(i);
-          keptrank[i] = static_cast<int16_t>(rank);
-          ++rank;
+          for (int o = 1; o < kFW; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int rank = incl - cnt;
+          if (lane < kFW) {
+            uint32_t m = kept;
+            while (m && rank < room) {
+              const int bit = __ffs(m) - 1;
+              m &= m - 1;
+              const int i = (lane << 5) + bit;
+              keptf[rank] = static_cast<uint16_t>(i);
+              keptrank[i] = static_cast<int16_t>(rank);
+              ++rank;
+            }
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, kFW - 1);
+          if (lane == 0) s_nk = min(total, room);
         }
-      }
-      const int total = __shfl_sync(0xffffffffu, incl, kFW - 1);
-      if (lane == 0) s_nk = min(total, room);
-    }
-    __syncthreads();
-    const int nk = s_nk;
-    lap(3);
+        __syncthreads();
+        nk = s_nk;
+        lap(3);
 
-    // ================= 4. publish the newly kept boxes =================
-    if (tid < nk) a.kept_pos[kbase + kept_total + tid] = front_pos[keptf[tid]];
-    if (kWeighted) {
-      // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr
-      // that comes no later than its first suppressor; kept boxes join themselves.
-      if (tid < nf) {
-        const int j = tid;
-        for (int t = 0; t < nk; ++t) {
-          const int i = keptf[t];
-          if (i > j) break;
-          const bool self = (i == j);
-          if (self || ((mrg[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) accumulate(kept_total + t, front_pos[j]);
-          if (self || ((sup[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) break;
+        // ================= 4. publish the newly kept boxes =================
+        if (tid < nk) {
+          const int fi = keptf[tid];
+          a.kept_pos[kbase + kept_total + tid] = front_pos[fi];
+          krec[tid] = frec[fi];
+          kx[tid] = fx[fi]; ky[tid] = fy[fi]; kr[tid] = fr[fi];
+        }
+        if (kWeighted) {
+          // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr
+          // that comes no later than its first suppressor; kept boxes join themselves.
+          if (tid < nf) {
+            const int j = tid;
+            for (int t = 0; t < nk; ++t) {
+              const int i = keptf[t];
+              if (i > j) break;
+              const bool self = (i == j);
+              if (self || ((mrg[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) accumulate(kept_total + t, front_pos[j]);
+              if (self || ((sup[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) break;
+            }
+          }
         }
       }
+      if (tid == 0) { s_round[0] = nf; s_round[1] = nk; s_qn = 0; }
+      if (tid == 1) s_round[2] = cursor_word;
     }
+    cluster.sync();   // (A) the leader's round state, kept boxes and bitmap are final
+    nf = lead_round[0];
+    nk = lead_round[1];
+    cursor_word = lead_round[2];
+    if (nf == 0) break;
+    const int slot0 = kept_total;
     kept_total += nk;
     // nms.py:53-56: only the first num_post_nms kept survive, so the scan can stop there.  The
     // weighted mode still owes the last kept boxes their merge sets from the candidates behind
     // the frontier, so it runs one more kill phase before leaving.
     const bool last_round = kept_total >= a.num_post;
     if (last_round && !kWeighted) break;
+    if (!leader) {
+      // helpers: this round's kept boxes and a snapshot of the alive bitmap, through DSMEM
+      const Rec *lrec = cluster.map_shared_rank(krec, 0);
+      const float *lx = cluster.map_shared_rank(kx, 0), *ly = cluster.map_shared_rank(ky, 0), *lr = cluster.map_shared_rank(kr, 0);
+      if (tid < nk) { krec[tid] = lrec[tid]; kx[tid] = lx[tid]; ky[tid] = ly[tid]; kr[tid] = lr[tid]; }
+      for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = lead_alive[w];   // all words: decided bits too
+      if (tid == 0) s_qn = 0;
+    }
+    __syncthreads();
 
     // ================= 5. kill scan: one warp per newly kept box over the static grid ==============
     // Lanes stride over the contiguous entries of each cell the kept box's circle touches (+ the
     // oversize list): alive test, circle test, hits compacted per warp so the IoU bound runs on full
-    // warps; pairs that pass go to the exact-IoU queue.
-    for (int t = wid; t < nk; t += kNmsThreads / 32) {
-      const int fi = keptf[t];
-      const Rec &rk = frec[fi];
-      const float kx = fx[fi], ky = fy[fi], kr = fr[fi];
+    // warps; pairs that pass go to the exact-IoU queue.  Kept boxes are dealt round-robin to the
+    // warps of the whole cluster.
+    for (int t = crank * (kNmsThreads / 32) + wid; t < nk; t += P * (kNmsThreads / 32)) {
+      const Rec &rk = krec[t];
+      const float qx = kx[t], qy = ky[t], qr = kr[t];
       int nbuf = 0;  // warp-uniform count of buffered hits
       auto flush = [&](int count) {   // run the bound on `count` (<= 32) buffered hits, lanes < count
         __syncwarp();
@@ -595,7 +651,7 @@ nms_segment_kernel(NmsArgs a) {
             s_overflow = 1;   // redo this round's kill phase with the exact serial fallback
           } else {            // hard mode only needs ANY suppressor: evaluate in place
             ++st_iou;
-            if (pair_iou(rk, recs[j]) > a.thr) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+            if (pair_iou(rk, recs[j]) > a.thr) kill(j);
           }
         }
         __syncwarp();
@@ -630,14 +686,14 @@ nms_segment_kernel(NmsArgs a) {
             if (eb + u * 32 + lane < e1 && (ge[u].meta & 0xffc00000u) == key && (ge[u].meta & need) == need &&
                 ((alive[j >> 5] >> (j & 31)) & 1u)) {
               ++st_circle;
-              const float dx = ge[u].x - kx, dy = ge[u].y - ky, rr = ge[u].r + kr;
+              const float dx = ge[u].x - qx, dy = ge[u].y - qy, rr = ge[u].r + qr;
               hit = dx * dx + dy * dy <= rr * rr;
             }
             offer(hit, j);
           }
         }
       };
-      const BoxCells kc = cells_of(kx, ky, kr, inv_cell, kMaxQueryCells);
+      const BoxCells kc = cells_of(qx, qy, qr, inv_cell, kMaxQueryCells);
       if (prune && kc.gridded) {
         for (int cy = kc.cy0; cy <= kc.cy1; ++cy)
           for (int cx = kc.cx0; cx <= kc.cx1; ++cx) {
@@ -654,7 +710,7 @@ nms_segment_kernel(NmsArgs a) {
             if ((alive[j >> 5] >> (j & 31)) & 1u) {
               ++st_circle;
               const Rec &rj = recs[j];
-              const float dx = rec_cx(rj) - kx, dy = rec_cy(rj) - ky, rr = rj.r + kr;
+              const float dx = rec_cx(rj) - qx, dy = rec_cy(rj) - qy, rr = rj.r + qr;
               hit = dx * dx + dy * dy <= rr * rr;
             }
           }
@@ -670,7 +726,7 @@ nms_segment_kernel(NmsArgs a) {
             hit = true;
             if (prune) {
               const Rec &rj = recs[j];
-              const float dx = rec_cx(rj) - kx, dy = rec_cy(rj) - ky, rr = rj.r + kr;
+              const float dx = rec_cx(rj) - qx, dy = rec_cy(rj) - qy, rr = rj.r + qr;
               hit = dx * dx + dy * dy <= rr * rr;
             }
           }
@@ -680,12 +736,11 @@ nms_segment_kernel(NmsArgs a) {
       if (nbuf > 0) flush(nbuf);
     }
     __syncthreads();
-    lap(4);
+    if (leader) lap(4);
 
     // ================= 6. exact IoU of the queued (candidate, kept) pairs =================
     {
       const int qn = min(s_qn, kQ2Cap);
-      const int slot0 = kept_total - nk;
       if (!kWeighted) {
         for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
           __syncwarp();
@@ -695,59 +750,68 @@ nms_segment_kernel(NmsArgs a) {
           const int j = e >> 8, t = e & 255;
           if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;  // already suppressed by another pair
           ++st_iou;
-          if (pair_iou(frec[keptf[t]], recs[j]) > a.thr) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
-        }
-      } else if (!s_overflow) {
-        // pass 1: IoU of every queued pair; remember each candidate's FIRST suppressor (rank order)
-        for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
-          __syncwarp();
-          const int q = q0 + tid;
-          if (q >= qn) continue;
-          const uint32_t e = queue2[q];
-          const int j = e >> 8, t = e & 255;
-          const float iou = pair_iou(frec[keptf[t]], recs[j]);
-          ++st_iou;
-          qiou[q] = iou;
-          if (iou > a.thr) atomicMin(&firstsup[j], t);
-        }
-        __syncthreads();
-        // pass 2: merges up to and including the first suppressor; the suppressor clears the bit
-        for (int q = tid; q < qn; q += kNmsThreads) {
-          const uint32_t e = queue2[q];
-          const int j = e >> 8, t = e & 255;
-          const int fs = firstsup[j];
-          if (t > fs) continue;
-          if (qiou[q] > a.mthr) accumulate(slot0 + t, j);
-          if (t == fs) atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+          if (pair_iou(krec[t], recs[j]) > a.thr) kill(j);
         }
       } else {
-        // exact serial fallback (queue overflow in weighted mode): one thread per alive candidate,
-        // kept boxes visited in rank order
-        for (int j = (cursor_word << 5) + tid; j < n; j += kNmsThreads) {
-          if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
-          const Rec rj = recs[j];
-          const float jx = rec_cx(rj), jy = rec_cy(rj);
-          for (int t = 0; t < nk; ++t) {
-            const int fi = keptf[t];
-            if (prune) {
-              const float dx = fx[fi] - jx, dy = fy[fi] - jy, rr = fr[fi] + rj.r;
-              if (!(dx * dx + dy * dy <= rr * rr)) continue;
-            }
-            const float iou = pair_iou(frec[fi], rj);
+        // the queue of ANY CTA overflowing sends the whole round to the exact serial fallback
+        cluster.sync();
+        bool overflow = false;
+        for (int r = 0; r < P; ++r) overflow |= *cluster.map_shared_rank(&s_overflow, r) != 0;
+        if (!overflow) {
+          // pass 1: IoU of every queued pair; remember each candidate's FIRST suppressor (rank order)
+          for (int q0 = 0; q0 < qn; q0 += kNmsThreads) {
+            __syncwarp();
+            const int q = q0 + tid;
+            if (q >= qn) continue;
+            const uint32_t e = queue2[q];
+            const int j = e >> 8, t = e & 255;
+            const float iou = pair_iou(krec[t], recs[j]);
             ++st_iou;
-            if (iou > a.mthr) accumulate(slot0 + t, j);
-            if (iou > a.thr) { atomicAnd(&alive[j >> 5], ~(1u << (j & 31))); break; }
+            qiou[q] = iou;
+            if (iou > a.thr) atomicMin(&firstsup[j], t);
+          }
+          __threadfence();
+          cluster.sync();   // (B) every CTA's first-suppressor votes are in
+          // pass 2: merges up to and including the first suppressor; the suppressor clears the bit
+          for (int q = tid; q < qn; q += kNmsThreads) {
+            const uint32_t e = queue2[q];
+            const int j = e >> 8, t = e & 255;
+            const int fs = __ldcg(&firstsup[j]);
+            if (t > fs) continue;
+            if (qiou[q] > a.mthr) accumulate(slot0 + t, j);
+            if (t == fs) kill(j);
+          }
+        } else {
+          cluster.sync();   // keep the barrier count uniform
+          if (leader) {
+            // exact serial fallback: one thread per alive candidate, kept boxes visited in rank order
+            for (int j = (cursor_word << 5) + tid; j < n; j += kNmsThreads) {
+              if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
+              const Rec rj = recs[j];
+              const float jx = rec_cx(rj), jy = rec_cy(rj);
+              for (int t = 0; t < nk; ++t) {
+                if (prune) {
+                  const float dx = kx[t] - jx, dy = ky[t] - jy, rr = kr[t] + rj.r;
+                  if (!(dx * dx + dy * dy <= rr * rr)) continue;
+                }
+                const float iou = pair_iou(krec[t], rj);
+                ++st_iou;
+                if (iou > a.mthr) accumulate(slot0 + t, j);
+                if (iou > a.thr) { kill(j); break; }
+              }
+            }
           }
         }
       }
-      __syncthreads();
-      if (tid == 0) s_overflow = 0;
     }
-    lap(5);
+    cluster.sync();   // (C) every kill has reached the leader's bitmap
+    if (tid == 0) s_overflow = 0;
+    if (leader) lap(5);
     if (last_round) break;
   }
+  cluster.sync();     // nobody leaves while its shared memory may still be read
 
-  if (tid == 0) a.kept_count[seg] = kept_total;
+  if (tid == 0 && leader) a.kept_count[seg] = kept_total;
   if (a.stats) {
     // warp-reduce then one atomic per warp
     for (int o = 16; o; o >>= 1) {
@@ -758,7 +822,7 @@ nms_segment_kernel(NmsArgs a) {
       atomicAdd(a.stats + 0, st_iou);
       atomicAdd(a.stats + 3, st_circle);
     }
-    if (tid == 0) {
+    if (tid == 0 && leader) {
       atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept_total));
       atomicAdd(a.stats + 2, static_cast<unsigned long long>(rounds));
       for (int k = 0; k < 6; ++k) atomicAdd(a.stats + 4 + k, static_cast<unsigned long long>(ph[k]));
@@ -911,7 +975,22 @@ static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStrea
   if (smem > 200 * 1024 || max_seg_n >= (1 << 20)) return RV3D_ERR_ARG;
   RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  nms_segment_kernel<Rec, kWeighted><<<S, kNmsThreads, smem, s>>>(a);
+  // one cluster per segment; as many CTAs per cluster as the 148 SMs allow (1 CTA / SM), at most 8
+  int P = kNumSMs / (S > 0 ? S : 1);
+  P = P < 1 ? 1 : (P > 8 ? 8 : P);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(S * P));
+  cfg.blockDim = dim3(kNmsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(P);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RV3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_segment_kernel<Rec, kWeighted>, a));
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
