@@ -825,7 +825,10 @@ nms_segment_kernel(NmsArgs a) {
     if (tid == 0 && leader) {
       atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept_total));
       atomicAdd(a.stats + 2, static_cast<unsigned long long>(rounds));
-      for (int k = 0; k < 6; ++k) atomicAdd(a.stats + 4 + k, static_cast<unsigned long long>(ph[k]));
+      unsigned long long tot = 0;
+      for (int k = 0; k < 6; ++k) { atomicAdd(a.stats + 4 + k, static_cast<unsigned long long>(ph[k])); tot += ph[k]; }
+      atomicMax(a.stats + 10, tot);                                  // slowest segment (cycles)
+      atomicMax(a.stats + 11, static_cast<unsigned long long>(n));   // largest segment (candidates)
     }
   }
 }
