@@ -56,11 +56,12 @@ template <> struct Ld<__nv_bfloat16> {
   static __device__ __forceinline__ __nv_bfloat16 cast(double x) { return __double2bfloat16(x); }
 };
 
-// sigmoid evaluated in fp64 and rounded ONCE to the tensor dtype (float32 scores for float32
-// logits; under fp16 autocast the reference's scores are fp16 too), returned widened to float
+// sigmoid the way the reference's own CUDA path evaluates it (range_decoder.py:49: torch's CUDA sigmoid
+// computes 1 / (1 + exp(-x)) in float32 opmath for float32 / float16 / bfloat16 tensors and rounds to the
+// tensor dtype), returned widened to float.  Different libms differ by an ulp here.
 template <typename T>
 __device__ __forceinline__ float sigmoid_t(float x) {
-  return static_cast<float>(Ld<T>::cast(1.0 / (1.0 + exp(-static_cast<double>(x)))));
+  return static_cast<float>(Ld<T>::cast(static_cast<double>(1.0f / (1.0f + expf(-x)))));
 }
 
 // coding.py:110-144 in fp64.  reg[8], cart[3] -> out[7] (double)
@@ -114,7 +115,14 @@ struct PartArgs {
   int n;
   float lower[RV3D_MAX_PARTITIONS], upper[RV3D_MAX_PARTITIONS];
   int rate[RV3D_MAX_PARTITIONS], wsub[RV3D_MAX_PARTITIONS], off[RV3D_MAX_PARTITIONS + 1];
+  // w / rate without an integer division: shift when rate is a power of two, else
+  // umulhi(w, magic) with magic = floor(2^32 / rate) + 1 (exact for w * rate < 2^32, i.e. any image width)
+  int shift[RV3D_MAX_PARTITIONS];
+  uint32_t magic[RV3D_MAX_PARTITIONS];
 };
+__device__ __forceinline__ int fast_div(int w, int shift, uint32_t magic) {
+  return shift >= 0 ? (w >> shift) : static_cast<int>(__umulhi(static_cast<uint32_t>(w), magic));
+}
 
 static PartArgs make_parts(const rv3d_partitions *p, int H, int W) {
   PartArgs a{};
@@ -123,6 +131,10 @@ static PartArgs make_parts(const rv3d_partitions *p, int H, int W) {
   for (int i = 0; i < a.n; ++i) {
     a.lower[i] = p->lower[i]; a.upper[i] = p->upper[i]; a.rate[i] = p->rate[i];
     a.wsub[i] = (W + p->rate[i] - 1) / p->rate[i];
+    a.shift[i] = -1;
+    for (int sh = 0; sh < 31; ++sh)
+      if (p->rate[i] == (1 << sh)) a.shift[i] = sh;
+    a.magic[i] = static_cast<uint32_t>((1ull << 32) / static_cast<unsigned long long>(p->rate[i])) + 1u;
     a.off[i] = off;
     off += H * a.wsub[i];
   }
@@ -181,134 +193,219 @@ struct DecodeArgs {
   PartArgs pa;
 };
 
-constexpr int kDecThreads = 256;
-constexpr int kPxPerThread = 4;
-constexpr int kPxPerBlock = kDecThreads * kPxPerThread;
+// ---- TMA 1-D bulk copy + mbarrier (inline PTX; SASS: UBLKCP / SYNCS) ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(kDecThreads)
+// shared-memory reads of 4 consecutive elements, widened to float
+template <typename T> struct Sm;
+template <> struct Sm<float> {
+  static __device__ __forceinline__ void four(const float *p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ float one(const float *p) { return *p; }
+};
+template <> struct Sm<__half> {
+  static __device__ __forceinline__ void four(const __half *p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2 *>(p);
+    const __half2 a = *reinterpret_cast<const __half2 *>(&t.x), b = *reinterpret_cast<const __half2 *>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ float one(const __half *p) { return __half2float(*p); }
+};
+template <> struct Sm<__nv_bfloat16> {
+  static __device__ __forceinline__ void four(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2 *>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ float one(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+};
+
+constexpr int kPxPerThread = 4;
+
+// bytes of dynamic shared memory for a tile of kTile pixels
+static size_t decode_smem_bytes(int C, int tile, size_t elem) {
+  size_t b = static_cast<size_t>(C + 11) * tile * elem;   // logits, regressands, cart planes
+  b += tile;                                              // mask
+  b = align_up(b, 16);
+  b += static_cast<size_t>(tile) * (2 + 2 + 1 + 2 + 2 + 4 + 4);   // q_pix, q_meta, q_emit, q_h, q_w, q_score, q_off
+  return align_up(b, 16) + 64;
+}
+
+// One CTA per tile of kTile consecutive pixels of one sweep, kTile / 4 threads.
+//   stage   every input plane's slice of the tile is brought into shared memory: with kBulk, C + 12
+//           TMA 1-D bulk copies issued by one thread, completion on an mbarrier (no registers, no
+//           per-thread loads; several resident CTAs overlap each other's copies and math); without
+//           (unaligned shapes) plain cooperative loads into the same layout.
+//   phase A / scan / phase B   as described at the top of this file, reading shared memory only.
+template <typename T, int kTile, bool kBulk>
+__global__ void __launch_bounds__(kTile / kPxPerThread)
 decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__restrict__ reg,
                       const T *__restrict__ cart, const uint8_t *__restrict__ mask,
                       unsigned long long *__restrict__ out_keys, float *__restrict__ out_boxes,
                       int32_t *__restrict__ counter) {
-  __shared__ uint32_t s_scan[kDecThreads / 32];
+  constexpr int kThreads = kTile / kPxPerThread;
+  constexpr int kWarps = kThreads / 32;
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ uint32_t s_scan[kWarps];
   __shared__ uint32_t s_base, s_total_live;
-  __shared__ uint16_t q_pix[kPxPerBlock];     // local pixel id of live pixel t
-  __shared__ uint16_t q_meta[kPxPerBlock];    // class index within the task
-  __shared__ uint8_t q_emit[kPxPerBlock];     // partition bit-mask
-  __shared__ float q_score[kPxPerBlock];
-  __shared__ uint32_t q_off[kPxPerBlock];     // exclusive emit offset inside the block
+  __shared__ __align__(8) uint64_t s_bar;
+  // partition constants out of the kernel-parameter bank (dynamic indexing there costs uniform moves)
+  __shared__ float s_lower[RV3D_MAX_PARTITIONS], s_upper[RV3D_MAX_PARTITIONS];
+  __shared__ int s_rate[RV3D_MAX_PARTITIONS], s_shift[RV3D_MAX_PARTITIONS], s_off[RV3D_MAX_PARTITIONS], s_wsub[RV3D_MAX_PARTITIONS];
+  __shared__ uint32_t s_magic[RV3D_MAX_PARTITIONS];
 
   const int b = blockIdx.y;
   const int HW = a.H * a.W;
   const int tid = threadIdx.x;
-  const int blk0 = blockIdx.x * kPxPerBlock;
+  const int blk0 = blockIdx.x * kTile;
+  const int npx = min(kTile, HW - blk0);
 
-  int pix[kPxPerThread];
-#pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) pix[j] = kVec ? blk0 + tid * 4 + j : blk0 + j * kDecThreads + tid;
+  // ---- carve shared memory: [C][kTile] logits | [8][kTile] reg | [3][kTile] cart | mask | queues
+  T *s_logits = reinterpret_cast<T *>(dsm);
+  T *s_reg = s_logits + static_cast<size_t>(a.C) * kTile;
+  T *s_cart = s_reg + 8 * kTile;
+  uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cart + 3 * kTile);
+  unsigned char *qp = dsm + align_up_c((static_cast<size_t>(a.C) + 11) * kTile * sizeof(T) + kTile, 16);
+  float *q_score = reinterpret_cast<float *>(qp);                    // score of live pixel t
+  uint32_t *q_off = reinterpret_cast<uint32_t *>(q_score + kTile);   // exclusive emit offset inside the block
+  uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_off + kTile);     // local pixel id of live pixel t
+  uint16_t *q_meta = q_pix + kTile;                                  // class index within the task
+  uint8_t *q_emit = reinterpret_cast<uint8_t *>(q_meta + kTile);     // partition bit-mask
+  uint16_t *q_h = reinterpret_cast<uint16_t *>(q_emit + kTile);      // image row / column of live pixel t
+  uint16_t *q_w = q_h + kTile;
 
-  // ---------------- phase A: class max ----------------
-  float best[kPxPerThread];
+  if (tid < RV3D_MAX_PARTITIONS) {
+    s_lower[tid] = a.pa.lower[tid]; s_upper[tid] = a.pa.upper[tid]; s_rate[tid] = a.pa.rate[tid];
+    s_shift[tid] = a.pa.shift[tid]; s_magic[tid] = a.pa.magic[tid]; s_off[tid] = a.pa.off[tid]; s_wsub[tid] = a.pa.wsub[tid];
+  }
+  const int n_parts = a.pa.n;
+
+  // ---------------- stage the tile ----------------
+  {
+    const T *lg = logits + static_cast<size_t>(b) * a.C * HW + blk0;
+    const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;
+    const T *ct = cart + static_cast<size_t>(b) * 3 * HW + blk0;
+    const uint8_t *mk = mask + static_cast<size_t>(b) * HW + blk0;
+    if (kBulk) {
+      if (tid == 0) mbar_init(&s_bar, 1);
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
+        mbar_expect_tx(&s_bar, plane * (a.C + 11) + npx);
+        for (int c = 0; c < a.C; ++c) bulk_g2s(s_logits + static_cast<size_t>(c) * kTile, lg + static_cast<size_t>(c) * HW, plane, &s_bar);
+        for (int k = 0; k < 8; ++k) bulk_g2s(s_reg + k * kTile, rg + static_cast<size_t>(k) * HW, plane, &s_bar);
+        for (int k = 0; k < 3; ++k) bulk_g2s(s_cart + k * kTile, ct + static_cast<size_t>(k) * HW, plane, &s_bar);
+        bulk_g2s(s_mask, mk, npx, &s_bar);
+      }
+      mbar_wait(&s_bar, 0);
+    } else {
+      __syncthreads();
+      for (int i = tid; i < npx; i += kThreads) {
+        for (int c = 0; c < a.C; ++c) s_logits[static_cast<size_t>(c) * kTile + i] = lg[static_cast<size_t>(c) * HW + i];
+        for (int k = 0; k < 8; ++k) s_reg[k * kTile + i] = rg[static_cast<size_t>(k) * HW + i];
+        for (int k = 0; k < 3; ++k) s_cart[k * kTile + i] = ct[static_cast<size_t>(k) * HW + i];
+        s_mask[i] = mk[i];
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---------------- phase A: class max over the staged logits ----------------
+  const int lp0 = tid * kPxPerThread;          // first local pixel of this thread
+  const int row0 = (blk0 + lp0) / a.W;         // one division per thread; (row, col) advance incrementally
+  const int col0 = (blk0 + lp0) - row0 * a.W;
+  float best[kPxPerThread], runner[kPxPerThread];   // runner = max logit among the classes before `cls`
   int cls[kPxPerThread];
   bool bad[kPxPerThread];
 #pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) { best[j] = -CUDART_INF_F; cls[j] = 0; bad[j] = false; }
-  const T *lg = logits + static_cast<size_t>(b) * a.C * HW;
-  const bool vec_ok = kVec && (pix[0] + 3 < HW);
-#pragma unroll 2
+  for (int j = 0; j < kPxPerThread; ++j) { best[j] = -CUDART_INF_F; runner[j] = -CUDART_INF_F; cls[j] = 0; bad[j] = false; }
+#pragma unroll 4
   for (int c = 0; c < a.C; ++c) {
     float v[4];
-    if (kVec) {
-      if (vec_ok) Ld<T>::four(lg + static_cast<size_t>(c) * HW + pix[0], v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = pix[j] < HW ? Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]) : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = pix[j] < HW ? Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]) : 0.f;
-    }
+    Sm<T>::four(s_logits + static_cast<size_t>(c) * kTile + lp0, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       bad[j] |= (v[j] != v[j]);
-      if (v[j] > best[j]) { best[j] = v[j]; cls[j] = c; }
+      if (v[j] > best[j]) { runner[j] = best[j]; best[j] = v[j]; cls[j] = c; }
     }
   }
-  uint32_t mbits = 0;
-  {
-    const uint8_t *mk = mask + static_cast<size_t>(b) * HW;
-    if (kVec && vec_ok) {
-      const uchar4 m4 = *reinterpret_cast<const uchar4 *>(mk + pix[0]);
-      mbits = (m4.x ? 1u : 0u) | (m4.y ? 2u : 0u) | (m4.z ? 4u : 0u) | (m4.w ? 8u : 0u);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (pix[j] < HW && mk[pix[j]]) mbits |= 1u << j;
-    }
-  }
+  const uchar4 m4 = *reinterpret_cast<const uchar4 *>(s_mask + lp0);
+  const uint32_t mbits = (m4.x ? 1u : 0u) | (m4.y ? 2u : 0u) | (m4.z ? 4u : 0u) | (m4.w ? 8u : 0u);
 
   // score + threshold + partition test
   float score[kPxPerThread];
   uint32_t emit[kPxPerThread];
   uint32_t n_live = 0, n_emit = 0;
+  const bool zero_passes = 0.0f >= a.thr;
+  float cx[4], cy[4], cz[4];
+  Sm<T>::four(s_cart + lp0, cx);
+  Sm<T>::four(s_cart + kTile + lp0, cy);
+  Sm<T>::four(s_cart + 2 * kTile + lp0, cz);
 #pragma unroll
   for (int j = 0; j < kPxPerThread; ++j) {
     emit[j] = 0;
     score[j] = 0.f;
-    if (pix[j] >= HW || bad[j]) continue;
+    if (lp0 + j >= npx || bad[j]) continue;
     if (mbits & (1u << j)) {
       score[j] = sigmoid_t<T>(best[j]);
       // torch.max returns the FIRST index attaining the max of the float32 scores: an earlier
       // class with a smaller logit can round to the same float32 sigmoid (always when saturated)
-      if (cls[j] > 0 && score[j] >= a.thr) {
+      if (cls[j] > 0 && score[j] >= a.thr && (best[j] >= 15.f || runner[j] > best[j] - 1.0f)) {
         for (int c = 0; c < cls[j]; ++c) {
-          const float x = Ld<T>::one(lg + static_cast<size_t>(c) * HW + pix[j]);
+          const float x = Sm<T>::one(s_logits + static_cast<size_t>(c) * kTile + lp0 + j);
           if ((best[j] >= 15.f || x > best[j] - 1.0f) && sigmoid_t<T>(x) == score[j]) { cls[j] = c; break; }
         }
       }
     } else {
       cls[j] = 0;  // sigmoid * 0 == 0 for every class -> argmax 0
     }
+    if (!(score[j] >= a.thr || zero_passes)) continue;
+    if (n_parts == 0) {
+      if (score[j] >= a.thr) emit[j] = 1u;
+    } else {
+      // bit i of part_in: the pixel's range lies in partition i; the column-stride test comes below
+      const float d = norm3(cx[j], cy[j], cz[j]);
+      uint32_t part_in = 0u;
+      for (int i = 0; i < n_parts; ++i) part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
+      emit[j] = score[j] >= a.thr ? part_in : 0u;
+      if (zero_passes) emit[j] = (1u << n_parts) - 1u;     // 0 >= thr: out-of-partition copies survive with score 0
+    }
   }
-  // range partitions (need ||cart|| only where something can pass)
-  const bool zero_passes = 0.0f >= a.thr;
-  bool any = false;
+  if (n_parts > 0) {
+    // column stride: partition i keeps the columns w with w % rate_i == 0
+    int wj[kPxPerThread];
 #pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) any |= (pix[j] < HW && !bad[j] && (score[j] >= a.thr || zero_passes));
-  if (any) {
-    if (a.pa.n == 0) {
+    for (int j = 0; j < kPxPerThread; ++j) { wj[j] = col0 + j; if (wj[j] >= a.W) wj[j] -= a.W; }   // W >= 4: one wrap at most
+    for (int i = 0; i < n_parts; ++i) {
+      const int sh = s_shift[i], rate = s_rate[i];
+      const uint32_t mg = s_magic[i];
 #pragma unroll
       for (int j = 0; j < kPxPerThread; ++j)
-        if (pix[j] < HW && !bad[j] && score[j] >= a.thr) emit[j] = 1u;
-    } else {
-      const T *ct = cart + static_cast<size_t>(b) * 3 * HW;
-      float cx[4], cy[4], cz[4];
-      if (kVec && vec_ok) {
-        Ld<T>::four(ct + pix[0], cx);
-        Ld<T>::four(ct + HW + pix[0], cy);
-        Ld<T>::four(ct + 2 * static_cast<size_t>(HW) + pix[0], cz);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = pix[j] < HW;
-          cx[j] = ok ? Ld<T>::one(ct + pix[j]) : 0.f;
-          cy[j] = ok ? Ld<T>::one(ct + HW + pix[j]) : 0.f;
-          cz[j] = ok ? Ld<T>::one(ct + 2 * static_cast<size_t>(HW) + pix[j]) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kPxPerThread; ++j) {
-        if (pix[j] >= HW || bad[j]) continue;
-        const float d = norm3(cx[j], cy[j], cz[j]);
-        const int w = pix[j] % a.W;
-        for (int i = 0; i < a.pa.n; ++i) {
-          if (w % a.pa.rate[i]) continue;
-          const bool in = (d > a.pa.lower[i]) && (d <= a.pa.upper[i]);
-          const float s = in ? score[j] : 0.0f;
-          if (s >= a.thr) emit[j] |= 1u << i;
-        }
-      }
+        if (wj[j] - fast_div(wj[j], sh, mg) * rate) emit[j] &= ~(1u << i);
     }
   }
 #pragma unroll
@@ -318,7 +415,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   }
 
   // ---------------- block scan of (live, emit) packed as hi16 | lo16 ----------------
-  // per block: live <= 1024, emit <= 1024 * 8 -> both fit 16 bits, no carry between the halves
+  // per block: live <= 512, emit <= 512 * 8 -> both fit 16 bits, no carry between the halves
   const uint32_t mine = (n_live << 16) | n_emit;
   uint32_t incl = mine;
   const int lane = tid & 31, wid = tid >> 5;
@@ -330,7 +427,6 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   if (lane == 31) s_scan[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    constexpr int kWarps = kDecThreads / 32;
     const uint32_t v = lane < kWarps ? s_scan[lane] : 0u;
     uint32_t inc2 = v;
 #pragma unroll
@@ -342,7 +438,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     if (lane == kWarps - 1) {
       const uint32_t total_emit = inc2 & 0xffffu;
       s_total_live = inc2 >> 16;
-      // ONE global atomic per 1024 pixels reserves the block's output rows
+      // ONE global atomic per tile reserves the block's output rows
       s_base = total_emit ? static_cast<uint32_t>(atomicAdd(counter, static_cast<int>(total_emit))) : 0u;
     }
   }
@@ -352,8 +448,13 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
 #pragma unroll
   for (int j = 0; j < kPxPerThread; ++j) {
     if (!emit[j]) continue;
-    q_pix[live_pos] = static_cast<uint16_t>(kVec ? tid * 4 + j : j * kDecThreads + tid);
+    q_pix[live_pos] = static_cast<uint16_t>(lp0 + j);
     q_meta[live_pos] = static_cast<uint16_t>(cls[j]);
+    {
+      const bool wrap = col0 + j >= a.W;
+      q_h[live_pos] = static_cast<uint16_t>(row0 + (wrap ? 1 : 0));
+      q_w[live_pos] = static_cast<uint16_t>(col0 + j - (wrap ? a.W : 0));
+    }
     q_emit[live_pos] = static_cast<uint8_t>(emit[j]);
     q_score[live_pos] = score[j];
     q_off[live_pos] = emit_pos;
@@ -365,13 +466,14 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   const uint32_t base = s_base;
 
   // ---------------- phase B: dense-lane fp64 decode of the live pixels ----------------
-  for (uint32_t t = tid; t < total_live; t += kDecThreads) {
-    const int p = blk0 + q_pix[t];
+  for (uint32_t t = tid; t < total_live; t += kThreads) {
+    const int lp = q_pix[t];
+    const int p = blk0 + lp;
     float r[8], c[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(reg + (static_cast<size_t>(b) * 8 + k) * HW + p);
+    for (int k = 0; k < 8; ++k) r[k] = Sm<T>::one(s_reg + k * kTile + lp);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = Ld<T>::one(cart + (static_cast<size_t>(b) * 3 + k) * HW + p);
+    for (int k = 0; k < 3; ++k) c[k] = Sm<T>::one(s_cart + k * kTile + lp);
     double o[7];
     decode_box(r, c, a.az_inv != 0, o);
     // decode_range_view casts back to the input dtype (coding.py:144); widen that to f32
@@ -379,7 +481,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
 #pragma unroll
     for (int k = 0; k < 7; ++k) box[k] = static_cast<float>(Ld<T>::cast(o[k]));
     const uint32_t seg = static_cast<uint32_t>(b) * a.total_classes + q_meta[t] + a.cat_off;
-    const int h = p / a.W, w = p - h * a.W;
+    const int h = q_h[t], w = q_w[t];   // (row, col) computed incrementally in phase A
     uint32_t e = q_emit[t];
     uint32_t row = base + q_off[t];
     const float sc = q_score[t];
@@ -388,13 +490,13 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       e &= e - 1;
       float s_out = sc;
       uint32_t cand;
-      if (a.pa.n == 0) {
+      if (n_parts == 0) {
         cand = p;
       } else {
-        cand = a.pa.off[i] + h * a.pa.wsub[i] + w / a.pa.rate[i];
+        cand = s_off[i] + h * s_wsub[i] + fast_div(w, s_shift[i], s_magic[i]);
         // the partition that does not contain the pixel contributes score 0 (only when 0 >= thr)
         const float d = norm3(c[0], c[1], c[2]);
-        if (!((d > a.pa.lower[i]) && (d <= a.pa.upper[i]))) s_out = 0.0f;
+        if (!((d > s_lower[i]) && (d <= s_upper[i]))) s_out = 0.0f;
       }
       if (row < static_cast<uint32_t>(a.capacity)) {
         out_keys[row] = a.kp.make(seg, s_out, cand + a.cand_off);
@@ -452,23 +554,39 @@ __global__ void yaw_to_quat_kernel(const float *__restrict__ yaw, float *__restr
   reinterpret_cast<float4 *>(quat)[i] = make_float4(static_cast<float>(c), 0.f, 0.f, static_cast<float>(s));
 }
 
+template <typename T, int kTile, bool kBulk>
+static int launch_decode_tile(const DecodeArgs &a, const void *logits, const void *reg, const void *cart,
+                              const uint8_t *mask, unsigned long long *keys, float *boxes, int32_t *counter,
+                              cudaStream_t s) {
+  const int HW = a.H * a.W;
+  const size_t smem = decode_smem_bytes(a.C, kTile, sizeof(T));
+  if (smem > 200 * 1024) return RV3D_ERR_ARG;   // too many classes for one tile
+  RV3D_CHECK_CUDA(cudaFuncSetAttribute(decode_compact_kernel<T, kTile, kBulk>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(ceil_div(HW, kTile), a.B);
+  decode_compact_kernel<T, kTile, kBulk><<<grid, kTile / kPxPerThread, smem, s>>>(
+      a, static_cast<const T *>(logits), static_cast<const T *>(reg), static_cast<const T *>(cart), mask, keys, boxes,
+      counter);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
 template <typename T>
 static int launch_decode_compact(const DecodeArgs &a, const void *logits, const void *reg, const void *cart,
                                  const uint8_t *mask, unsigned long long *keys, float *boxes, int32_t *counter,
                                  cudaStream_t s) {
   const int HW = a.H * a.W;
-  dim3 grid(ceil_div(HW, kPxPerBlock), a.B);
-  const bool vec = (HW % 4 == 0) && aligned(logits, 16) && aligned(cart, 16) && aligned(mask, 4);
-  if (vec)
-    decode_compact_kernel<T, true><<<grid, kDecThreads, 0, s>>>(a, static_cast<const T *>(logits),
-                                                                 static_cast<const T *>(reg),
-                                                                 static_cast<const T *>(cart), mask, keys, boxes, counter);
-  else
-    decode_compact_kernel<T, false><<<grid, kDecThreads, 0, s>>>(a, static_cast<const T *>(logits),
-                                                                  static_cast<const T *>(reg),
-                                                                  static_cast<const T *>(cart), mask, keys, boxes, counter);
-  RV3D_CHECK_LAUNCH();
-  return RV3D_OK;
+  // TMA bulk copies need 16-byte aligned sources and sizes: every plane slice of a tile must start on a
+  // 16-byte boundary (HW % 16 == 0 covers the 1-byte mask plane too)
+  const bool bulk = (HW % 16 == 0) && aligned(logits, 16) && aligned(reg, 16) && aligned(cart, 16) && aligned(mask, 16);
+  // tile size: keep a CTA's stage under ~48 KB so 4-6 CTAs are resident per SM
+  const bool small_tile = static_cast<size_t>(a.C + 11) * 512 * sizeof(T) > 48 * 1024;
+  if (bulk) {
+    if (small_tile) return launch_decode_tile<T, 256, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+    return launch_decode_tile<T, 512, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+  }
+  if (small_tile) return launch_decode_tile<T, 256, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+  return launch_decode_tile<T, 512, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
 }
 
 }  // namespace rv3d
