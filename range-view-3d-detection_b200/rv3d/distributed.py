@@ -51,3 +51,31 @@ def gather_detections(rows: Tensor, group: Optional[dist.ProcessGroup] = None) -
     bufs = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(bufs, padded, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def gather_detections_fixed(rows: Tensor, capacity: int, group: Optional[dist.ProcessGroup] = None) -> Tensor:
+    """Latency-optimised form for a steady-state loop: ONE collective, fixed shape, no host read.
+
+    Every rank contributes a ``(capacity + 1, 13)`` block whose row 0 holds its row count; the result is
+    the ``(world, capacity + 1, 13)`` stack, still on the device.  ``unpack_fixed`` turns it into the same
+    concatenated rows ``gather_detections`` returns (that is where the host learns the counts)."""
+    m = rows.shape[0]
+    if m > capacity:
+        raise ValueError(f"{m} detections exceed the gather capacity {capacity}")
+    block = torch.zeros((capacity + 1, ROW), dtype=torch.float32, device=rows.device)
+    block[0, 0] = float(m)
+    block[1 : m + 1] = rows
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return block[None]
+    world = dist.get_world_size(group)
+    out = torch.empty((world, capacity + 1, ROW), dtype=torch.float32, device=rows.device)
+    if rows.is_cuda:
+        dist.all_gather_into_tensor(out, block, group=group)        # NCCL: one contiguous collective
+    else:                                                           # gloo (CPU tests) has no _allgather_base
+        dist.all_gather(list(out.unbind(0)), block, group=group)
+    return out
+
+
+def unpack_fixed(stacked: Tensor) -> Tensor:
+    counts = stacked[:, 0, 0].to(torch.int64).tolist()
+    return torch.cat([stacked[r, 1 : c + 1] for r, c in enumerate(counts)], dim=0)

@@ -18,7 +18,7 @@ def _free_port():
 def _worker(rank, world, port, n_sweeps, out):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                     "range-view-3d-detection_b200"))
-    from rv3d.distributed import gather_detections, pack_rows, shard_bounds
+    from rv3d.distributed import gather_detections, gather_detections_fixed, pack_rows, shard_bounds, unpack_fixed
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = shard_bounds(n_sweeps, rank, world)
@@ -32,6 +32,7 @@ def _worker(rank, world, port, n_sweeps, out):
     allrows = gather_detections(rows)
     expect = torch.cat([bidx[:, None].float(), table[:, 0:1], table[:, 1:2], table[:, 2:]], 1)
     ok = torch.equal(allrows, expect)
+    ok = ok and torch.equal(unpack_fixed(gather_detections_fixed(rows, 64)), expect)
     dist.barrier()
     dist.destroy_process_group()
     out[rank] = bool(ok)
