@@ -353,7 +353,7 @@ def run_ours(args):
             "stage_ms": {"rasterize": float(np.mean(t_raster)), "decode_compact": float(np.mean(t_decode)),
                          "sort+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": t_wall / args.steps * 1e3},
             "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "iou_evals_per_step": st[0],
-                    "kept_per_step": st[1], "pairs_above_thr_per_step": float(stats[18].item()) / args.steps, "approx_iou_per_step": float(stats[19].item()) / args.steps, "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3], "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]], "slowest_segment_mcycles": round(float(stats[10].item()) / 1e6, 3), "largest_segment": int(stats[11].item()), "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()],
+                    "kept_per_step": st[1], "pairs_above_thr_per_step": float(stats[18].item()) / args.steps, "approx_iou_per_step": float(stats[19].item()) / args.steps, "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3], "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]] + [round(float(stats[20].item()) / args.steps / 1e6, 3), round(float(stats[21].item()) / args.steps / 1e6, 3)], "slowest_segment_mcycles": round(float(stats[10].item()) / 1e6, 3), "largest_segment": int(stats[11].item()), "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()],
                     "segments": B * C},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -115,7 +115,7 @@ struct NmsArgs {
   int *kept_pos;           // [kept_base[s] + i] = position inside the segment
   int *kept_count;         // [s]
   // static candidate grid (scratch, per segment at 4*seg_begin / seg_begin)
-  void *grid_entries;      // GridEntry[4 * n_total]
+  void *grid_entries;      // GridEntry[n_total]
   uint32_t *oversize;      // [n_total] candidates that are not in the grid
   int *firstsup;           // [n_total] weighted: first suppressor rank of a candidate in the current round
   // weighted merge
@@ -126,54 +126,36 @@ struct NmsArgs {
   unsigned long long *stats;
 };
 
-// ---- static spatial hash over a segment's candidates ----------------------------------------
-// Built once per segment.  Cells are `cell` metres wide, chosen from the segment's mean box radius
-// (classes have characteristic sizes) so that nearly every candidate's padded circle spans at most
-// 2x2 cells; such a candidate is registered in every cell its circle's bounding square touches.
-// Bigger / far-away / non-finite candidates go to an "oversize" list that every query scans.
-// Entries are counting-sorted by hash bucket, so one cell's entries are contiguous.
-//
-// Two boxes can only interact if their circle AABBs intersect, and then the cell holding the lower
-// corner of that intersection is registered by the candidate and visited by the query: a query
-// visiting cell c accepts an entry only if c is the FIRST cell of the query or the FIRST cell of the
-// entry on each axis, which finds every interacting pair exactly once.
+// ---- static dense grid over a segment's candidates --------------------------------------------
+// Built once per segment by the leader CTA.  kG x kG cells cover mean +- 3.5 sigma of the candidate
+// centres (cell >= half the mean padded radius); a candidate is registered ONCE, in the cell of its
+// centre, coordinates clamped to the grid (clamping is monotone, so a clamped window still covers every
+// clamped candidate: far outliers just land in a border cell and cost a wasted circle test).  Entries are
+// counting-sorted by row-major cell index, so the cells cx0..cx1 of one grid row are ONE contiguous run.
+// Candidates with a padded radius above r_cap = 2 x mean (or non-finite) go to an "oversize" list that
+// every query scans.  A kept box (x, y, r) must look at centres within r + r_cap: rows cy0..cy1, one
+// run each; no hashing, no duplicates, no per-entry cell checks.
+constexpr int kG = 64;
+constexpr int kCells = kG * kG;
 constexpr float kPosCap = 1.0e6f;
-constexpr int kNB = 1024;                // hash buckets (2 per thread in the scan)
-constexpr int kMaxQueryCells = 6;        // a query spanning more cells per axis scans everything
 constexpr int kQ2Cap = 8192;             // exact-IoU work queue (pairs that passed circle + bound)
 constexpr int kWBuf = 64;                // per-warp hit buffer
-static_assert(kNB == 2 * kNmsThreads, "two hash buckets per scan lane");
+static_assert(kCells % kNmsThreads == 0, "whole cells per scan lane");
 
-// 16-byte grid entry: circle of the candidate + meta = idx (20 bits) | first_x << 20 | first_y << 21 |
-// cell key << 22.  The 10-bit cell key only filters hash collisions cheaply; a false match is still
-// rejected by the circle test, so aliasing cannot create or lose a pair.
-struct __align__(16) GridEntry { float x, y, r; uint32_t meta; };
-constexpr uint32_t kIdxMask = (1u << 20) - 1u;
+struct __align__(16) GridEntry { float x, y, r; uint32_t idx; };
 
-__device__ __forceinline__ uint32_t cell_key(int cx, int cy) {
-  return ((static_cast<uint32_t>(cx) & 31u) | ((static_cast<uint32_t>(cy) & 31u) << 5)) << 22;
-}
-__device__ __forceinline__ int bucket_of(int cx, int cy) {
-  return static_cast<int>((static_cast<uint32_t>(cx) * 73856093u) ^ (static_cast<uint32_t>(cy) * 19349663u)) & (kNB - 1);
-}
-
-struct BoxCells {
-  int cx0, cy0, cx1, cy1;
-  bool gridded;   // false: not representable in the grid -> handled by the "everything" paths
-};
-
-// cells overlapped by the circle's bounding square; at most `max_span` cells per axis
-__device__ __forceinline__ BoxCells cells_of(float x, float y, float r, float inv_cell, int max_span) {
-  BoxCells c;
-  c.gridded = (r == r) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap) && (r * inv_cell <= 0.49f * (max_span - 1));
-  if (c.gridded) {
-    c.cx0 = __float2int_rd((x - r) * inv_cell); c.cx1 = __float2int_rd((x + r) * inv_cell);
-    c.cy0 = __float2int_rd((y - r) * inv_cell); c.cy1 = __float2int_rd((y + r) * inv_cell);
-    c.gridded = (c.cx1 - c.cx0 < max_span) && (c.cy1 - c.cy0 < max_span);
+struct GridGeom {
+  float x0, y0, inv_cell, r_cap;
+  __device__ __forceinline__ int cell_x(float x) const {
+    return static_cast<int>(fminf(fmaxf((x - x0) * inv_cell, 0.f), static_cast<float>(kG - 1)));
   }
-  if (!c.gridded) c.cx0 = c.cy0 = c.cx1 = c.cy1 = 0;
-  return c;
-}
+  __device__ __forceinline__ int cell_y(float y) const {
+    return static_cast<int>(fminf(fmaxf((y - y0) * inv_cell, 0.f), static_cast<float>(kG - 1)));
+  }
+  __device__ __forceinline__ bool gridded(float x, float y, float r) const {
+    return (r <= r_cap) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap);   // false for NaN
+  }
+};
 
 // ---- cheap, safe upper bound on the IoU (separating axes + projected overlap) -----------------
 // The intersection lies inside box A and inside B's bounding box in A's frame, so its area is at
@@ -272,11 +254,11 @@ __host__ __device__ inline size_t nms_smem_bytes(int nwords) {
   b += sizeof(float) * kF * 6;                                     // fx, fy, fr, kx, ky, kr
   b += sizeof(int) * kF;                                           // front_pos
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
-  b += sizeof(int) * (kNB + 1) * 2;                                // b_start, b_cursor
+  b += sizeof(int) * (kCells + 1);                                 // cell_start (the build's cursors alias queue2 + wbuf)
   b += sizeof(uint32_t) * kQ2Cap;                                  // queue2
   b += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;              // per-warp hit buffers
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
-  if (kWeighted) b += sizeof(uint32_t) * kQ2Cap;                   // qflag
+  if (kWeighted) b += sizeof(uint32_t) * kQ2Cap + sizeof(int) * kF;  // qflag, killer
   return b;
 }
 
@@ -314,8 +296,10 @@ nms_segment_kernel(NmsArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsThreads / 32 + 1];
   __shared__ int s_qn, s_nk, s_nos, s_overflow;
-  __shared__ int s_round[8];   // leader -> cluster: {nf, nk, cursor_word, -, n oversize, inv_cell bits}
-  __shared__ float s_red[kNmsThreads / 32 * 2];
+  __shared__ int s_next;       // leader: next kept box to hand out in the kill scan (dynamic load balance)
+  __shared__ int s_round[8];   // leader -> cluster: {nf, nk, cursor_word, -, n oversize}
+  __shared__ GridGeom s_geom;  // leader -> cluster
+  __shared__ float s_red[kNmsThreads / 32 * 6];
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
 
   // A cluster of P CTAs works on one segment.  CTA 0 (the leader) owns the alive bitmap and runs the
@@ -336,7 +320,7 @@ nms_segment_kernel(NmsArgs a) {
   }
   const int nwords = (n + 31) >> 5;
   const Rec *recs = static_cast<const Rec *>(a.recs) + beg;
-  GridEntry *entries = static_cast<GridEntry *>(a.grid_entries) + 4 * static_cast<size_t>(beg);
+  GridEntry *entries = static_cast<GridEntry *>(a.grid_entries) + beg;
   uint32_t *os_list = a.oversize + beg;
   int *firstsup = kWeighted ? a.firstsup + beg : nullptr;
   const int kbase = a.kept_base[seg];
@@ -358,19 +342,20 @@ nms_segment_kernel(NmsArgs a) {
   uint32_t *sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
   uint32_t *mrg = sup;
   if (kWeighted) { mrg = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW; }
-  int *b_start = reinterpret_cast<int *>(p); p += sizeof(int) * (kNB + 1);
-  int *b_cursor = reinterpret_cast<int *>(p); p += sizeof(int) * (kNB + 1);
+  int *cell_start = reinterpret_cast<int *>(p); p += sizeof(int) * (kCells + 1);
   uint32_t *queue2 = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kQ2Cap;
+  int *cell_cursor = reinterpret_cast<int *>(queue2);   // kCells ints, build phase only (kQ2Cap >= kCells)
   uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;
   uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
   int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
   p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
   uint32_t *qflag = kWeighted ? reinterpret_cast<uint32_t *>(p) : nullptr;   // per queued pair: bit0 iou > thr, bit1 iou > merge_thr
+  int *killer = kWeighted ? reinterpret_cast<int *>(qflag + kQ2Cap) : nullptr;  // frontier box -> rank of its first suppressor
 
   unsigned long long st_iou = 0, st_circle = 0, st_hit = 0, st_approx = 0;   // exact IoUs, circle tests, pairs above thr, approximate IoUs
   // per-phase cycle counters (thread 0, only when stats are requested):
   // [0] grid build + frontier gather, [1] frontier load, [2] frontier pairs, [3] greedy, [4] kill scan, [5] exact IoU
-  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [6] publish (+ weighted frontier merges), [7] cluster sync A + helper copies
   long long t_mark = clock64();
   auto lap = [&](int k) {
     if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
@@ -380,34 +365,45 @@ nms_segment_kernel(NmsArgs a) {
   for (int w = tid; w < nwords; w += kNmsThreads)
     alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
   if (tid == 0) { s_nos = 0; s_overflow = 0; s_qn = 0; }
-  float inv_cell = 0.f;
   if (leader) {
-    for (int b = tid; b <= kNB; b += kNmsThreads) b_cursor[b] = 0;
+    for (int c = tid; c < kCells; c += kNmsThreads) cell_cursor[c] = 0;
     {
-      // mean padded radius of the finite, sane candidates -> cell size = 4 * mean radius
-      float sum = 0.f, cnt = 0.f;
+      // first and second moments of the sane candidates -> grid origin / cell size / radius cap
+      float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sum x, y, x^2, y^2, r, count
       for (int i = tid; i < n; i += kNmsThreads) {
-        const float r = recs[i].r;
-        if (r > 0.f && r < 1.0e4f) { sum += r; cnt += 1.f; }
+        const Rec rc = recs[i];
+        const float x = rec_cx(rc), y = rec_cy(rc), r = rc.r;
+        if (r > 0.f && r < 1.0e4f && fabsf(x) <= kPosCap && fabsf(y) <= kPosCap) {
+          acc[0] += x; acc[1] += y; acc[2] += x * x; acc[3] += y * y; acc[4] += r; acc[5] += 1.f;
+        }
       }
-      for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-      if (lane == 0) { s_red[wid] = sum; s_red[kNmsThreads / 32 + wid] = cnt; }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == 0) s_red[k * (kNmsThreads / 32) + wid] = acc[k];
+      }
       __syncthreads();
-      float ts = 0.f, tc = 0.f;
-      for (int w = 0; w < kNmsThreads / 32; ++w) { ts += s_red[w]; tc += s_red[kNmsThreads / 32 + w]; }
-      const float cell = fminf(fmaxf(4.0f * (tc > 0.f ? ts / tc : 1.0f), 0.25f), 4.0e4f);
-      inv_cell = 1.0f / cell;
+      if (tid == 0) {
+        float t[6];
+        for (int k = 0; k < 6; ++k) { t[k] = 0.f; for (int w = 0; w < kNmsThreads / 32; ++w) t[k] += s_red[k * (kNmsThreads / 32) + w]; }
+        const float cnt = fmaxf(t[5], 1.f);
+        const float mx = t[0] / cnt, my = t[1] / cnt, mr = t[5] > 0.f ? t[4] / cnt : 1.f;
+        const float sx = sqrtf(fmaxf(t[2] / cnt - mx * mx, 0.f)), sy = sqrtf(fmaxf(t[3] / cnt - my * my, 0.f));
+        const float cell = fminf(fmaxf(fmaxf(7.f * fmaxf(sx, sy) / kG, 0.5f * mr), 1e-3f), 1.0e5f);
+        s_geom.inv_cell = 1.0f / cell;
+        s_geom.x0 = mx - 0.5f * kG * cell;
+        s_geom.y0 = my - 0.5f * kG * cell;
+        s_geom.r_cap = 2.0f * mr;
+      }
+      __syncthreads();
     }
+    const GridGeom g = s_geom;
     if (prune) {
       for (int i = tid; i < n; i += kNmsThreads) {           // count
-        const Rec r = recs[i];
-        const BoxCells c = cells_of(rec_cx(r), rec_cy(r), r.r, inv_cell, 2);
-        if (c.gridded) {
-          for (int cy = c.cy0; cy <= c.cy1; ++cy)
-            for (int cx = c.cx0; cx <= c.cx1; ++cx) atomicAdd(&b_cursor[bucket_of(cx, cy)], 1);
-        } else {
-          os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
-        }
+        const Rec rc = recs[i];
+        const float x = rec_cx(rc), y = rec_cy(rc);
+        if (g.gridded(x, y, rc.r)) atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1);
+        else os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
       }
     } else {
       for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
@@ -415,42 +411,39 @@ nms_segment_kernel(NmsArgs a) {
     }
     __syncthreads();
     {
+      constexpr int kPer = kCells / kNmsThreads;
+      int cnt[kPer], sum = 0;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) { cnt[k] = cell_cursor[tid * kPer + k]; sum += cnt[k]; }
       int total;
-      const int c0 = b_cursor[2 * tid], c1 = b_cursor[2 * tid + 1];
-      const int off = block_exclusive_scan(c0 + c1, s_warp, total);
-      b_start[2 * tid] = off; b_start[2 * tid + 1] = off + c0;
-      b_cursor[2 * tid] = off; b_cursor[2 * tid + 1] = off + c0;
-      if (tid == 0) b_start[kNB] = total;
+      int off = block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) { cell_start[tid * kPer + k] = off; cell_cursor[tid * kPer + k] = off; off += cnt[k]; }
+      if (tid == 0) cell_start[kCells] = total;
     }
     __syncthreads();
     if (prune) {
       for (int i = tid; i < n; i += kNmsThreads) {           // fill
-        const Rec r = recs[i];
-        const float x = rec_cx(r), y = rec_cy(r);
-        const BoxCells c = cells_of(x, y, r.r, inv_cell, 2);
-        if (!c.gridded) continue;
-        for (int cy = c.cy0; cy <= c.cy1; ++cy)
-          for (int cx = c.cx0; cx <= c.cx1; ++cx) {
-            const uint32_t meta = static_cast<uint32_t>(i) | (cx == c.cx0 ? (1u << 20) : 0u) |
-                                  (cy == c.cy0 ? (1u << 21) : 0u) | cell_key(cx, cy);
-            entries[atomicAdd(&b_cursor[bucket_of(cx, cy)], 1)] = GridEntry{x, y, r.r, meta};
-          }
+        const Rec rc = recs[i];
+        const float x = rec_cx(rc), y = rec_cy(rc);
+        if (!g.gridded(x, y, rc.r)) continue;
+        entries[atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1)] = GridEntry{x, y, rc.r, static_cast<uint32_t>(i)};
       }
     }
     if (kWeighted)
       for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
-    if (tid == 0) { s_round[4] = s_nos; s_round[5] = __float_as_int(inv_cell); }
+    if (tid == 0) s_round[4] = s_nos;
     __threadfence();
   }
-  cluster.sync();   // grid (global) + bucket offsets (leader's shared memory) are ready
+  cluster.sync();   // grid entries (global) + cell offsets (leader's shared memory) are ready
   uint32_t *lead_alive = cluster.map_shared_rank(alive, 0);
   const int *lead_round = cluster.map_shared_rank(s_round, 0);
   if (!leader) {
-    const int *lead_bstart = cluster.map_shared_rank(b_start, 0);
-    for (int b = tid; b <= kNB; b += kNmsThreads) b_start[b] = lead_bstart[b];
+    const int *lead_cs = cluster.map_shared_rank(cell_start, 0);
+    for (int c = tid; c <= kCells; c += kNmsThreads) cell_start[c] = lead_cs[c];
   }
   const int nos = lead_round[4];
-  inv_cell = __int_as_float(lead_round[5]);
+  const GridGeom geom = *cluster.map_shared_rank(&s_geom, 0);
   __syncthreads();
 
   int kept_total = 0;
@@ -463,10 +456,15 @@ nms_segment_kernel(NmsArgs a) {
     if (kWeighted && iou > a.mthr) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
   };
   auto accumulate = [&](int slot, int row_in_seg) {  // merge candidate `row_in_seg` into kept slot
-    const size_t rowj = static_cast<size_t>(beg + row_in_seg) * a.D;
-    const double sj = a.data[rowj + a.D - 1];
+    const float *row = a.data + static_cast<size_t>(beg + row_in_seg) * a.D;
+    float v[kMaxD];
+#pragma unroll
+    for (int c = 0; c < kMaxD; ++c) v[c] = c < a.D ? row[c] : 0.f;   // independent loads first: one latency, not D
+    const double sj = row[a.D - 1];
     double *acc = a.acc + static_cast<size_t>(kbase + slot) * a.D;
-    for (int c = 0; c < a.D - 1; ++c) atomicAdd(acc + c, sj * static_cast<double>(a.data[rowj + c]));
+#pragma unroll
+    for (int c = 0; c < kMaxD; ++c)
+      if (c < a.D - 1) atomicAdd(acc + c, sj * static_cast<double>(v[c]));
     atomicAdd(acc + a.D - 1, sj);
     atomicAdd(a.merge_count + kbase + slot, 1);
   };
@@ -700,20 +698,45 @@ nms_segment_kernel(NmsArgs a) {
         }
         if (kWeighted) {
           // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr
-          // that comes no later than its first suppressor; kept boxes join themselves.
-          if (tid < nf) {
-            const int j = tid;
-            for (int t = 0; t < nk; ++t) {
-              const int i = keptf[t];
-              if (i > j) break;
-              const bool self = (i == j);
-              if (self || ((mrg[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) accumulate(kept_total + t, front_pos[j]);
-              if (self || ((sup[i * kFW + (j >> 5)] >> (j & 31)) & 1u)) break;
+          // that comes no later than its first suppressor; kept boxes join themselves.  The (j, slot)
+          // pairs are queued first and accumulated afterwards, one pair per lane: done in place, each
+          // lane's global loads + fp64 atomics would run alone (lanes reach their merges at different t).
+          // Work is proportional to the set bits of the kept rows: (1) first suppressor of every frontier
+          // box = min rank over the kept rows that contain it; (2) each kept row queues itself and the
+          // boxes of its merge row that it reaches no later than their first suppressor.
+          if (tid == 0) s_qn = 0;
+          if (tid < nf) killer[tid] = 0x7fffffff;
+          __syncthreads();
+          if (tid < nk) {
+            const int i = keptf[tid];
+            for (int w = 0; w < kFW; ++w) {
+              uint32_t bits = sup[i * kFW + w];
+              while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; atomicMin(&killer[j], tid); }
             }
           }
+          __syncthreads();
+          if (tid < nk) {
+            const int i = keptf[tid];
+            auto push = [&](int j) {
+              const int slot = atomicAdd(&s_qn, 1);
+              if (slot < kQ2Cap) queue2[slot] = (static_cast<uint32_t>(j) << 16) | static_cast<uint32_t>(tid);
+              else accumulate(kept_total + tid, front_pos[j]);   // (cannot happen: <= kF * kF / 2 only if every pair merges)
+            };
+            push(i);                                             // a kept box joins its own merge set
+            for (int w = 0; w < kFW; ++w) {
+              uint32_t bits = mrg[i * kFW + w];
+              while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; if (tid <= killer[j]) push(j); }
+            }
+          }
+          __syncthreads();
+          const int nq = min(s_qn, kQ2Cap);
+          for (int q = tid; q < nq; q += kNmsThreads)
+            accumulate(kept_total + static_cast<int>(queue2[q] & 0xffffu), front_pos[queue2[q] >> 16]);
         }
       }
-      if (tid == 0) { s_round[0] = nf; s_round[1] = nk; s_qn = 0; }
+      __syncthreads();
+      lap(6);
+      if (tid == 0) { s_round[0] = nf; s_round[1] = nk; s_qn = 0; s_next = 0; }
       if (tid == 1) s_round[2] = cursor_word;
     }
     cluster.sync();   // (A) the leader's round state, kept boxes and bitmap are final
@@ -737,13 +760,20 @@ nms_segment_kernel(NmsArgs a) {
       if (tid == 0) s_qn = 0;
     }
     __syncthreads();
+    if (leader) lap(7);
 
     // ================= 5. kill scan: one warp per newly kept box over the static grid ==============
     // Lanes stride over the contiguous entries of each cell the kept box's circle touches (+ the
     // oversize list): alive test, circle test, hits compacted per warp so the IoU bound runs on full
-    // warps; pairs that pass go to the exact-IoU queue.  Kept boxes are dealt round-robin to the
-    // warps of the whole cluster.
-    for (int t = crank * (kNmsThreads / 32) + wid; t < nk; t += P * (kNmsThreads / 32)) {
+    // warps; pairs that pass go to the exact-IoU queue.
+    // Kept boxes are handed out one at a time from a counter in the leader's shared memory: a box in a dense
+    // cell costs 10x one at the periphery, a static split leaves most warps idle.
+    int *lead_next = cluster.map_shared_rank(&s_next, 0);
+    while (true) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(lead_next, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= nk) break;
       const Rec &rk = krec[t];
       const float qx = kx[t], qy = ky[t], qr = kr[t];
       int nbuf = 0;  // warp-uniform count of buffered hits
@@ -777,7 +807,7 @@ nms_segment_kernel(NmsArgs a) {
           __syncwarp();
         }
       };
-      auto scan_range = [&](const GridEntry *ents, int e0, int e1, uint32_t key, uint32_t need) {
+      auto scan_range = [&](const GridEntry *ents, int e0, int e1) {
         // kUnroll independent 16-byte loads in flight per lane: the scan is L2-latency bound otherwise
         constexpr int kUnroll = 4;
         for (int eb = e0; eb < e1; eb += 32 * kUnroll) {
@@ -785,15 +815,14 @@ nms_segment_kernel(NmsArgs a) {
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
             const int e = eb + u * 32 + lane;
-            ge[u] = (e < e1) ? ents[e] : GridEntry{0.f, 0.f, 0.f, 0xffffffffu};
+            ge[u] = (e < e1) ? ents[e] : GridEntry{0.f, 0.f, 0.f, 0u};
           }
 #pragma unroll
           for (int u = 0; u < kUnroll; ++u) {
             if (eb + u * 32 >= e1) break;   // warp-uniform
-            const uint32_t j = ge[u].meta & kIdxMask;
+            const uint32_t j = ge[u].idx;
             bool hit = false;
-            if (eb + u * 32 + lane < e1 && (ge[u].meta & 0xffc00000u) == key && (ge[u].meta & need) == need &&
-                ((alive[j >> 5] >> (j & 31)) & 1u)) {
+            if (eb + u * 32 + lane < e1 && ((alive[j >> 5] >> (j & 31)) & 1u)) {
               ++st_circle;
               const float dx = ge[u].x - qx, dy = ge[u].y - qy, rr = ge[u].r + qr;
               hit = dx * dx + dy * dy <= rr * rr;
@@ -802,14 +831,12 @@ nms_segment_kernel(NmsArgs a) {
           }
         }
       };
-      const BoxCells kc = cells_of(qx, qy, qr, inv_cell, kMaxQueryCells);
-      if (prune && kc.gridded) {
-        for (int cy = kc.cy0; cy <= kc.cy1; ++cy)
-          for (int cx = kc.cx0; cx <= kc.cx1; ++cx) {
-            const int b = bucket_of(cx, cy);
-            const uint32_t need = (cx == kc.cx0 ? 0u : (1u << 20)) | (cy == kc.cy0 ? 0u : (1u << 21));
-            scan_range(entries, b_start[b], b_start[b + 1], cell_key(cx, cy), need);
-          }
+      if (prune) {
+        // every gridded candidate whose circle can touch has its centre within qr + r_cap
+        const float reach = qr + geom.r_cap;
+        const int cx0 = geom.cell_x(qx - reach), cx1 = geom.cell_x(qx + reach);
+        const int cy0 = geom.cell_y(qy - reach), cy1 = geom.cell_y(qy + reach);
+        for (int cy = cy0; cy <= cy1; ++cy) scan_range(entries, cell_start[cy * kG + cx0], cell_start[cy * kG + cx1 + 1]);
         for (int ob = 0; ob < nos; ob += 32) {               // oversize candidates
           const int o = ob + lane;
           bool hit = false;
@@ -826,19 +853,11 @@ nms_segment_kernel(NmsArgs a) {
           offer(hit, j);
         }
       } else {
-        // kept box too big / far for the grid, or pruning disabled: every alive candidate
+        // pruning disabled (negative thresholds): every alive candidate interacts
         for (int jb = cursor_word << 5; jb < n; jb += 32) {
           const int j = jb + lane;
-          bool hit = false;
-          if (j < n && ((alive[j >> 5] >> (j & 31)) & 1u)) {
-            ++st_circle;
-            hit = true;
-            if (prune) {
-              const Rec &rj = recs[j];
-              const float dx = rec_cx(rj) - qx, dy = rec_cy(rj) - qy, rr = rj.r + qr;
-              hit = dx * dx + dy * dy <= rr * rr;
-            }
-          }
+          const bool hit = j < n && ((alive[j >> 5] >> (j & 31)) & 1u);
+          if (hit) ++st_circle;
           offer(hit, static_cast<uint32_t>(j));
         }
       }
@@ -931,6 +950,8 @@ nms_segment_kernel(NmsArgs a) {
       const unsigned long long prev = atomicMax(a.stats + 10, tot);  // slowest segment (cycles)
       if (tot > prev)                                                // (diagnostic, last writer wins) its phases
         for (int k = 0; k < 6; ++k) a.stats[12 + k] = static_cast<unsigned long long>(ph[k]);
+      atomicAdd(a.stats + 20, static_cast<unsigned long long>(ph[6]));
+      atomicAdd(a.stats + 21, static_cast<unsigned long long>(ph[7]));
       atomicMax(a.stats + 11, static_cast<unsigned long long>(n));   // largest segment (candidates)
     }
   }
@@ -1064,7 +1085,7 @@ static NmsLayout nms_layout(void *scratch, int n, int S, bool weighted, int D, i
     L.acc = c.take<double>(static_cast<size_t>(nn) * D);   // acc + merge_count contiguous (one memset)
     L.merge_count = c.take<int>(nn);
   }
-  L.grid_entries = c.take<GridEntry>(4 * static_cast<size_t>(nn));
+  L.grid_entries = c.take<GridEntry>(nn);
   L.oversize = c.take<uint32_t>(nn);
   L.firstsup = weighted ? c.take<int>(nn) : nullptr;
   L.cub_bytes = cub_sort_bytes(nn, end_bit);
@@ -1350,7 +1371,7 @@ static OpLayout op_layout(void *scratch, int n, bool weighted, int D, bool sort)
     L.acc = c.take<double>(static_cast<size_t>(nn) * D);
     L.merge_count = c.take<int>(nn);
   }
-  L.grid_entries = c.take<GridEntry>(4 * static_cast<size_t>(nn));
+  L.grid_entries = c.take<GridEntry>(nn);
   L.oversize = c.take<uint32_t>(nn);
   L.firstsup = weighted ? c.take<int>(nn) : nullptr;
   L.cub_bytes = sort ? cub_sort_bytes(nn, 64) : 0;
