@@ -186,3 +186,39 @@ def test_range_decoder_full_size_vs_oracle(shape, mode):
         kept7 = ref[0].to(DEV)
         again = batched_multiclass_nms(kept7[None], s[None], c[None].long() + 1000 * b[None].long(), 50000, 1000, 0.3, 0.1, "HARD")
         assert again[1].shape == s.shape
+
+
+@pytest.mark.parametrize("mode", ["HARD", "WEIGHTED"])
+def test_single_class_stress_queue_overflow(mode):
+    """BASELINE config 3 in miniature: one class, 60 k heavily clustered candidates (hundreds of boxes per
+    object), num_pre_nms truncation active.  Drives the work queues past their capacity, so the in-place
+    (hard) and serial-fallback (weighted) overflow paths are part of the parity check."""
+    from rv3d.math.ops.nms import batched_multiclass_nms
+    cub, sc, ca = synth.make_nms_candidates(1, 60000, 1, 48, seed=77, spread=40.0, frac_clustered=0.97)
+    ref = oracle.batched_multiclass_nms(cub, sc, ca, 50000, 300, 0.3, 0.03, mode)
+    got = batched_multiclass_nms(cub.to(DEV), sc.to(DEV), ca.to(DEV), 50000, 300, 0.3, 0.03, mode)
+    assert torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[2].cpu(), ref[2]) and torch.equal(got[3].cpu(), ref[3])
+    if mode == "HARD":
+        assert torch.equal(got[0].cpu(), ref[0])
+    else:
+        np.testing.assert_allclose(got[0].cpu().numpy(), ref[0].numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_degenerate_boxes():
+    """Tiny, huge, NaN and duplicated boxes: the pruning structures must not change the result."""
+    from rv3d.math.ops.nms import batched_multiclass_nms
+    cub, sc, ca = synth.make_nms_candidates(1, 4000, 2, 10, seed=5)
+    cub[0, 10:40, 3:5] = 1e-4                      # degenerate extents (vertex-inside tolerance dominates)
+    cub[0, 50:60, 3:5] = 300.0                     # huge boxes: oversize list
+    cub[0, 70:75, 0] = 5e6                         # far away: clamped into a border cell
+    cub[0, 80:90] = cub[0, 100:110]                # exact duplicates (different scores)
+    cub[0, 120, 0] = float("nan")                  # NaN never interacts
+    for mode in ("HARD", "WEIGHTED"):
+        ref = oracle.batched_multiclass_nms(cub, sc, ca, 50000, 1000, 0.3, 0.1, mode)
+        got = batched_multiclass_nms(cub.to(DEV), sc.to(DEV), ca.to(DEV), 50000, 1000, 0.3, 0.1, mode)
+        assert torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[2].cpu(), ref[2]), mode
+        np.testing.assert_allclose(got[0].cpu().numpy(), ref[0].numpy(), rtol=1e-5, atol=1e-5, equal_nan=True)
+    # negative threshold: even disjoint boxes suppress each other -> one box per class survives
+    ref = oracle.batched_multiclass_nms(cub, sc, ca, 50000, 1000, -1.0, 0.1, "HARD")
+    got = batched_multiclass_nms(cub.to(DEV), sc.to(DEV), ca.to(DEV), 50000, 1000, -1.0, 0.1, "HARD")
+    assert torch.equal(got[1].cpu(), ref[1]) and got[1].shape[0] <= 3
