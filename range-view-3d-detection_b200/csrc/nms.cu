@@ -36,8 +36,9 @@ namespace cg = cooperative_groups;
 namespace rv3d {
 
 constexpr int kNmsThreads = 512;
-constexpr int kF = 256;                 // frontier size
-constexpr int kFW = kF / 32;            // words per bit-matrix row
+// frontier size: 512 boxes per round in hard mode (one 32 KB bit-matrix), 256 in weighted mode (two
+// matrices, 64-byte records): fewer, fuller rounds cost fewer barriers and leader-only phases
+template <bool kWeighted> struct Frontier { static constexpr int kF = kWeighted ? 256 : 512; };
 constexpr int kMaxD = 16;               // max data columns of the weighted merge
 
 // ------------------------------------------------------------------------------------------
@@ -246,8 +247,9 @@ __device__ __forceinline__ int decide_vs(float approx, float thr) {
   return approx > thr + m ? 1 : (approx < thr - m ? -1 : 0);
 }
 
-template <typename Rec, bool kWeighted>
+template <typename Rec, bool kWeighted, int kF>
 __host__ __device__ inline size_t nms_smem_bytes(int nwords) {
+  constexpr int kFW = kF / 32;
   size_t b = 0;
   b += align_up_c(sizeof(uint32_t) * nwords, 16);                  // alive
   b += sizeof(Rec) * kF * 2;                                       // frec, krec
@@ -290,9 +292,11 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &tot
   return s_warp[wid] + incl - v;
 }
 
-template <typename Rec, bool kWeighted>
+template <typename Rec, bool kWeighted, int kF>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_segment_kernel(NmsArgs a) {
+  constexpr int kFW = kF / 32;   // words per bit-matrix row
+  static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsThreads / 32 + 1];
   __shared__ int s_qn, s_nk, s_nos, s_overflow;
@@ -517,7 +521,9 @@ nms_segment_kernel(NmsArgs a) {
         get(q, ra, rb);
         const Obb oa = obb_of(ra), ob = obb_of(rb);
         int d1 = 0, d2 = 0;
-        if (prune && obb_sane(oa) && obb_sane(ob)) {
+        if (prune && !iou_may_exceed(ra, rb, thr_any)) {
+          d1 = -1; d2 = -1;                       // even the upper bound stays below both thresholds
+        } else if (prune && obb_sane(oa) && obb_sane(ob)) {
           const float ap = approx_iou(oa, ob);
           ++st_approx;
           d1 = decide_vs(ap, a.thr);
@@ -565,13 +571,10 @@ nms_segment_kernel(NmsArgs a) {
       lap(0);
       if (nf > 0) {
         ++rounds;
-        // the frontier is decided this round: clear its bits, load its records, reset per-round state
+        // the frontier is decided this round: clear its bits, reset the per-round state
         if (tid < nf) {
           const int pos = front_pos[tid];
           atomicAnd(&alive[pos >> 5], ~(1u << (pos & 31)));
-          const Rec r = recs[pos];
-          frec[tid] = r;
-          fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
           keptrank[tid] = -1;
         }
         for (int i = tid; i < kF * kFW; i += kNmsThreads) {
@@ -579,57 +582,82 @@ nms_segment_kernel(NmsArgs a) {
           if (kWeighted) mrg[i] = 0u;
         }
         if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
-        if (tid == 0) s_qn = 0;
-        __syncthreads();
         cursor_word = front_pos[0] >> 5;
-        lap(1);
+      }
+      if (tid == 0) { s_round[0] = nf; s_round[2] = cursor_word; }
+    }
+    cluster.sync();   // (A0) the frontier (positions) is published, the leader's bit-matrices are zeroed
+    nf = lead_round[0];
+    cursor_word = lead_round[2];
+    if (nf == 0) break;
 
-        // ================= 2. interacting pairs inside the frontier =================
-        // warp per row i, lanes over the columns j > i: circle test, IoU bound, queue, exact IoU
-        for (int i = wid; i < nf - 1; i += kNmsThreads / 32) {
-          const float xi = fx[i], yi = fy[i], ri = fr[i];
-          for (int jb = i + 1; jb < nf; jb += 32) {
-            const int j = jb + lane;
-            bool hit = false;
-            if (j < nf) {
-              ++st_circle;
-              hit = true;
-              if (prune) {
-                const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
-                hit = (dx * dx + dy * dy <= rr * rr) && iou_may_exceed(frec[i], frec[j], thr_any);
-              }
-            }
-            if (!q2_push(hit, static_cast<uint32_t>((i << 8) | j))) {  // queue full: evaluate in place (rare)
-              ++st_iou;
-              mark_pair(i, j, pair_iou(frec[i], frec[j]));
+    // ================= 2. interacting pairs inside the frontier (whole cluster) =================
+    // Every CTA loads the frontier's records; the rows of the upper-triangular pair matrix are dealt
+    // round-robin to the warps of the cluster (row i costs nf - i tests, so interleaving balances):
+    // warp per row, lanes over the columns j > i, circle test -> work queue; then bound / approximate /
+    // exact IoU on dense lanes, results OR-ed into the leader's bit-matrices through DSMEM.
+    {
+      const int *lead_front = cluster.map_shared_rank(front_pos, 0);
+      if (tid < nf) {
+        const int pos = lead_front[tid];
+        const Rec r = recs[pos];
+        frec[tid] = r;
+        fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
+      }
+      if (tid == 0) s_qn = 0;
+      __syncthreads();
+      if (leader) lap(1);
+      uint32_t *lead_sup = cluster.map_shared_rank(sup, 0);
+      uint32_t *lead_mrg = cluster.map_shared_rank(mrg, 0);
+      auto mark_remote = [&](int i, int j, bool above, bool above_m) {
+        if (above) { ++st_hit; atomicOr(&lead_sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
+        if (kWeighted && above_m) atomicOr(&lead_mrg[i * kFW + (j >> 5)], 1u << (j & 31));
+      };
+      for (int i = crank * (kNmsThreads / 32) + wid; i < nf - 1; i += P * (kNmsThreads / 32)) {
+        const float xi = fx[i], yi = fy[i], ri = fr[i];
+        for (int jb = i + 1; jb < nf; jb += 32) {
+          const int j = jb + lane;
+          bool hit = false;
+          if (j < nf) {
+            ++st_circle;
+            hit = true;
+            if (prune) {
+              const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
+              hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
             }
           }
+          if (!q2_push(hit, static_cast<uint32_t>((i << 10) | j))) {  // queue full: evaluate in place (rare)
+            ++st_iou;
+            const float iou = pair_iou(frec[i], frec[j]);
+            mark_remote(i, j, iou > a.thr, kWeighted && iou > a.mthr);
+          }
         }
-        __syncthreads();
-        eval_queue(min(s_qn, kQ2Cap),
-                   [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 8]; rb = frec[queue2[q] & 255]; },
-                   [&](int q, bool above, bool above_m) {
-                     const int i = queue2[q] >> 8, j = queue2[q] & 255;
-                     if (above) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
-                     if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
-                   });
-        __syncthreads();
-        lap(2);
-
+      }
+      __syncthreads();
+      eval_queue(min(s_qn, kQ2Cap),
+                 [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
+                 [&](int q, bool above, bool above_m) {
+                   mark_remote(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
+                 });
+    }
+    cluster.sync();   // (A1) every CTA's pair results are in the leader's bit-matrices
+    if (leader) {
+      lap(2);
+      {
         // ================= 3. greedy resolution of the frontier =================
         // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
         // parallel; only the rest needs the dependent scan, done by one warp.
         {
           const int w = tid & (kFW - 1);
           uint32_t colbits = 0u;
-          for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
+          for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
           if (colbits) atomicOr(&s_haspred[w], colbits);
         }
         __syncthreads();
         {
           const int w = tid & (kFW - 1);
           uint32_t rm = 0u;
-          for (int i = tid >> 3; i < nf; i += kNmsThreads / kFW)
+          for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW)
             if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
           if (rm) atomicOr(&s_removed[w], rm);
         }
@@ -785,7 +813,7 @@ nms_segment_kernel(NmsArgs a) {
           j = wbuf[lane];
           pass = !prune || iou_may_exceed(rk, recs[j], thr_any);
         }
-        if (!q2_push(pass, (j << 8) | static_cast<uint32_t>(t))) {
+        if (!q2_push(pass, (j << 10) | static_cast<uint32_t>(t))) {
           if (kWeighted) {
             s_overflow = 1;   // redo this round's kill phase with the exact serial fallback
           } else {            // hard mode only needs ANY suppressor: evaluate in place
@@ -870,9 +898,9 @@ nms_segment_kernel(NmsArgs a) {
     {
       const int qn = min(s_qn, kQ2Cap);
       if (!kWeighted) {
-        eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 255]; rb = recs[queue2[q] >> 8]; },
+        eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 1023]; rb = recs[queue2[q] >> 10]; },
                    [&](int q, bool above, bool) {
-                     if (above) { ++st_hit; kill(static_cast<int>(queue2[q] >> 8)); }
+                     if (above) { ++st_hit; kill(static_cast<int>(queue2[q] >> 10)); }
                    });
       } else {
         // the queue of ANY CTA overflowing sends the whole round to the exact serial fallback
@@ -881,17 +909,17 @@ nms_segment_kernel(NmsArgs a) {
         for (int r = 0; r < P; ++r) overflow |= *cluster.map_shared_rank(&s_overflow, r) != 0;
         if (!overflow) {
           // pass 1: the two comparisons of every queued pair; remember each candidate's FIRST suppressor
-          eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 255]; rb = recs[queue2[q] >> 8]; },
+          eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 1023]; rb = recs[queue2[q] >> 10]; },
                      [&](int q, bool above, bool above_m) {
                        qflag[q] = (above ? 1u : 0u) | (above_m ? 2u : 0u);
-                       if (above) atomicMin(&firstsup[queue2[q] >> 8], static_cast<int>(queue2[q] & 255));
+                       if (above) atomicMin(&firstsup[queue2[q] >> 10], static_cast<int>(queue2[q] & 1023));
                      });
           __threadfence();
           cluster.sync();   // (B) every CTA's first-suppressor votes are in
           // pass 2: merges up to and including the first suppressor; the suppressor clears the bit
           for (int q = tid; q < qn; q += kNmsThreads) {
             const uint32_t e = queue2[q];
-            const int j = e >> 8, t = e & 255;
+            const int j = e >> 10, t = e & 1023;
             const int fs = __ldcg(&firstsup[j]);
             if (t > fs) continue;
             if (qflag[q] & 2u) accumulate(slot0 + t, j);
@@ -1097,10 +1125,11 @@ static NmsLayout nms_layout(void *scratch, int n, int S, bool weighted, int D, i
 template <typename Rec, bool kWeighted>
 static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStream_t s) {
   const int nwords = (max_seg_n + 31) / 32;
-  const size_t smem = nms_smem_bytes<Rec, kWeighted>(nwords);
+  constexpr int kF = Frontier<kWeighted>::kF;
+  const size_t smem = nms_smem_bytes<Rec, kWeighted, kF>(nwords);
   // the alive bitmap lives in shared memory and grid entries index candidates with 20 bits
   if (smem > 200 * 1024 || max_seg_n >= (1 << 20)) return RV3D_ERR_ARG;
-  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted>,
+  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted, kF>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   // one cluster per segment; as many CTAs per cluster as the 148 SMs allow (1 CTA / SM), at most 8
   int P = kNumSMs / (S > 0 ? S : 1);
@@ -1117,7 +1146,7 @@ static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStrea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RV3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_segment_kernel<Rec, kWeighted>, a));
+  RV3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_segment_kernel<Rec, kWeighted, kF>, a));
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
