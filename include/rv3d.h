@@ -101,6 +101,30 @@ int rv3d_range_view_coordinates(double *sph, const int64_t *laser, const int64_t
                                 int32_t n_azimuth_bins, int32_t col_mode, double *hybrid,
                                 rv3d_stream_t stream);
 
+/* Loader-side post-processing of a rasterized range image, fused:
+ * feature / cart / mask assembly (prototype/loader.py:623-650: column selection, Waymo tanh(intensity),
+ * mask = range > 0) and subsample_range_view (prototype/loader.py:792-815: features *= mask, pad
+ * [pad, pad] along W in `circular` or `constant` mode, keep every x_stride-th column).
+ * image (B,7,H,W) f32 [az,inc,range,x,y,z,intensity] -> features (B,F,H,Wo), cart (B,3,H,Wo) f32,
+ * mask (B,1,H,Wo) u8, Wo = ceil((W + 2 pad) / x_stride). */
+#define RV3D_PAD_CIRCULAR 0
+#define RV3D_PAD_CONSTANT 1
+typedef struct {
+  int32_t batch, height, width;
+  int32_t x_stride, pad, pad_mode;
+  int32_t n_features;
+  int32_t feature_channel[8]; /* channel of `image` feeding feature f (0..6) */
+  int32_t tanh_channel;       /* image channel passed through tanh (Waymo intensity = 6), or -1 */
+} rv3d_inputs_params;
+int rv3d_range_view_inputs(const rv3d_inputs_params *p, const float *image, float *features, float *cart,
+                           uint8_t *mask, rv3d_stream_t stream);
+/* subsample_range_view alone (prototype/loader.py:792-815) on already assembled tensors:
+ * range_view (B,C,H,W) f32, mask (B,1,H,W) u8, cart (B,3,H,W) f32 -> the same three, padded and strided. */
+int rv3d_subsample_range_view(const float *range_view, const uint8_t *mask, const float *cart, int32_t batch,
+                              int32_t channels, int32_t height, int32_t width, int32_t x_stride, int32_t pad,
+                              int32_t pad_mode, float *out_range_view, uint8_t *out_mask, float *out_cart,
+                              rv3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * 2. Decoding
  * replaces: math/ops/coding.py:110-144 decode_range_view (+ :79-107 egovehicle_from_azimuth)

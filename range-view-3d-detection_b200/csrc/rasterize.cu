@@ -204,6 +204,71 @@ __global__ void rv_coordinates_kernel(double *__restrict__ sph, const int64_t *_
   hybrid[3 * i + 2] = sph[3 * i + 2];
 }
 
+// ---------------------------------------------------------------------------------------------
+// loader-side post-processing: feature / cart / mask assembly + subsample_range_view, one pass
+// ---------------------------------------------------------------------------------------------
+struct InputsArgs {
+  int B, H, W, Wo, stride, pad, mode, F, tanh_ch;
+  int ch[8];
+};
+
+__global__ void __launch_bounds__(256)
+range_view_inputs_kernel(InputsArgs a, const float *__restrict__ image, float *__restrict__ features,
+                         float *__restrict__ cart, uint8_t *__restrict__ mask) {
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;   // output pixel h * Wo + wo
+  if (o >= a.H * a.Wo) return;
+  const int h = o / a.Wo, wo = o - h * a.Wo;
+  int w = wo * a.stride - a.pad;                          // column in the unpadded image
+  bool inside = true;
+  if (w < 0 || w >= a.W) {
+    if (a.mode == RV3D_PAD_CIRCULAR) { w %= a.W; if (w < 0) w += a.W; }
+    else inside = false;                                  // constant (zero) padding
+  }
+  const int HW = a.H * a.W, HWo = a.H * a.Wo;
+  const float *src = image + static_cast<size_t>(b) * 7 * HW + h * a.W + w;
+  const bool valid = inside && src[2 * HW] > 0.0f;        // mask = range > 0 (loader.py:645-650)
+  for (int f = 0; f < a.F; ++f) {
+    float v = 0.f;
+    if (inside) {
+      v = src[static_cast<size_t>(a.ch[f]) * HW];
+      if (a.ch[f] == a.tanh_ch) v = tanhf(v);             // Waymo: intensity.tanh() (loader.py:625-626)
+      v = valid ? v : v * 0.0f;                           // range_view *= mask (loader.py:808)
+    }
+    features[(static_cast<size_t>(b) * a.F + f) * HWo + o] = v;
+  }
+  for (int k = 0; k < 3; ++k)
+    cart[(static_cast<size_t>(b) * 3 + k) * HWo + o] = inside ? src[static_cast<size_t>(3 + k) * HW] : 0.f;
+  mask[static_cast<size_t>(b) * HWo + o] = valid ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+subsample_range_view_kernel(const float *__restrict__ rv, const uint8_t *__restrict__ mask,
+                            const float *__restrict__ cart, int C, int H, int W, int Wo, int stride, int pad,
+                            int mode, float *__restrict__ o_rv, uint8_t *__restrict__ o_mask,
+                            float *__restrict__ o_cart) {
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= H * Wo) return;
+  const int h = o / Wo, wo = o - h * Wo;
+  int w = wo * stride - pad;
+  bool inside = true;
+  if (w < 0 || w >= W) {
+    if (mode == RV3D_PAD_CIRCULAR) { w %= W; if (w < 0) w += W; }
+    else inside = false;
+  }
+  const int HW = H * W, HWo = H * Wo, p = h * W + w;
+  const uint8_t m = inside ? mask[static_cast<size_t>(b) * HW + p] : 0;
+  for (int c = 0; c < C; ++c) {
+    float v = 0.f;
+    if (inside) { v = rv[(static_cast<size_t>(b) * C + c) * HW + p]; v = m ? v : v * 0.0f; }   // range_view *= mask
+    o_rv[(static_cast<size_t>(b) * C + c) * HWo + o] = v;
+  }
+  for (int k = 0; k < 3; ++k)
+    o_cart[(static_cast<size_t>(b) * 3 + k) * HWo + o] = inside ? cart[(static_cast<size_t>(b) * 3 + k) * HW + p] : 0.f;
+  o_mask[static_cast<size_t>(b) * HWo + o] = m ? 1 : 0;
+}
+
 static RasterArgs make_args(const rv3d_raster_params *p) {
   RasterArgs a;
   a.B = p->batch; a.max_points = p->max_points; a.H = p->height; a.W = p->width;
@@ -308,6 +373,43 @@ extern "C" int rv3d_range_view_coordinates(double *sph, const int64_t *laser, co
   a.bin_scale = static_cast<double>(n_azimuth_bins) / 6.283185307179586;
   rv_coordinates_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       sph, laser, laser_mapping, n_mapping, n, n_inclination_bins, a, hybrid);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_range_view_inputs(const rv3d_inputs_params *p, const float *image, float *features,
+                                      float *cart, uint8_t *mask, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && image && features && cart && mask);
+  RV3D_CHECK_ARG(p->batch > 0 && p->height > 0 && p->width > 0 && p->x_stride > 0 && p->pad >= 0);
+  RV3D_CHECK_ARG(p->pad_mode == RV3D_PAD_CIRCULAR || p->pad_mode == RV3D_PAD_CONSTANT);
+  RV3D_CHECK_ARG(p->n_features >= 0 && p->n_features <= 8 && p->tanh_channel >= -1 && p->tanh_channel < 7);
+  RV3D_CHECK_ARG(p->pad_mode != RV3D_PAD_CIRCULAR || p->pad <= p->width);   // torch's circular pad limit
+  InputsArgs a{};
+  a.B = p->batch; a.H = p->height; a.W = p->width; a.stride = p->x_stride; a.pad = p->pad; a.mode = p->pad_mode;
+  a.Wo = (p->width + 2 * p->pad + p->x_stride - 1) / p->x_stride;
+  a.F = p->n_features; a.tanh_ch = p->tanh_channel;
+  for (int f = 0; f < a.F; ++f) {
+    RV3D_CHECK_ARG(p->feature_channel[f] >= 0 && p->feature_channel[f] < 7);
+    a.ch[f] = p->feature_channel[f];
+  }
+  dim3 grid(ceil_div(static_cast<int64_t>(a.H) * a.Wo, 256), a.B);
+  range_view_inputs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, image, features, cart, mask);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_subsample_range_view(const float *range_view, const uint8_t *mask, const float *cart,
+                                         int32_t batch, int32_t channels, int32_t height, int32_t width,
+                                         int32_t x_stride, int32_t pad, int32_t pad_mode, float *out_range_view,
+                                         uint8_t *out_mask, float *out_cart, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(range_view && mask && cart && out_range_view && out_mask && out_cart);
+  RV3D_CHECK_ARG(batch > 0 && channels >= 0 && height > 0 && width > 0 && x_stride > 0 && pad >= 0);
+  RV3D_CHECK_ARG(pad_mode == RV3D_PAD_CIRCULAR || pad_mode == RV3D_PAD_CONSTANT);
+  RV3D_CHECK_ARG(pad_mode != RV3D_PAD_CIRCULAR || pad <= width);
+  const int Wo = (width + 2 * pad + x_stride - 1) / x_stride;
+  dim3 grid(ceil_div(static_cast<int64_t>(height) * Wo, 256), batch);
+  subsample_range_view_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      range_view, mask, cart, channels, height, width, Wo, x_stride, pad, pad_mode, out_range_view, out_mask, out_cart);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }

@@ -25,6 +25,12 @@ class RasterParams(C.Structure):
                 ("reserved", C.c_int32), ("lidar_offset", C.c_double * 3), ("min_distance", C.c_double)]
 
 
+class InputsParams(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("x_stride", C.c_int32),
+                ("pad", C.c_int32), ("pad_mode", C.c_int32), ("n_features", C.c_int32),
+                ("feature_channel", C.c_int32 * 8), ("tanh_channel", C.c_int32)]
+
+
 class Partitions(C.Structure):
     _fields_ = [("n_partitions", C.c_int32), ("lower", C.c_float * MAX_PARTITIONS),
                 ("upper", C.c_float * MAX_PARTITIONS), ("rate", C.c_int32 * MAX_PARTITIONS)]
@@ -60,6 +66,8 @@ _SIGNATURES = {
     "rv3d_zbuffer": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _I64, _I32, _I32, _D, _P, _P, _P, _SZ, _P]),
     "rv3d_cart_to_sph": (C.c_int, [_P, _P, _I64, _P]),
     "rv3d_range_view_coordinates": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P]),
+    "rv3d_range_view_inputs": (C.c_int, [C.POINTER(InputsParams), _P, _P, _P, _P, _P]),
+    "rv3d_subsample_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rv3d_decode_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "rv3d_num_candidates": (_I64, [C.POINTER(Partitions), _I32, _I32]),
     "rv3d_sample_by_range": (C.c_int, [_P, _P, _P, _P, C.POINTER(Partitions), _I32, _I32, _I32, _P, _P, _P, _P]),

@@ -45,7 +45,7 @@ REF = Path("/root/reference")
 OUT = Path(__file__).resolve().parent
 
 _STUB_TOPLEVEL = {"polars", "omegaconf", "weighted_nms_ext", "detectron2", "kornia", "mmcv", "av2",
-                  "pytorch_lightning", "lightning", "hydra", "wandb", "filelock", "cv2", "kornia", "pyarrow"}
+                  "pytorch_lightning", "lightning", "hydra", "wandb", "filelock", "cv2", "kornia", "pyarrow", "joblib", "tqdm"}
 
 
 class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
@@ -177,6 +177,26 @@ def main():
         np.savez_compressed(OUT / f"nms_{mode.lower()}.npz", cuboids=cub.numpy(), scores=sc.numpy(),
                             categories=ca.numpy(), out_cuboids=o[0].numpy(), out_scores=o[1].numpy(),
                             out_categories=o[2].numpy(), out_batch_index=o[3].numpy())
+    # ---------------- loader-side subsample_range_view -------------------------
+    # the module itself cannot be imported (its Lightning base classes are stubs), so the function's own
+    # source is extracted with ast and executed verbatim
+    import ast
+    import types
+    src = (REF / "src/torchbox3d/prototype/loader.py").read_text()
+    fn_src = next(ast.get_source_segment(src, n) for n in ast.parse(src).body
+                  if isinstance(n, ast.FunctionDef) and n.name == "subsample_range_view")
+    ref_loader = types.SimpleNamespace()
+    ns = {"torch": torch, "Tensor": torch.Tensor, "Tuple": __import__("typing").Tuple}
+    exec(fn_src, ns)
+    ref_loader.subsample_range_view = ns["subsample_range_view"]
+    xyz, inten, laser = synth.make_points(12000, 16, 21, offset=off)
+    img = torch.from_numpy(ref_rasterize(xyz, inten, laser, np.arange(16), off, 16, 300))
+    feats, cart, mask = img[[6, 2, 3, 4, 5]].clone(), img[3:6].clone(), img[2:3] > 0
+    outs = {}
+    for ds, stride, mode in (("av2", 1, "circular"), ("av2", 4, "circular"), ("waymo", 4, "constant")):
+        f, m, c = ref_loader.subsample_range_view(feats.clone(), mask.clone(), cart.clone(), ds, stride, mode)
+        outs[f"{ds}_{stride}_{mode}_f"], outs[f"{ds}_{stride}_{mode}_m"], outs[f"{ds}_{stride}_{mode}_c"] = f.numpy(), m.numpy(), c.numpy()
+    np.savez_compressed(OUT / "subsample.npz", features=feats.numpy(), cart=cart.numpy(), mask=mask.numpy(), **outs)
     print("golden vectors written to", OUT)
 
 

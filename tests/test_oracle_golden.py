@@ -90,3 +90,13 @@ def test_empty_and_bad_mode():
     assert [tuple(x.shape) for x in o] == [(0, 7), (0, 1), (0, 1), (0, 1)]      # nms.py:250-253
     with pytest.raises(NotImplementedError):
         oracle.batched_multiclass_nms(cub, sc, ca, 10, 10, 0.3, 0.1, "soft")
+
+
+def test_subsample_range_view_matches_reference():
+    g = _load("subsample.npz")
+    feats, cart, mask = (torch.from_numpy(g[k]) for k in ("features", "cart", "mask"))
+    for ds, stride, mode in (("av2", 1, "circular"), ("av2", 4, "circular"), ("waymo", 4, "constant")):
+        f, m, c = oracle.subsample_range_view(feats.clone(), mask.clone(), cart.clone(), ds, stride, mode)
+        assert np.array_equal(f.numpy(), g[f"{ds}_{stride}_{mode}_f"])
+        assert np.array_equal(m.numpy(), g[f"{ds}_{stride}_{mode}_m"])
+        assert np.array_equal(c.numpy(), g[f"{ds}_{stride}_{mode}_c"])
