@@ -299,7 +299,7 @@ nms_segment_kernel(NmsArgs a) {
   static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsThreads / 32 + 1];
-  __shared__ int s_qn, s_nk, s_nos, s_overflow;
+  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_overflow;
   __shared__ int s_next;       // leader: next kept box to hand out in the kill scan (dynamic load balance)
   __shared__ int s_round[8];   // leader -> cluster: {nf, nk, cursor_word, -, n oversize}
   __shared__ GridGeom s_geom;  // leader -> cluster
@@ -493,6 +493,26 @@ nms_segment_kernel(NmsArgs a) {
     return true;
   };
 
+  // bound -> approximate -> exact for ONE pair, in place (overflow paths; divergent, so only a fallback)
+  auto classify_pair = [&](const Rec &ra, const Rec &rb, bool &above, bool &above_m) {
+    int d1 = 0, d2 = 0;
+    if (prune) {
+      if (!iou_may_exceed(ra, rb, thr_any)) { above = false; above_m = false; return; }
+      const Obb oa = obb_of(ra), ob = obb_of(rb);
+      if (obb_sane(oa) && obb_sane(ob)) {
+        const float ap = approx_iou(oa, ob);
+        ++st_approx;
+        d1 = decide_vs(ap, a.thr);
+        d2 = kWeighted ? decide_vs(ap, a.mthr) : 1;
+      }
+    }
+    if (d1 != 0 && d2 != 0) { above = d1 > 0; above_m = kWeighted && d2 > 0; return; }
+    const float iou = pair_iou(ra, rb);
+    ++st_iou;
+    above = iou > a.thr;
+    above_m = kWeighted && iou > a.mthr;
+  };
+
   // Two-stage evaluation of a queue of pairs, warp-converged: every lane classifies its pair with the
   // approximate IoU; the few undecided pairs are compacted per warp (wbuf) so that the exact routine
   // always runs on (nearly) full warps.  get(q, ra, rb) loads the pair, emit(q, above_thr, above_mthr)
@@ -604,7 +624,7 @@ nms_segment_kernel(NmsArgs a) {
         frec[tid] = r;
         fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
       }
-      if (tid == 0) s_qn = 0;
+      if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
       __syncthreads();
       if (leader) lap(1);
       uint32_t *lead_sup = cluster.map_shared_rank(sup, 0);
@@ -613,32 +633,66 @@ nms_segment_kernel(NmsArgs a) {
         if (above) { ++st_hit; atomicOr(&lead_sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
         if (kWeighted && above_m) atomicOr(&lead_mrg[i * kFW + (j >> 5)], 1u << (j & 31));
       };
-      for (int i = crank * (kNmsThreads / 32) + wid; i < nf - 1; i += P * (kNmsThreads / 32)) {
-        const float xi = fx[i], yi = fy[i], ri = fr[i];
-        for (int jb = i + 1; jb < nf; jb += 32) {
-          const int j = jb + lane;
-          bool hit = false;
-          if (j < nf) {
-            ++st_circle;
-            hit = true;
-            if (prune) {
-              const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
-              hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
+      // One queue reservation per ROW (a single-address shared atomic per 32-column batch serialises the
+      // CTA on dense frontiers): lane b keeps the hit mask of the row's b-th batch, the warp reserves the
+      // row's total once and every lane writes out its own batch.  A row that does not fit waits for the
+      // next drain: reservations are handed out in order, so everything before the first refused one
+      // (s_qvalid) is written and everything after it is refused too.
+      static_assert(kF <= 1024, "a row's batches must fit one mask per lane");
+      constexpr int kWarps = kNmsThreads / 32;
+      int i = crank * kWarps + wid;
+      for (;;) {
+        while (i < nf - 1) {
+          const float xi = fx[i], yi = fy[i], ri = fr[i];
+          uint32_t mymask = 0;
+          for (int jb = i + 1, b = 0; jb < nf; jb += 32, ++b) {
+            const int j = jb + lane;
+            bool hit = false;
+            if (j < nf) {
+              ++st_circle;
+              hit = true;
+              if (prune) {
+                const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
+                hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
+              }
             }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (lane == b) mymask = m;
           }
-          if (!q2_push(hit, static_cast<uint32_t>((i << 10) | j))) {  // queue full: evaluate in place (rare)
-            ++st_iou;
-            const float iou = pair_iou(frec[i], frec[j]);
-            mark_remote(i, j, iou > a.thr, kWeighted && iou > a.mthr);
+          const int mine = __popc(mymask);
+          int incl = mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
           }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_qn, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + total > kQ2Cap) {
+              if (lane == 0) atomicMin(&s_qvalid, base);
+              break;   // this row is redone after the drain
+            }
+            int slot = base + incl - mine;
+            const int j0 = i + 1 + 32 * lane;
+            for (uint32_t m = mymask; m; m &= m - 1)
+              queue2[slot++] = static_cast<uint32_t>((i << 10) | (j0 + __ffs(m) - 1));
+          }
+          i += P * kWarps;
         }
+        const int more = __syncthreads_or(i < nf - 1);
+        eval_queue(min(s_qn, s_qvalid),
+                   [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
+                   [&](int q, bool above, bool above_m) {
+                     mark_remote(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
+                   });
+        if (!more) break;
+        __syncthreads();
+        if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
+        __syncthreads();
       }
-      __syncthreads();
-      eval_queue(min(s_qn, kQ2Cap),
-                 [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
-                 [&](int q, bool above, bool above_m) {
-                   mark_remote(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
-                 });
     }
     cluster.sync();   // (A1) every CTA's pair results are in the leader's bit-matrices
     if (leader) {
@@ -817,8 +871,9 @@ nms_segment_kernel(NmsArgs a) {
           if (kWeighted) {
             s_overflow = 1;   // redo this round's kill phase with the exact serial fallback
           } else {            // hard mode only needs ANY suppressor: evaluate in place
-            ++st_iou;
-            if (pair_iou(rk, recs[j]) > a.thr) kill(j);
+            bool above, above_m;
+            classify_pair(rk, recs[j], above, above_m);
+            if (above) { ++st_hit; kill(j); }
           }
         }
         __syncwarp();
@@ -938,10 +993,10 @@ nms_segment_kernel(NmsArgs a) {
                   const float dx = kx[t] - jx, dy = ky[t] - jy, rr = kr[t] + rj.r;
                   if (!(dx * dx + dy * dy <= rr * rr)) continue;
                 }
-                const float iou = pair_iou(krec[t], rj);
-                ++st_iou;
-                if (iou > a.mthr) accumulate(slot0 + t, j);
-                if (iou > a.thr) { kill(j); break; }
+                bool above, above_m;
+                classify_pair(krec[t], rj, above, above_m);
+                if (above_m) accumulate(slot0 + t, j);
+                if (above) { kill(j); break; }
               }
             }
           }

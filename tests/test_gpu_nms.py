@@ -222,3 +222,15 @@ def test_degenerate_boxes():
     ref = oracle.batched_multiclass_nms(cub, sc, ca, 50000, 1000, -1.0, 0.1, "HARD")
     got = batched_multiclass_nms(cub.to(DEV), sc.to(DEV), ca.to(DEV), 50000, 1000, -1.0, 0.1, "HARD")
     assert torch.equal(got[1].cpu(), ref[1]) and got[1].shape[0] <= 3
+
+
+def test_config3_weighted_stress_200k():
+    """BASELINE config 3: one class, 200 000 candidates >= 0.1 clustered around 256 objects,
+    num_pre_nms = 200 000, WEIGHTED (TorchEx is not installable here: compared against the oracle)."""
+    from rv3d.math.ops.nms import batched_multiclass_nms
+    cub, sc, ca = synth.make_nms_candidates(1, 200_000, 1, 256, seed=123, spread=75.0, frac_clustered=0.97)
+    sc = 0.1 + 0.9 * sc                                           # every candidate passes min_confidence
+    ref = oracle.batched_multiclass_nms(cub, sc, ca, 200_000, 1000, 0.3, 0.1, "WEIGHTED")
+    got = batched_multiclass_nms(cub.to(DEV), sc.to(DEV), ca.to(DEV), 200_000, 1000, 0.3, 0.1, "WEIGHTED")
+    assert torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[2].cpu(), ref[2])
+    np.testing.assert_allclose(got[0].cpu().numpy(), ref[0].numpy(), rtol=1e-5, atol=1e-5)

@@ -130,3 +130,20 @@ def test_idempotent_and_deterministic():
     c = _run(xyz[perm], inten[perm], laser[perm], np.arange(64), synth.LIDAR_OFFSET, 64, 1800)
     ref = oracle.build_range_view(xyz[perm], inten[perm], laser[perm], np.arange(64), synth.LIDAR_OFFSET, 64, 1800, 1800)
     _check_image(c[0], ref)
+
+
+@pytest.mark.parametrize("W", [900, 1800, 3600])
+def test_config4_multi_resolution(W):
+    """BASELINE config 4: the same sweeps rasterized at 64 x {900, 1800, 3600}."""
+    from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
+    dev = torch.device("cuda:0")
+    sweeps = [synth.make_points(100_000, 64, 40 + s) for s in range(4)]
+    pts, las, cnt = pack_sweeps(sweeps, dev)
+    mapping = torch.as_tensor(oracle.ROW_MAPPING_64.astype(np.int32), device=dev)
+    img, win = rasterize_sweeps(pts.to(dev), las.to(dev), cnt.to(dev), mapping, synth.LIDAR_OFFSET, height=64,
+                                width=W, return_winner=True)
+    for b, (xyz, inten, laser) in enumerate(sweeps):
+        ref_img, ref_win = oracle.build_range_view(xyz, inten, laser, oracle.ROW_MAPPING_64, synth.LIDAR_OFFSET,
+                                                   num_lasers=64, width=W, n_azimuth_bins=W, return_winner=True)
+        assert np.array_equal(win[b].cpu().numpy(), ref_win)
+        _check_image(img[b].cpu().numpy(), ref_img)
