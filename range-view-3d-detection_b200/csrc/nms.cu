@@ -25,6 +25,7 @@
 // have IoU exactly 0 (iou.cuh padded_radius).  IoU evaluations drop from O(N * kept) on
 // every candidate to (alive candidates near a kept box).
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
 
@@ -1186,21 +1187,30 @@ static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStrea
   if (smem > 200 * 1024 || max_seg_n >= (1 << 20)) return RV3D_ERR_ARG;
   RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted, kF>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  // one cluster per segment; as many CTAs per cluster as the 148 SMs allow (1 CTA / SM), at most 8
-  int P = kNumSMs / (S > 0 ? S : 1);
-  P = P < 1 ? 1 : (P > 8 ? 8 : P);
+  // One cluster per segment, 1 CTA / SM, P = ceil(148 / S) CTAs per cluster (at most 4).  Rounding UP
+  // oversubscribes the machine a little (S = 48 -> 192 CTAs; GPC boundaries only let 45 clusters of 3 or
+  // 36 of 4 be co-resident anyway): segments finish at different times, so late clusters start in the
+  // gaps, and the larger cluster shortens every segment.  Measured at S = 48: P = 2 / 3 / 4 / 6 / 8 ->
+  // 1.03 / 0.99 / 0.96 / 1.00 / 1.12 ms for the whole sort + NMS + pack stage; at S = 24: P = 3 / 4 / 7 / 8
+  // -> 0.80 / 0.71 / 0.78 / 0.77 ms (the leader-only phases and the cluster barriers stop paying beyond 4).
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(S * P));
   cfg.blockDim = dim3(kNmsThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(P);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int P = (kNumSMs + S - 1) / (S > 0 ? S : 1);
+  P = P < 1 ? 1 : (P > 4 ? 4 : P);
+  if (const char *e = getenv("RV3D_NMS_CLUSTER")) {   // experiments only
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) P = v;
+  }
+  attr[0].val.clusterDim.x = static_cast<unsigned>(P);
+  cfg.gridDim = dim3(static_cast<unsigned>(S * P));
   RV3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_segment_kernel<Rec, kWeighted, kF>, a));
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
