@@ -136,11 +136,13 @@ int rv3d_subsample_range_view(const float *range_view, const uint8_t *mask, cons
 #define RV3D_BF16 2
 #define RV3D_MAX_PARTITIONS 8
 
-/* decode_range_view: regressands (B,8,H,W), cart (B,3,H,W) -> out (B,7,H,W), all `dtype`;
- * arithmetic in f64 (coding.py:126-128), one cast at the end (:144). */
+/* decode_range_view: regressands (B,8,H,W) in `dtype`, cart (B,3,H,W) in `cart_dtype` -> out (B,7,H,W) in
+ * `dtype` (coding.py:126: the result takes the regressands' dtype); arithmetic in f64 (coding.py:127-128),
+ * one cast at the end (:144).  Supported pairs: cart_dtype == dtype, or RV3D_F32 cart with F16 / BF16
+ * regressands (the autocast case, nn/arch/detector.py:329-333); anything else is RV3D_ERR_ARG. */
 int rv3d_decode_range_view(const void *regressands, const void *cart, void *out, int32_t dtype,
-                           int32_t batch, int32_t height, int32_t width, int32_t azimuth_invariant,
-                           rv3d_stream_t stream);
+                           int32_t cart_dtype, int32_t batch, int32_t height, int32_t width,
+                           int32_t azimuth_invariant, rv3d_stream_t stream);
 
 typedef struct {
   int32_t n_partitions;                 /* 0 = sample_by_range disabled (BCHW_to_BKC) */
@@ -161,7 +163,8 @@ int rv3d_sample_by_range(const float *scores, const int64_t *categories, const f
 
 typedef struct {
   int32_t batch, n_classes, height, width;
-  int32_t dtype;             /* RV3D_F32 / F16 / BF16 of logits, regressands, cart          */
+  int32_t dtype;             /* RV3D_F32 / F16 / BF16 of logits and regressands             */
+  int32_t cart_dtype;        /* dtype of cart: == dtype, or RV3D_F32 under autocast         */
   int32_t azimuth_invariant; /* enable_azimuth_invariant_targets                            */
   int32_t category_offset;   /* task_offset (range_decoder.py:77)                           */
   int32_t candidate_offset;  /* index of this (stride, task)'s first candidate in the
@@ -175,7 +178,8 @@ typedef struct {
 
 /* Fused: sigmoid * mask, max over classes, threshold, decode of the survivors only,
  * range-partition subsampling, warp-aggregated compaction.
- * logits (B,C,H,W), regressands (B,8,H,W), cart (B,3,H,W) in `dtype`; mask (B,1,H,W) u8/bool.
+ * logits (B,C,H,W), regressands (B,8,H,W) in `dtype`, cart (B,3,H,W) in `cart_dtype`; mask (B,1,H,W) u8/bool.
+ * Scores, threshold and boxes are rounded to `dtype`, the range partition (cart.norm) to `cart_dtype`.
  * Survivor r gets: out_keys[r] = sort key (sweep, class | score desc | candidate asc),
  * out_boxes[r] = 8 f32 [x,y,z,l,w,h,yaw,score].  *counter (device i32) is advanced
  * atomically, so several (stride, task) calls append to the same arrays; rows past

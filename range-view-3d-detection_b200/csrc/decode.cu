@@ -36,6 +36,7 @@ template <> struct Ld<float> {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ float cast(double x) { return static_cast<float>(x); }
+  static __device__ __forceinline__ float round_f32(float x) { return x; }
 };
 template <> struct Ld<__half> {
   static __device__ __forceinline__ float one(const __half *p) { return __half2float(*p); }
@@ -45,6 +46,7 @@ template <> struct Ld<__half> {
     v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
   }
   static __device__ __forceinline__ __half cast(double x) { return __double2half(x); }
+  static __device__ __forceinline__ float round_f32(float x) { return __half2float(__float2half_rn(x)); }
 };
 template <> struct Ld<__nv_bfloat16> {
   static __device__ __forceinline__ float one(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
@@ -54,6 +56,7 @@ template <> struct Ld<__nv_bfloat16> {
     v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
   }
   static __device__ __forceinline__ __nv_bfloat16 cast(double x) { return __double2bfloat16(x); }
+  static __device__ __forceinline__ float round_f32(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 };
 
 // sigmoid the way the reference's own CUDA path evaluates it (range_decoder.py:49: torch's CUDA sigmoid
@@ -90,9 +93,11 @@ __device__ __forceinline__ void decode_box(const float (&reg)[8], const float (&
 // ------------------------------------------------------------------------------------------
 // decode_range_view as a dense operator: (B,8,H,W) + (B,3,H,W) -> (B,7,H,W)
 // ------------------------------------------------------------------------------------------
-template <typename T>
+// T = dtype of the regressands and of the result (coding.py:126,144); TC = dtype of cart, widened on its own
+// (coding.py:128) -- under autocast the heads are half precision while cart stays float32
+template <typename T, typename TC>
 __global__ void __launch_bounds__(256)
-decode_dense_kernel(const T *__restrict__ reg, const T *__restrict__ cart, T *__restrict__ out, int HW,
+decode_dense_kernel(const T *__restrict__ reg, const TC *__restrict__ cart, T *__restrict__ out, int HW,
                     int az_inv) {
   const int b = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,7 +106,7 @@ decode_dense_kernel(const T *__restrict__ reg, const T *__restrict__ cart, T *__
 #pragma unroll
   for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(reg + (static_cast<size_t>(b) * 8 + k) * HW + p);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) c[k] = Ld<T>::one(cart + (static_cast<size_t>(b) * 3 + k) * HW + p);
+  for (int k = 0; k < 3; ++k) c[k] = Ld<TC>::one(cart + (static_cast<size_t>(b) * 3 + k) * HW + p);
   double o[7];
   decode_box(r, c, az_inv != 0, o);
 #pragma unroll
@@ -247,8 +252,8 @@ template <> struct Sm<__nv_bfloat16> {
 constexpr int kPxPerThread = 4;
 
 // bytes of dynamic shared memory for a tile of kTile pixels
-static size_t decode_smem_bytes(int C, int tile, size_t elem) {
-  size_t b = static_cast<size_t>(C + 11) * tile * elem;   // logits, regressands, cart planes
+static size_t decode_smem_bytes(int C, int tile, size_t elem, size_t cart_elem) {
+  size_t b = static_cast<size_t>(C + 8) * tile * elem + static_cast<size_t>(3) * tile * cart_elem;   // logits, regressands, cart planes
   b += tile;                                              // mask
   b = align_up(b, 16);
   b += static_cast<size_t>(tile) * (2 + 2 + 1 + 2 + 2 + 4 + 4);   // q_pix, q_meta, q_emit, q_h, q_w, q_score, q_off
@@ -261,10 +266,10 @@ static size_t decode_smem_bytes(int C, int tile, size_t elem) {
 //           per-thread loads; several resident CTAs overlap each other's copies and math); without
 //           (unaligned shapes) plain cooperative loads into the same layout.
 //   phase A / scan / phase B   as described at the top of this file, reading shared memory only.
-template <typename T, int kTile, bool kBulk>
+template <typename T, typename TC, int kTile, bool kBulk>
 __global__ void __launch_bounds__(kTile / kPxPerThread)
 decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__restrict__ reg,
-                      const T *__restrict__ cart, const uint8_t *__restrict__ mask,
+                      const TC *__restrict__ cart, const uint8_t *__restrict__ mask,
                       unsigned long long *__restrict__ out_keys, float *__restrict__ out_boxes,
                       int32_t *__restrict__ counter) {
   constexpr int kThreads = kTile / kPxPerThread;
@@ -287,9 +292,9 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   // ---- carve shared memory: [C][kTile] logits | [8][kTile] reg | [3][kTile] cart | mask | queues
   T *s_logits = reinterpret_cast<T *>(dsm);
   T *s_reg = s_logits + static_cast<size_t>(a.C) * kTile;
-  T *s_cart = s_reg + 8 * kTile;
+  TC *s_cart = reinterpret_cast<TC *>(s_reg + 8 * kTile);   // (C + 8) * kTile * sizeof(T) is a multiple of 16
   uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cart + 3 * kTile);
-  unsigned char *qp = dsm + align_up_c((static_cast<size_t>(a.C) + 11) * kTile * sizeof(T) + kTile, 16);
+  unsigned char *qp = dsm + align_up_c((static_cast<size_t>(a.C) + 8) * kTile * sizeof(T) + 3 * kTile * sizeof(TC) + kTile, 16);
   float *q_score = reinterpret_cast<float *>(qp);                    // score of live pixel t
   uint32_t *q_off = reinterpret_cast<uint32_t *>(q_score + kTile);   // exclusive emit offset inside the block
   uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_off + kTile);     // local pixel id of live pixel t
@@ -308,17 +313,18 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   {
     const T *lg = logits + static_cast<size_t>(b) * a.C * HW + blk0;
     const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;
-    const T *ct = cart + static_cast<size_t>(b) * 3 * HW + blk0;
+    const TC *ct = cart + static_cast<size_t>(b) * 3 * HW + blk0;
     const uint8_t *mk = mask + static_cast<size_t>(b) * HW + blk0;
     if (kBulk) {
       if (tid == 0) mbar_init(&s_bar, 1);
       __syncthreads();
       if (tid == 0) {
         const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
-        mbar_expect_tx(&s_bar, plane * (a.C + 11) + npx);
+        const uint32_t cplane = static_cast<uint32_t>(npx) * sizeof(TC);
+        mbar_expect_tx(&s_bar, plane * (a.C + 8) + cplane * 3 + npx);
         for (int c = 0; c < a.C; ++c) bulk_g2s(s_logits + static_cast<size_t>(c) * kTile, lg + static_cast<size_t>(c) * HW, plane, &s_bar);
         for (int k = 0; k < 8; ++k) bulk_g2s(s_reg + k * kTile, rg + static_cast<size_t>(k) * HW, plane, &s_bar);
-        for (int k = 0; k < 3; ++k) bulk_g2s(s_cart + k * kTile, ct + static_cast<size_t>(k) * HW, plane, &s_bar);
+        for (int k = 0; k < 3; ++k) bulk_g2s(s_cart + k * kTile, ct + static_cast<size_t>(k) * HW, cplane, &s_bar);
         bulk_g2s(s_mask, mk, npx, &s_bar);
       }
       mbar_wait(&s_bar, 0);
@@ -362,9 +368,9 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   uint32_t n_live = 0, n_emit = 0;
   const bool zero_passes = 0.0f >= a.thr;
   float cx[4], cy[4], cz[4];
-  Sm<T>::four(s_cart + lp0, cx);
-  Sm<T>::four(s_cart + kTile + lp0, cy);
-  Sm<T>::four(s_cart + 2 * kTile + lp0, cz);
+  Sm<TC>::four(s_cart + lp0, cx);
+  Sm<TC>::four(s_cart + kTile + lp0, cy);
+  Sm<TC>::four(s_cart + 2 * kTile + lp0, cz);
 #pragma unroll
   for (int j = 0; j < kPxPerThread; ++j) {
     emit[j] = 0;
@@ -388,7 +394,8 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       if (score[j] >= a.thr) emit[j] = 1u;
     } else {
       // bit i of part_in: the pixel's range lies in partition i; the column-stride test comes below
-      const float d = norm3(cx[j], cy[j], cz[j]);
+      // cart.norm(dim=1) accumulates in float32 and rounds to cart's dtype; the bounds are a float32 tensor
+      const float d = Ld<TC>::round_f32(norm3(cx[j], cy[j], cz[j]));
       uint32_t part_in = 0u;
       for (int i = 0; i < n_parts; ++i) part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
       emit[j] = score[j] >= a.thr ? part_in : 0u;
@@ -473,7 +480,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
 #pragma unroll
     for (int k = 0; k < 8; ++k) r[k] = Sm<T>::one(s_reg + k * kTile + lp);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = Sm<T>::one(s_cart + k * kTile + lp);
+    for (int k = 0; k < 3; ++k) c[k] = Sm<TC>::one(s_cart + k * kTile + lp);
     double o[7];
     decode_box(r, c, a.az_inv != 0, o);
     // decode_range_view casts back to the input dtype (coding.py:144); widen that to f32
@@ -495,7 +502,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       } else {
         cand = s_off[i] + h * s_wsub[i] + fast_div(w, s_shift[i], s_magic[i]);
         // the partition that does not contain the pixel contributes score 0 (only when 0 >= thr)
-        const float d = norm3(c[0], c[1], c[2]);
+        const float d = Ld<TC>::round_f32(norm3(c[0], c[1], c[2]));
         if (!((d > s_lower[i]) && (d <= s_upper[i]))) s_out = 0.0f;
       }
       if (row < static_cast<uint32_t>(a.capacity)) {
@@ -554,24 +561,24 @@ __global__ void yaw_to_quat_kernel(const float *__restrict__ yaw, float *__restr
   reinterpret_cast<float4 *>(quat)[i] = make_float4(static_cast<float>(c), 0.f, 0.f, static_cast<float>(s));
 }
 
-template <typename T, int kTile, bool kBulk>
+template <typename T, typename TC, int kTile, bool kBulk>
 static int launch_decode_tile(const DecodeArgs &a, const void *logits, const void *reg, const void *cart,
                               const uint8_t *mask, unsigned long long *keys, float *boxes, int32_t *counter,
                               cudaStream_t s) {
   const int HW = a.H * a.W;
-  const size_t smem = decode_smem_bytes(a.C, kTile, sizeof(T));
+  const size_t smem = decode_smem_bytes(a.C, kTile, sizeof(T), sizeof(TC));
   if (smem > 200 * 1024) return RV3D_ERR_ARG;   // too many classes for one tile
-  RV3D_CHECK_CUDA(cudaFuncSetAttribute(decode_compact_kernel<T, kTile, kBulk>,
+  RV3D_CHECK_CUDA(cudaFuncSetAttribute(decode_compact_kernel<T, TC, kTile, kBulk>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(ceil_div(HW, kTile), a.B);
-  decode_compact_kernel<T, kTile, kBulk><<<grid, kTile / kPxPerThread, smem, s>>>(
-      a, static_cast<const T *>(logits), static_cast<const T *>(reg), static_cast<const T *>(cart), mask, keys, boxes,
+  decode_compact_kernel<T, TC, kTile, kBulk><<<grid, kTile / kPxPerThread, smem, s>>>(
+      a, static_cast<const T *>(logits), static_cast<const T *>(reg), static_cast<const TC *>(cart), mask, keys, boxes,
       counter);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
 
-template <typename T>
+template <typename T, typename TC>
 static int launch_decode_compact(const DecodeArgs &a, const void *logits, const void *reg, const void *cart,
                                  const uint8_t *mask, unsigned long long *keys, float *boxes, int32_t *counter,
                                  cudaStream_t s) {
@@ -580,44 +587,46 @@ static int launch_decode_compact(const DecodeArgs &a, const void *logits, const 
   // 16-byte boundary (HW % 16 == 0 covers the 1-byte mask plane too)
   const bool bulk = (HW % 16 == 0) && aligned(logits, 16) && aligned(reg, 16) && aligned(cart, 16) && aligned(mask, 16);
   // tile size: keep a CTA's stage under ~48 KB so 4-6 CTAs are resident per SM
-  const bool small_tile = static_cast<size_t>(a.C + 11) * 512 * sizeof(T) > 48 * 1024;
+  const bool small_tile = (static_cast<size_t>(a.C + 8) * sizeof(T) + 3 * sizeof(TC)) * 512 > 48 * 1024;
   if (bulk) {
-    if (small_tile) return launch_decode_tile<T, 256, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
-    return launch_decode_tile<T, 512, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+    if (small_tile) return launch_decode_tile<T, TC, 256, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+    return launch_decode_tile<T, TC, 512, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
   }
-  if (small_tile) return launch_decode_tile<T, 256, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
-  return launch_decode_tile<T, 512, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+  if (small_tile) return launch_decode_tile<T, TC, 256, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
+  return launch_decode_tile<T, TC, 512, false>(a, logits, reg, cart, mask, keys, boxes, counter, s);
 }
 
 }  // namespace rv3d
 
 using namespace rv3d;
 
+template <typename T, typename TC>
+static void launch_decode_dense(const void *reg, const void *cart, void *out, int HW, int batch, int az_inv, cudaStream_t s) {
+  dim3 grid(ceil_div(HW, 256), batch);
+  decode_dense_kernel<T, TC><<<grid, 256, 0, s>>>(static_cast<const T *>(reg), static_cast<const TC *>(cart),
+                                                  static_cast<T *>(out), HW, az_inv);
+}
+
+// the dtype pairs the path meets: everything in one dtype, or half-precision heads with float32 cart (autocast)
+#define RV3D_DISPATCH_DTYPES(dtype, cart_dtype, CALL)                                             \
+  do {                                                                                            \
+    if ((dtype) == RV3D_F32 && (cart_dtype) == RV3D_F32) { CALL(float, float); }                  \
+    else if ((dtype) == RV3D_F16 && (cart_dtype) == RV3D_F16) { CALL(__half, __half); }           \
+    else if ((dtype) == RV3D_BF16 && (cart_dtype) == RV3D_BF16) { CALL(__nv_bfloat16, __nv_bfloat16); } \
+    else if ((dtype) == RV3D_F16 && (cart_dtype) == RV3D_F32) { CALL(__half, float); }            \
+    else if ((dtype) == RV3D_BF16 && (cart_dtype) == RV3D_F32) { CALL(__nv_bfloat16, float); }    \
+    else return RV3D_ERR_ARG;                                                                     \
+  } while (0)
+
 extern "C" int rv3d_decode_range_view(const void *regressands, const void *cart, void *out, int32_t dtype,
-                                      int32_t batch, int32_t height, int32_t width, int32_t azimuth_invariant,
-                                      rv3d_stream_t stream) {
+                                      int32_t cart_dtype, int32_t batch, int32_t height, int32_t width,
+                                      int32_t azimuth_invariant, rv3d_stream_t stream) {
   RV3D_CHECK_ARG(regressands && cart && out && batch > 0 && height > 0 && width > 0);
   const int HW = height * width;
-  dim3 grid(ceil_div(HW, 256), batch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (dtype) {
-    case RV3D_F32:
-      decode_dense_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(regressands),
-                                                      static_cast<const float *>(cart), static_cast<float *>(out), HW,
-                                                      azimuth_invariant);
-      break;
-    case RV3D_F16:
-      decode_dense_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(regressands),
-                                                       static_cast<const __half *>(cart), static_cast<__half *>(out),
-                                                       HW, azimuth_invariant);
-      break;
-    case RV3D_BF16:
-      decode_dense_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(regressands),
-                                                              static_cast<const __nv_bfloat16 *>(cart),
-                                                              static_cast<__nv_bfloat16 *>(out), HW, azimuth_invariant);
-      break;
-    default: return RV3D_ERR_ARG;
-  }
+#define RV3D_CALL(T, TC) launch_decode_dense<T, TC>(regressands, cart, out, HW, batch, azimuth_invariant, s)
+  RV3D_DISPATCH_DTYPES(dtype, cart_dtype, RV3D_CALL);
+#undef RV3D_CALL
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
@@ -668,13 +677,10 @@ extern "C" int rv3d_decode_compact(const rv3d_decode_params *p, const void *logi
   if (bits_for(static_cast<int64_t>(p->batch) * p->total_classes) + 32 + a.kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto *keys = reinterpret_cast<unsigned long long *>(out_keys);
-  switch (p->dtype) {
-    case RV3D_F32: return launch_decode_compact<float>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
-    case RV3D_F16: return launch_decode_compact<__half>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
-    case RV3D_BF16:
-      return launch_decode_compact<__nv_bfloat16>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s);
-    default: return RV3D_ERR_ARG;
-  }
+#define RV3D_CALL(T, TC) return launch_decode_compact<T, TC>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s)
+  RV3D_DISPATCH_DTYPES(p->dtype, p->cart_dtype, RV3D_CALL);
+#undef RV3D_CALL
+  return RV3D_ERR_ARG;
 }
 
 extern "C" int rv3d_compact_candidates(const float *cuboids, const float *scores, const int64_t *categories,

@@ -38,7 +38,7 @@ class Partitions(C.Structure):
 
 class DecodeParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_classes", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
-                ("dtype", C.c_int32), ("azimuth_invariant", C.c_int32), ("category_offset", C.c_int32),
+                ("dtype", C.c_int32), ("cart_dtype", C.c_int32), ("azimuth_invariant", C.c_int32), ("category_offset", C.c_int32),
                 ("candidate_offset", C.c_int32), ("total_candidates", C.c_int32), ("total_classes", C.c_int32),
                 ("capacity", C.c_int32), ("min_confidence", C.c_float), ("parts", Partitions)]
 
@@ -68,7 +68,7 @@ _SIGNATURES = {
     "rv3d_range_view_coordinates": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P]),
     "rv3d_range_view_inputs": (C.c_int, [C.POINTER(InputsParams), _P, _P, _P, _P, _P]),
     "rv3d_subsample_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
-    "rv3d_decode_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "rv3d_decode_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "rv3d_num_candidates": (_I64, [C.POINTER(Partitions), _I32, _I32]),
     "rv3d_sample_by_range": (C.c_int, [_P, _P, _P, _P, C.POINTER(Partitions), _I32, _I32, _I32, _P, _P, _P, _P]),
     "rv3d_decode_compact": (C.c_int, [C.POINTER(DecodeParams), _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -20,6 +20,17 @@ def dtype_code(dt: torch.dtype) -> int:
         raise TypeError(f"rv3d: unsupported dtype {dt}; use float32, float16 or bfloat16") from None
 
 
+def cart_as(head_dtype: torch.dtype, cart: torch.Tensor) -> torch.Tensor:
+    """cart keeps its own dtype (coding.py:128 widens it separately from the regressands; under autocast the
+    heads are half precision and cart float32).  The library takes cart in the heads' dtype or in float32:
+    half-precision cart next to float32 heads is widened (exact); float64 is not part of the path."""
+    if cart.dtype == head_dtype or cart.dtype == torch.float32:
+        return cart.contiguous()
+    if cart.dtype in (torch.float16, torch.bfloat16):
+        return cart.float().contiguous()
+    raise TypeError(f"rv3d: unsupported cart dtype {cart.dtype}; use float32, float16 or bfloat16")
+
+
 def threshold_as(dt: torch.dtype, value: float) -> float:
     """torch compares ``scores >= python_float`` in the tensor's dtype: round the scalar the same way."""
     return float(torch.tensor(float(value), dtype=dt).float())

@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from ... import _native as N
-from ..._pipeline import Workspace, dtype_code, new_candidates, run_nms, threshold_as
+from ..._pipeline import Workspace, cart_as, dtype_code, new_candidates, run_nms, threshold_as
 from ..._util import ptr, require_cuda, scratch, stream_ptr
 
 __all__ = ["RangeDecoder", "sample_by_range"]
@@ -77,12 +77,12 @@ class RangeDecoder:
             logits = out["logits"].contiguous()
             dt = logits.dtype
             reg = out["regressands"].to(dt).contiguous()
-            cart = ms["cart"].to(dt).contiguous()
+            cart = cart_as(dt, ms["cart"])
             mask = _mask_u8(ms["mask"])
             require_cuda(logits, reg, cart, mask)
             p = N.DecodeParams()
             p.batch, p.n_classes, p.height, p.width = B, logits.shape[1], H, W
-            p.dtype = dtype_code(dt)
+            p.dtype, p.cart_dtype = dtype_code(dt), dtype_code(cart.dtype)
             p.azimuth_invariant = int(bool(self.enable_azimuth_invariant_targets))
             p.category_offset, p.candidate_offset = task_offset, cand_offset
             p.total_candidates, p.total_classes = total_candidates, total_classes

@@ -158,3 +158,81 @@ def test_decode_fp16_inputs():
     got_set = set(zip(got["sweep"].tolist(), got["k"].tolist()))
     # fp16 sigmoid has ~1e-3 resolution: allow disagreement only right at the threshold
     assert all(abs(scores[b, k] - 0.1) < 2e-3 for b, k in ref_set ^ got_set)
+
+
+# ------------------------------------------------------------------------------------------------------
+# autocast: half-precision heads next to float32 cart (detector.py:329-333 runs decode under autocast;
+# coding.py:126-128 widens regressands and cart separately, the result takes the regressands' dtype)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_decode_range_view_mixed_dtypes(dtype):
+    from rv3d.math.ops.coding import decode_range_view
+    head = synth.make_head_outputs(2, 3, 8, 256, 15, n_objects=6)
+    reg, cart = head["regressands"].to(dtype), head["cart"]          # cart stays float32
+    for flag in (True, False):
+        ref = oracle.decode_range_view(reg, cart, flag)
+        out = decode_range_view(reg.to(DEV), cart.to(DEV), flag)
+        assert out.dtype == dtype and ref.dtype == dtype
+        assert torch.equal(out.cpu(), ref)
+    # and it is NOT what rounding cart to the heads' dtype first would give
+    lossy = oracle.decode_range_view(reg, cart.to(dtype), True)
+    assert not torch.equal(lossy, oracle.decode_range_view(reg, cart, True))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_candidates_mixed_dtypes(dtype):
+    from rv3d.nn.decoders.range_decoder import RangeDecoder
+    head = synth.make_head_outputs(2, 3, 16, 256, seed=16, n_objects=8)
+    hm = dict(head, logits=head["logits"].to(dtype), regressands=head["regressands"].to(dtype))
+    tasks = {0: ["a", "b", "c"]}
+    dec = RangeDecoder(True, True, *SBR)
+    cand = dec.candidates(ms_outputs(to_dev(hm, DEV)), PP, tasks)
+    got = unpack_candidates(cand, cand.count())
+    params, scores, cats = oracle.range_decoder_decode(ms_outputs(hm), PP, tasks, True, True, *SBR, return_candidates=True)
+    assert scores.dtype == dtype and params.dtype == dtype
+    thr = float(torch.tensor(PP["min_confidence"], dtype=dtype))
+    sc = scores.float().numpy()
+    ref_set = set(zip(*[a.tolist() for a in np.nonzero(sc >= thr)]))
+    got_set = set(zip(got["sweep"].tolist(), got["k"].tolist()))
+    # a half-precision sigmoid has ~1e-3 (f16) / ~8e-3 (bf16) resolution: disagreement only right at the threshold
+    band = 2e-3 if dtype == torch.float16 else 1.6e-2
+    assert all(abs(sc[b, k] - thr) < band for b, k in ref_set ^ got_set)
+    assert len(ref_set & got_set) > 500
+    both = sorted(ref_set & got_set)
+    pos = {bk: i for i, bk in enumerate(zip(got["sweep"].tolist(), got["k"].tolist()))}
+    rows = np.array([pos[bk] for bk in both])
+    bi, ki = np.array([b for b, _ in both]), np.array([k for _, k in both])
+    # boxes: one rounding of the same fp64 value to the half type on both sides
+    assert np.array_equal(got["boxes"][rows, :7], params.float().numpy()[bi, ki])
+    assert np.array_equal(got["category"][rows], cats.numpy()[bi, ki])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_partition_uses_cart_dtype(dtype):
+    """cart.norm(dim=1) is rounded to cart's dtype before it meets the float32 bounds (range_decoder.py:140-143):
+    pixels whose float32 norm is just above a bound can round down onto it and stay in the nearer partition."""
+    from rv3d.nn.decoders.range_decoder import RangeDecoder
+    rng = np.random.default_rng(77)
+    B, C, H, W = 1, 2, 8, 512
+    n = B * H * W
+    r = np.where(rng.random(n) < 0.5, 15.0, 30.0) + rng.uniform(-0.08, 0.08, size=n)
+    az = rng.uniform(-math.pi, math.pi, size=n)
+    z = rng.uniform(-1.0, 1.0, size=n)
+    rho = np.sqrt(np.maximum(r * r - z * z, 0.0))
+    cart = torch.from_numpy(np.stack([rho * np.cos(az), rho * np.sin(az), z], 0).reshape(1, 3, H, W).astype(np.float32)).to(dtype)
+    head = {"logits": torch.from_numpy(rng.normal(2.0, 1.0, size=(B, C, H, W)).astype(np.float32)).to(dtype),
+            "regressands": torch.from_numpy(rng.normal(0.0, 0.3, size=(B, 8, H, W)).astype(np.float32)).to(dtype),
+            "cart": cart, "mask": torch.ones((B, 1, H, W), dtype=torch.bool)}
+    tasks = {0: ["a", "b"]}
+    dec = RangeDecoder(True, True, *SBR)
+    cand = dec.candidates(ms_outputs(to_dev(head, DEV)), PP, tasks)
+    got = unpack_candidates(cand, cand.count())
+    _, scores, _ = oracle.range_decoder_decode(ms_outputs(head), PP, tasks, True, True, *SBR, return_candidates=True)
+    thr = float(torch.tensor(PP["min_confidence"], dtype=dtype))
+    ref_set = set(zip(*[a.tolist() for a in np.nonzero(scores.float().numpy() >= thr)]))
+    got_set = set(zip(got["sweep"].tolist(), got["k"].tolist()))
+    assert ref_set == got_set          # logits ~ N(2, 1): nothing sits at the score threshold
+    if dtype != torch.float32:         # the test has teeth: float32 norms would assign some pixels differently
+        d32 = cart.float().norm(dim=1)
+        dt = cart.norm(dim=1).float()
+        assert int(((d32 > 15) != (dt > 15)).sum() + ((d32 > 30) != (dt > 30)).sum()) > 0
