@@ -53,6 +53,9 @@ const char *rv3d_strerror(int status);
  * ------------------------------------------------------------------------------------ */
 #define RV3D_COL_LIBRARY 0   /* col = rint(W - az' - 1)   numpy/conversions.py:35      */
 #define RV3D_COL_CONVERTER 1 /* col = W - rint(az')       converters/av2/utils.py:137  */
+#define RV3D_COL_CONVERTER_UNIFORM 2 /* converter column + rows uniform in inclination over +-10 deg
+                                        (build_uniform_inclination, utils.py:138-145); only
+                                        rv3d_range_view_coordinates takes it                 */
 
 typedef struct {
   int32_t batch;        /* B sweeps in one launch                                        */
@@ -265,6 +268,40 @@ int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n_candidate
                          int32_t total_classes, int32_t total_candidates, float *out_params,
                          float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
                          size_t scratch_bytes, rv3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 4. Sweep preparation in front of the rasterizer -- fp64 like the numpy code
+ * replaces: converters/av2/utils.py:229-295 unmotion_compensate, :43-57 sensor_SE3_egovehicle
+ *           (av2 SE3.inverse().transform_point_cloud), :211-226 correct_laser_numbers
+ * ------------------------------------------------------------------------------------ */
+
+/* unmotion_compensate: xyz (N,3) f64, offset_ns (N,) i64 (device).  Pose table (device, sorted by time):
+ * pose_timestamps_ns (M,) i64, pose_quat_xyzw (M,4) f64 scalar-last as scipy's from_quat takes the
+ * reference's (qx,qy,qz,qw) columns, pose_translation (M,3) f64.  target_* (HOST, 4 + 3 doubles): the pose
+ * whose timestamp equals `timestamp_ns` (utils.py:258-273; the caller looks it up and fails like the
+ * reference when it is absent).  Per point: t = timestamp_ns + offset; rows outside (min, max) pose time
+ * are dropped by the reference -> out_valid = 0 and NaN coordinates here (the caller compacts);
+ * rotation = scipy Slerp on float64 timestamps, translation = t_low*alpha + (1-alpha)*t_high (:275-276,
+ * weights as in the reference); out_xyz = inv(city_SE3_laser) @ city_SE3_roll @ [x y z 1]. */
+int rv3d_unmotion_compensate(const double *xyz, const int64_t *offset_ns, int64_t n, int64_t timestamp_ns,
+                             const int64_t *pose_timestamps_ns, const double *pose_quat_xyzw,
+                             const double *pose_translation, int32_t n_poses, const double *target_quat_xyzw,
+                             const double *target_translation, double *out_xyz, uint8_t *out_valid,
+                             rv3d_stream_t stream);
+
+/* Rigid transform of (N,3) f64 points: out = xyz @ R^T + t, or with `inverse` the transform of
+ * SE3(R, t).inverse() (R^T, R^T.(-t)) as utils.py:54-57 builds sensor_SE3_egovehicle.
+ * rotation (9, row-major) and translation (3): HOST doubles. */
+int rv3d_transform_points(const double *xyz, int64_t n, const double *rotation, const double *translation,
+                          int32_t inverse, double *out, rv3d_stream_t stream);
+
+/* correct_laser_numbers: laser_numbers (N,) i64 -> out (N,) i64 = row_mapping[remap(laser)].
+ * laser_mapping (32,) i64 device or NULL (log not in LOG_IDS): l >= 32 -> laser_mapping[l-32]+32,
+ * l < 32 -> laser_mapping[l].  row_mapping (n_rows,) i64 = ROW_MAPPING_32 / ROW_MAPPING_64.
+ * *out_of_range (device i32, may be NULL) is set to 1 where numpy would raise IndexError. */
+int rv3d_correct_laser_numbers(const int64_t *laser_numbers, int64_t n, const int64_t *laser_mapping,
+                               const int64_t *row_mapping, int32_t n_rows, int64_t *out,
+                               int32_t *out_of_range, rv3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -196,9 +196,18 @@ __global__ void rv_coordinates_kernel(double *__restrict__ sph, const int64_t *_
   const double nb = static_cast<double>(a.az_bins);
   double c = (a.col_mode == RV3D_COL_LIBRARY) ? rint((nb - t) - 1.0) : (nb - rint(t));
   c = fmin(fmax(c, 0.0), nb - 1.0);
-  int64_t l = laser[i];
-  if (l < 0) l += n_mapping;  // numpy negative indexing
-  const double row = (l >= 0 && l < n_mapping) ? static_cast<double>(n_inc - mapping[l] - 1) : CUDART_NAN;
+  double row;
+  if (a.col_mode == RV3D_COL_CONVERTER_UNIFORM) {
+    // converters/av2/utils.py:138-145: rows uniform in inclination over a +-10 degree field of view
+    const double fov = (10.0 / 180.0) * CUDART_PI;   // |(-10.0 / 180.0) * pi| == (10 / 180.0) * pi
+    double r = 1.0 - (sph[3 * i + 1] + fov) / (fov + fov);
+    r = r * static_cast<double>(n_inc);
+    row = fmin(fmax(rint(r), 0.0), static_cast<double>(n_inc - 1));
+  } else {
+    int64_t l = laser[i];
+    if (l < 0) l += n_mapping;  // numpy negative indexing
+    row = (l >= 0 && l < n_mapping) ? static_cast<double>(n_inc - mapping[l] - 1) : CUDART_NAN;
+  }
   hybrid[3 * i] = row;
   hybrid[3 * i + 1] = c;
   hybrid[3 * i + 2] = sph[3 * i + 2];
@@ -364,8 +373,10 @@ extern "C" int rv3d_range_view_coordinates(double *sph, const int64_t *laser, co
                                            int32_t n_mapping, int64_t n, int32_t n_inclination_bins,
                                            int32_t n_azimuth_bins, int32_t col_mode, double *hybrid,
                                            rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(n >= 0 && n_mapping > 0 && n_azimuth_bins > 0 && (n == 0 || (sph && laser && laser_mapping && hybrid)));
-  RV3D_CHECK_ARG(col_mode == RV3D_COL_LIBRARY || col_mode == RV3D_COL_CONVERTER);
+  const bool uniform = col_mode == RV3D_COL_CONVERTER_UNIFORM;   // rows from the inclination: no laser tables needed
+  RV3D_CHECK_ARG(n >= 0 && n_azimuth_bins > 0 && n_inclination_bins > 0 && (n == 0 || (sph && hybrid)));
+  RV3D_CHECK_ARG(uniform || (n_mapping > 0 && (n == 0 || (laser && laser_mapping))));
+  RV3D_CHECK_ARG(col_mode == RV3D_COL_LIBRARY || col_mode == RV3D_COL_CONVERTER || uniform);
   if (n == 0) return RV3D_OK;
   RasterArgs a{};
   a.az_bins = n_azimuth_bins;

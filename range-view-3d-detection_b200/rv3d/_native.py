@@ -13,7 +13,7 @@ MAX_PARTITIONS = 8
 
 RV3D_OK = 0
 ERR_KEYBITS = -5
-COL_LIBRARY, COL_CONVERTER = 0, 1
+COL_LIBRARY, COL_CONVERTER, COL_CONVERTER_UNIFORM = 0, 1, 2
 F32, F16, BF16 = 0, 1, 2
 NMS_HARD, NMS_WEIGHTED = 0, 1
 OUT_QUAT, OUT_YAW = 0, 1
@@ -83,6 +83,9 @@ _SIGNATURES = {
     "rv3d_yaw_to_quat": (C.c_int, [_P, _P, _I64, _P]),
     "rv3d_pack_candidates_scratch_bytes": (_SZ, [_I32]),
     "rv3d_pack_candidates": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
+    "rv3d_unmotion_compensate": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
+    "rv3d_transform_points": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P]),
+    "rv3d_correct_laser_numbers": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P, _P]),
 }
 
 _NOT_YET_BUILT: set = set()

@@ -47,7 +47,8 @@ def build_range_view_coordinates(cart, sph, laser_numbers, laser_mapping, n_incl
     las = _to_dev(laser_numbers, torch.int64, dev)
     mp = _to_dev(laser_mapping, torch.int64, dev)
     hybrid = torch.empty((n, 3), dtype=torch.float64, device=dev)
-    mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
+    # "converter_uniform": converters/av2/utils.py:138-145 (build_uniform_inclination=True)
+    mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER, "converter_uniform": N.COL_CONVERTER_UNIFORM}[col_mode]
     N.check(N.lib().rv3d_range_view_coordinates(ptr(s), ptr(las), ptr(mp), mp.numel(), n, n_inclination_bins,
                                                 n_azimuth_bins, mode, ptr(hybrid), stream_ptr(dev)),
             "rv3d_range_view_coordinates")

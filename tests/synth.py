@@ -220,3 +220,40 @@ def make_nms_candidates(B: int, K: int, n_classes: int, n_objects: int, seed: in
         sc[b] = (0.02 + 0.97 * s).astype(np.float32)
         assert len(np.unique(sc[b])) == K
     return torch.from_numpy(cub), torch.from_numpy(sc), torch.from_numpy(cat)
+
+
+def make_pose_table(n_poses: int, seed: int, t0_ns: int = 315969904359876000, period_ns: int = 10_000_000):
+    """A city_SE3_egovehicle-like log: -> (timestamps (M,) i64 strictly increasing, quat_xyzw (M,4) f64 (not exactly
+    unit, like a feather file's rounded columns), translation (M,3) f64 in city coordinates).  A car driving a gentle
+    curve at ~10 m/s with small roll / pitch."""
+    rng = np.random.default_rng(seed)
+    ts = t0_ns + np.arange(n_poses, dtype=np.int64) * period_ns + rng.integers(-400_000, 400_000, size=n_poses)
+    ts = np.sort(ts)
+    sec = (ts - ts[0]).astype(np.float64) * 1e-9
+    yaw = 0.7 + 0.25 * sec + 0.05 * np.sin(1.3 * sec)
+    pitch = 0.01 * np.sin(2.1 * sec) + rng.normal(0, 1e-4, n_poses)
+    roll = 0.008 * np.cos(1.7 * sec) + rng.normal(0, 1e-4, n_poses)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    qw = cr * cp * cy + sr * sp * sy
+    qx = sr * cp * cy - cr * sp * sy
+    qy = cr * sp * cy + sr * cp * sy
+    qz = cr * cp * sy - sr * sp * cy
+    quat = np.stack([qx, qy, qz, qw], 1)
+    quat = np.round(quat, 12)                                  # stored columns are not exactly unit length
+    if n_poses > 8:
+        quat[5] = -quat[5]                                     # the double cover shows up in real logs
+    speed = 10.0
+    x = 2000.0 + np.cumsum(np.r_[0.0, np.diff(sec)] * speed * np.cos(yaw))
+    y = 1500.0 + np.cumsum(np.r_[0.0, np.diff(sec)] * speed * np.sin(yaw))
+    z = 20.0 + 0.05 * np.sin(0.9 * sec)
+    return ts, quat, np.stack([x, y, z], 1)
+
+
+def make_raw_sweep(n: int, seed: int, sweep_ns: int = 100_000_000):
+    """-> (xyz (N,3) f64 holding float32 values, like the exporter's cast of the feather columns,
+    offset_ns (N,) i64 in [0, sweep_ns), intensity (N,) f64, laser_number (N,) i64 in [0, 64), roi (N,) f64)."""
+    rng = np.random.default_rng(seed)
+    xyz32, inten, laser = make_points(n, 64, seed, offset=LIDAR_OFFSET)
+    off = rng.integers(0, sweep_ns, size=n).astype(np.int64)
+    roi = (rng.random(n) < 0.8).astype(np.float64)
+    return xyz32.astype(np.float64), off, inten.astype(np.float64), laser.astype(np.int64), roi
