@@ -258,6 +258,12 @@ int rv3d_wnms(const float *boxes, const float *data, int32_t n, int32_t d, float
 int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b, int64_t n, float *iou3d,
                        float *iou_bev, int32_t *status, rv3d_stream_t stream);
 
+/* mmcv.ops.box_iou_rotated(bboxes1, bboxes2, aligned) (call sites: math/ops/assignment.py:24-26,67-69 aligned,
+ * prototype/loader.py:785-788 all pairs): boxes (N,5) / (M,5) f32 (xc, yc, w, h, angle in radians) ->
+ * out (N,M) f32 row-major, or (N,) when `aligned` (then n == m).  Same arithmetic as the NMS routine. */
+int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int32_t aligned,
+                         float *out, rv3d_stream_t stream);
+
 /* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
 int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);
 
@@ -302,6 +308,19 @@ int rv3d_transform_points(const double *xyz, int64_t n, const double *rotation, 
 int rv3d_correct_laser_numbers(const int64_t *laser_numbers, int64_t n, const int64_t *laser_mapping,
                                const int64_t *row_mapping, int32_t n_rows, int64_t *out,
                                int32_t *out_of_range, rv3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 5. Training-time callers of the same operators
+ * replaces: the per-instance loop of compute_classification_targets, math/ops/assignment.py:121-139
+ *           (per panoptic instance: topk(min(k, n)) of the pixel affinities, everything else zeroed)
+ * ------------------------------------------------------------------------------------ */
+
+/* affinity (N,) f32 and segment (N,) i32 in [0, n_segments) per foreground pixel, pixels of one instance in the
+ * reference's masked_select (raster) order -> likelihood (N,) f32: the affinity where the pixel is among the k
+ * largest of its segment (ties: earlier pixel first; NaN ranks highest like torch.topk), else 0. */
+size_t rv3d_instance_topk_scratch_bytes(int64_t n);
+int rv3d_instance_topk(const float *affinity, const int32_t *segment, int64_t n, int32_t n_segments, int32_t k,
+                       float *likelihood, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
 
 #ifdef __cplusplus
 }

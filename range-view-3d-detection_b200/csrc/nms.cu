@@ -1399,6 +1399,19 @@ iou3d_aligned_kernel(const float *__restrict__ A, const float *__restrict__ B, i
   iou_bev[i] = bev;
 }
 
+// mmcv box_iou_rotated(bboxes1 (N,5), bboxes2 (M,5), aligned): (xc,yc,w,h,angle rad) -> (N,M) or (N,) IoU.
+// One thread per output element, consecutive threads along M so box b is read coalesced and box a broadcast.
+__global__ void __launch_bounds__(128)
+box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__restrict__ B, int64_t m, int aligned,
+                       float *__restrict__ out) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = aligned ? n : n * m;
+  if (t >= total) return;
+  const int64_t i = aligned ? t : t / m, j = aligned ? t : t - i * m;
+  const float *a = A + i * 5, *b = B + j * 5;
+  out[t] = rot_iou(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 1.0), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 1.0));
+}
+
 // threshold-only branch: rows ordered by (sweep, candidate index)
 __global__ void remap_keys_kernel(const unsigned long long *__restrict__ keys, int n, int idx_bits,
                                   int total_classes, unsigned long long *__restrict__ out, uint32_t *__restrict__ order,
@@ -1562,6 +1575,18 @@ extern "C" int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b
   if (n == 0) return RV3D_OK;
   RV3D_CHECK_ARG(cuboids_a && cuboids_b && iou3d && iou_bev);
   iou3d_aligned_kernel<<<ceil_div(n, 128), 128, 0, s>>>(cuboids_a, cuboids_b, n, iou3d, iou_bev, status);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int32_t aligned,
+                                    float *out, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && m >= 0 && (!aligned || n == m));
+  const int64_t total = aligned ? n : n * m;
+  if (total == 0) return RV3D_OK;
+  RV3D_CHECK_ARG(boxes_a && boxes_b && out && total < (int64_t(1) << 37));
+  box_iou_rotated_kernel<<<ceil_div(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(boxes_a, n, boxes_b, m,
+                                                                                            aligned, out);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }

@@ -10,7 +10,7 @@ from torch import Tensor
 from .. import _native as N
 from .._util import ptr, require_cuda, stream_ptr
 
-__all__ = ["subsample_range_view", "range_view_inputs", "IMAGE_CHANNELS"]
+__all__ = ["subsample_range_view", "range_view_inputs", "intersection_test", "IMAGE_CHANNELS"]
 
 # channel order of rv3d.math.range_view images (math/range_view.py:33)
 IMAGE_CHANNELS = ("azimuth", "inclination", "range", "x", "y", "z", "intensity")
@@ -75,3 +75,12 @@ def subsample_range_view(range_view: Tensor, mask: Tensor, cart: Tensor, dataset
                                               stream_ptr(dev)), "rv3d_subsample_range_view")
     out_mask = o_mk.view(torch.bool) if mask.dtype == torch.bool else o_mk.to(mask.dtype)
     return o_rv.to(range_view.dtype), out_mask, o_ct.to(cart.dtype)
+
+
+def intersection_test(annotations_tch: Tensor, db_samples_tch: Tensor) -> Tensor:
+    """prototype/loader.py:775-789 (`_intersection_test`, the GT-database collision test of the copy-paste
+    augmentation) on the already converted tensors: rows are ``TCH_COLUMN_NAMES`` cuboids
+    ``(x, y, z, l, w, h, ..., yaw)``; -> (N, M) rotated BEV IoU of ``[:, [0, 1, 3, 4, -1]]``."""
+    from ..math.ops.assignment import box_iou_rotated
+    cols = [0, 1, 3, 4, -1]
+    return box_iou_rotated(annotations_tch.float()[:, cols], db_samples_tch.float()[:, cols])

@@ -257,3 +257,33 @@ def make_raw_sweep(n: int, seed: int, sweep_ns: int = 100_000_000):
     off = rng.integers(0, sweep_ns, size=n).astype(np.int64)
     roi = (rng.random(n) < 0.8).astype(np.float64)
     return xyz32.astype(np.float64), off, inten.astype(np.float64), laser.astype(np.int64), roi
+
+
+def make_assignment_inputs(B: int, C: int, H: int, W: int, seed: int, n_instances: int = 12):
+    """Training-time inputs of compute_classification_targets: predictions `input` and encoded `target` (B,8,H,W) f32,
+    labels (B,H,W) i64 in [0, C] (C = background), cart, mask (B,1,H,W) bool, panoptics (B,1,H,W) i64 (0 = background).
+    Instances are rectangular pixel patches; predictions are the targets plus noise so the BEV IoUs spread over (0, 1)."""
+    rng = np.random.default_rng(seed)
+    cart, mask = _range_image_cart(B, H, W, rng)
+    target = np.zeros((B, 8, H, W), dtype=np.float32)
+    target[:, 0:3] = rng.normal(0.0, 0.8, size=(B, 3, H, W))
+    pri = _PRIORS[rng.integers(0, len(_PRIORS), size=(B, H, W))]
+    target[:, 3:6] = np.log(pri).transpose(0, 3, 1, 2)
+    ang = rng.uniform(-math.pi, math.pi, size=(B, H, W))
+    target[:, 6], target[:, 7] = np.sin(ang), np.cos(ang)
+    inp = target + rng.normal(0.0, 0.25, size=target.shape).astype(np.float32)
+    inp[:, 3:6] = target[:, 3:6] + rng.normal(0.0, 0.1, size=(B, 3, H, W)).astype(np.float32)
+    labels = np.full((B, H, W), C, dtype=np.int64)
+    pan = np.zeros((B, 1, H, W), dtype=np.int64)
+    for b in range(B):
+        for inst in range(1, n_instances + 1):
+            if inst == 3:
+                continue                                            # an id that never appears (one_hot column of zeros)
+            h0, w0 = int(rng.integers(0, H - 2)), int(rng.integers(0, W - 12))
+            hh, ww = int(rng.integers(1, 4)), int(rng.integers(1, 12))
+            pan[b, 0, h0:h0 + hh, w0:w0 + ww] = inst
+            labels[b, h0:h0 + hh, w0:w0 + ww] = int(rng.integers(0, C))
+    pan[~mask] = 0
+    t = torch.from_numpy
+    return {"input": t(inp), "target": t(target), "labels": t(labels), "cart": t(cart), "mask": t(mask),
+            "panoptics": t(pan)}
