@@ -322,6 +322,29 @@ size_t rv3d_instance_topk_scratch_bytes(int64_t n);
 int rv3d_instance_topk(const float *affinity, const int32_t *segment, int64_t n, int32_t n_segments, int32_t k,
                        float *likelihood, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * 6. Detection wire format
+ * replaces: math/ops/coding.py:31-58 build_dataframe's per-column .tolist() reads,
+ *           nn/arch/detector.py:45-60 SERIALIZED_SCHEMA, :573-584 the evaluation range filter
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  float params[10];        /* tx_m ty_m tz_m length_m width_m height_m qw qx qy qz */
+  float score;
+  int32_t category_index;
+  int64_t timestamp_ns;    /* of the detection's sweep (uuids joined on batch_index, coding.py:69) */
+  int32_t batch_index;
+  float range_m;           /* float32 ||(tx,ty,tz)||, the quantity detector.py:573-576 filters on */
+} rv3d_detection_record;   /* 64 bytes */
+
+/* The decoder's outputs (params (N,10), scores / categories / batch_index (N,) f32 as RangeDecoder.decode returns
+ * them) -> out (<= N records, order preserved), *out_count (device i32).  sweep_timestamp_ns (batch,) i64 device or
+ * NULL.  apply_range_filter: keep range_m <= max_range_m only (detector.py:580). */
+size_t rv3d_detection_records_scratch_bytes(int64_t n);
+int rv3d_detection_records(const float *params, const float *scores, const float *categories,
+                           const float *batch_index, int64_t n, const int64_t *sweep_timestamp_ns, int32_t batch,
+                           float max_range_m, int32_t apply_range_filter, rv3d_detection_record *out,
+                           int32_t *out_count, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

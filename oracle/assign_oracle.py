@@ -62,3 +62,26 @@ def compute_classification_targets(inp, target, labels, cart, cfg, mask, panopti
             fgm[i, 0][m] = like.bool().type_as(aff)
     bgm = torch.logical_and(fgm.logical_not(), mask)
     return aff * onehot, fgm, bgm, onehot.any(dim=1, keepdim=True)
+
+
+# --------------------------------------------------------------------------------------------
+# detection wire format: math/ops/coding.py:31-76, nn/arch/detector.py:45-60,573-581.
+# polars is not installed, so build_dataframe's joins are restated over numpy columns: parity unpinned for the
+# frame plumbing; there is no arithmetic besides the float32 range norm.
+# --------------------------------------------------------------------------------------------
+def detection_rows(params, scores, categories, batch_index, timestamps_ns=None, max_range_m=None):
+    """-> dict of numpy columns, decoder order kept, optionally range-filtered (detector.py:573-581)."""
+    p = params.float().numpy()
+    cols = {n: p[:, i].copy() for i, n in enumerate(("tx_m", "ty_m", "tz_m", "length_m", "width_m", "height_m", "qw", "qx", "qy", "qz"))}
+    cols["score"] = scores.float().flatten().numpy()
+    cols["category_index"] = categories.int().flatten().numpy()                  # coding.py:54
+    cols["batch_index"] = batch_index.int().flatten().numpy()                    # coding.py:55
+    if timestamps_ns is not None:
+        ts = np.asarray(timestamps_ns, dtype=np.int64)
+        cols["timestamp_ns"] = ts[cols["batch_index"]]
+    norms = np.linalg.norm(p[:, :3], axis=-1)                                     # float32 in, float32 out (detector.py:573-576)
+    cols["range_m"] = norms
+    if max_range_m is not None:
+        keep = norms.astype(np.float64) <= float(max_range_m)                     # .le(lit(cfg.max_range_m))
+        cols = {k: v[keep] for k, v in cols.items()}
+    return cols
