@@ -22,6 +22,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace rv3d {
 
@@ -72,12 +73,20 @@ __device__ __forceinline__ void decode_box(const float (&reg)[8], const float (&
                                            double (&out)[7]) {
   double ox = reg[0], oy = reg[1];
   const double oz = reg[2];
-  double yaw = atan2(static_cast<double>(reg[6]), static_cast<double>(reg[7]));  // :136
+  double yaw = fast_atan2(static_cast<double>(reg[6]), static_cast<double>(reg[7]));  // :136 (fastmath.cuh: <= 1 ulp)
   const double cx = cart[0], cy = cart[1], cz = cart[2];
   if (az_inv) {                                                                    // :79-107
-    const double phi = atan2(cy, cx);
+    const double phi = fast_atan2(cy, cx);
+    // cos / sin of atan2(cy, cx) are cx / h and cy / h (one reciprocal instead of a sincos); degenerate or
+    // non-finite rays take the library path
+    const double h2 = cx * cx + cy * cy;
     double s, c;
-    sincos(phi, &s, &c);
+    if (h2 > 1e-60 && h2 < 1e60) {
+      const double rh = 1.0 / sqrt(h2);
+      c = cx * rh; s = cy * rh;
+    } else {
+      sincos(phi, &s, &c);
+    }
     const double x = c * ox - s * oy;
     const double y = s * ox + c * oy;
     ox = x; oy = y;
@@ -253,7 +262,7 @@ constexpr int kPxPerThread = 4;
 
 // bytes of dynamic shared memory for a tile of kTile pixels
 static size_t decode_smem_bytes(int C, int tile, size_t elem, size_t cart_elem) {
-  size_t b = static_cast<size_t>(C + 8) * tile * elem + static_cast<size_t>(3) * tile * cart_elem;   // logits, regressands, cart planes
+  size_t b = static_cast<size_t>(C) * tile * elem + static_cast<size_t>(3) * tile * cart_elem;   // logit and cart planes (regressands are gathered)
   b += tile;                                              // mask
   b = align_up(b, 16);
   b += static_cast<size_t>(tile) * (2 + 2 + 1 + 2 + 2 + 4 + 4);   // q_pix, q_meta, q_emit, q_h, q_w, q_score, q_off
@@ -261,10 +270,13 @@ static size_t decode_smem_bytes(int C, int tile, size_t elem, size_t cart_elem) 
 }
 
 // One CTA per tile of kTile consecutive pixels of one sweep, kTile / 4 threads.
-//   stage   every input plane's slice of the tile is brought into shared memory: with kBulk, C + 12
-//           TMA 1-D bulk copies issued by one thread, completion on an mbarrier (no registers, no
+//   stage   the logit, cart and mask planes' slices of the tile are brought into shared memory: with kBulk,
+//           C + 4 TMA 1-D bulk copies issued by one thread, completion on an mbarrier (no registers, no
 //           per-thread loads; several resident CTAs overlap each other's copies and math); without
-//           (unaligned shapes) plain cooperative loads into the same layout.
+//           (unaligned shapes) plain cooperative loads into the same layout.  The 8 regressand planes are
+//           NOT staged: only live pixels need them, phase B gathers them (8 independent loads per pixel),
+//           which halves the tile's shared memory (more resident CTAs) and, at realistic candidate
+//           densities, skips most of their bytes.
 //   phase A / scan / phase B   as described at the top of this file, reading shared memory only.
 template <typename T, typename TC, int kTile, bool kBulk>
 __global__ void __launch_bounds__(kTile / kPxPerThread)
@@ -289,12 +301,11 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   const int blk0 = blockIdx.x * kTile;
   const int npx = min(kTile, HW - blk0);
 
-  // ---- carve shared memory: [C][kTile] logits | [8][kTile] reg | [3][kTile] cart | mask | queues
+  // ---- carve shared memory: [C][kTile] logits | [3][kTile] cart | mask | queues
   T *s_logits = reinterpret_cast<T *>(dsm);
-  T *s_reg = s_logits + static_cast<size_t>(a.C) * kTile;
-  TC *s_cart = reinterpret_cast<TC *>(s_reg + 8 * kTile);   // (C + 8) * kTile * sizeof(T) is a multiple of 16
+  TC *s_cart = reinterpret_cast<TC *>(s_logits + static_cast<size_t>(a.C) * kTile);   // C * kTile * sizeof(T) is a multiple of 16
   uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cart + 3 * kTile);
-  unsigned char *qp = dsm + align_up_c((static_cast<size_t>(a.C) + 8) * kTile * sizeof(T) + 3 * kTile * sizeof(TC) + kTile, 16);
+  unsigned char *qp = dsm + align_up_c(static_cast<size_t>(a.C) * kTile * sizeof(T) + 3 * kTile * sizeof(TC) + kTile, 16);
   float *q_score = reinterpret_cast<float *>(qp);                    // score of live pixel t
   uint32_t *q_off = reinterpret_cast<uint32_t *>(q_score + kTile);   // exclusive emit offset inside the block
   uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_off + kTile);     // local pixel id of live pixel t
@@ -309,10 +320,11 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   }
   const int n_parts = a.pa.n;
 
+  const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;   // regressands: gathered in phase B for the live pixels only
+
   // ---------------- stage the tile ----------------
   {
     const T *lg = logits + static_cast<size_t>(b) * a.C * HW + blk0;
-    const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;
     const TC *ct = cart + static_cast<size_t>(b) * 3 * HW + blk0;
     const uint8_t *mk = mask + static_cast<size_t>(b) * HW + blk0;
     if (kBulk) {
@@ -321,9 +333,8 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       if (tid == 0) {
         const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
         const uint32_t cplane = static_cast<uint32_t>(npx) * sizeof(TC);
-        mbar_expect_tx(&s_bar, plane * (a.C + 8) + cplane * 3 + npx);
+        mbar_expect_tx(&s_bar, plane * a.C + cplane * 3 + npx);
         for (int c = 0; c < a.C; ++c) bulk_g2s(s_logits + static_cast<size_t>(c) * kTile, lg + static_cast<size_t>(c) * HW, plane, &s_bar);
-        for (int k = 0; k < 8; ++k) bulk_g2s(s_reg + k * kTile, rg + static_cast<size_t>(k) * HW, plane, &s_bar);
         for (int k = 0; k < 3; ++k) bulk_g2s(s_cart + k * kTile, ct + static_cast<size_t>(k) * HW, cplane, &s_bar);
         bulk_g2s(s_mask, mk, npx, &s_bar);
       }
@@ -332,7 +343,6 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       __syncthreads();
       for (int i = tid; i < npx; i += kThreads) {
         for (int c = 0; c < a.C; ++c) s_logits[static_cast<size_t>(c) * kTile + i] = lg[static_cast<size_t>(c) * HW + i];
-        for (int k = 0; k < 8; ++k) s_reg[k * kTile + i] = rg[static_cast<size_t>(k) * HW + i];
         for (int k = 0; k < 3; ++k) s_cart[k * kTile + i] = ct[static_cast<size_t>(k) * HW + i];
         s_mask[i] = mk[i];
       }
@@ -478,7 +488,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     const int p = blk0 + lp;
     float r[8], c[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = Sm<T>::one(s_reg + k * kTile + lp);
+    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(rg + static_cast<size_t>(k) * HW + lp);   // 8 independent loads in flight
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[k] = Sm<TC>::one(s_cart + k * kTile + lp);
     double o[7];
@@ -585,9 +595,9 @@ static int launch_decode_compact(const DecodeArgs &a, const void *logits, const 
   const int HW = a.H * a.W;
   // TMA bulk copies need 16-byte aligned sources and sizes: every plane slice of a tile must start on a
   // 16-byte boundary (HW % 16 == 0 covers the 1-byte mask plane too)
-  const bool bulk = (HW % 16 == 0) && aligned(logits, 16) && aligned(reg, 16) && aligned(cart, 16) && aligned(mask, 16);
+  const bool bulk = (HW % 16 == 0) && aligned(logits, 16) && aligned(cart, 16) && aligned(mask, 16);
   // tile size: keep a CTA's stage under ~48 KB so 4-6 CTAs are resident per SM
-  const bool small_tile = (static_cast<size_t>(a.C + 8) * sizeof(T) + 3 * sizeof(TC)) * 512 > 48 * 1024;
+  const bool small_tile = (static_cast<size_t>(a.C) * sizeof(T) + 3 * sizeof(TC)) * 512 > 40 * 1024;
   if (bulk) {
     if (small_tile) return launch_decode_tile<T, TC, 256, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);
     return launch_decode_tile<T, TC, 512, true>(a, logits, reg, cart, mask, keys, boxes, counter, s);

@@ -22,6 +22,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace rv3d {
 
@@ -80,17 +81,15 @@ __device__ __forceinline__ double column_of_fast(double cx, double cy, const Ras
   return column_of(atan2(cy, cx), a);
 }
 
-__global__ void __launch_bounds__(256)
-raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uint8_t *__restrict__ laser,
-                      const int32_t *__restrict__ n_points, const int32_t *__restrict__ laser_mapping,
-                      unsigned long long *__restrict__ keys) {
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_points[b]) return;
-  const size_t gi = static_cast<size_t>(b) * a.max_points + i;
-  const int l = laser[gi];
+// Two points per thread, every load issued before the first use: the kernel is a latency-bound stream
+// (laser byte -> branch -> float4 -> ~150 dependent fp64 instructions -> one L2 atomic), so the memory-level
+// parallelism per thread is what sets its speed.
+constexpr int kScatterPerThread = 2;
+
+__device__ __forceinline__ void scatter_point(const RasterArgs &a, int b, int i, int l, float4 p,
+                                              const int32_t *__restrict__ laser_mapping,
+                                              unsigned long long *__restrict__ keys) {
   if (l >= a.num_lasers) return;  // range_view.py:23-26
-  const float4 p = ldg_stream_f4(points + gi);
   const double cx = static_cast<double>(p.x) - a.ox;  // range_view.py:29
   const double cy = static_cast<double>(p.y) - a.oy;
   const double cz = static_cast<double>(p.z) - a.oz;
@@ -107,38 +106,72 @@ raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uin
 }
 
 __global__ void __launch_bounds__(256)
-raster_resolve_kernel(RasterArgs a, const float4 *__restrict__ points,
-                      const unsigned long long *__restrict__ keys, float *__restrict__ image,
-                      int32_t *__restrict__ winner) {
+raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uint8_t *__restrict__ laser,
+                      const int32_t *__restrict__ n_points, const int32_t *__restrict__ laser_mapping,
+                      unsigned long long *__restrict__ keys) {
   const int b = blockIdx.y;
-  const int HW = a.H * a.W;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= HW) return;
-  const unsigned long long key = keys[static_cast<size_t>(b) * HW + pix];
-  float *out = image + static_cast<size_t>(b) * 7 * HW + pix;
-  float az = 0.f, inc = 0.f, rr = 0.f, x = 0.f, y = 0.f, z = 0.f, it = 0.f;
-  int32_t w = -1;
+  const int n = n_points[b];
+  const int i0 = blockIdx.x * (blockDim.x * kScatterPerThread) + threadIdx.x;
+  if (i0 >= n) return;
+  int l[kScatterPerThread];
+  float4 p[kScatterPerThread];
+#pragma unroll
+  for (int u = 0; u < kScatterPerThread; ++u) {
+    const int i = i0 + u * blockDim.x;
+    const size_t gi = static_cast<size_t>(b) * a.max_points + (i < n ? i : i0);
+    l[u] = laser[gi];
+    p[u] = ldg_stream_f4(points + gi);
+  }
+#pragma unroll
+  for (int u = 0; u < kScatterPerThread; ++u) {
+    const int i = i0 + u * blockDim.x;
+    if (i < n) scatter_point(a, b, i, l[u], p[u], laser_mapping, keys);
+  }
+}
+
+// K1b: one pixel per thread.  The kernel is bound by the rate at which an SM can keep random 32-byte sector
+// gathers in flight (key -> winning point; synthetic sweeps are in random point order, the worst case), not
+// by instruction issue: four pixels per thread with all gathers issued up front and 16-byte plane stores
+// measured SLOWER (46.5 vs 43.1 us at B = 16 Waymo: 76 registers, 33 % occupancy), so the simple form stays.
+struct PixelOut { float az, inc, rr, x, y, z, it; int32_t w; };
+
+__device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned long long key, float4 p) {
+  PixelOut o{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, -1};
   if (key != kEmptyKey) {
-    w = static_cast<int32_t>(key_index(key));
-    const float4 p = points[static_cast<size_t>(b) * a.max_points + w];
+    o.w = static_cast<int32_t>(key_index(key));
     const double cx = static_cast<double>(p.x) - a.ox;
     const double cy = static_cast<double>(p.y) - a.oy;
     const double cz = static_cast<double>(p.z) - a.oz;
     const double hxy = norm2d(cx, cy);
     // features are snapshotted BEFORE the in-place azimuth rescale (range_view.py:33, H3)
-    az = static_cast<float>(atan2(cy, cx));
-    inc = static_cast<float>(atan2(cz, hxy));
-    rr = static_cast<float>(norm_hz(hxy, cz));
-    x = p.x; y = p.y; z = p.z; it = p.w;
+    o.az = static_cast<float>(fast_atan2(cy, cx));    // fastmath.cuh: <= 1 ulp of fp64 before the cast
+    o.inc = static_cast<float>(fast_atan2(cz, hxy));
+    o.rr = static_cast<float>(norm_hz(hxy, cz));
+    o.x = p.x; o.y = p.y; o.z = p.z; o.it = p.w;
   }
-  out[0 * HW] = az;
-  out[1 * HW] = inc;
-  out[2 * HW] = rr;
-  out[3 * HW] = x;
-  out[4 * HW] = y;
-  out[5 * HW] = z;
-  out[6 * HW] = it;
-  if (winner) winner[static_cast<size_t>(b) * HW + pix] = w;
+  return o;
+}
+
+__global__ void __launch_bounds__(256)
+raster_resolve_kernel(RasterArgs a, const float4 *__restrict__ points, const unsigned long long *__restrict__ keys,
+                      float *__restrict__ image, int32_t *__restrict__ winner) {
+  const int b = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const unsigned long long key = keys[static_cast<size_t>(b) * HW + pix];
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (key != kEmptyKey) p = __ldg(points + static_cast<size_t>(b) * a.max_points + key_index(key));
+  const PixelOut o = resolve_pixel(a, key, p);
+  float *out = image + static_cast<size_t>(b) * 7 * HW + pix;
+  out[0 * static_cast<size_t>(HW)] = o.az;
+  out[1 * static_cast<size_t>(HW)] = o.inc;
+  out[2 * static_cast<size_t>(HW)] = o.rr;
+  out[3 * static_cast<size_t>(HW)] = o.x;
+  out[4 * static_cast<size_t>(HW)] = o.y;
+  out[5 * static_cast<size_t>(HW)] = o.z;
+  out[6 * static_cast<size_t>(HW)] = o.it;
+  if (winner) winner[static_cast<size_t>(b) * HW + pix] = o.w;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,7 +345,7 @@ extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, 
   const RasterArgs a = make_args(p);
   auto *keys = static_cast<unsigned long long *>(scratch);
   RV3D_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, need, s));
-  dim3 g1(ceil_div(p->max_points, 256), p->batch);
+  dim3 g1(ceil_div(p->max_points, 256 * kScatterPerThread), p->batch);
   raster_scatter_kernel<<<g1, 256, 0, s>>>(a, reinterpret_cast<const float4 *>(points), laser, n_points,
                                            laser_mapping, keys);
   RV3D_CHECK_LAUNCH();
