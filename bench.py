@@ -164,7 +164,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            # the CUDA arm's config; each step here is a bounded sample of it (1 of the batch's sweeps, see `sample`)
+            "config": dict(workload_config(args, args.batch), l2="n/a (host arm)", sample_per_step="1 sweep"),
             "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample,
                              "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in ("rasterize_ms", "decode_ms", "nms_ms")}},
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
