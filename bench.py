@@ -69,7 +69,7 @@ def ncu_traffic(args, batch: int):
     one `ncu --set full` capture of the default workload (profiles/r01_ncu_full_final.md); other workloads were
     not captured -> None."""
     if args.shape == "waymo" and batch == 16:
-        return int((70.645 + 0.761 + 67.771 + 36.286 + 154.729 + 19.292) * 1e6)
+        return int((70.651 + 0.346 + 67.777 + 35.712 + 154.737 + 20.664) * 1e6)
     return None
 
 

@@ -1078,7 +1078,9 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
   const int seg = blockIdx.x;
   const int cnt = a.kept_count[seg];
   const int off = a.out_off[seg], kb = a.kept_base[seg], beg = a.seg_begin[seg];
-  for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+  // grid = (segments, chunks of the kept list): every kept box has its own thread (the kernel is three dependent
+  // loads and a sincos per row, i.e. pure latency)
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
     const int row = off + t;
     if (row >= a.out_capacity) return;
     const float4 *src = reinterpret_cast<const float4 *>(a.boxes + static_cast<size_t>(a.order[beg + a.kept_pos[kb + t]]) * 8);
@@ -1297,7 +1299,10 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   pa.kept_pos = L.kept_pos; pa.order = order; pa.boxes = boxes; pa.acc = L.acc;
   pa.total_classes = p->total_classes; pa.out_capacity = p->out_capacity; pa.weighted = weighted ? 1 : 0; pa.yaw_layout = p->out_layout == RV3D_OUT_YAW;
   pa.out_params = out_params; pa.out_scores = out_scores; pa.out_cats = out_categories; pa.out_batch = out_batch;
-  pack_kernel<<<S, 128, 0, s>>>(pa);
+  {
+    const int chunks = ceil_div(p->num_post_nms < (1 << 20) ? p->num_post_nms : (1 << 20), 128);
+    pack_kernel<<<dim3(S, chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks)), 128, 0, s>>>(pa);
+  }
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
