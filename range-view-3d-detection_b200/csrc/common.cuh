@@ -58,4 +58,27 @@ __device__ __forceinline__ float ldg_stream_f(const float *p) {
   return r;
 }
 
+// L2 residency hints (createpolicy + .L2::cache_hint): data that a later kernel re-reads is marked evict_last,
+// write-once streams evict_first, so the 126 MB L2 keeps the former while the latter pass through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4 *ptr, uint64_t policy) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(ptr), "l"(policy));
+  return r;
+}
+__device__ __forceinline__ void st_f_hint(float *ptr, float v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(policy) : "memory");
+}
+
 }  // namespace rv3d

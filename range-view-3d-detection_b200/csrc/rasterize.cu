@@ -115,12 +115,13 @@ raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uin
   if (i0 >= n) return;
   int l[kScatterPerThread];
   float4 p[kScatterPerThread];
+  const uint64_t keep = l2_policy_evict_last();   // resolve gathers the winners from these lines: keep them in L2
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
     const int i = i0 + u * blockDim.x;
     const size_t gi = static_cast<size_t>(b) * a.max_points + (i < n ? i : i0);
     l[u] = laser[gi];
-    p[u] = ldg_stream_f4(points + gi);
+    p[u] = ldg_f4_hint(points + gi, keep);
   }
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
@@ -164,13 +165,14 @@ raster_resolve_kernel(RasterArgs a, const float4 *__restrict__ points, const uns
   if (key != kEmptyKey) p = __ldg(points + static_cast<size_t>(b) * a.max_points + key_index(key));
   const PixelOut o = resolve_pixel(a, key, p);
   float *out = image + static_cast<size_t>(b) * 7 * HW + pix;
-  out[0 * static_cast<size_t>(HW)] = o.az;
-  out[1 * static_cast<size_t>(HW)] = o.inc;
-  out[2 * static_cast<size_t>(HW)] = o.rr;
-  out[3 * static_cast<size_t>(HW)] = o.x;
-  out[4 * static_cast<size_t>(HW)] = o.y;
-  out[5 * static_cast<size_t>(HW)] = o.z;
-  out[6 * static_cast<size_t>(HW)] = o.it;
+  const uint64_t stream = l2_policy_evict_first();   // the 76 MB image must not push the points out of L2
+  st_f_hint(out + 0 * static_cast<size_t>(HW), o.az, stream);
+  st_f_hint(out + 1 * static_cast<size_t>(HW), o.inc, stream);
+  st_f_hint(out + 2 * static_cast<size_t>(HW), o.rr, stream);
+  st_f_hint(out + 3 * static_cast<size_t>(HW), o.x, stream);
+  st_f_hint(out + 4 * static_cast<size_t>(HW), o.y, stream);
+  st_f_hint(out + 5 * static_cast<size_t>(HW), o.z, stream);
+  st_f_hint(out + 6 * static_cast<size_t>(HW), o.it, stream);
   if (winner) winner[static_cast<size_t>(b) * HW + pix] = o.w;
 }
 
