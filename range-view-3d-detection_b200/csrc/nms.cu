@@ -366,6 +366,25 @@ nms_segment_kernel(NmsArgs a) {
     if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
   };
 
+  // The three passes of the grid build read (centre, radius) of every candidate; each is a chain of dependent
+  // global loads unless several are in flight per thread: 4 records are loaded before the first is used.
+  auto for_each_centre = [&](auto &&fn) {
+    constexpr int kU = 4;
+    for (int i0 = tid; i0 < n; i0 += kU * kNmsThreads) {
+      float x[kU], y[kU], r[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * kNmsThreads;
+        if (i < n) { x[u] = rec_cx(recs[i]); y[u] = rec_cy(recs[i]); r[u] = recs[i].r; }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * kNmsThreads;
+        if (i < n) fn(i, x[u], y[u], r[u]);
+      }
+    }
+  };
+
   // ======================= 0. alive bitmap + static candidate grid (leader) =======================
   for (int w = tid; w < nwords; w += kNmsThreads)
     alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
@@ -375,13 +394,11 @@ nms_segment_kernel(NmsArgs a) {
     {
       // first and second moments of the sane candidates -> grid origin / cell size / radius cap
       float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sum x, y, x^2, y^2, r, count
-      for (int i = tid; i < n; i += kNmsThreads) {
-        const Rec rc = recs[i];
-        const float x = rec_cx(rc), y = rec_cy(rc), r = rc.r;
+      for_each_centre([&](int, float x, float y, float r) {
         if (r > 0.f && r < 1.0e4f && fabsf(x) <= kPosCap && fabsf(y) <= kPosCap) {
           acc[0] += x; acc[1] += y; acc[2] += x * x; acc[3] += y * y; acc[4] += r; acc[5] += 1.f;
         }
-      }
+      });
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
@@ -404,12 +421,10 @@ nms_segment_kernel(NmsArgs a) {
     }
     const GridGeom g = s_geom;
     if (prune) {
-      for (int i = tid; i < n; i += kNmsThreads) {           // count
-        const Rec rc = recs[i];
-        const float x = rec_cx(rc), y = rec_cy(rc);
-        if (g.gridded(x, y, rc.r)) atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1);
+      for_each_centre([&](int i, float x, float y, float r) {   // count
+        if (g.gridded(x, y, r)) atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1);
         else os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
-      }
+      });
     } else {
       for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
       if (tid == 0) s_nos = n;
@@ -428,12 +443,10 @@ nms_segment_kernel(NmsArgs a) {
     }
     __syncthreads();
     if (prune) {
-      for (int i = tid; i < n; i += kNmsThreads) {           // fill
-        const Rec rc = recs[i];
-        const float x = rec_cx(rc), y = rec_cy(rc);
-        if (!g.gridded(x, y, rc.r)) continue;
-        entries[atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1)] = GridEntry{x, y, rc.r, static_cast<uint32_t>(i)};
-      }
+      for_each_centre([&](int i, float x, float y, float r) {   // fill
+        if (!g.gridded(x, y, r)) return;
+        entries[atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1)] = GridEntry{x, y, r, static_cast<uint32_t>(i)};
+      });
     }
     if (kWeighted)
       for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
