@@ -209,6 +209,7 @@ int rv3d_compact_candidates(const float *cuboids, const float *scores, const int
 #define RV3D_NMS_WEIGHTED 1
 #define RV3D_OUT_QUAT 0
 #define RV3D_OUT_YAW 1
+#define RV3D_MAX_PEERS 8
 
 typedef struct {
   int32_t batch, total_classes, total_candidates;
@@ -221,6 +222,15 @@ typedef struct {
   int32_t out_layout;        /* RV3D_OUT_QUAT: out_params (cap,10) [x,y,z,l,w,h,qw,qx,qy,qz]
                                 (RangeDecoder.decode); RV3D_OUT_YAW: out_params (cap,7)
                                 [x,y,z,l,w,h,yaw] (batched_multiclass_nms)               */
+  /* Fused detection gather over peer memory (the path's one exchange step, multi-GPU; replaces the per-sweep
+   * feather files + dist.barrier() of nn/arch/detector.py:366-380,415-421).  peer_world > 0: the pack kernel
+   * ALSO stores every detection as a 16-float row [sweep + sweep_offset, class, score, 0, x,y,z,l, w,h,qw,qx,
+   * qy,qz,0,0] into slot `peer_rank` of each rank's (peer_world, peer_capacity + 1, 16) f32 buffer, row 0 of
+   * the slot being [rows written, rows kept, 0, 0], with plain 16-byte stores through peer-mapped (NVLink)
+   * pointers.  The caller orders readers behind the writers (a device-side barrier over the ranks).
+   * RV3D_OUT_QUAT only.  peer_world == 0: off. */
+  int32_t peer_world, peer_rank, peer_capacity, sweep_offset;
+  float *peer_rows[RV3D_MAX_PEERS];
 } rv3d_nms_params;
 
 size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);

@@ -1085,6 +1085,10 @@ struct PackArgs {
   const double *acc;
   int total_classes, out_capacity, weighted, yaw_layout;
   float *out_params, *out_scores, *out_cats, *out_batch;
+  // fused gather: every rank's buffer is (world, peer_capacity + 1, 16) f32; this rank writes slot `peer_rank` of each
+  const int *out_count;
+  int n_peers, peer_rank, peer_capacity, sweep_offset;
+  float *peer_rows[RV3D_MAX_PEERS];
 };
 
 __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
@@ -1124,6 +1128,29 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
     a.out_scores[row] = b1.w;
     a.out_cats[row] = static_cast<float>(seg % a.total_classes);   // nms.py:51: full_like(scores, j)
     a.out_batch[row] = static_cast<float>(seg / a.total_classes);  // nms.py:242
+    if (a.n_peers > 0 && row < a.peer_capacity) {
+      // the path's one exchange step, fused: the detection goes straight into every rank's gather buffer with
+      // 16-byte stores through the NVLink-mapped peer pointers (no staging copy, no collective call)
+      double s, c;
+      sincos(static_cast<double>(p[6] * 0.5f), &s, &c);
+      const float4 r0 = make_float4(static_cast<float>(seg / a.total_classes + a.sweep_offset),
+                                    static_cast<float>(seg % a.total_classes), b1.w, 0.f);
+      const float4 r1 = make_float4(p[0], p[1], p[2], p[3]);
+      const float4 r2 = make_float4(p[4], p[5], static_cast<float>(c), 0.f);
+      const float4 r3 = make_float4(0.f, static_cast<float>(s), 0.f, 0.f);
+      const size_t at = (static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) + 1 + row) * 16;
+      for (int q = 0; q < a.n_peers; ++q) {
+        float4 *dst = reinterpret_cast<float4 *>(a.peer_rows[q] + at);
+        dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
+      }
+    }
+  }
+  if (a.n_peers > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {   // header row: [rows written, rows kept]
+    const int total = *a.out_count;
+    const float4 h = make_float4(static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity),
+                                 static_cast<float>(total), 0.f, 0.f);
+    for (int q = 0; q < a.n_peers; ++q)
+      *reinterpret_cast<float4 *>(a.peer_rows[q] + static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) * 16) = h;
   }
 }
 
@@ -1250,6 +1277,11 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   RV3D_CHECK_ARG(p->num_pre_nms > 0 && p->num_post_nms > 0 && p->out_capacity >= 0);
   RV3D_CHECK_ARG(p->mode == RV3D_NMS_HARD || p->mode == RV3D_NMS_WEIGHTED);
   RV3D_CHECK_ARG(p->out_layout == RV3D_OUT_QUAT || p->out_layout == RV3D_OUT_YAW);
+  RV3D_CHECK_ARG(p->peer_world >= 0 && p->peer_world <= RV3D_MAX_PEERS);
+  if (p->peer_world > 0) {
+    RV3D_CHECK_ARG(p->out_layout == RV3D_OUT_QUAT && p->peer_rank >= 0 && p->peer_rank < p->peer_world && p->peer_capacity > 0);
+    for (int q = 0; q < p->peer_world; ++q) RV3D_CHECK_ARG(p->peer_rows[q] && aligned(p->peer_rows[q], 16));
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n = p->n_candidates;
   if (n == 0) {
@@ -1312,6 +1344,9 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   pa.kept_pos = L.kept_pos; pa.order = order; pa.boxes = boxes; pa.acc = L.acc;
   pa.total_classes = p->total_classes; pa.out_capacity = p->out_capacity; pa.weighted = weighted ? 1 : 0; pa.yaw_layout = p->out_layout == RV3D_OUT_YAW;
   pa.out_params = out_params; pa.out_scores = out_scores; pa.out_cats = out_categories; pa.out_batch = out_batch;
+  pa.out_count = out_count;
+  pa.n_peers = p->peer_world; pa.peer_rank = p->peer_rank; pa.peer_capacity = p->peer_capacity; pa.sweep_offset = p->sweep_offset;
+  for (int q = 0; q < p->peer_world; ++q) pa.peer_rows[q] = p->peer_rows[q];
   {
     const int chunks = ceil_div(p->num_post_nms < (1 << 20) ? p->num_post_nms : (1 << 20), 128);
     pack_kernel<<<dim3(S, chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks)), 128, 0, s>>>(pa);

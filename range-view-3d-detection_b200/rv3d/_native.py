@@ -47,7 +47,9 @@ class NmsParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("total_classes", C.c_int32), ("total_candidates", C.c_int32),
                 ("num_pre_nms", C.c_int32), ("num_post_nms", C.c_int32), ("mode", C.c_int32),
                 ("iou_threshold", C.c_float), ("merge_threshold", C.c_float), ("n_candidates", C.c_int32),
-                ("out_capacity", C.c_int32), ("out_layout", C.c_int32)]
+                ("out_capacity", C.c_int32), ("out_layout", C.c_int32),
+                ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_capacity", C.c_int32),
+                ("sweep_offset", C.c_int32), ("peer_rows", C.c_void_p * 8)]
 
 
 class Rv3dError(RuntimeError):

@@ -91,8 +91,11 @@ def new_candidates(ws: Workspace, batch: int, total_classes: int, total_candidat
 
 
 def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_nms: int, iou_threshold: float,
-            mode: str, layout: int, merge_threshold: float = 0.5, stats: Optional[torch.Tensor] = None):
-    """-> (params (M,10|7) f32, scores (M,) f32, categories (M,) f32, batch_index (M,) f32)."""
+            mode: str, layout: int, merge_threshold: float = 0.5, stats: Optional[torch.Tensor] = None,
+            peer=None, peer_slot: int = 0, sweep_offset: int = 0):
+    """-> (params (M,10|7) f32, scores (M,) f32, categories (M,) f32, batch_index (M,) f32).
+    ``peer`` (rv3d.distributed.PeerGather): also store the detections into every rank's gather buffer from inside the
+    pack kernel (slot ``peer_slot``, sweep indices shifted by ``sweep_offset``)."""
     mode = mode.upper()                                                      # nms.py:207
     if mode not in ("HARD", "WEIGHTED"):
         raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")   # nms.py:239-240
@@ -113,6 +116,12 @@ def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_
     p.iou_threshold = float(torch.tensor(float(iou_threshold), dtype=torch.float32))
     p.merge_threshold = float(merge_threshold)
     p.n_candidates, p.out_capacity, p.out_layout = n, cap, layout
+    if peer is not None:
+        if layout != N.OUT_QUAT:
+            raise ValueError("the fused gather carries params(10) rows (RangeDecoder.decode layout)")
+        p.peer_world, p.peer_rank, p.peer_capacity, p.sweep_offset = peer.world, peer.rank, peer.capacity, int(sweep_offset)
+        for q, addr in enumerate(peer.slot_ptrs(peer_slot)):
+            p.peer_rows[q] = addr
     lib = N.lib()
     need = lib.rv3d_nms_scratch_bytes(p)
     work = ws.bytes("nms_scratch", need, dev)

@@ -79,3 +79,53 @@ def gather_detections_fixed(rows: Tensor, capacity: int, group: Optional[dist.Pr
 def unpack_fixed(stacked: Tensor) -> Tensor:
     counts = stacked[:, 0, 0].to(torch.int64).tolist()
     return torch.cat([stacked[r, 1 : c + 1] for r, c in enumerate(counts)], dim=0)
+
+
+class PeerGather:
+    """The gather of detections as peer-memory stores fused into the NMS pack kernel (``rv3d_nms`` with ``peer_world``).
+
+    Every rank owns a ``(slots, world, capacity + 1, 16)`` float32 buffer in symmetric memory (torch's symmetric-memory
+    allocator maps all ranks' buffers into each process: plumbing only).  Rank r's pack kernel writes its detections
+    into slot ``r`` of EVERY rank's buffer through the NVLink-mapped pointers; ``arrive_and_wait`` is a device-side
+    barrier over the ranks on the current stream (no host synchronisation), after which ``rows`` / ``unpack`` read the
+    complete gather locally.  Two slots alternate between consecutive steps so a step's writers never race the previous
+    step's readers.  Raises if symmetric memory is unavailable (callers fall back to ``gather_detections_fixed``)."""
+
+    ROW16 = 16
+
+    def __init__(self, capacity: int, device: torch.device, group: Optional[dist.ProcessGroup] = None, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerGather handles up to 8 ranks (one NVSwitch domain)")
+        self.capacity, self.slots = int(capacity), int(slots)
+        self.buf = symm_mem.empty((self.slots, self.world, self.capacity + 1, self.ROW16), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.slot_bytes = self.world * (self.capacity + 1) * self.ROW16 * 4
+        self.hdl.barrier()
+
+    def slot_ptrs(self, slot: int):
+        return [p + (slot % self.slots) * self.slot_bytes for p in self.ptrs]
+
+    def write_empty(self, slot: int) -> None:
+        """This rank has no detections this step: publish a zero header to every rank."""
+        for q in range(self.world):
+            peer = self.hdl.get_buffer(q, (self.slots, self.world, self.capacity + 1, self.ROW16), torch.float32)
+            peer[slot % self.slots, self.rank, 0, :4] = 0.0
+
+    def arrive_and_wait(self) -> None:
+        self.hdl.barrier()
+
+    def rows(self, slot: int) -> Tensor:
+        """(world, capacity + 1, 16): row 0 of each rank's block is [rows written, rows kept, 0, 0]."""
+        return self.buf[slot % self.slots]
+
+    def unpack(self, slot: int) -> Tensor:
+        """-> (M, 13) rows [sweep, class, score, params(10)] of all ranks in rank order (host reads the counts)."""
+        blk = self.rows(slot)
+        counts = blk[:, 0, 0].to(torch.int64).tolist()
+        cols = [0, 1, 2] + list(range(4, 14))
+        return torch.cat([blk[r, 1 : c + 1][:, cols] for r, c in enumerate(counts)], dim=0)

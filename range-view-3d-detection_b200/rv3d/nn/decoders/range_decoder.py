@@ -99,7 +99,12 @@ class RangeDecoder:
                use_nms: bool = True, **kwargs: Any) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         """Drop-in for RangeDecoder.decode (nn/decoders/range_decoder.py:29-124) ->
         (params (K,10) [x,y,z,l,w,h,qw,qx,qy,qz], scores (K,), categories (K,), batch_index (K,)).
-        With NMS, categories / batch_index are float32 (math/ops/nms.py:51,242); without, int64."""
+        With NMS, categories / batch_index are float32 (math/ops/nms.py:51,242); without, int64.
+
+        Multi-GPU extra (not in the reference): ``gather=(PeerGather, slot, sweep_offset)`` makes the pack kernel also
+        store this rank's detections into every rank's gather buffer (rv3d.distributed.PeerGather); the caller then
+        calls ``PeerGather.arrive_and_wait()``."""
+        gather = kwargs.pop("gather", None)
         del kwargs                                                         # tools/benchmark.py passes data=
         first = next(iter(multiscale_outputs.values()))
         dt = first[next(iter(task_config.keys()))]["logits"].dtype
@@ -111,11 +116,14 @@ class RangeDecoder:
                 mode = str(post_processing_config["nms_mode"]).upper()
                 if mode not in ("HARD", "WEIGHTED"):
                     raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
+                if gather is not None:
+                    gather[0].write_empty(gather[1])
                 e = torch.empty((0,), dtype=dt, device=dev)
                 return torch.empty((0, 10), dtype=dt, device=dev), e.view(0, 1), e.view(0, 1), e.view(0, 1)
+            peer_kw = {} if gather is None else dict(peer=gather[0], peer_slot=gather[1], sweep_offset=gather[2])
             params, scores, cats, bidx = run_nms(
                 self._ws, cand, n, post_processing_config["num_pre_nms"], post_processing_config["num_post_nms"],
-                post_processing_config["nms_threshold"], str(post_processing_config["nms_mode"]), N.OUT_QUAT)
+                post_processing_config["nms_threshold"], str(post_processing_config["nms_mode"]), N.OUT_QUAT, **peer_kw)
             return params.to(dt), scores.to(dt), cats.to(dt), bidx.to(dt)
         params = torch.empty((n, 10), dtype=torch.float32, device=dev)
         scores = torch.empty((n,), dtype=torch.float32, device=dev)

@@ -1,0 +1,50 @@
+"""Multi-rank check of the fused detection gather (run under torchrun, or with RANK/WORLD_SIZE=0/1 on one GPU):
+every rank decodes ITS sweeps with gather=(PeerGather, slot, sweep_offset); after the device-side barrier each rank
+must hold, for every rank, exactly the rows pack_rows() would have produced there."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "range-view-3d-detection_b200")]
+from rv3d.distributed import PeerGather, gather_detections, pack_rows  # noqa: E402
+from rv3d.nn.decoders.range_decoder import RangeDecoder  # noqa: E402
+from tests import synth  # noqa: E402
+from tests.util import PP, SBR, ms_outputs, to_dev  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    B, C = 3, 3
+    dec = RangeDecoder(True, True, *SBR)
+    tasks = {0: ["a", "b", "c"]}
+    pp = dict(PP, nms_mode="HARD")
+    peer = PeerGather(B * C * pp["num_post_nms"], dev)
+    for step in range(5):                                  # alternating slots, different data every step
+        head = synth.make_head_outputs(B, C, 16, 256, seed=100 * step + rank, n_objects=8)
+        if step == 3 and rank == world - 1:
+            head["logits"].fill_(-20.0)                    # one rank without any detection
+        out = dec.decode(ms_outputs(to_dev(head, dev)), pp, tasks, gather=(peer, step, rank * B))
+        peer.arrive_and_wait()
+        got = peer.unpack(step)
+        ref = gather_detections(pack_rows(*out, batch_offset=rank * B))   # the NCCL form of the same gather
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert torch.equal(got, ref), f"step {step}: rows differ"
+        hdr = peer.rows(step)[:, 0, :2].cpu()
+        assert torch.equal(hdr[:, 0], hdr[:, 1])           # nothing dropped
+        if step == 3:
+            assert int(hdr[world - 1, 0]) == 0
+    dist.barrier()
+    if rank == 0:
+        print(f"peer gather ok: world {world}, {got.shape[0]} rows in the last step", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
