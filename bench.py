@@ -345,7 +345,9 @@ def run_ours(args):
                 out = dec.decode(ms_of(b["head"]), pp, tasks, gather=(peer, slot, rank * B))
                 b["free"].record(cur)
                 peer.arrive_and_wait()
-                rows = peer.rows(slot).flatten(0, 1)
+                # every rank holds the full gather on the device; the host copy is the whole set on rank 0 and the
+                # rank's own detections elsewhere (the reference's ranks each write only their own sweeps' files)
+                rows = peer.rows(slot).flatten(0, 1) if rank == 0 else peer.rows(slot)[rank]
             else:
                 out = dec.decode(ms_of(b["head"]), pp, tasks)
                 b["free"].record(cur)
