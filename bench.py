@@ -206,7 +206,9 @@ def run_ours(args):
 
     B = args.batch
     n, H, W, C, M, ident = WORKLOADS[args.shape]
-    sweeps, head, mapping = make_inputs(args.shape, B, 1000 + 100 * rank)
+    # weak scaling: every rank gets the SAME synthetic sweeps, so the per-GPU work is identical at every N (NMS time is
+    # data dependent; with different seeds the max over ranks would measure the unluckiest seed, not the scaling)
+    sweeps, head, mapping = make_inputs(args.shape, B, 1000)
     pts_h, las_h, cnt_h = pack_sweeps(sweeps, dev, pin=True)
     head_h = {k: v.pin_memory() for k, v in head.items()}
     from rv3d.constants import ROW_MAPPING_64
@@ -250,6 +252,8 @@ def run_ours(args):
         slot = step_no[0] & 1
         step_no[0] += 1
         kw = dict(peer=peer, peer_slot=slot, sweep_offset=rank * B) if peer is not None else {}
+        if peer is not None:
+            peer.begin(slot)
         out = run_nms(dec._ws, cand, ncand, pp["num_pre_nms"], pp["num_post_nms"], pp["nms_threshold"], pp["nms_mode"],
                       N.OUT_QUAT, stats=stats, **kw) if ncand else None
         if out is None:
@@ -258,8 +262,8 @@ def run_ours(args):
             if peer is not None:
                 peer.write_empty(slot)
         if peer is not None:
-            peer.arrive_and_wait()
-            rows = peer.rows(slot)
+            peer.publish(slot)        # barrier over the ranks on a side stream: overlaps the next step's rasterize + decode
+            rows = peer.rows(slot)    # complete once peer.wait(slot) has passed
         elif world > 1:
             rows = gather_detections_fixed(pack_rows(*out, batch_offset=rank * B), gather_cap)
         else:
@@ -292,6 +296,8 @@ def run_ours(args):
         flush.zero_()
         ev[k][0].record()
         ncand, out, _ = step(pts, las, cnt, hd, ev[k])
+        if peer is not None and k == args.steps - 1:
+            peer.wait((step_no[0] - 1) & 1)      # the last step's gather is inside the timed region too
         ev[k][3].record()
         ndet = out[0].shape[0]
     barrier()
@@ -342,9 +348,11 @@ def run_ours(args):
             if peer is not None:
                 slot = step_no[0] & 1
                 step_no[0] += 1
+                peer.begin(slot)
                 out = dec.decode(ms_of(b["head"]), pp, tasks, gather=(peer, slot, rank * B))
                 b["free"].record(cur)
-                peer.arrive_and_wait()
+                peer.publish(slot)
+                peer.wait(slot)
                 # every rank holds the full gather on the device; the host copy is the whole set on rank 0 and the
                 # rank's own detections elsewhere (the reference's ranks each write only their own sweeps' files)
                 rows = peer.rows(slot).flatten(0, 1) if rank == 0 else peer.rows(slot)[rank]
@@ -385,7 +393,8 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "ms_per_step_median_rank0": float(np.median(t_step)), "ms_per_step_max_rank0": float(np.max(t_step)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args, B), detection_gather=gather_kind),
+            "config": dict(workload_config(args, B), detection_gather=gather_kind,
+                           per_rank_data="identical synthetic sweeps on every rank (seed 1000)"),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             # own kernels per step: raster scatter + resolve, decode_compact, iota, segment_bounds, capacity scan,
             # prepare_records, nms_segment, kept_scan, pack (the CUB sort passes and memsets are not counted)

@@ -117,7 +117,41 @@ class PeerGather:
             peer[slot % self.slots, self.rank, 0, :4] = 0.0
 
     def arrive_and_wait(self) -> None:
+        """Synchronous form: barrier on the current stream right after the writes."""
         self.hdl.barrier()
+
+    # ---- pipelined form: the barrier runs on a side stream, so a rank may run one step ahead of the slowest one ----
+    #   begin(slot)    before the NMS call that writes `slot`: wait until the barrier of the PREVIOUS step is through
+    #                  (then every rank has finished reading this slot's previous contents, two steps back)
+    #   publish(slot)  after the NMS call: the side stream waits for the writes, runs the barrier, marks the slot gathered
+    #   wait(slot)     a consumer's stream waits for the slot to be gathered;  side_stream runs consumers off-path
+    def _lazy_async(self):
+        if not hasattr(self, "side_stream"):
+            self.side_stream = torch.cuda.Stream(self.buf.device)
+            self._written = [torch.cuda.Event() for _ in range(self.slots)]
+            self._done = [torch.cuda.Event() for _ in range(self.slots)]
+            self._published = [False] * self.slots
+
+    def begin(self, slot: int) -> None:
+        self._lazy_async()
+        prev = (slot - 1) % self.slots
+        if self._published[prev]:
+            torch.cuda.current_stream(self.buf.device).wait_event(self._done[prev])
+
+    def publish(self, slot: int) -> None:
+        self._lazy_async()
+        s = slot % self.slots
+        self._written[s].record(torch.cuda.current_stream(self.buf.device))
+        with torch.cuda.stream(self.side_stream):
+            self.side_stream.wait_event(self._written[s])
+            self.hdl.barrier()
+            self._done[s].record(self.side_stream)
+        self._published[s] = True
+
+    def wait(self, slot: int) -> None:
+        self._lazy_async()
+        if self._published[slot % self.slots]:
+            torch.cuda.current_stream(self.buf.device).wait_event(self._done[slot % self.slots])
 
     def rows(self, slot: int) -> Tensor:
         """(world, capacity + 1, 16): row 0 of each rank's block is [rows written, rows kept, 0, 0]."""

@@ -40,6 +40,22 @@ def main():
         assert torch.equal(hdr[:, 0], hdr[:, 1])           # nothing dropped
         if step == 3:
             assert int(hdr[world - 1, 0]) == 0
+    # pipelined form: the barrier runs on a side stream, a step is consumed after the NEXT one has been launched
+    torch.cuda.synchronize()
+    pending = None
+    for step in range(5, 12):
+        head = synth.make_head_outputs(B, C, 16, 256, seed=100 * step + rank, n_objects=8)
+        peer.begin(step)
+        out = dec.decode(ms_outputs(to_dev(head, dev)), pp, tasks, gather=(peer, step, rank * B))
+        peer.publish(step)
+        ref = gather_detections(pack_rows(*out, batch_offset=rank * B))
+        if pending is not None:
+            pstep, pref = pending
+            peer.wait(pstep)
+            assert torch.equal(peer.unpack(pstep), pref), f"pipelined step {pstep}: rows differ"
+        pending = (step, ref)
+    peer.wait(pending[0])
+    assert torch.equal(peer.unpack(pending[0]), pending[1])
     dist.barrier()
     if rank == 0:
         print(f"peer gather ok: world {world}, {got.shape[0]} rows in the last step", flush=True)
