@@ -148,7 +148,7 @@ def run_reference(args):
     if rank != 0:
         return
     import oracle  # noqa: F401  (builds the C part)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     sweeps, head, mapping = make_inputs(args.shape, 1, 1000)
     pool = ThreadPoolExecutor(max_workers=cores)
@@ -182,6 +182,25 @@ def workload_config(args, batch):
             "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)"}
 
 
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (torchrun does not bind ranks): the pinned host
+    buffers of the e2e leg are then first-touched on the GPU's own NUMA node.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} CPUs local to GPU {index}"
+        return "GPU-local CPU set == current affinity"
+    except Exception as exc:   # noqa: BLE001
+        return f"not bound ({type(exc).__name__})"
+
+
 # --------------------------------------------------------------------------------------- #
 # the CUDA arm                                                                             #
 # --------------------------------------------------------------------------------------- #
@@ -203,6 +222,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     N.lib()
+
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: host buffers land next to the GPU's PCIe root
 
     B = args.batch
     n, H, W, C, M, ident = WORKLOADS[args.shape]
@@ -394,7 +416,7 @@ def run_ours(args):
             "ms_per_step_median_rank0": float(np.median(t_step)), "ms_per_step_max_rank0": float(np.max(t_step)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, B), detection_gather=gather_kind,
-                           per_rank_data="identical synthetic sweeps on every rank (seed 1000)"),
+                           per_rank_data="identical synthetic sweeps on every rank (seed 1000)", host_affinity=numa),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             # own kernels per step: raster scatter + resolve, decode_compact, iota, segment_bounds, capacity scan,
             # prepare_records, nms_segment, kept_scan, pack (the CUB sort passes and memsets are not counted)
@@ -421,7 +443,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             import oracle  # noqa: F401
-            cores = os.cpu_count() or 1
+            os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
+            cores = len(all_cpus)
             torch.set_num_threads(cores)
             pool = ThreadPoolExecutor(max_workers=cores)
             h1 = {k: v[:1] for k, v in head.items()}
