@@ -80,13 +80,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, enabled: bool = True):
+        self.index, self.proc, self.lines, self.enabled = index, None, [], enabled
 
     def __enter__(self):
+        if not self.enabled:   # one sampler per job (rank 0): nvidia-smi polls take a driver-wide lock
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
@@ -298,7 +300,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # clocks are sampled from the warm-up to the end of the e2e loop (the device is under load throughout)
-    clk = ClockSampler(local)
+    clk = ClockSampler(local, enabled=(rank == 0))
     clk.__enter__()
     for _ in range(max(args.warmup, 3)):
         step(pts, las, cnt, hd)
