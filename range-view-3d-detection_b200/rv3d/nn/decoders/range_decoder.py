@@ -17,7 +17,7 @@ from torch import Tensor
 
 from ... import _native as N
 from ..._pipeline import Workspace, cart_as, dtype_code, new_candidates, run_nms, threshold_as
-from ..._util import ptr, require_cuda, scratch, stream_ptr
+from ..._util import ptr, require_cuda, stream_ptr
 
 __all__ = ["RangeDecoder", "sample_by_range"]
 
