@@ -212,6 +212,7 @@ def run_ours(args):
     from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
     from rv3d.nn.decoders.range_decoder import RangeDecoder
     from rv3d import _native as N
+    from rv3d._pipeline import run_nms
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -272,7 +273,6 @@ def run_ours(args):
         cand = dec.candidates(ms_of(h), pp, tasks)
         if evs: evs[2].record()
         ncand = cand.count()
-        from rv3d._pipeline import run_nms
         slot = step_no[0] & 1
         step_no[0] += 1
         kw = dict(peer=peer, peer_slot=slot, sweep_offset=rank * B) if peer is not None else {}
@@ -439,9 +439,18 @@ def run_ours(args):
                                        "note": "sort + nms_segment_kernel + pack; not HBM-bound (ncu: DRAM 0.6 %, IPC 1.4)"}},
             "stage_ms": {"rasterize": float(np.mean(t_raster)), "decode_compact": float(np.mean(t_decode)),
                          "sort+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": t_wall / args.steps * 1e3},
-            "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "iou_evals_per_step": st[0],
-                    "kept_per_step": st[1], "pairs_above_thr_per_step": float(stats[18].item()) / args.steps, "approx_iou_per_step": float(stats[19].item()) / args.steps, "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3], "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]] + [round(float(stats[20].item()) / args.steps / 1e6, 3), round(float(stats[21].item()) / args.steps / 1e6, 3)], "slowest_segment_mcycles": round(float(stats[10].item()) / 1e6, 3), "largest_segment": int(stats[11].item()), "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()],
-                    "segments": B * C},
+            # work units of the suppression stage (device counters of nms_segment_kernel, averaged over the timed steps)
+            "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "segments": B * C,
+                    "iou_evals_per_step": st[0], "kept_per_step": st[1], "frontier_rounds_per_step": st[2],
+                    "circle_tests_per_step": st[3],
+                    "pairs_above_thr_per_step": float(stats[18].item()) / args.steps,
+                    "approx_iou_per_step": float(stats[19].item()) / args.steps,
+                    # leader CTAs' cycles per phase: build, frontier load, frontier pairs, greedy, kill scan, IoU, publish, sync
+                    "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]]
+                                              + [round(float(stats[i].item()) / args.steps / 1e6, 3) for i in (20, 21)],
+                    "slowest_segment_mcycles": round(float(stats[10].item()) / 1e6, 3),
+                    "largest_segment": int(stats[11].item()),
+                    "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()]},
         }
         if world == 1 and not args.no_cpu_baseline:
             import oracle  # noqa: F401
