@@ -47,10 +47,10 @@ SBR = ([0, 15, 30], [15, 30, math.inf], [8, 2, 1])                              
 FP_RATE = 0.95   # fraction of valid background pixels that fire (S ~ 20 % of K pass 0.1)
 
 
-def make_inputs(shape: str, batch: int, seed0: int):
+def make_inputs(shape: str, batch: int, seed0: int, fp_rate: float = None):
     n, H, W, C, M, ident = WORKLOADS[shape]
     sweeps = [synth.make_points(n, H, seed0 + s) for s in range(batch)]
-    head = synth.make_head_outputs(batch, C, H, W, seed=seed0, n_objects=M, fp_rate=FP_RATE, distinct_scores=False)
+    head = synth.make_head_outputs(batch, C, H, W, seed=seed0, n_objects=M, fp_rate=FP_RATE if fp_rate is None else fp_rate, distinct_scores=False)
     mapping = np.arange(H) if ident else None
     return sweeps, head, mapping
 
@@ -152,7 +152,7 @@ def run_reference(args):
     import oracle  # noqa: F401  (builds the C part)
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    sweeps, head, mapping = make_inputs(args.shape, 1, 1000)
+    sweeps, head, mapping = make_inputs(args.shape, 1, 1000, args.fp_rate)
     pool = ThreadPoolExecutor(max_workers=cores)
     for _ in range(args.warmup):
         cpu_step(sweeps[0], head, mapping, args.shape, args.nms_mode, pool)
@@ -180,7 +180,7 @@ def workload_config(args, batch):
                         f"({C} classes, sample_by_range [8,2,1], azimuth-invariant) + {args.nms_mode} rotated NMS "
                         f"(pre {PP['num_pre_nms']}, post {PP['num_post_nms']}, iou {PP['nms_threshold']}, conf {PP['min_confidence']})",
             "batch_per_gpu": batch, "points_per_sweep": n, "height": H, "width": W, "classes": C,
-            "objects_per_sweep": M, "fp_rate": FP_RATE, "nms_mode": args.nms_mode,
+            "objects_per_sweep": M, "fp_rate": FP_RATE if getattr(args, "fp_rate", None) is None else args.fp_rate, "nms_mode": args.nms_mode,
             "l2": "256 MiB L2 flush between timed steps (outside the per-step CUDA events)"}
 
 
@@ -233,7 +233,7 @@ def run_ours(args):
     n, H, W, C, M, ident = WORKLOADS[args.shape]
     # weak scaling: every rank gets the SAME synthetic sweeps, so the per-GPU work is identical at every N (NMS time is
     # data dependent; with different seeds the max over ranks would measure the unluckiest seed, not the scaling)
-    sweeps, head, mapping = make_inputs(args.shape, B, 1000)
+    sweeps, head, mapping = make_inputs(args.shape, B, 1000, args.fp_rate)
     pts_h, las_h, cnt_h = pack_sweeps(sweeps, dev, pin=True)
     head_h = {k: v.pin_memory() for k, v in head.items()}
     from rv3d.constants import ROW_MAPPING_64
@@ -482,6 +482,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="sweeps per GPU per step")
     ap.add_argument("--nms-mode", default="HARD", choices=["HARD", "WEIGHTED"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp-rate", type=float, default=None,
+                    help="exploration only: fraction of background pixels that fire (default: the SURVEY 8d density, 0.95)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
