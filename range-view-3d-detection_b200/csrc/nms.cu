@@ -60,26 +60,6 @@ __global__ void segment_bounds_kernel(const unsigned long long *__restrict__ key
   if (i == n - 1 || static_cast<uint32_t>(keys[i + 1] >> shift) != s) seg_end[s] = i + 1;
 }
 
-// exclusive scan of min(seg size, cap) over S segments (S is small: one block, serial chunks)
-__global__ void segment_capacity_scan_kernel(const int *__restrict__ seg_begin, const int *__restrict__ seg_end,
-                                             int S, int cap, int *__restrict__ base) {
-  __shared__ int s_part[1024];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int per = (S + nt - 1) / nt;
-  const int lo = min(S, tid * per), hi = min(S, lo + per);
-  int sum = 0;
-  for (int s = lo; s < hi; ++s) sum += min(seg_end[s] - seg_begin[s], cap);
-  s_part[tid] = sum;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int t = 0; t < nt; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; }
-  }
-  __syncthreads();
-  int run = s_part[tid];
-  for (int s = lo; s < hi; ++s) { base[s] = run; run += min(seg_end[s] - seg_begin[s], cap); }
-}
-
 // sorted position -> suppression record (+ merge row for the weighted mode)
 template <bool kWeighted>
 __global__ void __launch_bounds__(256)
@@ -1200,7 +1180,7 @@ static NmsLayout nms_layout(void *scratch, int n, int S, bool weighted, int D, i
   L.order_alt = c.take<uint32_t>(nn);
   L.seg_begin = c.take<int>(2 * static_cast<size_t>(S));  // seg_begin + seg_end contiguous (one memset)
   L.seg_end = L.seg_begin ? L.seg_begin + S : nullptr;
-  L.kept_base = c.take<int>(S);
+  L.kept_base = L.seg_begin;   // see rv3d_nms: a segment's kept rows live in its own [seg_begin, seg_end) slice
   L.kept_count = c.take<int>(S);
   L.out_off = c.take<int>(S);
   L.kept_pos = c.take<int>(nn);
@@ -1312,11 +1292,11 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   RV3D_CHECK_CUDA(cudaMemsetAsync(L.seg_begin, 0, sizeof(int) * 2 * S, s));
   segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(skeys, n, 32 + idx_bits, L.seg_begin, L.seg_end);
   RV3D_CHECK_LAUNCH();
-  segment_capacity_scan_kernel<<<1, 1024, 0, s>>>(L.seg_begin, L.seg_end, S, p->num_post_nms, L.kept_base);
-  RV3D_CHECK_LAUNCH();
 
+  // a segment keeps at most as many boxes as it has candidates, so its slice [seg_begin, seg_end) of the n-sized
+  // kept_pos / acc / merge_count arrays is its private, sufficient region: kept_base == seg_begin (no scan kernel)
   NmsArgs a{};
-  a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
+  a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.seg_begin;
   a.num_pre = p->num_pre_nms; a.num_post = p->num_post_nms; a.thr = p->iou_threshold; a.mthr = p->merge_threshold;
   a.prune = (p->iou_threshold >= 0.f && (p->mode != RV3D_NMS_WEIGHTED || p->merge_threshold >= 0.f)) ? 1 : 0;
   a.kept_pos = L.kept_pos; a.kept_count = L.kept_count; a.data = L.data; a.D = 9; a.acc = L.acc;
@@ -1340,7 +1320,7 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   kept_scan_kernel<<<1, 1024, 0, s>>>(L.kept_count, S, L.out_off, out_count, p->out_capacity);
   RV3D_CHECK_LAUNCH();
   PackArgs pa{};
-  pa.seg_begin = L.seg_begin; pa.kept_base = L.kept_base; pa.kept_count = L.kept_count; pa.out_off = L.out_off;
+  pa.seg_begin = L.seg_begin; pa.kept_base = L.seg_begin; pa.kept_count = L.kept_count; pa.out_off = L.out_off;
   pa.kept_pos = L.kept_pos; pa.order = order; pa.boxes = boxes; pa.acc = L.acc;
   pa.total_classes = p->total_classes; pa.out_capacity = p->out_capacity; pa.weighted = weighted ? 1 : 0; pa.yaw_layout = p->out_layout == RV3D_OUT_YAW;
   pa.out_params = out_params; pa.out_scores = out_scores; pa.out_cats = out_categories; pa.out_batch = out_batch;
