@@ -55,12 +55,13 @@ def make_inputs(shape: str, batch: int, seed0: int, fp_rate: float = None):
     return sweeps, head, mapping
 
 
-def algorithmic_bytes(shape: str, batch: int, survivors: int):
+def algorithmic_bytes(shape: str, batch: int, survivors: int, head_bytes: int = 4):
     """rasterize reads N*(16+1) B and writes 7*H*W*4 B per sweep; decode reads
-    H*W*(4*(C+8+3)+1) B per sweep (dense count: every input once) and writes 40 B per survivor."""
+    H*W*(4*(C+8+3)+1) B per sweep (dense count: every input once) and writes 40 B per survivor.
+    (`head_bytes` = 2 with --head-dtype f16: logits and regressands in half precision, cart stays float32.)"""
     n, H, W, C, _, _ = WORKLOADS[shape]
     raster = batch * (n * 17 + 7 * H * W * 4)
-    decode = batch * (H * W * (4 * (C + 8 + 3) + 1)) + 40 * survivors
+    decode = batch * (H * W * (head_bytes * (C + 8) + 4 * 3 + 1)) + 40 * survivors
     return raster, decode
 
 
@@ -234,6 +235,8 @@ def run_ours(args):
     # weak scaling: every rank gets the SAME synthetic sweeps, so the per-GPU work is identical at every N (NMS time is
     # data dependent; with different seeds the max over ranks would measure the unluckiest seed, not the scaling)
     sweeps, head, mapping = make_inputs(args.shape, B, 1000, args.fp_rate)
+    if args.head_dtype == "f16":   # exploration: the reference's own eval_precision = 16 operating point (range_view.yaml:26,
+        head = dict(head, logits=head["logits"].half(), regressands=head["regressands"].half())   # detector.py:329-333)
     pts_h, las_h, cnt_h = pack_sweeps(sweeps, dev, pin=True)
     head_h = {k: v.pin_memory() for k, v in head.items()}
     from rv3d.constants import ROW_MAPPING_64
@@ -403,7 +406,7 @@ def run_ours(args):
     clocks = clk.summary()
 
     if rank == 0:
-        raster_b, decode_b = algorithmic_bytes(args.shape, B, ncand)
+        raster_b, decode_b = algorithmic_bytes(args.shape, B, ncand, 2 if args.head_dtype == "f16" else 4)
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -418,7 +421,8 @@ def run_ours(args):
             "ms_per_step_median_rank0": float(np.median(t_step)), "ms_per_step_max_rank0": float(np.max(t_step)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, B), detection_gather=gather_kind,
-                           per_rank_data="identical synthetic sweeps on every rank (seed 1000)", host_affinity=numa),
+                           per_rank_data="identical synthetic sweeps on every rank (seed 1000)", host_affinity=numa,
+                           head_dtype=args.head_dtype),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             # own kernels per step: raster scatter + resolve, decode_compact, iota, segment_bounds,
             # prepare_records, nms_segment, kept_scan, pack (the CUB sort passes and memsets are not counted)
@@ -452,7 +456,7 @@ def run_ours(args):
                     "largest_segment": int(stats[11].item()),
                     "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()]},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.head_dtype == "f32":
             import oracle  # noqa: F401
             os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
             cores = len(all_cpus)
@@ -482,6 +486,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="sweeps per GPU per step")
     ap.add_argument("--nms-mode", default="HARD", choices=["HARD", "WEIGHTED"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"],
+                    help="exploration only: f16 = half-precision logits / regressands next to float32 cart (autocast); "
+                         "the CPU baseline leg is skipped")
     ap.add_argument("--fp-rate", type=float, default=None,
                     help="exploration only: fraction of background pixels that fire (default: the SURVEY 8d density, 0.95)")
     args = ap.parse_args()
