@@ -92,3 +92,55 @@ def test_product_does_not_import_oracle():
         text = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
         assert "liboracle" not in text and "oracle.c" not in text.replace("oracle/csrc/oracle.c", ""), f
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The Python mirror's ctypes structures must have the C compiler's layout of include/rv3d.h (a drift would corrupt
+    every call silently): sizes and field offsets are printed by a tiny C program built against the header."""
+    import shutil
+    import subprocess
+    from rv3d import _native as N
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"rv3d_raster_params": N.RasterParams, "rv3d_inputs_params": N.InputsParams, "rv3d_partitions": N.Partitions,
+               "rv3d_decode_params": N.DecodeParams, "rv3d_nms_params": N.NmsParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rv3d.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append('  printf("rv3d_detection_record %zu\\n", sizeof(rv3d_detection_record));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+    from rv3d.math.ops.coding import RECORD_DTYPE
+    assert int(out["rv3d_detection_record"]) == RECORD_DTYPE.itemsize == 64
+
+
+def test_host_side_helpers():
+    """Pure host logic of the mirror (no device): dtype codes, threshold rounding, cart dtype rule, partitions."""
+    from rv3d import _native as N
+    from rv3d._pipeline import cart_as, dtype_code, threshold_as
+    assert [dtype_code(d) for d in (torch.float32, torch.float16, torch.bfloat16)] == [0, 1, 2]
+    with pytest.raises(TypeError):
+        dtype_code(torch.float64)
+    # torch compares `scores >= 0.1` in the tensor's dtype
+    assert threshold_as(torch.float32, 0.1) == float(torch.tensor(0.1))
+    assert threshold_as(torch.float16, 0.1) == float(torch.tensor(0.1, dtype=torch.float16)) != 0.1
+    c32, c16 = torch.zeros(1, 3, 2, 2), torch.zeros(1, 3, 2, 2, dtype=torch.float16)
+    assert cart_as(torch.float16, c32).dtype == torch.float32          # autocast: cart keeps float32 next to half heads
+    assert cart_as(torch.float16, c16).dtype == torch.float16
+    assert cart_as(torch.float32, c16).dtype == torch.float32          # widened (exact)
+    with pytest.raises(TypeError):
+        cart_as(torch.float32, c32.double())
+    parts = N.make_partitions([0, 15, 30], [15, 30, float("inf")], [8, 2, 1])
+    assert parts.n_partitions == 3 and list(parts.rate)[:3] == [8, 2, 1] and parts.upper[2] == float("inf")
+    with pytest.raises(ValueError):
+        N.make_partitions([0] * 9, [1] * 9, [1] * 9)                  # more than RV3D_MAX_PARTITIONS
