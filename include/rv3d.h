@@ -138,6 +138,11 @@ int rv3d_subsample_range_view(const float *range_view, const uint8_t *mask, cons
 #define RV3D_F16 1
 #define RV3D_BF16 2
 #define RV3D_MAX_PARTITIONS 8
+/* Width of the score field of the 64-bit sort keys [segment | ~order(score) | candidate]:
+ * rv3d_decode_compact writes 31 bits (its scores, sigmoid * mask, are never negative, so the top bit of the
+ * order-preserving code is constant -- one radix pass less downstream); rv3d_compact_candidates, whose scores are
+ * the caller's, writes 32.  rv3d_nms / rv3d_pack_candidates are told which through `score_bits`. */
+#define RV3D_SCORE_BITS_DECODE 31
 
 /* decode_range_view: regressands (B,8,H,W) in `dtype`, cart (B,3,H,W) in `cart_dtype` -> out (B,7,H,W) in
  * `dtype` (coding.py:126: the result takes the regressands' dtype); arithmetic in f64 (coding.py:127-128),
@@ -222,6 +227,8 @@ typedef struct {
   int32_t out_layout;        /* RV3D_OUT_QUAT: out_params (cap,10) [x,y,z,l,w,h,qw,qx,qy,qz]
                                 (RangeDecoder.decode); RV3D_OUT_YAW: out_params (cap,7)
                                 [x,y,z,l,w,h,yaw] (batched_multiclass_nms)               */
+  int32_t score_bits;        /* score field of the keys: 31 (rv3d_decode_compact) or 32
+                                (rv3d_compact_candidates); 0 means 32                     */
   /* Fused detection gather over peer memory (the path's one exchange step, multi-GPU; replaces the per-sweep
    * feather files + dist.barrier() of nn/arch/detector.py:366-380,415-421).  peer_world > 0: the pack kernel
    * ALSO stores every detection as a 16-float row [sweep + sweep_offset, class, score, 0, x,y,z,l, w,h,qw,qx,
@@ -281,7 +288,7 @@ int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t str
  * compaction output -> rows ordered by (sweep, candidate). */
 size_t rv3d_pack_candidates_scratch_bytes(int32_t n_candidates);
 int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n_candidates, int32_t batch,
-                         int32_t total_classes, int32_t total_candidates, float *out_params,
+                         int32_t total_classes, int32_t total_candidates, int32_t score_bits, float *out_params,
                          float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
                          size_t scratch_bytes, rv3d_stream_t stream);
 

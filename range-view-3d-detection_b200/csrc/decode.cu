@@ -192,10 +192,13 @@ sample_by_range_kernel(const float *__restrict__ scores, const int64_t *__restri
 // Ascending key order == segment asc, score desc, candidate index asc: the total order the
 // suppression step works in (DESIGN.md "K3").
 struct KeyPack {
-  int idx_bits;  // width of the low field (candidate index)
+  int idx_bits;    // width of the low field (candidate index)
+  int score_bits;  // 32, or 31 when every score is >= 0 (then the top bit of the order code is constant):
+                   // one radix pass less at the Waymo shape (6 + 31 + 19 = 56 key bits instead of 57)
   __device__ __forceinline__ unsigned long long make(uint32_t seg, float score, uint32_t cand) const {
-    const uint32_t desc = ~orderable_f32(__float_as_uint(score));
-    return (static_cast<unsigned long long>(seg) << (32 + idx_bits)) |
+    uint32_t desc = ~orderable_f32(__float_as_uint(score));
+    if (score_bits < 32) desc &= (1u << score_bits) - 1u;
+    return (static_cast<unsigned long long>(seg) << (score_bits + idx_bits)) |
            (static_cast<unsigned long long>(desc) << idx_bits) | cand;
   }
 };
@@ -684,7 +687,8 @@ extern "C" int rv3d_decode_compact(const rv3d_decode_params *p, const void *logi
   a.pa = make_parts(&p->parts, p->height, p->width);
   RV3D_CHECK_ARG(p->total_candidates >= p->candidate_offset + a.pa.off[a.pa.n]);
   a.kp.idx_bits = bits_for(p->total_candidates);
-  if (bits_for(static_cast<int64_t>(p->batch) * p->total_classes) + 32 + a.kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
+  a.kp.score_bits = RV3D_SCORE_BITS_DECODE;   // sigmoid * mask is never negative
+  if (bits_for(static_cast<int64_t>(p->batch) * p->total_classes) + a.kp.score_bits + a.kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto *keys = reinterpret_cast<unsigned long long *>(out_keys);
 #define RV3D_CALL(T, TC) return launch_decode_compact<T, TC>(a, logits, regressands, cart, mask, keys, out_boxes, counter, s)
@@ -703,6 +707,7 @@ extern "C" int rv3d_compact_candidates(const float *cuboids, const float *scores
   if (!aligned(out_boxes, 16) || !aligned(out_keys, 8)) return RV3D_ERR_ALIGN;
   KeyPack kp;
   kp.idx_bits = bits_for(k);
+  kp.score_bits = 32;                         // caller-supplied scores may be negative
   if (bits_for(static_cast<int64_t>(batch) * total_classes) + 32 + kp.idx_bits > 64) return RV3D_ERR_KEYBITS;
   dim3 grid(ceil_div(k, 256), batch);
   compact_candidates_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(

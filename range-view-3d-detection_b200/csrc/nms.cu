@@ -1245,7 +1245,7 @@ using namespace rv3d;
 extern "C" size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p) {
   if (!p || p->batch <= 0 || p->total_classes <= 0 || p->n_candidates < 0) return 0;
   const int S = p->batch * p->total_classes;
-  const int end_bit = bits_for(S) + 32 + bits_for(p->total_candidates);
+  const int end_bit = bits_for(S) + (p->score_bits ? p->score_bits : 32) + bits_for(p->total_candidates);
   return nms_layout(nullptr, p->n_candidates, S, p->mode == RV3D_NMS_WEIGHTED, 9, end_bit > 64 ? 64 : end_bit).total;
 }
 
@@ -1272,7 +1272,9 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   if (!aligned(boxes, 16) || !aligned(keys_in, 8) || !aligned(scratch, 256)) return RV3D_ERR_ALIGN;
   const int S = p->batch * p->total_classes;
   const int idx_bits = bits_for(p->total_candidates);
-  const int end_bit = bits_for(S) + 32 + idx_bits;
+  const int score_bits = p->score_bits ? p->score_bits : 32;
+  RV3D_CHECK_ARG(score_bits == 31 || score_bits == 32);
+  const int end_bit = bits_for(S) + score_bits + idx_bits;
   if (end_bit > 64) return RV3D_ERR_KEYBITS;
   const bool weighted = p->mode == RV3D_NMS_WEIGHTED;
   const NmsLayout L = nms_layout(scratch, n, S, weighted, 9, end_bit);
@@ -1290,7 +1292,7 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   const uint32_t *order = vb.Current();
 
   RV3D_CHECK_CUDA(cudaMemsetAsync(L.seg_begin, 0, sizeof(int) * 2 * S, s));
-  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(skeys, n, 32 + idx_bits, L.seg_begin, L.seg_end);
+  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(skeys, n, score_bits + idx_bits, L.seg_begin, L.seg_end);
   RV3D_CHECK_LAUNCH();
 
   // a segment keeps at most as many boxes as it has candidates, so its slice [seg_begin, seg_end) of the n-sized
@@ -1446,13 +1448,13 @@ box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__re
 }
 
 // threshold-only branch: rows ordered by (sweep, candidate index)
-__global__ void remap_keys_kernel(const unsigned long long *__restrict__ keys, int n, int idx_bits,
+__global__ void remap_keys_kernel(const unsigned long long *__restrict__ keys, int n, int idx_bits, int score_bits,
                                   int total_classes, unsigned long long *__restrict__ out, uint32_t *__restrict__ order,
                                   uint32_t *__restrict__ seg_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long k = keys[i];
-  const uint32_t seg = static_cast<uint32_t>(k >> (32 + idx_bits));
+  const uint32_t seg = static_cast<uint32_t>(k >> (score_bits + idx_bits));
   const unsigned long long cand = k & ((1ull << idx_bits) - 1ull);
   out[i] = (static_cast<unsigned long long>(seg / total_classes) << idx_bits) | cand;
   order[i] = i;
@@ -1627,10 +1629,11 @@ extern "C" int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float
 extern "C" size_t rv3d_pack_candidates_scratch_bytes(int32_t n) { return op_layout(nullptr, n, false, 0, true).total; }
 
 extern "C" int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n, int32_t batch,
-                                    int32_t total_classes, int32_t total_candidates, float *out_params,
+                                    int32_t total_classes, int32_t total_candidates, int32_t score_bits, float *out_params,
                                     float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
                                     size_t scratch_bytes, rv3d_stream_t stream) {
   RV3D_CHECK_ARG(n >= 0 && batch > 0 && total_classes > 0 && total_candidates > 0 && scratch);
+  RV3D_CHECK_ARG(score_bits == 31 || score_bits == 32);
   if (n == 0) return RV3D_OK;
   RV3D_CHECK_ARG(keys && boxes && out_params && out_scores && out_categories && out_batch);
   if (!aligned(scratch, 256) || !aligned(boxes, 16)) return RV3D_ERR_ALIGN;
@@ -1638,7 +1641,7 @@ extern "C" int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t 
   if (scratch_bytes < L.total) return RV3D_ERR_SCRATCH;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int idx_bits = bits_for(total_candidates);
-  remap_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(reinterpret_cast<unsigned long long *>(keys), n, idx_bits,
+  remap_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(reinterpret_cast<unsigned long long *>(keys), n, idx_bits, score_bits,
                                                      total_classes, L.keys, L.order, L.segs);
   RV3D_CHECK_LAUNCH();
   cub::DoubleBuffer<unsigned long long> kb(L.keys, L.keys_alt);

@@ -14,6 +14,7 @@ MAX_PARTITIONS = 8
 RV3D_OK = 0
 ERR_KEYBITS = -5
 COL_LIBRARY, COL_CONVERTER, COL_CONVERTER_UNIFORM = 0, 1, 2
+SCORE_BITS_DECODE = 31   # include/rv3d.h RV3D_SCORE_BITS_DECODE
 F32, F16, BF16 = 0, 1, 2
 NMS_HARD, NMS_WEIGHTED = 0, 1
 OUT_QUAT, OUT_YAW = 0, 1
@@ -47,7 +48,7 @@ class NmsParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("total_classes", C.c_int32), ("total_candidates", C.c_int32),
                 ("num_pre_nms", C.c_int32), ("num_post_nms", C.c_int32), ("mode", C.c_int32),
                 ("iou_threshold", C.c_float), ("merge_threshold", C.c_float), ("n_candidates", C.c_int32),
-                ("out_capacity", C.c_int32), ("out_layout", C.c_int32),
+                ("out_capacity", C.c_int32), ("out_layout", C.c_int32), ("score_bits", C.c_int32),
                 ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_capacity", C.c_int32),
                 ("sweep_offset", C.c_int32), ("peer_rows", C.c_void_p * 8)]
 
@@ -84,7 +85,7 @@ _SIGNATURES = {
     "rv3d_iou3d_aligned": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "rv3d_yaw_to_quat": (C.c_int, [_P, _P, _I64, _P]),
     "rv3d_pack_candidates_scratch_bytes": (_SZ, [_I32]),
-    "rv3d_pack_candidates": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
+    "rv3d_pack_candidates": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "rv3d_box_iou_rotated": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P]),
     "rv3d_instance_topk_scratch_bytes": (_SZ, [_I64]),
     "rv3d_instance_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),

@@ -45,6 +45,7 @@ class Candidates:
     batch: int
     total_classes: int
     total_candidates: int
+    score_bits: int = 32    # width of the keys' score field: 31 from rv3d_decode_compact, 32 from rv3d_compact_candidates
 
     def count(self) -> int:
         n = int(self.counter.item())                    # host read #1 (stream sync)
@@ -79,7 +80,8 @@ class Workspace:
         return t
 
 
-def new_candidates(ws: Workspace, batch: int, total_classes: int, total_candidates: int, device) -> Candidates:
+def new_candidates(ws: Workspace, batch: int, total_classes: int, total_candidates: int, device,
+                   score_bits: int = 32) -> Candidates:
     cap = batch * total_candidates
     if cap >= 2 ** 31:
         raise N.Rv3dError(N.ERR_KEYBITS, "candidate compaction (batch * candidates >= 2^31; split the batch)")
@@ -87,7 +89,7 @@ def new_candidates(ws: Workspace, batch: int, total_classes: int, total_candidat
     boxes = ws.get("boxes", (cap, 8), torch.float32, device)
     counter = ws.get("counter", (1,), torch.int32, device)
     counter.zero_()
-    return Candidates(keys, boxes, counter, batch, total_classes, total_candidates)
+    return Candidates(keys, boxes, counter, batch, total_classes, total_candidates, score_bits)
 
 
 def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_nms: int, iou_threshold: float,
@@ -116,6 +118,7 @@ def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_
     p.iou_threshold = float(torch.tensor(float(iou_threshold), dtype=torch.float32))
     p.merge_threshold = float(merge_threshold)
     p.n_candidates, p.out_capacity, p.out_layout = n, cap, layout
+    p.score_bits = cand.score_bits
     if peer is not None:
         if layout != N.OUT_QUAT:
             raise ValueError("the fused gather carries params(10) rows (RangeDecoder.decode layout)")

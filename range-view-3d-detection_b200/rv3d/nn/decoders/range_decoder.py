@@ -69,7 +69,7 @@ class RangeDecoder:
             raise ValueError("empty multiscale_outputs / task_config")
         B = plan[0][6]
         dev = require_cuda(plan[0][0]["cart"])
-        cand = new_candidates(self._ws, B, total_classes, total_candidates, dev)
+        cand = new_candidates(self._ws, B, total_classes, total_candidates, dev, score_bits=N.SCORE_BITS_DECODE)
         for ms, task_id, task_offset, cand_offset, H, W, b in plan:
             if b != B:
                 raise ValueError("all strides must share the batch size")
@@ -132,7 +132,7 @@ class RangeDecoder:
         lib = N.lib()
         work = self._ws.bytes("pack_scratch", lib.rv3d_pack_candidates_scratch_bytes(n), dev)
         N.check(lib.rv3d_pack_candidates(ptr(cand.keys), ptr(cand.boxes), n, cand.batch, cand.total_classes,
-                                         cand.total_candidates, ptr(params), ptr(scores), ptr(cats), ptr(bidx),
+                                         cand.total_candidates, cand.score_bits, ptr(params), ptr(scores), ptr(cats), ptr(bidx),
                                          ptr(work), work.numel(), stream_ptr(dev)), "rv3d_pack_candidates")
         return params.to(dt), scores.to(dt), cats, bidx
 

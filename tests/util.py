@@ -27,7 +27,7 @@ def unpack_candidates(cand, n):
     idx_bits = max(int(math.ceil(math.log2(cand.total_candidates))), 0) if cand.total_candidates > 1 else 0
     while (1 << idx_bits) < cand.total_candidates:
         idx_bits += 1
-    seg = (keys >> np.uint64(32 + idx_bits)).astype(np.int64)
+    seg = (keys >> np.uint64(cand.score_bits + idx_bits)).astype(np.int64)
     k = (keys & np.uint64((1 << idx_bits) - 1)).astype(np.int64)
     return {"sweep": seg // cand.total_classes, "category": seg % cand.total_classes, "k": k,
             "boxes": boxes[:, :7], "score": boxes[:, 7]}
