@@ -1067,6 +1067,8 @@ struct PackArgs {
   float *out_params, *out_scores, *out_cats, *out_batch;
   // fused gather: every rank's buffer is (world, peer_capacity + 1, 16) f32; this rank writes slot `peer_rank` of each
   const int *out_count;
+  int *out_count_w;
+  int n_segments, fused_scan;
   int n_peers, peer_rank, peer_capacity, sweep_offset;
   float *peer_rows[RV3D_MAX_PEERS];
 };
@@ -1074,7 +1076,35 @@ struct PackArgs {
 __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
   const int seg = blockIdx.x;
   const int cnt = a.kept_count[seg];
-  const int off = a.out_off[seg], kb = a.kept_base[seg], beg = a.seg_begin[seg];
+  const int kb = a.kept_base[seg], beg = a.seg_begin[seg];
+  // Output offset of the segment = kept boxes of the segments before it.  With few segments every block sums that
+  // prefix itself (<= 4 loads per thread) instead of waiting for a separate one-block scan kernel; block (0, 0) also
+  // publishes the total.  Many segments (n_segments > kPackFusedScan): kept_scan_kernel ran before, out_off is ready.
+  __shared__ int s_part[8];
+  int off, total = 0;
+  const bool first = blockIdx.x == 0 && blockIdx.y == 0;
+  if (a.fused_scan) {
+    int part = 0, tot = 0;
+    const int upto = first ? a.n_segments : seg;
+    for (int s = threadIdx.x; s < upto; s += blockDim.x) {
+      const int v = a.kept_count[s];
+      tot += v;
+      if (s < seg) part += v;
+    }
+    for (int o = 16; o; o >>= 1) {
+      part += __shfl_xor_sync(0xffffffffu, part, o);
+      tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_part[threadIdx.x >> 5] = part; s_part[4 + (threadIdx.x >> 5)] = tot; }
+    __syncthreads();
+    off = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+    total = s_part[4] + s_part[5] + s_part[6] + s_part[7];
+    total = total < a.out_capacity ? total : a.out_capacity;
+    if (first && threadIdx.x == 0) *a.out_count_w = total;
+  } else {
+    off = a.out_off[seg];
+    if (first) total = *a.out_count;
+  }
   // grid = (segments, chunks of the kept list): every kept box has its own thread (the kernel is three dependent
   // loads and a sincos per row, i.e. pure latency)
   for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
@@ -1125,8 +1155,7 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
       }
     }
   }
-  if (a.n_peers > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {   // header row: [rows written, rows kept]
-    const int total = *a.out_count;
+  if (a.n_peers > 0 && first && threadIdx.x == 0) {   // header row: [rows written, rows kept]
     const float4 h = make_float4(static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity),
                                  static_cast<float>(total), 0.f, 0.f);
     for (int q = 0; q < a.n_peers; ++q)
@@ -1319,9 +1348,14 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   }
   if (rc != RV3D_OK) return rc;
 
-  kept_scan_kernel<<<1, 1024, 0, s>>>(L.kept_count, S, L.out_off, out_count, p->out_capacity);
-  RV3D_CHECK_LAUNCH();
+  constexpr int kPackFusedScan = 512;   // up to this many segments the pack blocks sum their own output offset
+  const bool fused_scan = S <= kPackFusedScan;
+  if (!fused_scan) {
+    kept_scan_kernel<<<1, 1024, 0, s>>>(L.kept_count, S, L.out_off, out_count, p->out_capacity);
+    RV3D_CHECK_LAUNCH();
+  }
   PackArgs pa{};
+  pa.out_count_w = out_count; pa.n_segments = S; pa.fused_scan = fused_scan ? 1 : 0;
   pa.seg_begin = L.seg_begin; pa.kept_base = L.seg_begin; pa.kept_count = L.kept_count; pa.out_off = L.out_off;
   pa.kept_pos = L.kept_pos; pa.order = order; pa.boxes = boxes; pa.acc = L.acc;
   pa.total_classes = p->total_classes; pa.out_capacity = p->out_capacity; pa.weighted = weighted ? 1 : 0; pa.yaw_layout = p->out_layout == RV3D_OUT_YAW;

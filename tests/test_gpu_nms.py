@@ -90,7 +90,10 @@ def test_batched_nms_golden(mode):
 
 
 @pytest.mark.parametrize("mode", ["HARD", "WEIGHTED"])
-@pytest.mark.parametrize("cfg", [(3, 20000, 5, 40, 50000, 1000), (2, 30000, 2, 25, 4000, 50), (1, 6000, 26, 30, 50000, 7)])
+# the last case has 24 x 26 = 624 (sweep, class) segments: above 512 the output offsets come from the scan kernel,
+# below from the pack kernel itself
+@pytest.mark.parametrize("cfg", [(3, 20000, 5, 40, 50000, 1000), (2, 30000, 2, 25, 4000, 50), (1, 6000, 26, 30, 50000, 7),
+                                 (24, 1500, 26, 20, 50000, 5)])
 def test_batched_nms_vs_oracle(mode, cfg):
     from rv3d.math.ops.nms import batched_multiclass_nms
     B, K, C, M, pre, post = cfg
