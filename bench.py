@@ -424,9 +424,9 @@ def run_ours(args):
                            per_rank_data="identical synthetic sweeps on every rank (seed 1000)", host_affinity=numa,
                            head_dtype=args.head_dtype),
             "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            # own kernels per step: raster scatter + resolve, decode_compact, iota, segment_bounds, prepare_records,
-            # nms_segment, pack (+ kept_scan above 512 segments); the CUB sort passes and memsets are not counted
-            "gpu_launches": (8 if B * C <= 512 else 9) * args.steps,
+            # own kernels per step: raster scatter + resolve, decode_compact, iota, prepare_records, nms_segment, pack
+            # (+ kept_scan above 512 segments); the CUB sort passes and memsets are not counted
+            "gpu_launches": (7 if B * C <= 512 else 8) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernels": "rasterize (scatter+resolve) + decode_compact", "achieved": achieved,
                          "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",

@@ -50,23 +50,21 @@ __global__ void iota_kernel(uint32_t *v, int n) {
   if (i < n) v[i] = i;
 }
 
-// seg_begin / seg_end from sorted keys (both zero-initialised: empty segments stay [0,0))
-__global__ void segment_bounds_kernel(const unsigned long long *__restrict__ keys, int n, int shift,
-                                      int *__restrict__ seg_begin, int *__restrict__ seg_end) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t s = static_cast<uint32_t>(keys[i] >> shift);
-  if (i == 0 || static_cast<uint32_t>(keys[i - 1] >> shift) != s) seg_begin[s] = i;
-  if (i == n - 1 || static_cast<uint32_t>(keys[i + 1] >> shift) != s) seg_end[s] = i + 1;
-}
-
-// sorted position -> suppression record (+ merge row for the weighted mode)
+// sorted position -> suppression record (+ merge row for the weighted mode); also seg_begin / seg_end from the
+// sorted keys (both zero-initialised: empty segments stay [0, 0))
 template <bool kWeighted>
 __global__ void __launch_bounds__(256)
 prepare_records_kernel(const uint32_t *__restrict__ order, const float *__restrict__ boxes, int n,
-                       void *__restrict__ recs, float *__restrict__ data) {
+                       void *__restrict__ recs, float *__restrict__ data,
+                       const unsigned long long *__restrict__ keys, int seg_shift, int *__restrict__ seg_begin,
+                       int *__restrict__ seg_end) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (keys) {   // segment boundaries of the sorted keys, in the same pass (was a kernel of its own)
+    const uint32_t sg = static_cast<uint32_t>(keys[i] >> seg_shift);
+    if (i == 0 || static_cast<uint32_t>(keys[i - 1] >> seg_shift) != sg) seg_begin[sg] = i;
+    if (i == n - 1 || static_cast<uint32_t>(keys[i + 1] >> seg_shift) != sg) seg_end[sg] = i + 1;
+  }
   const float4 *src = reinterpret_cast<const float4 *>(boxes + static_cast<size_t>(order[i]) * 8);
   const float4 b0 = src[0], b1 = src[1];  // x y z l | w h yaw score
   if (!kWeighted) {
@@ -1321,8 +1319,6 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   const uint32_t *order = vb.Current();
 
   RV3D_CHECK_CUDA(cudaMemsetAsync(L.seg_begin, 0, sizeof(int) * 2 * S, s));
-  segment_bounds_kernel<<<ceil_div(n, 256), 256, 0, s>>>(skeys, n, score_bits + idx_bits, L.seg_begin, L.seg_end);
-  RV3D_CHECK_LAUNCH();
 
   // a segment keeps at most as many boxes as it has candidates, so its slice [seg_begin, seg_end) of the n-sized
   // kept_pos / acc / merge_count arrays is its private, sufficient region: kept_base == seg_begin (no scan kernel)
@@ -1338,11 +1334,13 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   if (weighted) {
     RV3D_CHECK_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * static_cast<size_t>(n) * 9, s));
     RV3D_CHECK_CUDA(cudaMemsetAsync(L.merge_count, 0, sizeof(int) * static_cast<size_t>(n), s));
-    prepare_records_kernel<true><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, L.data);
+    prepare_records_kernel<true><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, L.data, skeys, score_bits + idx_bits,
+                                                                  L.seg_begin, L.seg_end);
     RV3D_CHECK_LAUNCH();
     rc = launch_nms_segments<WRec, true>(a, S, max_seg_n, s);
   } else {
-    prepare_records_kernel<false><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, nullptr);
+    prepare_records_kernel<false><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, nullptr, skeys, score_bits + idx_bits,
+                                                                   L.seg_begin, L.seg_end);
     RV3D_CHECK_LAUNCH();
     rc = launch_nms_segments<HardRec, false>(a, S, max_seg_n, s);
   }
