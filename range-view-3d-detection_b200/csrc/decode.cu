@@ -201,6 +201,12 @@ struct KeyPack {
     return (static_cast<unsigned long long>(seg) << (score_bits + idx_bits)) |
            (static_cast<unsigned long long>(desc) << idx_bits) | cand;
   }
+  // the decode kernel's form: score_bits is the compile-time RV3D_SCORE_BITS_DECODE and the score is >= 0
+  __device__ __forceinline__ unsigned long long make_nonneg(uint32_t seg, float score, uint32_t cand) const {
+    const uint32_t desc = ~__float_as_uint(score) & ((1u << RV3D_SCORE_BITS_DECODE) - 1u);   // ~(bits | 0x80000000), 31 bits
+    return (static_cast<unsigned long long>(seg) << (RV3D_SCORE_BITS_DECODE + idx_bits)) |
+           (static_cast<unsigned long long>(desc) << idx_bits) | cand;
+  }
 };
 
 struct DecodeArgs {
@@ -519,7 +525,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
         if (!((d > s_lower[i]) && (d <= s_upper[i]))) s_out = 0.0f;
       }
       if (row < static_cast<uint32_t>(a.capacity)) {
-        out_keys[row] = a.kp.make(seg, s_out, cand + a.cand_off);
+        out_keys[row] = a.kp.make_nonneg(seg, s_out, cand + a.cand_off);
         float4 *ob = reinterpret_cast<float4 *>(out_boxes + static_cast<size_t>(row) * 8);
         ob[0] = make_float4(box[0], box[1], box[2], box[3]);
         ob[1] = make_float4(box[4], box[5], box[6], s_out);
