@@ -16,6 +16,9 @@ from .._util import ptr, require_cuda, scratch, stream_ptr
 __all__ = ["build_range_view", "rasterize_sweeps", "pack_sweeps"]
 
 
+_RASTER_PARAMS: dict = {}
+
+
 def rasterize_sweeps(points: torch.Tensor, laser: torch.Tensor, n_points: torch.Tensor,
                      laser_mapping: torch.Tensor, lidar_offset: Sequence[float], height: int = 64,
                      width: int = 1800, n_azimuth_bins: Optional[int] = None, num_lasers: Optional[int] = None,
@@ -36,17 +39,26 @@ def rasterize_sweeps(points: torch.Tensor, laser: torch.Tensor, n_points: torch.
         raise ValueError("laser must be uint8; n_points and laser_mapping int32")
     points, laser = points.contiguous(), laser.contiguous()
     B, nmax, _ = points.shape
-    p = N.RasterParams()
-    p.batch, p.max_points, p.height, p.width = B, nmax, height, width
-    p.azimuth_bins = width if n_azimuth_bins is None else n_azimuth_bins
-    p.num_lasers = laser_mapping.numel() if num_lasers is None else num_lasers
-    if p.num_lasers > laser_mapping.numel():
-        raise ValueError("laser_mapping is shorter than num_lasers")
-    p.col_mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
-    p.lidar_offset[:] = [float(v) for v in lidar_offset]
-    p.min_distance = float(min_distance)
     lib = N.lib()
-    need = lib.rv3d_rasterize_scratch_bytes(p)
+    # the parameter block (and the scratch size it implies) only depends on shapes and options: built once per key,
+    # so that the launch is not waiting on host work every step
+    key = (B, nmax, height, width, n_azimuth_bins, num_lasers, laser_mapping.numel(), col_mode,
+           tuple(float(v) for v in lidar_offset), float(min_distance))
+    hit = _RASTER_PARAMS.get(key)
+    if hit is None:
+        p = N.RasterParams()
+        p.batch, p.max_points, p.height, p.width = B, nmax, height, width
+        p.azimuth_bins = width if n_azimuth_bins is None else n_azimuth_bins
+        p.num_lasers = laser_mapping.numel() if num_lasers is None else num_lasers
+        if p.num_lasers > laser_mapping.numel():
+            raise ValueError("laser_mapping is shorter than num_lasers")
+        p.col_mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
+        p.lidar_offset[:] = [float(v) for v in lidar_offset]
+        p.min_distance = float(min_distance)
+        if len(_RASTER_PARAMS) > 64:
+            _RASTER_PARAMS.clear()
+        hit = _RASTER_PARAMS[key] = (p, lib.rv3d_rasterize_scratch_bytes(p))
+    p, need = hit
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = scratch(need, dev)
     image = out if out is not None else torch.empty((B, 7, height, width), dtype=torch.float32, device=dev)
