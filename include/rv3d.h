@@ -9,8 +9,8 @@
  *     temporary storage, which is carved out of the caller's scratch), never changes
  *     the current device, and enqueues all work on the caller's stream;
  *   - functions return RV3D_OK (0) or a negative rv3d_status; no exceptions, no aborts;
- *   - counts that only the device knows are returned in device memory; the two
- *     entry points that need one on the host (rv3d_nms: n_candidates) say so;
+ *   - counts that only the device knows stay in device memory: rv3d_nms reads the candidate
+ *     count from the compaction counter and leaves the detection count on the device;
  *   - re-entrant, no global mutable state; one host thread per GPU.
  *
  * Each entry point names the reference interface it replaces (paths relative to
@@ -215,6 +215,7 @@ int rv3d_compact_candidates(const float *cuboids, const float *scores, const int
 #define RV3D_OUT_QUAT 0
 #define RV3D_OUT_YAW 1
 #define RV3D_MAX_PEERS 8
+#define RV3D_NMS_EXACT_ONLY 1 /* flags: decide every pair with the bit-exact IoU routine (no approximate shortcut) */
 
 typedef struct {
   int32_t batch, total_classes, total_candidates;
@@ -222,37 +223,55 @@ typedef struct {
   int32_t mode;              /* RV3D_NMS_*                                              */
   float iou_threshold;       /* float32(iou_threshold): nms.py:44 passes an f32 tensor  */
   float merge_threshold;     /* weighted only (0.5, nms.py:106)                         */
-  int32_t n_candidates;      /* HOST copy of the compaction counter                     */
+  int32_t capacity;          /* rows available in keys / boxes; the LIVE count is read from device memory
+                                (n_candidates) and clamped to this -- no host copy of it is needed      */
   int32_t out_capacity;      /* rows available in the out_* arrays                      */
   int32_t out_layout;        /* RV3D_OUT_QUAT: out_params (cap,10) [x,y,z,l,w,h,qw,qx,qy,qz]
                                 (RangeDecoder.decode); RV3D_OUT_YAW: out_params (cap,7)
                                 [x,y,z,l,w,h,yaw] (batched_multiclass_nms)               */
   int32_t score_bits;        /* score field of the keys: 31 (rv3d_decode_compact) or 32
                                 (rv3d_compact_candidates); 0 means 32                     */
+  float score_lo, score_hi;  /* range the scores are known to lie in (decode: [min_confidence, 1]); only balances the
+                                score bins, any scores stay correct.  score_hi <= score_lo: unknown, the library
+                                reduces min / max on the device first                     */
+  int32_t flags;             /* RV3D_NMS_EXACT_ONLY                                      */
   /* Fused detection gather over peer memory (the path's one exchange step, multi-GPU; replaces the per-sweep
    * feather files + dist.barrier() of nn/arch/detector.py:366-380,415-421).  peer_world > 0: the pack kernel
    * ALSO stores every detection as a 16-float row [sweep + sweep_offset, class, score, 0, x,y,z,l, w,h,qw,qx,
    * qy,qz,0,0] into slot `peer_rank` of each rank's (peer_world, peer_capacity + 1, 16) f32 buffer, row 0 of
-   * the slot being [rows written, rows kept, 0, 0], with plain 16-byte stores through peer-mapped (NVLink)
-   * pointers.  The caller orders readers behind the writers (a device-side barrier over the ranks).
+   * the slot being [rows written, rows kept, seq, 0], with plain 16-byte stores through peer-mapped (NVLink)
+   * pointers.  peer_seq == 0: the caller orders readers behind the writers (a device-side barrier over the
+   * ranks).  peer_seq != 0: the last pack block to finish publishes the header with uint32 `peer_seq` in its
+   * third word behind a system-scope fence; readers wait for it with rv3d_peer_wait -- no barrier kernel.
    * RV3D_OUT_QUAT only.  peer_world == 0: off. */
   int32_t peer_world, peer_rank, peer_capacity, sweep_offset;
+  uint32_t peer_seq;
+  int32_t reserved;
   float *peer_rows[RV3D_MAX_PEERS];
+  int32_t *host_count;       /* optional HOST pointer (mapped pinned memory, device-accessible): the detection count
+                                is also stored there, so a caller waiting on an event can read it without a copy */
 } rv3d_nms_params;
 
 size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);
 
-/* keys / boxes: the compaction output (keys are sorted in place -> clobbered).
+/* keys / boxes: the compaction output (left untouched); n_candidates: DEVICE i32, the compaction counter.
  * Outputs, in the reference's order (sweep asc, class asc, score desc):
  *   out_params (out_capacity,10|7) f32, see out_layout          (range_decoder.py:122-123)
  *   out_scores, out_categories, out_batch (out_capacity,) f32      (nms.py:51,113,242)
  *   out_count device i32: rows written.
- * stats (device, 16 x i64, may be NULL): [0] rotated-IoU evaluations, [1] kept, [2] frontier rounds,
- * [3] pair considerations, [4..9] SM cycles summed over segments per phase (frontier gather, grid
- * build, frontier pairs, greedy, kill scan, kill drain). */
-int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys, const float *boxes, float *out_params,
-             float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
+ * Nothing in this call depends on a host copy of a device count: fixed launch geometry, safe under CUDA-graph
+ * capture (replaces the per-sweep host sync of nms.py:210-215).
+ * stats (device, 24 x i64, may be NULL): [0] exact rotated-IoU evaluations, [1] kept, [2] frontier rounds,
+ * [3] circle tests, [4..9] SM cycles summed over segments per phase (window sort, pull walk, pull IoU, frontier
+ * pairs, greedy, publish), [10] slowest segment (cycles), [11] largest segment, [12..17] its phases, [18] pairs
+ * above the threshold, [19] approximate-IoU evaluations, [20] candidates consumed by the scan. */
+int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys, const float *boxes, const int32_t *n_candidates,
+             float *out_params, float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
              int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
+/* Consumer side of the peer_seq protocol: enqueue a wait until every rank's header in THIS rank's slot buffer
+ * `rows` ((world, peer_capacity + 1, 16) f32) carries `seq`. */
+int rv3d_peer_wait(const float *rows, int32_t world, int32_t peer_capacity, uint32_t seq, rv3d_stream_t stream);
 
 /* detectron2-style entry: boxes (N,5) f32 (xc,yc,w,h,angle_deg), scores (N,) f32 ->
  * keep (N,) i64 original indices in score order, *n_keep device i32.
@@ -281,13 +300,19 @@ int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b, int64_t n
 int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int32_t aligned,
                          float *out, rv3d_stream_t stream);
 
+/* Test hook for the two-stage IoU comparison of the NMS kernels: aligned pairs of (N,5) f32 boxes (xc, yc, w, h,
+ * angle in degrees) -> decision (N,) i8 (2: skipped by the upper bound, +1 / -1: decided by the approximate IoU,
+ * 0: sent to the exact routine), approx (N,) f32, exact (N,) f32 (the bit-exact routine's value). */
+int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold, int8_t *decision,
+                        float *approx, float *exact, rv3d_stream_t stream);
+
 /* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
 int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);
 
 /* Threshold-only branch of RangeDecoder.decode (use_nms=False, range_decoder.py:110-120):
  * compaction output -> rows ordered by (sweep, candidate). */
 size_t rv3d_pack_candidates_scratch_bytes(int32_t n_candidates);
-int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n_candidates, int32_t batch,
+int rv3d_pack_candidates(const uint64_t *keys, const float *boxes, int32_t n_candidates, int32_t batch,
                          int32_t total_classes, int32_t total_candidates, int32_t score_bits, float *out_params,
                          float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
                          size_t scratch_bytes, rv3d_stream_t stream);

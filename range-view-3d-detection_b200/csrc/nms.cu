@@ -1,4 +1,4 @@
-// nms.cu -- segment sort (K3), exact greedy rotated NMS / weighted NMS (K4 / K5), output pack.
+// nms.cu -- score bucketing (K3), exact greedy rotated NMS / weighted NMS (K4 / K5), output pack.
 //
 // Replaces (paths relative to /root/reference):
 //   math/ops/nms.py:181-266  batched_multiclass_nms  (per-sweep Python loop, host sync each)
@@ -6,80 +6,251 @@
 //   math/ops/nms.py:64-123   weighted_multiclass_nms -> weighted_nms (:126-177) -> TorchEx wnms_gpu
 //   nn/decoders/range_decoder.py:110-123  threshold-only branch, yaw_to_quat, final cat
 //
-// The third-party kernels build an N x N/64 suppression mask (313 MB at N = 50 k), copy it to
-// the host and scan it serially.  Here the greedy scan stays on the device and only tests a
-// candidate against boxes that were actually KEPT ("frontier" algorithm, DESIGN.md "K4"):
+// The third-party kernels build an N x N/64 suppression mask (313 MB at N = 50 k), copy it to the host and scan
+// it serially.  Here nothing leaves the device and NO count is needed on the host: the candidate count, the
+// per-segment counts and the detection count live in device memory, every kernel below has a fixed launch
+// geometry, so rasterize -> decode -> NMS -> pack replays as one CUDA graph (DESIGN.md "K3", "K4").
 //
-//   one CTA per (sweep, class) segment, candidates sorted by (score desc, index asc);
-//   alive bitmap in shared memory; repeat
-//     1. frontier  = the first F alive candidates in rank order
-//     2. all pairs inside the frontier -> suppression bit-matrix (circle pre-test, then exact IoU
-//        through a shared-memory work queue so the expensive routine runs with full warps)
-//     3. one warp resolves the frontier greedily from the bit-matrix (<= F dependent steps)
-//     4. every alive candidate behind the frontier is tested against the NEWLY kept boxes only
-//        (circle pre-test -> work queue -> IoU), and cleared from the bitmap if suppressed
-//   until num_post_nms boxes are kept or nothing is alive.
-//
-// The result is identical to the sequential greedy scan: a candidate enters a frontier only if
-// no earlier kept box suppressed it, the frontier is resolved in rank order, and pruned pairs
-// have IoU exactly 0 (iou.cuh padded_radius).  IoU evaluations drop from O(N * kept) on
-// every candidate to (alive candidates near a kept box).
-#include <cooperative_groups.h>
+//   K3  hist / bin_scan / scatter_records: a counting sort of the compacted candidates by
+//       (segment = sweep x class, coarse score bin).  No global multi-pass radix sort: the exact order inside a
+//       bin is established lazily by the NMS kernel, only for the candidates it actually consumes.
+//   K4  nms_pull_kernel, one CTA per segment, "pull" form of the greedy scan:
+//         repeat: take the next window (<= 2048 candidates = whole score bins), sort it exactly in shared
+//                 memory by (score desc, candidate asc);
+//           a. PULL: every window candidate looks up the boxes KEPT so far in a spatial hash of kept boxes
+//              (circle pre-test -> work queue -> approximate / exact IoU on dense lanes) and dies if suppressed;
+//           b. the first kF survivors form a frontier: all pairs inside it -> suppression bit-matrix ->
+//              greedy resolution in rank order -> newly kept boxes join the hash;
+//           c. the remaining survivors pull again, against the NEW kept boxes only; back to b.
+//         until num_post_nms boxes are kept or the candidates run out.
+//       A candidate is only ever tested against kept boxes, candidates behind the last consumed window are never
+//       touched in hard mode, and nothing is tested twice.  The result equals the sequential greedy scan: a
+//       candidate reaches a frontier only if no earlier kept box suppressed it, frontiers are resolved in rank
+//       order, pruned pairs have IoU exactly 0 (iou.cuh padded_radius).
+//   K5  weighted mode: the same scan, every (candidate, kept) comparison also feeds the merge sets; after the
+//       last kept box the candidates behind it are pulled once more for their merge contributions only.
 #include <cstdlib>
+#include <cstring>
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
 
 #include "common.cuh"
 #include "iou.cuh"
 
-namespace cg = cooperative_groups;
-
 namespace rv3d {
 
 constexpr int kNmsThreads = 512;
-// frontier size: 512 boxes per round in hard mode (one 32 KB bit-matrix), 256 in weighted mode (two
-// matrices, 64-byte records): fewer, fuller rounds cost fewer barriers and leader-only phases
+constexpr int kNmsWarps = kNmsThreads / 32;
+// frontier size: 512 boxes per round in hard mode (one 32 KB bit-matrix), 256 in weighted mode (two matrices,
+// 64-byte records)
 template <bool kWeighted> struct Frontier { static constexpr int kF = kWeighted ? 256 : 512; };
-constexpr int kMaxD = 16;               // max data columns of the weighted merge
+constexpr int kMaxD = 16;            // max data columns of the weighted merge
+constexpr int kWin = 2048;           // window: candidates sorted and pulled together
+constexpr int kMaxBins = 2048;       // coarse score bins per segment (bin offsets live in shared memory)
+constexpr int kQ2Cap = 8192;         // IoU work queue (pairs that passed the circle test)
+constexpr int kWBuf = 64;            // per-warp buffer of pairs waiting for the exact routine
+constexpr int kKeptSmem = 2048;      // kept boxes tracked in shared memory when num_post_nms <= this, else in global memory
+constexpr int kBucketsSmem = 4096;   // hash buckets of the kept-box grid (shared-memory form)
+constexpr float kPosCap = 1.0e6f;
+constexpr int kMaxCellsPerQuery = 25;
 
 // ------------------------------------------------------------------------------------------
-// small kernels around the sort
+// K3: counting sort by (segment, coarse score bin)
 // ------------------------------------------------------------------------------------------
-__global__ void iota_kernel(uint32_t *v, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] = i;
+// Keys are [segment | desc | candidate] with desc = ~orderable(score) truncated to score_bits, so ascending desc ==
+// descending score.  Bin of a key = min((desc - lo) >> shift, nb - 1), 0 below lo: ascending bin == descending
+// score.  (lo, shift) come from the score range when the caller knows it (decode: [min_confidence, 1]) or from a
+// device-side min / max reduction; a bad range only unbalances the bins, the order stays exact.
+struct KeyGeom { int idx_bits, score_bits, nb; };
+struct BinMap { uint32_t lo; int shift; };
+struct BinMapArg {
+  BinMap m;
+  const BinMap *dev;   // non-null: read the map from device memory (computed by binmap_from_minmax_kernel)
+  __device__ __forceinline__ BinMap get() const { return dev ? *dev : m; }
+};
+__device__ __forceinline__ int bin_of(uint32_t desc, const BinMap &m, int nb) {
+  if (desc <= m.lo) return 0;
+  const uint32_t b = (desc - m.lo) >> m.shift;
+  return b < static_cast<uint32_t>(nb) ? static_cast<int>(b) : nb - 1;
+}
+__device__ __forceinline__ int live_count(const int32_t *n_ptr, int capacity) {
+  const int n = *n_ptr;
+  return n < 0 ? 0 : (n < capacity ? n : capacity);
 }
 
-// sorted position -> suppression record (+ merge row for the weighted mode); also seg_begin / seg_end from the
-// sorted keys (both zero-initialised: empty segments stay [0, 0))
-template <bool kWeighted>
 __global__ void __launch_bounds__(256)
-prepare_records_kernel(const uint32_t *__restrict__ order, const float *__restrict__ boxes, int n,
-                       void *__restrict__ recs, float *__restrict__ data,
-                       const unsigned long long *__restrict__ keys, int seg_shift, int *__restrict__ seg_begin,
-                       int *__restrict__ seg_end) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (keys) {   // segment boundaries of the sorted keys, in the same pass (was a kernel of its own)
-    const uint32_t sg = static_cast<uint32_t>(keys[i] >> seg_shift);
-    if (i == 0 || static_cast<uint32_t>(keys[i - 1] >> seg_shift) != sg) seg_begin[sg] = i;
-    if (i == n - 1 || static_cast<uint32_t>(keys[i + 1] >> seg_shift) != sg) seg_end[sg] = i + 1;
+minmax_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ n_ptr, int capacity, KeyGeom g,
+              uint32_t *__restrict__ mm) {   // mm[0] = min desc (init 0xffffffff), mm[1] = max desc (init 0)
+  const int n = live_count(n_ptr, capacity);
+  const uint32_t smask = g.score_bits >= 32 ? 0xffffffffu : ((1u << g.score_bits) - 1u);
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t d = static_cast<uint32_t>(keys[i] >> g.idx_bits) & smask;
+    lo = min(lo, d); hi = max(hi, d);
   }
-  const float4 *src = reinterpret_cast<const float4 *>(boxes + static_cast<size_t>(order[i]) * 8);
-  const float4 b0 = src[0], b1 = src[1];  // x y z l | w h yaw score
-  if (!kWeighted) {
+  for (int o = 16; o; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+__host__ __device__ inline BinMap make_binmap(uint32_t lo, uint32_t hi, int nb) {
+  BinMap m{lo, 0};
+  const uint32_t span = hi >= lo ? hi - lo : 0u;
+  while ((span >> m.shift) >= static_cast<uint32_t>(nb)) ++m.shift;
+  return m;
+}
+__global__ void binmap_from_minmax_kernel(const uint32_t *__restrict__ mm, int nb, BinMap *__restrict__ out) {
+  *out = make_binmap(mm[0], mm[1] >= mm[0] ? mm[1] : mm[0], nb);
+}
+
+__global__ void __launch_bounds__(256)
+hist_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ n_ptr, int capacity, KeyGeom g,
+            BinMapArg bma, int n_segments, int *__restrict__ hist) {
+  const int n = live_count(n_ptr, capacity);
+  const BinMap bm = bma.get();
+  const uint32_t smask = g.score_bits >= 32 ? 0xffffffffu : ((1u << g.score_bits) - 1u);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const uint32_t seg = static_cast<uint32_t>(k >> (g.score_bits + g.idx_bits));
+    if (seg >= static_cast<uint32_t>(n_segments)) continue;   // corrupt key: ignored everywhere
+    atomicAdd(hist + static_cast<size_t>(seg) * g.nb + bin_of(static_cast<uint32_t>(k >> g.idx_bits) & smask, bm, g.nb), 1);
+  }
+}
+
+// One CTA per segment: exclusive scan of the segment's histogram -> bin_start[seg][0..nb] (relative to the segment),
+// seg_count[seg]; the histogram is zeroed again (scatter uses it as the per-bin cursor).  The last CTA to finish
+// turns the per-segment counts into seg_begin (exclusive prefix over the segments).
+__global__ void __launch_bounds__(256)
+bin_scan_kernel(int *__restrict__ hist, int nb, int S, int *__restrict__ bin_start, int *__restrict__ seg_count,
+                int *__restrict__ seg_begin, int *__restrict__ ticket) {
+  __shared__ int s_w[9];
+  __shared__ int s_last;
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = nb >= 256 ? nb / 256 : 1;
+  int *h = hist + static_cast<size_t>(seg) * nb;
+  int *bs = bin_start + static_cast<size_t>(seg) * (nb + 1);
+  int cnt[kMaxBins / 256];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < kMaxBins / 256; ++k) {
+    const int b = tid * per + k;
+    cnt[k] = (k < per && b < nb) ? h[b] : 0;
+    sum += cnt[k];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_w[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < 8; ++w) { const int v = s_w[w]; s_w[w] = run; run += v; }
+    s_w[8] = run;
+  }
+  __syncthreads();
+  int off = s_w[wid] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < kMaxBins / 256; ++k) {
+    const int b = tid * per + k;
+    if (k < per && b < nb) { bs[b] = off; h[b] = 0; off += cnt[k]; }
+  }
+  if (tid == 0) { bs[nb] = s_w[8]; seg_count[seg] = s_w[8]; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(ticket, 1) == S - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // exclusive prefix over the S segment counts (S is small: sweeps x classes)
+  const int chunk = (S + 255) / 256;
+  const int lo = min(S, tid * chunk), hi = min(S, lo + chunk);
+  int part = 0;
+  for (int s = lo; s < hi; ++s) part += __ldcg(seg_count + s);
+  int inc2 = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc2, o);
+    if (lane >= o) inc2 += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_w[wid] = inc2;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < 8; ++w) { const int v = s_w[w]; s_w[w] = run; run += v; }
+  }
+  __syncthreads();
+  int run = s_w[wid] + inc2 - part;
+  for (int s = lo; s < hi; ++s) { seg_begin[s] = run; run += __ldcg(seg_count + s); }
+}
+
+// candidate row -> suppression record (+ merge row for the weighted mode)
+struct RecFromBoxes8 {   // compaction rows [x,y,z,l,w,h,yaw,score]
+  const float *boxes;
+  __device__ __forceinline__ void hard(int i, HardRec &r) const {
+    const float4 *src = reinterpret_cast<const float4 *>(boxes + static_cast<size_t>(i) * 8);
+    const float4 b0 = src[0], b1 = src[1];
     // nms.py:33,40: boxes [x, y, l, w, -rad2deg(yaw)] with rad2deg evaluated in float32
     const float angle = -(b1.z * 57.29577951308232f);
-    static_cast<HardRec *>(recs)[i] = make_hard_rec(b0.x, b0.y, b0.w, b1.x, angle, 0.01745329251);
-  } else {
+    r = make_hard_rec(b0.x, b0.y, b0.w, b1.x, angle, 0.01745329251);
+  }
+  __device__ __forceinline__ void weighted(int i, WRec &r, float *d) const {
+    const float4 *src = reinterpret_cast<const float4 *>(boxes + static_cast<size_t>(i) * 8);
+    const float4 b0 = src[0], b1 = src[1];
     // nms.py:87-100: [x - l/2, y - w/2, x + l/2, y + w/2, yaw]; merge row [x,y,z,l,w,h,sin,cos,score]
-    static_cast<WRec *>(recs)[i] =
-        make_w_rec(b0.x - b0.w / 2, b0.y - b1.x / 2, b0.x + b0.w / 2, b0.y + b1.x / 2, b1.z);
-    float *d = data + static_cast<size_t>(i) * 9;
+    r = make_w_rec(b0.x - b0.w / 2, b0.y - b1.x / 2, b0.x + b0.w / 2, b0.y + b1.x / 2, b1.z);
     d[0] = b0.x; d[1] = b0.y; d[2] = b0.z; d[3] = b0.w; d[4] = b1.x; d[5] = b1.y;
     d[6] = static_cast<float>(sin(static_cast<double>(b1.z)));
     d[7] = static_cast<float>(cos(static_cast<double>(b1.z)));
     d[8] = b1.w;
+  }
+};
+struct RecFromBoxes5 {   // detectron2 rows (xc, yc, w, h, angle in degrees)
+  const float *boxes;
+  __device__ __forceinline__ void hard(int i, HardRec &r) const {
+    const float *b = boxes + static_cast<size_t>(i) * 5;
+    r = make_hard_rec(b[0], b[1], b[2], b[3], b[4], 0.01745329251);
+  }
+  __device__ __forceinline__ void weighted(int, WRec &, float *) const {}
+};
+
+template <bool kWeighted, typename Builder>
+__global__ void __launch_bounds__(256)
+scatter_records_kernel(const unsigned long long *__restrict__ keys, Builder build, const int32_t *__restrict__ n_ptr,
+                       int capacity, KeyGeom g, BinMapArg bma, int n_segments, int *__restrict__ cursor,
+                       const int *__restrict__ bin_start, const int *__restrict__ seg_begin, void *__restrict__ recs,
+                       unsigned long long *__restrict__ skey, uint32_t *__restrict__ src, float *__restrict__ data) {
+  const int n = live_count(n_ptr, capacity);
+  const BinMap bm = bma.get();
+  const uint32_t smask = g.score_bits >= 32 ? 0xffffffffu : ((1u << g.score_bits) - 1u);
+  const unsigned long long lowmask = (1ull << (g.score_bits + g.idx_bits)) - 1ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const uint32_t seg = static_cast<uint32_t>(k >> (g.score_bits + g.idx_bits));
+    if (seg >= static_cast<uint32_t>(n_segments)) continue;
+    const int bin = bin_of(static_cast<uint32_t>(k >> g.idx_bits) & smask, bm, g.nb);
+    const int slot = atomicAdd(cursor + static_cast<size_t>(seg) * g.nb + bin, 1);
+    const int pos = seg_begin[seg] + bin_start[static_cast<size_t>(seg) * (g.nb + 1) + bin] + slot;
+    skey[pos] = k & lowmask;
+    src[pos] = static_cast<uint32_t>(i);
+    if (!kWeighted) {
+      HardRec r;
+      build.hard(i, r);
+      static_cast<HardRec *>(recs)[pos] = r;
+    } else {
+      WRec r;
+      float d[9];
+      build.weighted(i, r, d);
+      static_cast<WRec *>(recs)[pos] = r;
+      float *o = data + static_cast<size_t>(pos) * 9;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) o[c] = d[c];
+    }
   }
 }
 
@@ -87,54 +258,30 @@ prepare_records_kernel(const uint32_t *__restrict__ order, const float *__restri
 // the suppression kernel
 // ------------------------------------------------------------------------------------------
 struct NmsArgs {
-  const void *recs;        // HardRec / WRec, sorted order
-  const int *seg_begin, *seg_end, *kept_base;
+  const void *recs;               // HardRec / WRec, grouped by (segment, score bin)
+  unsigned long long *skey;       // [pos] low key bits (score desc | candidate), the fine sort key
+  uint32_t *gorder;               // scratch for bins larger than a window (sorted through global memory)
+  const int *seg_begin, *seg_count;
+  const int *bin_start;           // [seg][nb + 1], null when presorted
+  int nb, presorted;              // presorted: position == rank (rv3d_wnms: the caller sorted)
   int num_pre, num_post;
   float thr, mthr;
-  int prune;               // 0: thresholds < 0 make even disjoint boxes interact -> test every pair
-  int *kept_pos;           // [kept_base[s] + i] = position inside the segment
-  int *kept_count;         // [s]
-  // static candidate grid (scratch, per segment at 4*seg_begin / seg_begin)
-  void *grid_entries;      // GridEntry[n_total]
-  uint32_t *oversize;      // [n_total] candidates that are not in the grid
-  int *firstsup;           // [n_total] weighted: first suppressor rank of a candidate in the current round
+  int prune;                      // 0: thresholds < 0 make even disjoint boxes interact -> test every pair
+  int exact_only;                 // 1: never decide a pair with the approximate IoU
+  int kept_stride;                // > 0: kept rows of segment s start at s * kept_stride; 0: at seg_begin[s]
+  int *kept_pos;                  // [kept_base + i] = position inside the segment
+  int *kept_count;                // [s]
+  // kept-box grid in global memory (num_post_nms > kKeptSmem), per segment at kept_base / seg * n_buckets
+  float4 *kxyr_g;
+  int *knext_g, *heads_g;
+  int n_buckets_g;
+  int *kos;                       // [kept_base + i] kept boxes that are not in the grid (oversize / far away)
   // weighted merge
-  const float *data;       // (n, D) rows in sorted order, score last
+  const float *data;              // (n, D) rows in record order, score last
   int D;
-  double *acc;             // [(kept_base[s] + i) * D + c]: c < D-1 weighted sums, c = D-1 weight sum
-  int *merge_count;        // [kept_base[s] + i]
+  double *acc;                    // [(kept_base + i) * D + c]: c < D-1 weighted sums, c = D-1 weight sum
+  int *merge_count;               // [kept_base + i]
   unsigned long long *stats;
-};
-
-// ---- static dense grid over a segment's candidates --------------------------------------------
-// Built once per segment by the leader CTA.  kG x kG cells cover mean +- 3.5 sigma of the candidate
-// centres (cell >= half the mean padded radius); a candidate is registered ONCE, in the cell of its
-// centre, coordinates clamped to the grid (clamping is monotone, so a clamped window still covers every
-// clamped candidate: far outliers just land in a border cell and cost a wasted circle test).  Entries are
-// counting-sorted by row-major cell index, so the cells cx0..cx1 of one grid row are ONE contiguous run.
-// Candidates with a padded radius above r_cap = 2 x mean (or non-finite) go to an "oversize" list that
-// every query scans.  A kept box (x, y, r) must look at centres within r + r_cap: rows cy0..cy1, one
-// run each; no hashing, no duplicates, no per-entry cell checks.
-constexpr int kG = 64;
-constexpr int kCells = kG * kG;
-constexpr float kPosCap = 1.0e6f;
-constexpr int kQ2Cap = 8192;             // exact-IoU work queue (pairs that passed circle + bound)
-constexpr int kWBuf = 64;                // per-warp hit buffer
-static_assert(kCells % kNmsThreads == 0, "whole cells per scan lane");
-
-struct __align__(16) GridEntry { float x, y, r; uint32_t idx; };
-
-struct GridGeom {
-  float x0, y0, inv_cell, r_cap;
-  __device__ __forceinline__ int cell_x(float x) const {
-    return static_cast<int>(fminf(fmaxf((x - x0) * inv_cell, 0.f), static_cast<float>(kG - 1)));
-  }
-  __device__ __forceinline__ int cell_y(float y) const {
-    return static_cast<int>(fminf(fmaxf((y - y0) * inv_cell, 0.f), static_cast<float>(kG - 1)));
-  }
-  __device__ __forceinline__ bool gridded(float x, float y, float r) const {
-    return (r <= r_cap) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap);   // false for NaN
-  }
 };
 
 // ---- cheap, safe upper bound on the IoU (separating axes + projected overlap) -----------------
@@ -166,11 +313,11 @@ __device__ __forceinline__ bool iou_may_exceed(const Rec &ra, const Rec &rb, flo
 }
 
 // ---- fast approximate IoU (float32 Sutherland-Hodgman clip in box A's frame) --------------------
-// NMS never needs the IoU value, only the comparisons `iou > thr` (and `> merge_thr`).  The clip below
-// is accurate to ~1e-5, the exact routines deviate from true geometry by <= ~1e-4 for sane boxes, so a
-// pair whose approximate IoU is outside a +-(2 % + 1e-3) band around a threshold is decided without the
-// bit-exact routine; pairs inside the band, and degenerate boxes, still run it.  ~98 % of the pairs that
-// survive the circle + bound filters are decided here at ~1/10 of the instructions.
+// NMS never needs the IoU value, only the comparisons `iou > thr` (and `> merge_thr`).  A pair whose approximate
+// IoU is outside a +-(2 % + 1e-3) band around a threshold is decided without the bit-exact routine; pairs inside
+// the band, and unusual boxes (obb_sane), still run it.  tests/test_gpu_iou_decisions.py measures, over 1e7
+// adversarial pairs, that no decided pair disagrees with the exact routine and reports the smallest margin;
+// rv3d_nms_params.flags & RV3D_NMS_EXACT_ONLY switches the shortcut off.
 __device__ __forceinline__ float approx_iou(const Obb &A, const Obb &B) {
   const float aw = fabsf(A.w) * 0.5f, ah = fabsf(A.h) * 0.5f, bw = fabsf(B.w) * 0.5f, bh = fabsf(B.h) * 0.5f;
   const float dx = B.x - A.x, dy = B.y - A.y;
@@ -215,11 +362,14 @@ __device__ __forceinline__ float approx_iou(const Obb &A, const Obb &B) {
   return uni > 0.f ? inter / uni : CUDART_NAN_F;
 }
 
-// -1: certainly below / equal, +1: certainly above, 0: too close to call (or unusual boxes) -> exact routine
+// boxes the approximate clip is trusted on: extents within [0.05 m, 1e4 m], aspect ratio <= 64, centres within
+// 1e6 m of the origin and within 1e4 m of each other (float32 cancellation in the centre difference)
 __device__ __forceinline__ bool obb_sane(const Obb &o) {
   const float w = fabsf(o.w), h = fabsf(o.h);
-  return fminf(w, h) >= 0.05f && fmaxf(w, h) <= 1.0e4f && fabsf(o.x) <= kPosCap && fabsf(o.y) <= kPosCap;
+  const float lo = fminf(w, h), hi = fmaxf(w, h);
+  return lo >= 0.05f && hi <= 1.0e4f && hi <= 64.f * lo && fabsf(o.x) <= kPosCap && fabsf(o.y) <= kPosCap;
 }
+// -1: certainly below / equal, +1: certainly above, 0: too close to call -> exact routine
 __device__ __forceinline__ int decide_vs(float approx, float thr) {
   if (!(approx == approx)) return 0;
   const float m = 0.02f * fabsf(thr) + 1e-3f;
@@ -227,24 +377,29 @@ __device__ __forceinline__ int decide_vs(float approx, float thr) {
 }
 
 template <typename Rec, bool kWeighted, int kF>
-__host__ __device__ inline size_t nms_smem_bytes(int nwords) {
+__host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   constexpr int kFW = kF / 32;
   size_t b = 0;
-  b += align_up_c(sizeof(uint32_t) * nwords, 16);                  // alive
-  b += sizeof(Rec) * kF * 2;                                       // frec, krec
-  b += sizeof(float) * kF * 6;                                     // fx, fy, fr, kx, ky, kr
-  b += sizeof(int) * kF;                                           // front_pos
+  b += align_up_c(sizeof(int) * (kMaxBins + 1), 16);                // s_bins
+  b += sizeof(uint32_t) * kWin;                                    // wpos
+  b += sizeof(uint16_t) * kWin * 2;                                // survivor lists (double buffer)
+  b += kWin;                                                       // walive
+  b += sizeof(uint16_t) * kNmsThreads;                             // batch slot -> window index
+  b += sizeof(Rec) * kF;                                           // frec
+  b += sizeof(float) * kF * 3;                                     // fx, fy, fr
+  b += sizeof(uint16_t) * kF;                                      // front_w
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
-  b += sizeof(int) * (kCells + 1);                                 // cell_start (the build's cursors alias queue2 + wbuf)
-  b += sizeof(uint32_t) * kQ2Cap;                                  // queue2
-  b += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;              // per-warp hit buffers
+  b += sizeof(uint32_t) * kQ2Cap;                                  // queue2 (the window sort's keys + indices alias it)
+  b += sizeof(uint32_t) * kNmsWarps * kWBuf;                       // per-warp exact-IoU buffers
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
-  if (kWeighted) b += sizeof(uint32_t) * kQ2Cap + sizeof(int) * kF;  // qflag, killer
-  return b;
+  if (kWeighted) b += sizeof(int) * kWin + kQ2Cap + sizeof(int) * kF; // wfs, qflag, killer
+  if (kept_in_smem) b += sizeof(float4) * kKeptSmem + sizeof(int) * kKeptSmem + sizeof(int) * kBucketsSmem;
+  return align_up_c(b, 16);
 }
+static_assert(sizeof(unsigned long long) * kWin + sizeof(uint16_t) * kWin <= sizeof(uint32_t) * kQ2Cap, "sort buffers alias the queue");
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total) {
-  // kNmsThreads threads; s_warp has kNmsThreads/32 + 1 ints
+  // kNmsThreads threads; s_warp has kNmsWarps + 1 ints
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -256,203 +411,193 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &tot
   if (lane == 31) s_warp[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    int w = lane < kNmsThreads / 32 ? s_warp[lane] : 0;
+    int w = lane < kNmsWarps ? s_warp[lane] : 0;
     int inc2 = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, inc2, o);
       if (lane >= o) inc2 += t;
     }
-    if (lane < kNmsThreads / 32) s_warp[lane] = inc2 - w;
-    if (lane == 31) s_warp[kNmsThreads / 32] = inc2;
+    if (lane < kNmsWarps) s_warp[lane] = inc2 - w;
+    if (lane == 31) s_warp[kNmsWarps] = inc2;
   }
   __syncthreads();
-  total = s_warp[kNmsThreads / 32];
+  total = s_warp[kNmsWarps];
   return s_warp[wid] + incl - v;
+}
+
+// Bitonic sort (normalised form: every compare-exchange is ascending, the first step of a stage mirrors), which
+// sorts ANY length without padding: a partner index >= n stands for +inf and never moves.  keys / vals may live
+// in shared or global memory; all kNmsThreads threads of the CTA call it.
+template <typename V>
+__device__ __forceinline__ void cta_bitonic_sort(unsigned long long *keys, V *vals, int n) {
+  if (n < 2) return;
+  int np2 = 2;
+  while (np2 < n) np2 <<= 1;
+  const int pairs = np2 >> 1;
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool mirror = (j == (k >> 1));
+      for (int p = threadIdx.x; p < pairs; p += kNmsThreads) {
+        int l, r;
+        if (mirror) {
+          const int blk = p / j, o = p - blk * j;
+          l = blk * k + o;
+          r = blk * k + (k - 1 - o);
+        } else {
+          l = 2 * p - (p & (j - 1));
+          r = l + j;
+        }
+        if (r < n) {
+          const unsigned long long a = keys[l], b = keys[r];
+          if (a > b) {
+            keys[l] = b; keys[r] = a;
+            const V t = vals[l]; vals[l] = vals[r]; vals[r] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 template <typename Rec, bool kWeighted, int kF>
 __global__ void __launch_bounds__(kNmsThreads, 1)
-nms_segment_kernel(NmsArgs a) {
+nms_pull_kernel(NmsArgs a, int kept_in_smem) {
   constexpr int kFW = kF / 32;   // words per bit-matrix row
-  static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0, "frontier size");
+  static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0 && kF <= kNmsThreads, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_warp[kNmsThreads / 32 + 1];
-  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_overflow;
-  __shared__ int s_next;       // leader: next kept box to hand out in the kill scan (dynamic load balance)
-  __shared__ int s_round[8];   // leader -> cluster: {nf, nk, cursor_word, -, n oversize}
-  __shared__ GridGeom s_geom;  // leader -> cluster
-  __shared__ float s_red[kNmsThreads / 32 * 6];
+  __shared__ int s_warp[kNmsWarps + 1];
+  __shared__ int s_qn, s_qvalid, s_nk, s_nos;
+  __shared__ float s_red[kNmsWarps * 2];
+  __shared__ float s_cell[2];   // inv_cell, r_cap
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
 
-  // A cluster of P CTAs works on one segment.  CTA 0 (the leader) owns the alive bitmap and runs the
-  // serial-ish phases (frontier, pairs, greedy); the kill scan and the exact IoU -- 80 % of the work --
-  // are split over all P CTAs, which read the leader's state and clear bits in its bitmap through
-  // distributed shared memory.  P = 1 degenerates to a plain CTA per segment.
-  cg::cluster_group cluster = cg::this_cluster();
-  const int P = static_cast<int>(cluster.num_blocks());
-  const int crank = static_cast<int>(cluster.block_rank());
-  const bool leader = crank == 0;
-  const int seg = blockIdx.x / P;
-  const int beg = a.seg_begin[seg];
-  const int n = min(a.seg_end[seg] - beg, a.num_pre);  // top num_pre_nms by score (nms.py:29-32)
+  const int seg = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (n <= 0) {   // uniform over the cluster
-    if (tid == 0 && leader) a.kept_count[seg] = 0;
+  const int n_seg = a.seg_count[seg];
+  const int n_use = min(n_seg, a.num_pre);   // top num_pre_nms by score (nms.py:29-32)
+  if (n_use <= 0) {
+    if (tid == 0) a.kept_count[seg] = 0;
     return;
   }
-  const int nwords = (n + 31) >> 5;
+  const int beg = a.seg_begin[seg];
   const Rec *recs = static_cast<const Rec *>(a.recs) + beg;
-  GridEntry *entries = static_cast<GridEntry *>(a.grid_entries) + beg;
-  uint32_t *os_list = a.oversize + beg;
-  int *firstsup = kWeighted ? a.firstsup + beg : nullptr;
-  const int kbase = a.kept_base[seg];
+  unsigned long long *skey = a.skey ? a.skey + beg : nullptr;
+  uint32_t *gorder = a.gorder ? a.gorder + beg : nullptr;
+  const int kbase = a.kept_stride > 0 ? seg * a.kept_stride : beg;
+  int *kept_pos = a.kept_pos + kbase;
+  int *kos = a.kos + kbase;
   const float thr_any = kWeighted ? fminf(a.thr, a.mthr) : a.thr;  // smallest IoU that matters
   const bool prune = a.prune != 0;
+  const bool use_approx = prune && !a.exact_only;
 
   // ---- carve shared memory
   unsigned char *p = smem_raw;
-  uint32_t *alive = reinterpret_cast<uint32_t *>(p); p += align_up_c(sizeof(uint32_t) * nwords, 16);
+  int *s_bins = reinterpret_cast<int *>(p); p += align_up_c(sizeof(int) * (kMaxBins + 1), 16);
+  uint32_t *wpos = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kWin;
+  uint16_t *surv_a = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kWin;
+  uint16_t *surv_b = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kWin;
+  uint8_t *walive = reinterpret_cast<uint8_t *>(p); p += kWin;
+  uint16_t *s_bj = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kNmsThreads;
   Rec *frec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;
   float *fx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
   float *fy = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
   float *fr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  Rec *krec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;   // this round's kept boxes, rank order
-  float *kx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  float *ky = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  float *kr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  int *front_pos = reinterpret_cast<int *>(p); p += sizeof(int) * kF;
+  uint16_t *front_w = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kF;
   uint32_t *sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
   uint32_t *mrg = sup;
   if (kWeighted) { mrg = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW; }
-  int *cell_start = reinterpret_cast<int *>(p); p += sizeof(int) * (kCells + 1);
   uint32_t *queue2 = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kQ2Cap;
-  int *cell_cursor = reinterpret_cast<int *>(queue2);   // kCells ints, build phase only (kQ2Cap >= kCells)
-  uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * (kNmsThreads / 32) * kWBuf;
+  unsigned long long *wkey = reinterpret_cast<unsigned long long *>(queue2);        // window sort only
+  uint16_t *widx = reinterpret_cast<uint16_t *>(wkey + kWin);
+  uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * kNmsWarps * kWBuf;
   uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
   int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
   p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
-  uint32_t *qflag = kWeighted ? reinterpret_cast<uint32_t *>(p) : nullptr;   // per queued pair: bit0 iou > thr, bit1 iou > merge_thr
-  int *killer = kWeighted ? reinterpret_cast<int *>(qflag + kQ2Cap) : nullptr;  // frontier box -> rank of its first suppressor
+  int *wfs = nullptr; uint8_t *qflag = nullptr; int *killer = nullptr;
+  if (kWeighted) {
+    wfs = reinterpret_cast<int *>(p); p += sizeof(int) * kWin;       // window candidate -> first suppressor (kept index) in the current pull
+    qflag = reinterpret_cast<uint8_t *>(p); p += kQ2Cap;             // per queued pair: bit0 iou > thr, bit1 iou > merge_thr
+    killer = reinterpret_cast<int *>(p); p += sizeof(int) * kF;      // frontier box -> rank of its first suppressor
+  }
+  // kept boxes: (x, y, padded radius, position) + hash chains; shared memory when num_post_nms is small
+  float4 *kxyr; int *knext, *heads; uint32_t bmask;
+  if (kept_in_smem) {
+    kxyr = reinterpret_cast<float4 *>(p); p += sizeof(float4) * kKeptSmem;
+    knext = reinterpret_cast<int *>(p); p += sizeof(int) * kKeptSmem;
+    heads = reinterpret_cast<int *>(p); p += sizeof(int) * kBucketsSmem;
+    bmask = kBucketsSmem - 1;
+    for (int i = tid; i < kBucketsSmem; i += kNmsThreads) heads[i] = -1;
+  } else {
+    kxyr = a.kxyr_g + kbase; knext = a.knext_g + kbase;
+    heads = a.heads_g + static_cast<size_t>(seg) * a.n_buckets_g;   // pre-set to -1 by the host (memset 0xFF)
+    bmask = static_cast<uint32_t>(a.n_buckets_g - 1);
+  }
+  if (!a.presorted)
+    for (int i = tid; i <= a.nb; i += kNmsThreads) s_bins[i] = a.bin_start[static_cast<size_t>(seg) * (a.nb + 1) + i];
+  if (tid == 0) { s_nos = 0; s_qn = 0; }
+  __syncthreads();
 
   unsigned long long st_iou = 0, st_circle = 0, st_hit = 0, st_approx = 0;   // exact IoUs, circle tests, pairs above thr, approximate IoUs
   // per-phase cycle counters (thread 0, only when stats are requested):
-  // [0] grid build + frontier gather, [1] frontier load, [2] frontier pairs, [3] greedy, [4] kill scan, [5] exact IoU
-  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // [6] publish (+ weighted frontier merges), [7] cluster sync A + helper copies
+  // [0] window assembly + sort, [1] pull: grid walks, [2] pull: IoU, [3] frontier pairs, [4] greedy, [5] publish (+ weighted merges)
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
   long long t_mark = clock64();
   auto lap = [&](int k) {
     if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
   };
 
-  // The three passes of the grid build read (centre, radius) of every candidate; each is a chain of dependent
-  // global loads unless several are in flight per thread: 4 records are loaded before the first is used.
-  auto for_each_centre = [&](auto &&fn) {
-    constexpr int kU = 4;
-    for (int i0 = tid; i0 < n; i0 += kU * kNmsThreads) {
-      float x[kU], y[kU], r[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * kNmsThreads;
-        if (i < n) { x[u] = rec_cx(recs[i]); y[u] = rec_cy(recs[i]); r[u] = recs[i].r; }
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int i = i0 + u * kNmsThreads;
-        if (i < n) fn(i, x[u], y[u], r[u]);
-      }
-    }
-  };
-
-  // ======================= 0. alive bitmap + static candidate grid (leader) =======================
-  for (int w = tid; w < nwords; w += kNmsThreads)
-    alive[w] = (w == nwords - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
-  if (tid == 0) { s_nos = 0; s_overflow = 0; s_qn = 0; }
-  if (leader) {
-    for (int c = tid; c < kCells; c += kNmsThreads) cell_cursor[c] = 0;
-    {
-      // first and second moments of the sane candidates -> grid origin / cell size / radius cap
-      float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sum x, y, x^2, y^2, r, count
-      for_each_centre([&](int, float x, float y, float r) {
-        if (r > 0.f && r < 1.0e4f && fabsf(x) <= kPosCap && fabsf(y) <= kPosCap) {
-          acc[0] += x; acc[1] += y; acc[2] += x * x; acc[3] += y * y; acc[4] += r; acc[5] += 1.f;
-        }
-      });
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-        if (lane == 0) s_red[k * (kNmsThreads / 32) + wid] = acc[k];
-      }
-      __syncthreads();
-      if (tid == 0) {
-        float t[6];
-        for (int k = 0; k < 6; ++k) { t[k] = 0.f; for (int w = 0; w < kNmsThreads / 32; ++w) t[k] += s_red[k * (kNmsThreads / 32) + w]; }
-        const float cnt = fmaxf(t[5], 1.f);
-        const float mx = t[0] / cnt, my = t[1] / cnt, mr = t[5] > 0.f ? t[4] / cnt : 1.f;
-        const float sx = sqrtf(fmaxf(t[2] / cnt - mx * mx, 0.f)), sy = sqrtf(fmaxf(t[3] / cnt - my * my, 0.f));
-        const float cell = fminf(fmaxf(fmaxf(7.f * fmaxf(sx, sy) / kG, 0.5f * mr), 1e-3f), 1.0e5f);
-        s_geom.inv_cell = 1.0f / cell;
-        s_geom.x0 = mx - 0.5f * kG * cell;
-        s_geom.y0 = my - 0.5f * kG * cell;
-        s_geom.r_cap = 2.0f * mr;
-      }
-      __syncthreads();
-    }
-    const GridGeom g = s_geom;
-    if (prune) {
-      for_each_centre([&](int i, float x, float y, float r) {   // count
-        if (g.gridded(x, y, r)) atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1);
-        else os_list[atomicAdd(&s_nos, 1)] = static_cast<uint32_t>(i);
-      });
-    } else {
-      for (int i = tid; i < n; i += kNmsThreads) os_list[i] = static_cast<uint32_t>(i);
-      if (tid == 0) s_nos = n;
-    }
-    __syncthreads();
-    {
-      constexpr int kPer = kCells / kNmsThreads;
-      int cnt[kPer], sum = 0;
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) { cnt[k] = cell_cursor[tid * kPer + k]; sum += cnt[k]; }
-      int total;
-      int off = block_exclusive_scan(sum, s_warp, total);
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) { cell_start[tid * kPer + k] = off; cell_cursor[tid * kPer + k] = off; off += cnt[k]; }
-      if (tid == 0) cell_start[kCells] = total;
-    }
-    __syncthreads();
-    if (prune) {
-      for_each_centre([&](int i, float x, float y, float r) {   // fill
-        if (!g.gridded(x, y, r)) return;
-        entries[atomicAdd(&cell_cursor[g.cell_y(y) * kG + g.cell_x(x)], 1)] = GridEntry{x, y, r, static_cast<uint32_t>(i)};
-      });
-    }
-    if (kWeighted)
-      for (int i = tid; i < n; i += kNmsThreads) firstsup[i] = 0x7fffffff;
-    if (tid == 0) s_round[4] = s_nos;
-    __threadfence();
-  }
-  cluster.sync();   // grid entries (global) + cell offsets (leader's shared memory) are ready
-  uint32_t *lead_alive = cluster.map_shared_rank(alive, 0);
-  const int *lead_round = cluster.map_shared_rank(s_round, 0);
-  if (!leader) {
-    const int *lead_cs = cluster.map_shared_rank(cell_start, 0);
-    for (int c = tid; c <= kCells; c += kNmsThreads) cell_start[c] = lead_cs[c];
-  }
-  const int nos = lead_round[4];
-  const GridGeom geom = *cluster.map_shared_rank(&s_geom, 0);
-  __syncthreads();
-
-  int kept_total = 0;
-  int cursor_word = 0;
+  int kept = 0;          // boxes kept so far (uniform)
   int rounds = 0;
+  float inv_cell = 0.f, r_cap = 0.f;
+  bool geom_set = false;
 
-  // record one evaluated pair in the frontier bit-matrices
-  auto mark_pair = [&](int i, int j, float iou) {
-    if (iou > a.thr) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
-    if (kWeighted && iou > a.mthr) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
+  auto cell_of = [&](float v) -> int { return static_cast<int>(fminf(fmaxf(floorf(v * inv_cell), -32768.f), 32767.f)); };
+  auto bucket_of = [&](int ix, int iy) -> uint32_t {
+    return ((static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u)) & bmask;
   };
-  auto accumulate = [&](int slot, int row_in_seg) {  // merge candidate `row_in_seg` into kept slot
-    const float *row = a.data + static_cast<size_t>(beg + row_in_seg) * a.D;
+  auto in_grid = [&](float x, float y, float r) -> bool {
+    return (r <= r_cap) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap);   // false for NaN
+  };
+
+  // Every kept box k >= since whose padded circle can touch (x, y, r): fn(k, kx, ky, kr).  Chains are newest-first
+  // (insertion prepends, kept indices only grow), so a walk stops at the first index below `since`.
+  auto for_each_near = [&](float x, float y, float r, int since, auto &&fn) {
+    const int hi = kept;
+    bool brute = !prune;
+    int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
+    if (!brute) {
+      if (!(x == x) || !(y == y) || !(r == r)) return;          // NaN never interacts (its circle test is false)
+      const float reach = r + r_cap;
+      if (!(reach <= kPosCap) || !(fabsf(x) <= kPosCap) || !(fabsf(y) <= kPosCap)) brute = true;
+      else {
+        ix0 = cell_of(x - reach); ix1 = cell_of(x + reach); iy0 = cell_of(y - reach); iy1 = cell_of(y + reach);
+        if ((ix1 - ix0 + 1) * (iy1 - iy0 + 1) > kMaxCellsPerQuery) brute = true;
+      }
+    }
+    if (brute) {
+      for (int k = since; k < hi; ++k) { const float4 q = kxyr[k]; fn(k, q.x, q.y, q.z); }
+      return;
+    }
+    for (int iy = iy0; iy <= iy1; ++iy)
+      for (int ix = ix0; ix <= ix1; ++ix) {
+        int k = heads[bucket_of(ix, iy)];
+        while (k >= since) {
+          const float4 q = kxyr[k];
+          if (cell_of(q.x) == ix && cell_of(q.y) == iy) fn(k, q.x, q.y, q.z);   // other cells share the bucket
+          k = knext[k];
+        }
+      }
+    const int nos = s_nos;
+    for (int o = 0; o < nos; ++o) {
+      const int k = kos[o];
+      if (k >= since) { const float4 q = kxyr[k]; fn(k, q.x, q.y, q.z); }
+    }
+  };
+
+  auto accumulate = [&](int slot, int pos) {  // merge the candidate at `pos` into kept slot
+    const float *row = a.data + static_cast<size_t>(beg + pos) * a.D;
     float v[kMaxD];
 #pragma unroll
     for (int c = 0; c < kMaxD; ++c) v[c] = c < a.D ? row[c] : 0.f;   // independent loads first: one latency, not D
@@ -464,26 +609,6 @@ nms_segment_kernel(NmsArgs a) {
     atomicAdd(acc + a.D - 1, sj);
     atomicAdd(a.merge_count + kbase + slot, 1);
   };
-  // a candidate is suppressed: clear it in the leader's bitmap (the truth) and in the local snapshot
-  auto kill = [&](int j) {
-    const uint32_t m = ~(1u << (j & 31));
-    atomicAnd(&lead_alive[j >> 5], m);
-    if (!leader) atomicAnd(&alive[j >> 5], m);
-  };
-  // warp-converged append of `item` (valid where `pred`) to the exact-IoU queue; returns false for the
-  // lanes whose item did not fit (caller handles them in place)
-  auto q2_push = [&](bool pred, uint32_t item) -> bool {
-    const uint32_t m = __ballot_sync(0xffffffffu, pred);
-    if (!m) return true;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&s_qn, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (!pred) return true;
-    const int slot = base + __popc(m & ((1u << lane) - 1u));
-    if (slot >= kQ2Cap) return false;
-    queue2[slot] = item;
-    return true;
-  };
 
   // bound -> approximate -> exact for ONE pair, in place (overflow paths; divergent, so only a fallback)
   auto classify_pair = [&](const Rec &ra, const Rec &rb, bool &above, bool &above_m) {
@@ -491,7 +616,7 @@ nms_segment_kernel(NmsArgs a) {
     if (prune) {
       if (!iou_may_exceed(ra, rb, thr_any)) { above = false; above_m = false; return; }
       const Obb oa = obb_of(ra), ob = obb_of(rb);
-      if (obb_sane(oa) && obb_sane(ob)) {
+      if (use_approx && obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
         const float ap = approx_iou(oa, ob);
         ++st_approx;
         d1 = decide_vs(ap, a.thr);
@@ -535,7 +660,7 @@ nms_segment_kernel(NmsArgs a) {
         int d1 = 0, d2 = 0;
         if (prune && !iou_may_exceed(ra, rb, thr_any)) {
           d1 = -1; d2 = -1;                       // even the upper bound stays below both thresholds
-        } else if (prune && obb_sane(oa) && obb_sane(ob)) {
+        } else if (use_approx && obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
           const float ap = approx_iou(oa, ob);
           ++st_approx;
           d1 = decide_vs(ap, a.thr);
@@ -559,450 +684,455 @@ nms_segment_kernel(NmsArgs a) {
     if (nbuf > 0) exact32(nbuf);
   };
 
-  while (true) {
-    int nf = 0, nk = 0;
-    if (leader) {
-      // ================= 1. frontier: first kF alive candidates =================
-      for (int base = cursor_word; base < nwords && nf < kF; base += kNmsThreads) {
-        const int wi = base + tid;
-        const uint32_t word = wi < nwords ? alive[wi] : 0u;
-        int total;
-        const int off = block_exclusive_scan(__popc(word), s_warp, total);
-        if (word && nf + off < kF) {
-          uint32_t m = word;
-          int r = nf + off;
-          while (m && r < kF) {
-            const int bit = __ffs(m) - 1;
-            m &= m - 1;
-            front_pos[r++] = (wi << 5) + bit;
+  // ---- PULL: the candidates list[0, ns) (window indices, rank order) against the kept boxes [since, kept).
+  // One candidate per thread: count its circle hits, block scan, write the (candidate, kept) pairs to the queue
+  // at the scanned offsets, evaluate the queue on dense lanes.  A batch whose pairs do not fit the queue is cut at
+  // the last thread that fits (the hits are a prefix sum, so the threads that fit form a prefix of the batch).
+  // merges_only: the scan is over (weighted, num_post_nms reached) -- candidates only contribute to merge sets.
+  auto pull = [&](const uint16_t *list, int ns, int since, bool merges_only) {
+    if (since >= kept || ns <= 0) return;
+    int bi = 0;
+    while (bi < ns) {
+      const int t = bi + tid;
+      const bool active = t < ns;
+      int j = 0, pos = 0, cnt = 0;
+      float x = 0.f, y = 0.f, r = 0.f;
+      if (active) {
+        j = list[t];
+        pos = static_cast<int>(wpos[j]);
+        x = rec_cx(recs[pos]); y = rec_cy(recs[pos]); r = recs[pos].r;
+        for_each_near(x, y, r, since, [&](int, float kx, float ky, float kr) {
+          ++st_circle;
+          if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+          ++cnt;
+        });
+      }
+      int total;
+      const int off = block_exclusive_scan(cnt, s_warp, total);
+      const bool ok = active && (off + cnt <= kQ2Cap);
+      int m = __syncthreads_count(ok);
+      if (tid == 0) s_qn = 0;
+      __syncthreads();
+      if (m == 0) {
+        // the first candidate alone overflows the queue: thread 0 evaluates its pairs in place, in kept order
+        if (tid == 0) {
+          const Rec rj = recs[pos];
+          int fs = 0x7fffffff;
+          for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
+            if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+            if (!kWeighted && fs != 0x7fffffff) return;
+            bool above, above_m;
+            classify_pair(recs[__float_as_int(kxyr[k].w)], rj, above, above_m);
+            if (above && k < fs) fs = k;
+          });
+          if (kWeighted) {
+            for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
+              if (k > fs) return;
+              if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+              bool above, above_m;
+              classify_pair(recs[__float_as_int(kxyr[k].w)], rj, above, above_m);
+              if (above_m) accumulate(k, pos);
+            });
           }
+          if (fs != 0x7fffffff) { walive[j] = 0; ++st_hit; }
         }
-        nf = min(kF, nf + total);
+        m = 1;
+        __syncthreads();
+        bi += m;
+        continue;
+      }
+      if (ok) {
+        s_bj[tid] = static_cast<uint16_t>(j);
+        if (kWeighted) wfs[j] = 0x7fffffff;
+        int w = off;
+        for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
+          if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+          queue2[w++] = (static_cast<uint32_t>(tid) << 20) | static_cast<uint32_t>(k);
+        });
+        if (tid == m - 1) s_qn = off + cnt;   // ok threads are exactly tid < m
       }
       __syncthreads();
-      lap(0);
-      if (nf > 0) {
-        ++rounds;
-        // the frontier is decided this round: clear its bits, reset the per-round state
-        if (tid < nf) {
-          const int pos = front_pos[tid];
-          atomicAnd(&alive[pos >> 5], ~(1u << (pos & 31)));
-          keptrank[tid] = -1;
+      lap(1);
+      const int qn = s_qn;
+      auto get = [&](int q, Rec &ra, Rec &rb) {
+        const uint32_t e = queue2[q];
+        ra = recs[__float_as_int(kxyr[e & 0xfffffu].w)];   // the kept box ranks higher: box1 of the routine
+        rb = recs[wpos[s_bj[e >> 20]]];
+      };
+      if (!kWeighted) {
+        eval_queue(qn, get, [&](int q, bool above, bool) {
+          if (above) { ++st_hit; walive[s_bj[queue2[q] >> 20]] = 0; }
+        });
+        __syncthreads();
+      } else {
+        // pass 1: the two comparisons of every queued pair; each candidate's FIRST suppressor
+        eval_queue(qn, get, [&](int q, bool above, bool above_m) {
+          qflag[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
+          if (above) atomicMin(&wfs[s_bj[queue2[q] >> 20]], static_cast<int>(queue2[q] & 0xfffffu));
+        });
+        __syncthreads();
+        // pass 2: merges up to and including the first suppressor; a suppressed candidate leaves the window
+        for (int q = tid; q < qn; q += kNmsThreads) {
+          const uint32_t e = queue2[q];
+          const int jj = s_bj[e >> 20], k = static_cast<int>(e & 0xfffffu);
+          const int fs = wfs[jj];
+          if (k > fs) continue;
+          if (qflag[q] & 2u) accumulate(k, static_cast<int>(wpos[jj]));
+          if (k == fs && !merges_only) walive[jj] = 0;
         }
-        for (int i = tid; i < kF * kFW; i += kNmsThreads) {
-          sup[i] = 0u;
-          if (kWeighted) mrg[i] = 0u;
-        }
-        if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
-        cursor_word = front_pos[0] >> 5;
+        __syncthreads();
       }
-      if (tid == 0) { s_round[0] = nf; s_round[2] = cursor_word; }
+      lap(2);
+      bi += m;
     }
-    cluster.sync();   // (A0) the frontier (positions) is published, the leader's bit-matrices are zeroed
-    nf = lead_round[0];
-    cursor_word = lead_round[2];
-    if (nf == 0) break;
+  };
 
-    // ================= 2. interacting pairs inside the frontier (whole cluster) =================
-    // Every CTA loads the frontier's records; the rows of the upper-triangular pair matrix are dealt
-    // round-robin to the warps of the cluster (row i costs nf - i tests, so interleaving balances):
-    // warp per row, lanes over the columns j > i, circle test -> work queue; then bound / approximate /
-    // exact IoU on dense lanes, results OR-ed into the leader's bit-matrices through DSMEM.
-    {
-      const int *lead_front = cluster.map_shared_rank(front_pos, 0);
+  // order-preserving compaction of a survivor list by walive
+  auto compact = [&](const uint16_t *in, int ns, uint16_t *out) -> int {
+    const int per = (ns + kNmsThreads - 1) / kNmsThreads;
+    const int lo = min(ns, tid * per), hi = min(ns, lo + per);
+    int c = 0;
+    for (int t = lo; t < hi; ++t) c += walive[in[t]] ? 1 : 0;
+    int total;
+    int off = block_exclusive_scan(c, s_warp, total);
+    for (int t = lo; t < hi; ++t) {
+      const uint16_t j = in[t];
+      if (walive[j]) out[off++] = j;
+    }
+    __syncthreads();
+    return total;
+  };
+
+  // ---- window assembly state (uniform)
+  int rank_base = 0;                 // candidates consumed so far == rank of the next window's first candidate
+  int bin_cur = 0;                   // next score bin
+  int chunk_lo = 0, chunk_hi = 0;    // pending part of a bin larger than a window (sorted through global memory)
+  bool done = false;                 // num_post_nms reached
+
+  // next window -> wpos[0, wn) in rank order; returns wn (0: no candidates left)
+  auto next_window = [&](bool need_order) -> int {
+    int wn = 0;
+    if (a.presorted) {
+      wn = min(kWin, n_use - rank_base);
+      for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(rank_base + t);
+      __syncthreads();
+      return wn;
+    }
+    for (;;) {
+      if (chunk_hi > chunk_lo) {
+        wn = min(kWin, chunk_hi - chunk_lo);
+        for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = gorder[chunk_lo + t];
+        chunk_lo += wn;
+        __syncthreads();
+        break;
+      }
+      if (bin_cur >= a.nb) return 0;
+      const int base = s_bins[bin_cur];
+      int lo = bin_cur, hi = a.nb;           // largest b with s_bins[b] - base <= kWin (every thread, same result)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_bins[mid] - base <= kWin) lo = mid; else hi = mid - 1;
+      }
+      if (lo == bin_cur) {
+        // this bin alone exceeds a window (massively tied / saturated scores): sort it once through global memory
+        const int m = s_bins[bin_cur + 1] - base;
+        for (int t = tid; t < m; t += kNmsThreads) gorder[base + t] = static_cast<uint32_t>(base + t);
+        __syncthreads();
+        cta_bitonic_sort(skey + base, gorder + base, m);
+        chunk_lo = base; chunk_hi = base + m;
+        ++bin_cur;
+        continue;
+      }
+      wn = s_bins[lo] - base;
+      bin_cur = lo;
+      if (wn == 0) continue;                 // only empty bins: go on (ends at bin_cur == nb)
+      // the order inside the window only matters when candidates are consumed in rank order (need_order) or the
+      // num_pre_nms cut falls inside it
+      if (need_order || rank_base + wn > n_use) {
+        for (int t = tid; t < wn; t += kNmsThreads) { wkey[t] = skey[base + t]; widx[t] = static_cast<uint16_t>(t); }
+        __syncthreads();
+        cta_bitonic_sort(wkey, widx, wn);
+        for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(base + widx[t]);
+      } else {
+        for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(base + t);
+      }
+      __syncthreads();
+      break;
+    }
+    return min(wn, n_use - rank_base);
+  };
+
+  while (rank_base < n_use && !done) {
+    const int wn = next_window(true);
+    if (wn <= 0) break;
+    if (!geom_set) {
+      // cell size of the kept-box grid from the padded radii of the first (top-scored) window
+      float sr = 0.f, sc = 0.f;
+      for (int t = tid; t < wn; t += kNmsThreads) {
+        const float r = recs[wpos[t]].r;
+        if (r > 0.f && r < 1.0e4f) { sr += r; sc += 1.f; }
+      }
+      for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); sc += __shfl_xor_sync(0xffffffffu, sc, o); }
+      if (lane == 0) { s_red[wid] = sr; s_red[kNmsWarps + wid] = sc; }
+      __syncthreads();
+      if (tid == 0) {
+        float tr = 0.f, tc = 0.f;
+        for (int w = 0; w < kNmsWarps; ++w) { tr += s_red[w]; tc += s_red[kNmsWarps + w]; }
+        const float mr = tc > 0.f ? tr / tc : 1.f;
+        s_cell[1] = 2.0f * mr;                                             // r_cap: larger kept boxes go to the oversize list
+        s_cell[0] = 1.0f / fminf(fmaxf(3.0f * mr, 1e-3f), 1.0e5f);         // cell = mean radius + r_cap: a typical query spans 3 x 3 cells
+      }
+      __syncthreads();
+      inv_cell = s_cell[0]; r_cap = s_cell[1];
+      geom_set = true;
+    }
+    for (int t = tid; t < wn; t += kNmsThreads) { surv_a[t] = static_cast<uint16_t>(t); walive[t] = 1; }
+    __syncthreads();
+    lap(0);
+    uint16_t *list = surv_a, *other = surv_b;
+    int ns = wn, since = 0;
+
+    while (true) {
+      // ================= a / c. pull against the kept boxes [since, kept), drop the suppressed =================
+      if (since < kept) {
+        pull(list, ns, since, false);
+        const int ns2 = compact(list, ns, other);
+        uint16_t *tmp = list; list = other; other = tmp;
+        ns = ns2;
+      }
+      if (ns == 0) break;
+      ++rounds;
+      // ================= b. frontier = the first nf survivors; all pairs inside it =================
+      const int nf = min(kF, ns);
       if (tid < nf) {
-        const int pos = lead_front[tid];
-        const Rec r = recs[pos];
+        const int j = list[tid];
+        const Rec r = recs[wpos[j]];
         frec[tid] = r;
         fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
+        front_w[tid] = static_cast<uint16_t>(j);
+        keptrank[tid] = -1;
       }
+      for (int i = tid; i < nf * kFW; i += kNmsThreads) {
+        sup[i] = 0u;
+        if (kWeighted) mrg[i] = 0u;
+      }
+      if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
       if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
       __syncthreads();
-      if (leader) lap(1);
-      uint32_t *lead_sup = cluster.map_shared_rank(sup, 0);
-      uint32_t *lead_mrg = cluster.map_shared_rank(mrg, 0);
-      auto mark_remote = [&](int i, int j, bool above, bool above_m) {
-        if (above) { ++st_hit; atomicOr(&lead_sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
-        if (kWeighted && above_m) atomicOr(&lead_mrg[i * kFW + (j >> 5)], 1u << (j & 31));
-      };
-      // One queue reservation per ROW (a single-address shared atomic per 32-column batch serialises the
-      // CTA on dense frontiers): lane b keeps the hit mask of the row's b-th batch, the warp reserves the
-      // row's total once and every lane writes out its own batch.  A row that does not fit waits for the
-      // next drain: reservations are handed out in order, so everything before the first refused one
-      // (s_qvalid) is written and everything after it is refused too.
-      static_assert(kF <= 1024, "a row's batches must fit one mask per lane");
-      constexpr int kWarps = kNmsThreads / 32;
-      int i = crank * kWarps + wid;
-      for (;;) {
-        while (i < nf - 1) {
-          const float xi = fx[i], yi = fy[i], ri = fr[i];
-          uint32_t mymask = 0;
-          for (int jb = i + 1, b = 0; jb < nf; jb += 32, ++b) {
-            const int j = jb + lane;
-            bool hit = false;
-            if (j < nf) {
-              ++st_circle;
-              hit = true;
-              if (prune) {
-                const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
-                hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
-              }
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (lane == b) mymask = m;
-          }
-          const int mine = __popc(mymask);
-          int incl = mine;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          if (total) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_qn, total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + total > kQ2Cap) {
-              if (lane == 0) atomicMin(&s_qvalid, base);
-              break;   // this row is redone after the drain
-            }
-            int slot = base + incl - mine;
-            const int j0 = i + 1 + 32 * lane;
-            for (uint32_t m = mymask; m; m &= m - 1)
-              queue2[slot++] = static_cast<uint32_t>((i << 10) | (j0 + __ffs(m) - 1));
-          }
-          i += P * kWarps;
-        }
-        const int more = __syncthreads_or(i < nf - 1);
-        eval_queue(min(s_qn, s_qvalid),
-                   [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
-                   [&](int q, bool above, bool above_m) {
-                     mark_remote(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
-                   });
-        if (!more) break;
-        __syncthreads();
-        if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
-        __syncthreads();
-      }
-    }
-    cluster.sync();   // (A1) every CTA's pair results are in the leader's bit-matrices
-    if (leader) {
-      lap(2);
       {
-        // ================= 3. greedy resolution of the frontier =================
-        // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
-        // parallel; only the rest needs the dependent scan, done by one warp.
-        {
-          const int w = tid & (kFW - 1);
-          uint32_t colbits = 0u;
-          for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
-          if (colbits) atomicOr(&s_haspred[w], colbits);
-        }
-        __syncthreads();
-        {
-          const int w = tid & (kFW - 1);
-          uint32_t rm = 0u;
-          for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW)
-            if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
-          if (rm) atomicOr(&s_removed[w], rm);
-        }
-        __syncthreads();
-        if (tid < 32) {
-          // lane w < kFW owns word w.  valid = bits < nf; free = valid & ~haspred (kept for sure)
-          uint32_t valid = 0u, removed = 0u, pending = 0u, kept = 0u;
-          if (lane < kFW) {
-            const int lo = lane << 5;
-            valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
-            removed = s_removed[lane];
-            pending = valid & s_haspred[lane];       // must be visited in rank order
-            kept = valid & ~s_haspred[lane];
-          }
-          while (true) {
-            const uint32_t cand = pending & ~removed;
-            const uint32_t have = __ballot_sync(0xffffffffu, cand != 0u);
-            if (!have) break;
-            const int wsel = __ffs(have) - 1;
-            const uint32_t cw = __shfl_sync(0xffffffffu, cand, wsel);
-            const int bit = __ffs(cw) - 1;
-            const int i = (wsel << 5) + bit;
-            if (lane == wsel) kept |= 1u << bit;
-            if (lane < kFW) {
-              // everything up to and including i is decided now
-              const int lo = lane << 5;
-              if (i >= lo + 31) pending = 0u;
-              else if (i >= lo) pending &= ~((2u << (i - lo)) - 1u);
-              removed |= sup[i * kFW + lane];
+        auto mark = [&](int i, int j, bool above, bool above_m) {
+          if (above) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
+          if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
+        };
+        // Rows of the upper-triangular pair matrix are dealt round-robin to the warps (row i costs nf - i tests):
+        // warp per row, lanes over the columns j > i, circle test -> work queue.  One queue reservation per ROW:
+        // lane b keeps the hit mask of the row's b-th 32-column batch, the warp reserves the row's total once.  A
+        // row that does not fit waits for the next drain: reservations are handed out in order, so everything
+        // before the first refused one (s_qvalid) is written and everything after it is refused too.
+        int i = wid;
+        for (;;) {
+          while (i < nf - 1) {
+            const float xi = fx[i], yi = fy[i], ri = fr[i];
+            uint32_t mymask = 0;
+            for (int jb = i + 1, b = 0; jb < nf; jb += 32, ++b) {
+              const int j = jb + lane;
+              bool hit = false;
+              if (j < nf) {
+                ++st_circle;
+                hit = true;
+                if (prune) {
+                  const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
+                  hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
+                }
+              }
+              const uint32_t m = __ballot_sync(0xffffffffu, hit);
+              if (lane == b) mymask = m;
             }
-          }
-          // kept boxes in rank order, truncated to the room left under num_post_nms
-          const int room = a.num_post - kept_total;
-          const int cnt = lane < kFW ? __popc(kept) : 0;
-          int incl = cnt;
+            const int mine = __popc(mymask);
+            int incl = mine;
 #pragma unroll
-          for (int o = 1; o < kFW; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          int rank = incl - cnt;
-          if (lane < kFW) {
-            uint32_t m = kept;
-            while (m && rank < room) {
-              const int bit = __ffs(m) - 1;
-              m &= m - 1;
-              const int i = (lane << 5) + bit;
-              keptf[rank] = static_cast<uint16_t>(i);
-              keptrank[i] = static_cast<int16_t>(rank);
-              ++rank;
+            for (int d = 1; d < 32; d <<= 1) {
+              const int v = __shfl_up_sync(0xffffffffu, incl, d);
+              if (lane >= d) incl += v;
             }
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, kFW - 1);
-          if (lane == 0) s_nk = min(total, room);
-        }
-        __syncthreads();
-        nk = s_nk;
-        lap(3);
-
-        // ================= 4. publish the newly kept boxes =================
-        if (tid < nk) {
-          const int fi = keptf[tid];
-          a.kept_pos[kbase + kept_total + tid] = front_pos[fi];
-          krec[tid] = frec[fi];
-          kx[tid] = fx[fi]; ky[tid] = fy[fi]; kr[tid] = fr[fi];
-        }
-        if (kWeighted) {
-          // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr
-          // that comes no later than its first suppressor; kept boxes join themselves.  The (j, slot)
-          // pairs are queued first and accumulated afterwards, one pair per lane: done in place, each
-          // lane's global loads + fp64 atomics would run alone (lanes reach their merges at different t).
-          // Work is proportional to the set bits of the kept rows: (1) first suppressor of every frontier
-          // box = min rank over the kept rows that contain it; (2) each kept row queues itself and the
-          // boxes of its merge row that it reaches no later than their first suppressor.
-          if (tid == 0) s_qn = 0;
-          if (tid < nf) killer[tid] = 0x7fffffff;
-          __syncthreads();
-          if (tid < nk) {
-            const int i = keptf[tid];
-            for (int w = 0; w < kFW; ++w) {
-              uint32_t bits = sup[i * kFW + w];
-              while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; atomicMin(&killer[j], tid); }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&s_qn, total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (base + total > kQ2Cap) {
+                if (lane == 0) atomicMin(&s_qvalid, base);
+                break;   // this row is redone after the drain
+              }
+              int slot = base + incl - mine;
+              const int j0 = i + 1 + 32 * lane;
+              for (uint32_t m = mymask; m; m &= m - 1)
+                queue2[slot++] = static_cast<uint32_t>((i << 10) | (j0 + __ffs(m) - 1));
             }
+            i += kNmsWarps;
           }
+          const int more = __syncthreads_or(i < nf - 1);
+          eval_queue(min(s_qn, s_qvalid),
+                     [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
+                     [&](int q, bool above, bool above_m) {
+                       mark(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
+                     });
           __syncthreads();
-          if (tid < nk) {
-            const int i = keptf[tid];
-            auto push = [&](int j) {
-              const int slot = atomicAdd(&s_qn, 1);
-              if (slot < kQ2Cap) queue2[slot] = (static_cast<uint32_t>(j) << 16) | static_cast<uint32_t>(tid);
-              else accumulate(kept_total + tid, front_pos[j]);   // (cannot happen: <= kF * kF / 2 only if every pair merges)
-            };
-            push(i);                                             // a kept box joins its own merge set
-            for (int w = 0; w < kFW; ++w) {
-              uint32_t bits = mrg[i * kFW + w];
-              while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; if (tid <= killer[j]) push(j); }
-            }
-          }
+          if (!more) break;
+          if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
           __syncthreads();
-          const int nq = min(s_qn, kQ2Cap);
-          for (int q = tid; q < nq; q += kNmsThreads)
-            accumulate(kept_total + static_cast<int>(queue2[q] & 0xffffu), front_pos[queue2[q] >> 16]);
         }
+      }
+      lap(3);
+      // ================= greedy resolution of the frontier =================
+      // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
+      // parallel; only the rest needs the dependent scan, done by one warp.
+      {
+        const int w = tid & (kFW - 1);
+        uint32_t colbits = 0u;
+        for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW) colbits |= sup[i * kFW + w];
+        if (colbits) atomicOr(&s_haspred[w], colbits);
       }
       __syncthreads();
-      lap(6);
-      if (tid == 0) { s_round[0] = nf; s_round[1] = nk; s_qn = 0; s_next = 0; }
-      if (tid == 1) s_round[2] = cursor_word;
-    }
-    cluster.sync();   // (A) the leader's round state, kept boxes and bitmap are final
-    nf = lead_round[0];
-    nk = lead_round[1];
-    cursor_word = lead_round[2];
-    if (nf == 0) break;
-    const int slot0 = kept_total;
-    kept_total += nk;
-    // nms.py:53-56: only the first num_post_nms kept survive, so the scan can stop there.  The
-    // weighted mode still owes the last kept boxes their merge sets from the candidates behind
-    // the frontier, so it runs one more kill phase before leaving.
-    const bool last_round = kept_total >= a.num_post;
-    if (last_round && !kWeighted) break;
-    if (!leader) {
-      // helpers: this round's kept boxes and a snapshot of the alive bitmap, through DSMEM
-      const Rec *lrec = cluster.map_shared_rank(krec, 0);
-      const float *lx = cluster.map_shared_rank(kx, 0), *ly = cluster.map_shared_rank(ky, 0), *lr = cluster.map_shared_rank(kr, 0);
-      if (tid < nk) { krec[tid] = lrec[tid]; kx[tid] = lx[tid]; ky[tid] = ly[tid]; kr[tid] = lr[tid]; }
-      for (int w = tid; w < nwords; w += kNmsThreads) alive[w] = lead_alive[w];   // all words: decided bits too
-      if (tid == 0) s_qn = 0;
-    }
-    __syncthreads();
-    if (leader) lap(7);
-
-    // ================= 5. kill scan: one warp per newly kept box over the static grid ==============
-    // Lanes stride over the contiguous entries of each cell the kept box's circle touches (+ the
-    // oversize list): alive test, circle test, hits compacted per warp so the IoU bound runs on full
-    // warps; pairs that pass go to the exact-IoU queue.
-    // Kept boxes are handed out one at a time from a counter in the leader's shared memory: a box in a dense
-    // cell costs 10x one at the periphery, a static split leaves most warps idle.
-    int *lead_next = cluster.map_shared_rank(&s_next, 0);
-    while (true) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(lead_next, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      if (t >= nk) break;
-      const Rec &rk = krec[t];
-      const float qx = kx[t], qy = ky[t], qr = kr[t];
-      int nbuf = 0;  // warp-uniform count of buffered hits
-      auto flush = [&](int count) {   // run the bound on `count` (<= 32) buffered hits, lanes < count
-        __syncwarp();
-        bool pass = false;
-        uint32_t j = 0;
-        if (lane < count) {
-          j = wbuf[lane];
-          pass = !prune || iou_may_exceed(rk, recs[j], thr_any);
-        }
-        if (!q2_push(pass, (j << 10) | static_cast<uint32_t>(t))) {
-          if (kWeighted) {
-            s_overflow = 1;   // redo this round's kill phase with the exact serial fallback
-          } else {            // hard mode only needs ANY suppressor: evaluate in place
-            bool above, above_m;
-            classify_pair(rk, recs[j], above, above_m);
-            if (above) { ++st_hit; kill(j); }
-          }
-        }
-        __syncwarp();
-      };
-      auto offer = [&](bool hit, uint32_t j) {  // warp-converged: buffer the hits, flush full warps
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (!m) return;
-        if (hit) wbuf[nbuf + __popc(m & ((1u << lane) - 1u))] = j;
-        nbuf += __popc(m);
-        if (nbuf >= 32) {
-          flush(32);
-          if (lane < nbuf - 32) wbuf[lane] = wbuf[32 + lane];   // disjoint halves: no hazard
-          nbuf -= 32;
-          __syncwarp();
-        }
-      };
-      auto scan_range = [&](const GridEntry *ents, int e0, int e1) {
-        // kUnroll independent 16-byte loads in flight per lane: the scan is L2-latency bound otherwise
-        constexpr int kUnroll = 4;
-        for (int eb = e0; eb < e1; eb += 32 * kUnroll) {
-          GridEntry ge[kUnroll];
-#pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
-            const int e = eb + u * 32 + lane;
-            ge[u] = (e < e1) ? ents[e] : GridEntry{0.f, 0.f, 0.f, 0u};
-          }
-#pragma unroll
-          for (int u = 0; u < kUnroll; ++u) {
-            if (eb + u * 32 >= e1) break;   // warp-uniform
-            const uint32_t j = ge[u].idx;
-            bool hit = false;
-            if (eb + u * 32 + lane < e1 && ((alive[j >> 5] >> (j & 31)) & 1u)) {
-              ++st_circle;
-              const float dx = ge[u].x - qx, dy = ge[u].y - qy, rr = ge[u].r + qr;
-              hit = dx * dx + dy * dy <= rr * rr;
-            }
-            offer(hit, j);
-          }
-        }
-      };
-      if (prune) {
-        // every gridded candidate whose circle can touch has its centre within qr + r_cap
-        const float reach = qr + geom.r_cap;
-        const int cx0 = geom.cell_x(qx - reach), cx1 = geom.cell_x(qx + reach);
-        const int cy0 = geom.cell_y(qy - reach), cy1 = geom.cell_y(qy + reach);
-        for (int cy = cy0; cy <= cy1; ++cy) scan_range(entries, cell_start[cy * kG + cx0], cell_start[cy * kG + cx1 + 1]);
-        for (int ob = 0; ob < nos; ob += 32) {               // oversize candidates
-          const int o = ob + lane;
-          bool hit = false;
-          uint32_t j = 0;
-          if (o < nos) {
-            j = os_list[o];
-            if ((alive[j >> 5] >> (j & 31)) & 1u) {
-              ++st_circle;
-              const Rec &rj = recs[j];
-              const float dx = rec_cx(rj) - qx, dy = rec_cy(rj) - qy, rr = rj.r + qr;
-              hit = dx * dx + dy * dy <= rr * rr;
-            }
-          }
-          offer(hit, j);
-        }
-      } else {
-        // pruning disabled (negative thresholds): every alive candidate interacts
-        for (int jb = cursor_word << 5; jb < n; jb += 32) {
-          const int j = jb + lane;
-          const bool hit = j < n && ((alive[j >> 5] >> (j & 31)) & 1u);
-          if (hit) ++st_circle;
-          offer(hit, static_cast<uint32_t>(j));
-        }
+      {
+        const int w = tid & (kFW - 1);
+        uint32_t rm = 0u;
+        for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW)
+          if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
+        if (rm) atomicOr(&s_removed[w], rm);
       }
-      if (nbuf > 0) flush(nbuf);
-    }
-    __syncthreads();
-    if (leader) lap(4);
-
-    // ================= 6. exact IoU of the queued (candidate, kept) pairs =================
-    {
-      const int qn = min(s_qn, kQ2Cap);
-      if (!kWeighted) {
-        eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 1023]; rb = recs[queue2[q] >> 10]; },
-                   [&](int q, bool above, bool) {
-                     if (above) { ++st_hit; kill(static_cast<int>(queue2[q] >> 10)); }
-                   });
-      } else {
-        // the queue of ANY CTA overflowing sends the whole round to the exact serial fallback
-        cluster.sync();
-        bool overflow = false;
-        for (int r = 0; r < P; ++r) overflow |= *cluster.map_shared_rank(&s_overflow, r) != 0;
-        if (!overflow) {
-          // pass 1: the two comparisons of every queued pair; remember each candidate's FIRST suppressor
-          eval_queue(qn, [&](int q, Rec &ra, Rec &rb) { ra = krec[queue2[q] & 1023]; rb = recs[queue2[q] >> 10]; },
-                     [&](int q, bool above, bool above_m) {
-                       qflag[q] = (above ? 1u : 0u) | (above_m ? 2u : 0u);
-                       if (above) atomicMin(&firstsup[queue2[q] >> 10], static_cast<int>(queue2[q] & 1023));
-                     });
-          __threadfence();
-          cluster.sync();   // (B) every CTA's first-suppressor votes are in
-          // pass 2: merges up to and including the first suppressor; the suppressor clears the bit
-          for (int q = tid; q < qn; q += kNmsThreads) {
-            const uint32_t e = queue2[q];
-            const int j = e >> 10, t = e & 1023;
-            const int fs = __ldcg(&firstsup[j]);
-            if (t > fs) continue;
-            if (qflag[q] & 2u) accumulate(slot0 + t, j);
-            if (t == fs) kill(j);
-          }
-        } else {
-          cluster.sync();   // keep the barrier count uniform
-          if (leader) {
-            // exact serial fallback: one thread per alive candidate, kept boxes visited in rank order
-            for (int j = (cursor_word << 5) + tid; j < n; j += kNmsThreads) {
-              if (!((alive[j >> 5] >> (j & 31)) & 1u)) continue;
-              const Rec rj = recs[j];
-              const float jx = rec_cx(rj), jy = rec_cy(rj);
-              for (int t = 0; t < nk; ++t) {
-                if (prune) {
-                  const float dx = kx[t] - jx, dy = ky[t] - jy, rr = kr[t] + rj.r;
-                  if (!(dx * dx + dy * dy <= rr * rr)) continue;
-                }
-                bool above, above_m;
-                classify_pair(krec[t], rj, above, above_m);
-                if (above_m) accumulate(slot0 + t, j);
-                if (above) { kill(j); break; }
-              }
-            }
+      __syncthreads();
+      if (tid < 32) {
+        // lane w < kFW owns word w.  valid = bits < nf; free = valid & ~haspred (kept for sure)
+        uint32_t valid = 0u, removed = 0u, pending = 0u, keptm = 0u;
+        if (lane < kFW) {
+          const int lo = lane << 5;
+          valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
+          removed = s_removed[lane];
+          pending = valid & s_haspred[lane];       // must be visited in rank order
+          keptm = valid & ~s_haspred[lane];
+        }
+        while (true) {
+          const uint32_t cand = pending & ~removed;
+          const uint32_t have = __ballot_sync(0xffffffffu, cand != 0u);
+          if (!have) break;
+          const int wsel = __ffs(have) - 1;
+          const uint32_t cw = __shfl_sync(0xffffffffu, cand, wsel);
+          const int bit = __ffs(cw) - 1;
+          const int i = (wsel << 5) + bit;
+          if (lane == wsel) keptm |= 1u << bit;
+          if (lane < kFW) {
+            // everything up to and including i is decided now
+            const int lo = lane << 5;
+            if (i >= lo + 31) pending = 0u;
+            else if (i >= lo) pending &= ~((2u << (i - lo)) - 1u);
+            removed |= sup[i * kFW + lane];
           }
         }
+        // kept boxes in rank order, truncated to the room left under num_post_nms
+        const int room = a.num_post - kept;
+        const int cnt = lane < kFW ? __popc(keptm) : 0;
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < kFW; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int rank = incl - cnt;
+        if (lane < kFW) {
+          uint32_t m = keptm;
+          while (m && rank < room) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int i = (lane << 5) + bit;
+            keptf[rank] = static_cast<uint16_t>(i);
+            keptrank[i] = static_cast<int16_t>(rank);
+            ++rank;
+          }
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, kFW - 1);
+        if (lane == 0) s_nk = min(total, room);
       }
+      __syncthreads();
+      const int nk = s_nk;
+      lap(4);
+
+      // ================= publish the newly kept boxes: output list + kept-box grid =================
+      if (tid < nk) {
+        const int fi = keptf[tid];
+        const int pos = static_cast<int>(wpos[front_w[fi]]);
+        const int k = kept + tid;
+        kept_pos[k] = pos;
+        const float x = fx[fi], y = fy[fi], r = fr[fi];
+        kxyr[k] = make_float4(x, y, r, __int_as_float(pos));
+        if (in_grid(x, y, r)) knext[k] = atomicExch(&heads[bucket_of(cell_of(x), cell_of(y))], k);
+        else kos[atomicAdd(&s_nos, 1)] = k;
+      }
+      if (kWeighted) {
+        // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr that comes no
+        // later than its first suppressor; kept boxes join themselves.  (1) first suppressor of every frontier box
+        // = min rank over the kept rows that contain it; (2) each kept row queues itself and the boxes of its merge
+        // row that it reaches no later than their first suppressor; (3) the queue is accumulated one pair per lane.
+        if (tid == 0) s_qn = 0;
+        if (tid < nf) killer[tid] = 0x7fffffff;
+        __syncthreads();
+        if (tid < nk) {
+          const int i = keptf[tid];
+          for (int w = 0; w < kFW; ++w) {
+            uint32_t bits = sup[i * kFW + w];
+            while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; atomicMin(&killer[j], tid); }
+          }
+        }
+        __syncthreads();
+        if (tid < nk) {
+          const int i = keptf[tid];
+          auto push = [&](int j) {
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < kQ2Cap) queue2[slot] = (static_cast<uint32_t>(j) << 16) | static_cast<uint32_t>(tid);
+            else accumulate(kept + tid, static_cast<int>(wpos[front_w[j]]));   // (<= kF * kF / 2 pairs: only if every pair merges)
+          };
+          push(i);                                             // a kept box joins its own merge set
+          for (int w = 0; w < kFW; ++w) {
+            uint32_t bits = mrg[i * kFW + w];
+            while (bits) { const int j = (w << 5) + __ffs(bits) - 1; bits &= bits - 1; if (tid <= killer[j]) push(j); }
+          }
+        }
+        __syncthreads();
+        const int nq = min(s_qn, kQ2Cap);
+        for (int q = tid; q < nq; q += kNmsThreads)
+          accumulate(kept + static_cast<int>(queue2[q] & 0xffffu), static_cast<int>(wpos[front_w[queue2[q] >> 16]]));
+      }
+      __syncthreads();
+      lap(5);
+      since = kept;
+      kept += nk;
+      list += nf;
+      ns -= nf;
+      // nms.py:53-56: only the first num_post_nms kept survive, so the scan can stop there
+      if (kept >= a.num_post) { done = true; break; }
+      if (ns == 0) break;
     }
-    cluster.sync();   // (C) every kill has reached the leader's bitmap
-    if (tid == 0) s_overflow = 0;
-    if (leader) lap(5);
-    if (last_round) break;
+    if (kWeighted && done) {
+      // the survivors behind the last frontier still owe the last kept boxes their merge contributions
+      // (they have met the kept boxes below `since` already)
+      pull(list, ns, since, true);
+    }
+    rank_base += wn;
   }
-  cluster.sync();     // nobody leaves while its shared memory may still be read
+  if (kWeighted && done) {
+    // ... and so do all candidates behind this window: one pull each against every kept box, merges only
+    while (rank_base < n_use) {
+      const int wn = next_window(false);
+      if (wn <= 0) break;
+      for (int t = tid; t < wn; t += kNmsThreads) surv_a[t] = static_cast<uint16_t>(t);
+      __syncthreads();
+      lap(0);
+      pull(surv_a, wn, 0, true);
+      rank_base += wn;
+    }
+  }
 
-  if (tid == 0 && leader) a.kept_count[seg] = kept_total;
+  if (tid == 0) a.kept_count[seg] = kept;
   if (a.stats) {
     // warp-reduce then one atomic per warp
     for (int o = 16; o; o >>= 1) {
@@ -1017,17 +1147,16 @@ nms_segment_kernel(NmsArgs a) {
       atomicAdd(a.stats + 18, st_hit);
       atomicAdd(a.stats + 19, st_approx);
     }
-    if (tid == 0 && leader) {
-      atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept_total));
+    if (tid == 0) {
+      atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept));
       atomicAdd(a.stats + 2, static_cast<unsigned long long>(rounds));
       unsigned long long tot = 0;
       for (int k = 0; k < 6; ++k) { atomicAdd(a.stats + 4 + k, static_cast<unsigned long long>(ph[k])); tot += ph[k]; }
       const unsigned long long prev = atomicMax(a.stats + 10, tot);  // slowest segment (cycles)
       if (tot > prev)                                                // (diagnostic, last writer wins) its phases
         for (int k = 0; k < 6; ++k) a.stats[12 + k] = static_cast<unsigned long long>(ph[k]);
-      atomicAdd(a.stats + 20, static_cast<unsigned long long>(ph[6]));
-      atomicAdd(a.stats + 21, static_cast<unsigned long long>(ph[7]));
-      atomicMax(a.stats + 11, static_cast<unsigned long long>(n));   // largest segment (candidates)
+      atomicMax(a.stats + 11, static_cast<unsigned long long>(n_seg));   // largest segment (candidates)
+      atomicAdd(a.stats + 20, static_cast<unsigned long long>(min(rank_base, n_use)));   // candidates consumed by the scan
     }
   }
 }
@@ -1057,33 +1186,40 @@ __global__ void kept_scan_kernel(const int *__restrict__ kept_count, int S, int 
 }
 
 struct PackArgs {
-  const int *seg_begin, *kept_base, *kept_count, *out_off, *kept_pos;
-  const uint32_t *order;
+  const int *seg_begin, *kept_count, *out_off, *kept_pos;
+  int kept_stride;
+  const uint32_t *src;
   const float *boxes;
   const double *acc;
   int total_classes, out_capacity, weighted, yaw_layout;
   float *out_params, *out_scores, *out_cats, *out_batch;
-  // fused gather: every rank's buffer is (world, peer_capacity + 1, 16) f32; this rank writes slot `peer_rank` of each
   const int *out_count;
   int *out_count_w;
+  int *host_count;   // optional: mapped pinned host int the total is also stored to (no D2H copy needed to read it)
   int n_segments, fused_scan;
+  // fused gather: every rank's buffer is (world, peer_capacity + 1, 16) f32; this rank writes slot `peer_rank` of each
   int n_peers, peer_rank, peer_capacity, sweep_offset;
   float *peer_rows[RV3D_MAX_PEERS];
+  uint32_t peer_seq;      // > 0: after its rows, the LAST block to finish stores this sequence number into the header
+  int *done_ticket;       // (zeroed per call) of slot `peer_rank` on every rank, behind a system-scope fence
 };
 
 __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
   const int seg = blockIdx.x;
   const int cnt = a.kept_count[seg];
-  const int kb = a.kept_base[seg], beg = a.seg_begin[seg];
+  const int beg = a.seg_begin[seg];
+  const int kb = a.kept_stride > 0 ? seg * a.kept_stride : beg;
   // Output offset of the segment = kept boxes of the segments before it.  With few segments every block sums that
   // prefix itself (<= 4 loads per thread) instead of waiting for a separate one-block scan kernel; block (0, 0) also
   // publishes the total.  Many segments (n_segments > kPackFusedScan): kept_scan_kernel ran before, out_off is ready.
   __shared__ int s_part[8];
+  __shared__ int s_last;
   int off, total = 0;
   const bool first = blockIdx.x == 0 && blockIdx.y == 0;
+  const bool need_total = first || (a.n_peers > 0 && a.peer_seq);
   if (a.fused_scan) {
     int part = 0, tot = 0;
-    const int upto = first ? a.n_segments : seg;
+    const int upto = need_total ? a.n_segments : seg;
     for (int s = threadIdx.x; s < upto; s += blockDim.x) {
       const int v = a.kept_count[s];
       tot += v;
@@ -1098,17 +1234,20 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
     off = s_part[0] + s_part[1] + s_part[2] + s_part[3];
     total = s_part[4] + s_part[5] + s_part[6] + s_part[7];
     total = total < a.out_capacity ? total : a.out_capacity;
-    if (first && threadIdx.x == 0) *a.out_count_w = total;
   } else {
     off = a.out_off[seg];
-    if (first) total = *a.out_count;
+    total = *a.out_count;
+  }
+  if (first && threadIdx.x == 0) {
+    if (a.fused_scan) *a.out_count_w = total;
+    if (a.host_count) *reinterpret_cast<volatile int *>(a.host_count) = total;
   }
   // grid = (segments, chunks of the kept list): every kept box has its own thread (the kernel is three dependent
   // loads and a sincos per row, i.e. pure latency)
   for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < cnt; t += gridDim.y * blockDim.x) {
     const int row = off + t;
-    if (row >= a.out_capacity) return;
-    const float4 *src = reinterpret_cast<const float4 *>(a.boxes + static_cast<size_t>(a.order[beg + a.kept_pos[kb + t]]) * 8);
+    if (row >= a.out_capacity) break;
+    const float4 *src = reinterpret_cast<const float4 *>(a.boxes + static_cast<size_t>(a.src[beg + a.kept_pos[kb + t]]) * 8);
     const float4 b0 = src[0], b1 = src[1];
     float p[7] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z};
     if (a.weighted) {
@@ -1122,16 +1261,16 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
       for (int c = 0; c < 6; ++c) p[c] = m[c];
       p[6] = static_cast<float>(atan2(static_cast<double>(m[6]), static_cast<double>(m[7])));
     }
+    double qs = 0.0, qc = 1.0;
+    if (!a.yaw_layout || a.n_peers > 0) sincos(static_cast<double>(p[6] * 0.5f), &qs, &qc);  // SO3.py:122-134
     if (a.yaw_layout) {
       float *o = a.out_params + static_cast<size_t>(row) * 7;
 #pragma unroll
       for (int c = 0; c < 7; ++c) o[c] = p[c];
     } else {
-      double s, c;
-      sincos(static_cast<double>(p[6] * 0.5f), &s, &c);  // SO3.py:122-134
       float *o = a.out_params + static_cast<size_t>(row) * 10;
       o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = p[3]; o[4] = p[4]; o[5] = p[5];
-      o[6] = static_cast<float>(c); o[7] = 0.f; o[8] = 0.f; o[9] = static_cast<float>(s);
+      o[6] = static_cast<float>(qc); o[7] = 0.f; o[8] = 0.f; o[9] = static_cast<float>(qs);
     }
     a.out_scores[row] = b1.w;
     a.out_cats[row] = static_cast<float>(seg % a.total_classes);   // nms.py:51: full_like(scores, j)
@@ -1139,26 +1278,56 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
     if (a.n_peers > 0 && row < a.peer_capacity) {
       // the path's one exchange step, fused: the detection goes straight into every rank's gather buffer with
       // 16-byte stores through the NVLink-mapped peer pointers (no staging copy, no collective call)
-      double s, c;
-      sincos(static_cast<double>(p[6] * 0.5f), &s, &c);
       const float4 r0 = make_float4(static_cast<float>(seg / a.total_classes + a.sweep_offset),
                                     static_cast<float>(seg % a.total_classes), b1.w, 0.f);
       const float4 r1 = make_float4(p[0], p[1], p[2], p[3]);
-      const float4 r2 = make_float4(p[4], p[5], static_cast<float>(c), 0.f);
-      const float4 r3 = make_float4(0.f, static_cast<float>(s), 0.f, 0.f);
+      const float4 r2 = make_float4(p[4], p[5], static_cast<float>(qc), 0.f);
+      const float4 r3 = make_float4(0.f, static_cast<float>(qs), 0.f, 0.f);
       const size_t at = (static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) + 1 + row) * 16;
-      for (int q = 0; q < a.n_peers; ++q) {
+      // consecutive lanes start at different peers, so a warp's stores fan out over all NVLink ports at once
+      for (int qq = 0; qq < a.n_peers; ++qq) {
+        const int q = (qq + threadIdx.x) % a.n_peers;
         float4 *dst = reinterpret_cast<float4 *>(a.peer_rows[q] + at);
         dst[0] = r0; dst[1] = r1; dst[2] = r2; dst[3] = r3;
       }
     }
   }
-  if (a.n_peers > 0 && first && threadIdx.x == 0) {   // header row: [rows written, rows kept]
-    const float4 h = make_float4(static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity),
-                                 static_cast<float>(total), 0.f, 0.f);
-    for (int q = 0; q < a.n_peers; ++q)
-      *reinterpret_cast<float4 *>(a.peer_rows[q] + static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) * 16) = h;
+  if (a.n_peers > 0) {
+    const size_t hdr = static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) * 16;
+    if (!a.peer_seq) {
+      if (first && threadIdx.x == 0) {   // header row: [rows written, rows kept]; the caller orders readers (barrier)
+        const float4 h = make_float4(static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity),
+                                     static_cast<float>(total), 0.f, 0.f);
+        for (int q = 0; q < a.n_peers; ++q) *reinterpret_cast<float4 *>(a.peer_rows[q] + hdr) = h;
+      }
+    } else {
+      // sequence-flag protocol: every block fences its peer stores system-wide, the last block to arrive publishes
+      // [rows written, rows kept, seq] to every rank; a reader that sees seq in a header sees the rows behind it
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(a.done_ticket, 1) == static_cast<int>(gridDim.x * gridDim.y) - 1) ? 1 : 0;
+      __syncthreads();
+      if (s_last && threadIdx.x < a.n_peers) {
+        __threadfence_system();
+        volatile float *h = a.peer_rows[threadIdx.x] + hdr;
+        h[0] = static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity);
+        h[1] = static_cast<float>(total);
+        __threadfence_system();
+        reinterpret_cast<volatile uint32_t *>(h)[2] = a.peer_seq;
+      }
+    }
   }
+}
+
+// consumer side of the sequence-flag protocol: spin until every rank's header in THIS rank's buffer carries `seq`
+__global__ void wait_peer_seq_kernel(const float *__restrict__ rows, int world, int peer_capacity, uint32_t seq) {
+  const int q = threadIdx.x;
+  if (q < world) {
+    const volatile uint32_t *h =
+        reinterpret_cast<const volatile uint32_t *>(rows + static_cast<size_t>(q) * (peer_capacity + 1) * 16);
+    while (h[2] != seq) __nanosleep(64);
+  }
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1176,174 +1345,240 @@ struct Carver {
   }
 };
 
-struct NmsLayout {
-  unsigned long long *keys_alt;
-  uint32_t *order, *order_alt;
-  int *seg_begin, *seg_end, *kept_base, *kept_count, *out_off, *kept_pos, *merge_count;
-  void *recs;
-  float *data;
-  double *acc;
-  void *grid_entries;
-  uint32_t *oversize;
-  int *firstsup;
-  void *cub_tmp;
-  size_t cub_bytes, total;
+// geometry of one suppression call, all host-known: capacity (rows of keys / boxes), segments, kept capacity
+struct NmsPlan {
+  int cap, S, nb, kc, kept_stride, kept_rows, n_buckets_g;
+  bool weighted, kept_in_smem;
+  int D;
 };
 
-static size_t cub_sort_bytes(int n, int end_bit) {
-  size_t bytes = 0;
-  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
-  cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, n, 0, end_bit, nullptr);
-  return bytes;
+static int pow2_ceil(int64_t v) { int p = 1; while (p < v) p *= 2; return p; }
+
+static NmsPlan make_plan(int cap, int S, int per_segment_max, int num_pre, int num_post, bool weighted, int D) {
+  NmsPlan pl{};
+  pl.cap = cap > 0 ? cap : 1; pl.S = S; pl.weighted = weighted; pl.D = D;
+  int nb = kMaxBins;
+  while (nb > 64 && static_cast<int64_t>(S) * nb > (int64_t(1) << 20)) nb >>= 1;
+  pl.nb = nb;
+  int kc = num_post < num_pre ? num_post : num_pre;
+  if (kc > per_segment_max) kc = per_segment_max;
+  if (kc > pl.cap) kc = pl.cap;
+  if (kc < 1) kc = 1;
+  pl.kc = kc;
+  // a segment keeps at most as many boxes as it has candidates, so its slice [seg_begin, seg_end) of cap-sized
+  // arrays is a private, sufficient region too: used when S * kc would be larger than that
+  if (static_cast<int64_t>(S) * kc <= pl.cap) { pl.kept_stride = kc; pl.kept_rows = S * kc; }
+  else { pl.kept_stride = 0; pl.kept_rows = pl.cap; }
+  pl.kept_in_smem = kc <= kKeptSmem;
+  pl.n_buckets_g = 0;
+  if (!pl.kept_in_smem) {
+    int64_t nbk = pow2_ceil(2 * static_cast<int64_t>(kc));
+    if (nbk < 4096) nbk = 4096;
+    if (nbk > (1 << 18)) nbk = 1 << 18;
+    while (nbk > 4096 && nbk * S > (int64_t(1) << 24)) nbk >>= 1;
+    pl.n_buckets_g = static_cast<int>(nbk);
+  }
+  return pl;
 }
 
-static NmsLayout nms_layout(void *scratch, int n, int S, bool weighted, int D, int end_bit) {
+struct NmsLayout {
+  // zero block (one memset): hist | ticket + pack ticket | kept_count | acc | merge_count
+  int *hist, *ticket, *kept_count;
+  double *acc;
+  int *merge_count;
+  size_t zero_bytes;
+  uint32_t *minmax;      // [2] + BinMap
+  BinMap *binmap;
+  int *bin_start, *seg_count, *seg_begin, *out_off, *kept_pos, *kos, *n_dev;
+  void *recs;
+  unsigned long long *skey, *keys_own;
+  uint32_t *src, *gorder;
+  float *data;
+  float4 *kxyr_g;
+  int *knext_g, *heads_g;
+  size_t heads_bytes, total;
+};
+
+static NmsLayout nms_layout(void *scratch, const NmsPlan &pl, bool own_keys, bool own_data) {
   Carver c(scratch);
   NmsLayout L{};
-  const int nn = n > 0 ? n : 1;
-  L.keys_alt = c.take<unsigned long long>(nn);
-  L.order = c.take<uint32_t>(nn);
-  L.order_alt = c.take<uint32_t>(nn);
-  L.seg_begin = c.take<int>(2 * static_cast<size_t>(S));  // seg_begin + seg_end contiguous (one memset)
-  L.seg_end = L.seg_begin ? L.seg_begin + S : nullptr;
-  L.kept_base = L.seg_begin;   // see rv3d_nms: a segment's kept rows live in its own [seg_begin, seg_end) slice
+  const size_t cap = static_cast<size_t>(pl.cap), S = static_cast<size_t>(pl.S), kr = static_cast<size_t>(pl.kept_rows);
+  L.hist = c.take<int>(S * pl.nb);
+  L.ticket = c.take<int>(4);
   L.kept_count = c.take<int>(S);
-  L.out_off = c.take<int>(S);
-  L.kept_pos = c.take<int>(nn);
-  L.recs = c.take<unsigned char>(static_cast<size_t>(nn) * (weighted ? sizeof(WRec) : sizeof(HardRec)));
-  L.data = nullptr; L.acc = nullptr; L.merge_count = nullptr;
-  if (weighted) {
-    L.data = c.take<float>(static_cast<size_t>(nn) * D);
-    L.acc = c.take<double>(static_cast<size_t>(nn) * D);   // acc + merge_count contiguous (one memset)
-    L.merge_count = c.take<int>(nn);
+  L.acc = nullptr; L.merge_count = nullptr;
+  if (pl.weighted) {
+    L.acc = c.take<double>(kr * pl.D);
+    L.merge_count = c.take<int>(kr);
   }
-  L.grid_entries = c.take<GridEntry>(nn);
-  L.oversize = c.take<uint32_t>(nn);
-  L.firstsup = weighted ? c.take<int>(nn) : nullptr;
-  L.cub_bytes = cub_sort_bytes(nn, end_bit);
-  L.cub_tmp = c.take<unsigned char>(L.cub_bytes);
+  L.zero_bytes = align_up(c.used, 256);
+  L.minmax = c.take<uint32_t>(2);
+  L.binmap = c.take<BinMap>(1);
+  L.n_dev = c.take<int>(1);
+  L.bin_start = c.take<int>(S * (pl.nb + 1));
+  L.seg_count = c.take<int>(S);
+  L.seg_begin = c.take<int>(S);
+  L.out_off = c.take<int>(S);
+  L.kept_pos = c.take<int>(kr);
+  L.kos = c.take<int>(kr);
+  L.recs = c.take<unsigned char>(cap * (pl.weighted ? sizeof(WRec) : sizeof(HardRec)));
+  L.skey = c.take<unsigned long long>(cap);
+  L.keys_own = own_keys ? c.take<unsigned long long>(cap) : nullptr;
+  L.src = c.take<uint32_t>(cap);
+  L.gorder = c.take<uint32_t>(cap);
+  L.data = (pl.weighted && own_data) ? c.take<float>(cap * pl.D) : nullptr;
+  L.kxyr_g = nullptr; L.knext_g = nullptr; L.heads_g = nullptr; L.heads_bytes = 0;
+  if (!pl.kept_in_smem) {
+    L.kxyr_g = c.take<float4>(kr);
+    L.knext_g = c.take<int>(kr);
+    L.heads_bytes = sizeof(int) * S * static_cast<size_t>(pl.n_buckets_g);
+    L.heads_g = c.take<int>(S * static_cast<size_t>(pl.n_buckets_g));
+  }
   L.total = align_up(c.used, 256);
   return L;
 }
 
-template <typename Rec, bool kWeighted>
-static int launch_nms_segments(const NmsArgs &a, int S, int max_seg_n, cudaStream_t s) {
-  const int nwords = (max_seg_n + 31) / 32;
-  constexpr int kF = Frontier<kWeighted>::kF;
-  const size_t smem = nms_smem_bytes<Rec, kWeighted, kF>(nwords);
-  // the alive bitmap lives in shared memory and grid entries index candidates with 20 bits
-  if (smem > 200 * 1024 || max_seg_n >= (1 << 20)) return RV3D_ERR_ARG;
-  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_segment_kernel<Rec, kWeighted, kF>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  // One cluster per segment, 1 CTA / SM, P = ceil(148 / S) CTAs per cluster (at most 4).  Rounding UP
-  // oversubscribes the machine a little (S = 48 -> 192 CTAs; GPC boundaries only let 45 clusters of 3 or
-  // 36 of 4 be co-resident anyway): segments finish at different times, so late clusters start in the
-  // gaps, and the larger cluster shortens every segment.  Measured at S = 48: P = 2 / 3 / 4 / 6 / 8 ->
-  // 1.03 / 0.99 / 0.96 / 1.00 / 1.12 ms for the whole sort + NMS + pack stage; at S = 24: P = 3 / 4 / 7 / 8
-  // -> 0.80 / 0.71 / 0.78 / 0.77 ms (the leader-only phases and the cluster barriers stop paying beyond 4).
-  cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kNmsThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int P = (kNumSMs + S - 1) / (S > 0 ? S : 1);
-  P = P < 1 ? 1 : (P > 4 ? 4 : P);
-  if (const char *e = getenv("RV3D_NMS_CLUSTER")) {   // experiments only
-    const int v = atoi(e);
-    if (v >= 1 && v <= 8) P = v;
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = kNumSMs;
   }
-  attr[0].val.clusterDim.x = static_cast<unsigned>(P);
-  cfg.gridDim = dim3(static_cast<unsigned>(S * P));
-  RV3D_CHECK_CUDA(cudaLaunchKernelEx(&cfg, nms_segment_kernel<Rec, kWeighted, kF>, a));
+  return n;
+}
+// grid of a grid-stride pass over at most `cap` rows (the live count is only known on the device)
+static int stride_grid(int cap) {
+  const int want = ceil_div(cap > 0 ? cap : 1, 256);
+  const int most = sm_count() * 8;
+  return want < most ? want : most;
+}
+
+template <typename Rec, bool kWeighted>
+static int launch_nms_segments(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s) {
+  constexpr int kF = Frontier<kWeighted>::kF;
+  const size_t smem = nms_smem_bytes<Rec, kWeighted, kF>(pl.kept_in_smem);
+  if (smem > 220 * 1024) return RV3D_ERR_ARG;
+  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_pull_kernel<Rec, kWeighted, kF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(nms_smem_bytes<Rec, kWeighted, kF>(true))));
+  nms_pull_kernel<Rec, kWeighted, kF><<<pl.S, kNmsThreads, smem, s>>>(a, pl.kept_in_smem ? 1 : 0);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
+}
+
+// hist -> bin_scan -> (caller's scatter) : shared front of every sorted entry point
+static int launch_bucketing(const unsigned long long *keys, const int32_t *n_ptr, const NmsPlan &pl, const NmsLayout &L,
+                            KeyGeom g, bool range_known, uint32_t desc_lo, uint32_t desc_hi, BinMapArg &bma, cudaStream_t s) {
+  bma.dev = nullptr;
+  if (range_known) {
+    bma.m = make_binmap(desc_lo, desc_hi, g.nb);
+  } else {
+    RV3D_CHECK_CUDA(cudaMemsetAsync(L.minmax, 0xFF, sizeof(uint32_t), s));
+    RV3D_CHECK_CUDA(cudaMemsetAsync(L.minmax + 1, 0, sizeof(uint32_t), s));
+    minmax_kernel<<<stride_grid(pl.cap), 256, 0, s>>>(keys, n_ptr, pl.cap, g, L.minmax);
+    RV3D_CHECK_LAUNCH();
+    binmap_from_minmax_kernel<<<1, 1, 0, s>>>(L.minmax, g.nb, L.binmap);
+    RV3D_CHECK_LAUNCH();
+    bma.m = BinMap{0, 0};
+    bma.dev = L.binmap;
+  }
+  hist_kernel<<<stride_grid(pl.cap), 256, 0, s>>>(keys, n_ptr, pl.cap, g, bma, pl.S, L.hist);
+  RV3D_CHECK_LAUNCH();
+  bin_scan_kernel<<<pl.S, 256, 0, s>>>(L.hist, g.nb, pl.S, L.bin_start, L.seg_count, L.seg_begin, L.ticket);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+static uint32_t desc_code(float score, int score_bits) {
+  uint32_t bits;
+  memcpy(&bits, &score, sizeof(bits));
+  const uint32_t d = ~orderable_f32(bits);
+  return score_bits >= 32 ? d : (d & ((1u << score_bits) - 1u));
+}
+
+static NmsArgs base_args(const NmsPlan &pl, const NmsLayout &L, int num_pre, int num_post, float thr, float mthr,
+                         bool weighted, int flags, int64_t *stats) {
+  NmsArgs a{};
+  a.recs = L.recs; a.skey = L.skey; a.gorder = L.gorder; a.seg_begin = L.seg_begin; a.seg_count = L.seg_count;
+  a.bin_start = L.bin_start; a.nb = pl.nb; a.presorted = 0;
+  a.num_pre = num_pre; a.num_post = num_post; a.thr = thr; a.mthr = mthr;
+  a.prune = (thr >= 0.f && (!weighted || mthr >= 0.f)) ? 1 : 0;
+  a.exact_only = (flags & RV3D_NMS_EXACT_ONLY) ? 1 : 0;
+  a.kept_stride = pl.kept_stride; a.kept_pos = L.kept_pos; a.kept_count = L.kept_count;
+  a.kxyr_g = L.kxyr_g; a.knext_g = L.knext_g; a.heads_g = L.heads_g; a.n_buckets_g = pl.n_buckets_g; a.kos = L.kos;
+  a.data = L.data; a.D = pl.D; a.acc = L.acc; a.merge_count = L.merge_count;
+  a.stats = reinterpret_cast<unsigned long long *>(stats);
+  return a;
 }
 
 }  // namespace rv3d
 
 using namespace rv3d;
 
-extern "C" size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p) {
-  if (!p || p->batch <= 0 || p->total_classes <= 0 || p->n_candidates < 0) return 0;
-  const int S = p->batch * p->total_classes;
-  const int end_bit = bits_for(S) + (p->score_bits ? p->score_bits : 32) + bits_for(p->total_candidates);
-  return nms_layout(nullptr, p->n_candidates, S, p->mode == RV3D_NMS_WEIGHTED, 9, end_bit > 64 ? 64 : end_bit).total;
+static bool nms_params_ok(const rv3d_nms_params *p) {
+  return p && p->batch > 0 && p->total_classes > 0 && p->total_candidates > 0 && p->capacity > 0 && p->num_pre_nms > 0 &&
+         p->num_post_nms > 0 && p->out_capacity >= 0 && (p->mode == RV3D_NMS_HARD || p->mode == RV3D_NMS_WEIGHTED) &&
+         (p->out_layout == RV3D_OUT_QUAT || p->out_layout == RV3D_OUT_YAW) &&
+         static_cast<int64_t>(p->batch) * p->total_classes < (int64_t(1) << 24);
 }
 
-extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float *boxes, float *out_params,
-                        float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
-                        int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(p && out_count && scratch);
-  RV3D_CHECK_ARG(p->batch > 0 && p->total_classes > 0 && p->total_candidates > 0 && p->n_candidates >= 0);
-  RV3D_CHECK_ARG(p->num_pre_nms > 0 && p->num_post_nms > 0 && p->out_capacity >= 0);
-  RV3D_CHECK_ARG(p->mode == RV3D_NMS_HARD || p->mode == RV3D_NMS_WEIGHTED);
-  RV3D_CHECK_ARG(p->out_layout == RV3D_OUT_QUAT || p->out_layout == RV3D_OUT_YAW);
+static NmsPlan plan_of(const rv3d_nms_params *p) {
+  return make_plan(p->capacity, p->batch * p->total_classes, p->total_candidates, p->num_pre_nms, p->num_post_nms,
+                   p->mode == RV3D_NMS_WEIGHTED, 9);
+}
+
+extern "C" size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p) {
+  if (!nms_params_ok(p)) return 0;
+  return nms_layout(nullptr, plan_of(p), false, true).total;
+}
+
+extern "C" int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys_in, const float *boxes,
+                        const int32_t *n_candidates, float *out_params, float *out_scores, float *out_categories,
+                        float *out_batch, int32_t *out_count, int64_t *stats, void *scratch, size_t scratch_bytes,
+                        rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(nms_params_ok(p) && out_count && scratch && n_candidates);
   RV3D_CHECK_ARG(p->peer_world >= 0 && p->peer_world <= RV3D_MAX_PEERS);
   if (p->peer_world > 0) {
     RV3D_CHECK_ARG(p->out_layout == RV3D_OUT_QUAT && p->peer_rank >= 0 && p->peer_rank < p->peer_world && p->peer_capacity > 0);
     for (int q = 0; q < p->peer_world; ++q) RV3D_CHECK_ARG(p->peer_rows[q] && aligned(p->peer_rows[q], 16));
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int n = p->n_candidates;
-  if (n == 0) {
-    RV3D_CHECK_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int32_t), s));
-    return RV3D_OK;
-  }
   RV3D_CHECK_ARG(keys_in && boxes && out_params && out_scores && out_categories && out_batch);
   if (!aligned(boxes, 16) || !aligned(keys_in, 8) || !aligned(scratch, 256)) return RV3D_ERR_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int S = p->batch * p->total_classes;
   const int idx_bits = bits_for(p->total_candidates);
   const int score_bits = p->score_bits ? p->score_bits : 32;
   RV3D_CHECK_ARG(score_bits == 31 || score_bits == 32);
-  const int end_bit = bits_for(S) + score_bits + idx_bits;
-  if (end_bit > 64) return RV3D_ERR_KEYBITS;
+  if (bits_for(S) + score_bits + idx_bits > 64) return RV3D_ERR_KEYBITS;
   const bool weighted = p->mode == RV3D_NMS_WEIGHTED;
-  const NmsLayout L = nms_layout(scratch, n, S, weighted, 9, end_bit);
+  const NmsPlan pl = plan_of(p);
+  RV3D_CHECK_ARG(pl.kc < (1 << 20));   // kept indices travel in 20 bits of a queue entry
+  const NmsLayout L = nms_layout(scratch, pl, false, true);
   if (scratch_bytes < L.total) return RV3D_ERR_SCRATCH;
-  auto *keys = reinterpret_cast<unsigned long long *>(keys_in);
+  const auto *keys = reinterpret_cast<const unsigned long long *>(keys_in);
 
-  // K3: sort (segment asc, score desc, candidate asc)
-  iota_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.order, n);
+  RV3D_CHECK_CUDA(cudaMemsetAsync(L.hist, 0, L.zero_bytes, s));
+  if (L.heads_g) RV3D_CHECK_CUDA(cudaMemsetAsync(L.heads_g, 0xFF, L.heads_bytes, s));
+
+  // K3: counting sort by (segment, score bin)
+  const KeyGeom g{idx_bits, score_bits, pl.nb};
+  const bool range_known = p->score_hi > p->score_lo;
+  BinMapArg bma{};
+  int rc = launch_bucketing(keys, n_candidates, pl, L, g, range_known, desc_code(p->score_hi, score_bits),
+                            desc_code(p->score_lo, score_bits), bma, s);
+  if (rc != RV3D_OK) return rc;
+  const RecFromBoxes8 build{boxes};
+  if (weighted)
+    scatter_records_kernel<true><<<stride_grid(pl.cap), 256, 0, s>>>(keys, build, n_candidates, pl.cap, g, bma, S, L.hist, L.bin_start,
+                                                                    L.seg_begin, L.recs, L.skey, L.src, L.data);
+  else
+    scatter_records_kernel<false><<<stride_grid(pl.cap), 256, 0, s>>>(keys, build, n_candidates, pl.cap, g, bma, S, L.hist, L.bin_start,
+                                                                     L.seg_begin, L.recs, L.skey, L.src, nullptr);
   RV3D_CHECK_LAUNCH();
-  cub::DoubleBuffer<unsigned long long> kb(keys, L.keys_alt);
-  cub::DoubleBuffer<uint32_t> vb(L.order, L.order_alt);
-  size_t cub_bytes = L.cub_bytes;
-  RV3D_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, kb, vb, n, 0, end_bit, s));
-  const unsigned long long *skeys = kb.Current();
-  const uint32_t *order = vb.Current();
 
-  RV3D_CHECK_CUDA(cudaMemsetAsync(L.seg_begin, 0, sizeof(int) * 2 * S, s));
-
-  // a segment keeps at most as many boxes as it has candidates, so its slice [seg_begin, seg_end) of the n-sized
-  // kept_pos / acc / merge_count arrays is its private, sufficient region: kept_base == seg_begin (no scan kernel)
-  NmsArgs a{};
-  a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.seg_begin;
-  a.num_pre = p->num_pre_nms; a.num_post = p->num_post_nms; a.thr = p->iou_threshold; a.mthr = p->merge_threshold;
-  a.prune = (p->iou_threshold >= 0.f && (p->mode != RV3D_NMS_WEIGHTED || p->merge_threshold >= 0.f)) ? 1 : 0;
-  a.kept_pos = L.kept_pos; a.kept_count = L.kept_count; a.data = L.data; a.D = 9; a.acc = L.acc;
-  a.merge_count = L.merge_count; a.stats = reinterpret_cast<unsigned long long *>(stats);
-  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
-  const int max_seg_n = n < p->num_pre_nms ? n : p->num_pre_nms;
-  int rc;
-  if (weighted) {
-    RV3D_CHECK_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * static_cast<size_t>(n) * 9, s));
-    RV3D_CHECK_CUDA(cudaMemsetAsync(L.merge_count, 0, sizeof(int) * static_cast<size_t>(n), s));
-    prepare_records_kernel<true><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, L.data, skeys, score_bits + idx_bits,
-                                                                  L.seg_begin, L.seg_end);
-    RV3D_CHECK_LAUNCH();
-    rc = launch_nms_segments<WRec, true>(a, S, max_seg_n, s);
-  } else {
-    prepare_records_kernel<false><<<ceil_div(n, 256), 256, 0, s>>>(order, boxes, n, L.recs, nullptr, skeys, score_bits + idx_bits,
-                                                                   L.seg_begin, L.seg_end);
-    RV3D_CHECK_LAUNCH();
-    rc = launch_nms_segments<HardRec, false>(a, S, max_seg_n, s);
-  }
+  // K4 / K5
+  const NmsArgs a = base_args(pl, L, p->num_pre_nms, p->num_post_nms, p->iou_threshold, p->merge_threshold, weighted, p->flags, stats);
+  rc = weighted ? launch_nms_segments<WRec, true>(a, pl, s) : launch_nms_segments<HardRec, false>(a, pl, s);
   if (rc != RV3D_OK) return rc;
 
   constexpr int kPackFusedScan = 512;   // up to this many segments the pack blocks sum their own output offset
@@ -1354,17 +1589,27 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
   }
   PackArgs pa{};
   pa.out_count_w = out_count; pa.n_segments = S; pa.fused_scan = fused_scan ? 1 : 0;
-  pa.seg_begin = L.seg_begin; pa.kept_base = L.seg_begin; pa.kept_count = L.kept_count; pa.out_off = L.out_off;
-  pa.kept_pos = L.kept_pos; pa.order = order; pa.boxes = boxes; pa.acc = L.acc;
+  pa.host_count = p->host_count;
+  pa.seg_begin = L.seg_begin; pa.kept_stride = pl.kept_stride; pa.kept_count = L.kept_count; pa.out_off = L.out_off;
+  pa.kept_pos = L.kept_pos; pa.src = L.src; pa.boxes = boxes; pa.acc = L.acc;
   pa.total_classes = p->total_classes; pa.out_capacity = p->out_capacity; pa.weighted = weighted ? 1 : 0; pa.yaw_layout = p->out_layout == RV3D_OUT_YAW;
   pa.out_params = out_params; pa.out_scores = out_scores; pa.out_cats = out_categories; pa.out_batch = out_batch;
   pa.out_count = out_count;
   pa.n_peers = p->peer_world; pa.peer_rank = p->peer_rank; pa.peer_capacity = p->peer_capacity; pa.sweep_offset = p->sweep_offset;
+  pa.peer_seq = p->peer_seq; pa.done_ticket = L.ticket + 1;
   for (int q = 0; q < p->peer_world; ++q) pa.peer_rows[q] = p->peer_rows[q];
   {
-    const int chunks = ceil_div(p->num_post_nms < (1 << 20) ? p->num_post_nms : (1 << 20), 128);
+    const int per_seg = p->num_post_nms < pl.kc ? p->num_post_nms : pl.kc;
+    const int chunks = ceil_div(per_seg < (1 << 20) ? per_seg : (1 << 20), 128);
     pack_kernel<<<dim3(S, chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks)), 128, 0, s>>>(pa);
   }
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_peer_wait(const float *rows, int32_t world, int32_t peer_capacity, uint32_t seq, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(rows && world > 0 && world <= RV3D_MAX_PEERS && peer_capacity > 0 && seq != 0);
+  wait_peer_seq_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(rows, world, peer_capacity, seq);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
@@ -1375,24 +1620,16 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, uint64_t *keys_in, const float
 namespace rv3d {
 
 __global__ void score_keys_kernel(const float *__restrict__ scores, int n, int idx_bits,
-                                  unsigned long long *__restrict__ keys, uint32_t *__restrict__ order) {
+                                  unsigned long long *__restrict__ keys, int *__restrict__ n_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *n_dev = n;
   if (i >= n) return;
   const uint32_t desc = ~orderable_f32(__float_as_uint(scores[i]));
   keys[i] = (static_cast<unsigned long long>(desc) << idx_bits) | static_cast<uint32_t>(i);
-  order[i] = i;
 }
 
-__global__ void single_segment_kernel(int n, int *seg_begin, int *seg_end, int *kept_base) {
-  seg_begin[0] = 0; seg_end[0] = n; kept_base[0] = 0;
-}
-
-__global__ void hard_recs_from_boxes5_kernel(const float *__restrict__ boxes5, const uint32_t *__restrict__ order,
-                                             int n, double angle_scale, HardRec *__restrict__ recs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float *b = boxes5 + static_cast<size_t>(order ? order[i] : i) * 5;
-  recs[i] = make_hard_rec(b[0], b[1], b[2], b[3], b[4], angle_scale);
+__global__ void single_segment_kernel(int n, int *seg_begin, int *seg_count) {
+  seg_begin[0] = 0; seg_count[0] = n;
 }
 
 __global__ void w_recs_from_boxes5_kernel(const float *__restrict__ boxes5, int n, WRec *__restrict__ recs) {
@@ -1403,12 +1640,12 @@ __global__ void w_recs_from_boxes5_kernel(const float *__restrict__ boxes5, int 
 }
 
 __global__ void keep_indices_kernel(const int *__restrict__ kept_pos, const int *__restrict__ kept_count,
-                                    const uint32_t *__restrict__ order, int64_t *__restrict__ keep,
+                                    const uint32_t *__restrict__ src, int64_t *__restrict__ keep,
                                     int32_t *__restrict__ n_keep) {
   const int cnt = kept_count[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *n_keep = cnt;
-  if (i < cnt) keep[i] = order ? order[kept_pos[i]] : kept_pos[i];
+  if (i < cnt) keep[i] = src ? src[kept_pos[i]] : kept_pos[i];
 }
 
 __global__ void wnms_finalize_kernel(const int *__restrict__ kept_pos, const int *__restrict__ kept_count,
@@ -1479,6 +1716,31 @@ box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__re
   out[t] = rot_iou(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 1.0), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 1.0));
 }
 
+// The approximate-vs-exact decision of the NMS kernels, exposed for tests/test_gpu_iou_decisions.py:
+// boxes (N,5) f32 (xc, yc, w, h, angle in degrees, detectron2 convention), aligned pairs.
+// decision[i]: 2 = skipped by the upper bound (certainly <= thr), +1 / -1 = decided by the approximate IoU
+// (above / not above), 0 = sent to the exact routine;  approx[i] / exact[i]: the two IoU values.
+__global__ void __launch_bounds__(128)
+pair_decisions_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t n, float thr,
+                      int8_t *__restrict__ decision, float *__restrict__ approx, float *__restrict__ exact) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *a = A + i * 5, *b = B + i * 5;
+  const HardRec ra = make_hard_rec(a[0], a[1], a[2], a[3], a[4], 0.01745329251);
+  const HardRec rb = make_hard_rec(b[0], b[1], b[2], b[3], b[4], 0.01745329251);
+  const Obb oa = obb_of(ra), ob = obb_of(rb);
+  int d = 0;
+  float ap = CUDART_NAN_F;
+  if (!iou_may_exceed(ra, rb, thr)) d = 2;
+  else if (obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
+    ap = approx_iou(oa, ob);
+    d = decide_vs(ap, thr);
+  }
+  decision[i] = static_cast<int8_t>(d);
+  approx[i] = ap;
+  exact[i] = rot_iou(ra, rb);
+}
+
 // threshold-only branch: rows ordered by (sweep, candidate index)
 __global__ void remap_keys_kernel(const unsigned long long *__restrict__ keys, int n, int idx_bits, int score_bits,
                                   int total_classes, unsigned long long *__restrict__ out, uint32_t *__restrict__ order,
@@ -1512,43 +1774,31 @@ __global__ void pack_candidates_kernel(const uint32_t *__restrict__ order, const
   out_batch[i] = segs[src] / total_classes;
 }
 
-struct OpLayout {
+struct SortLayout {
   unsigned long long *keys, *keys_alt;
   uint32_t *order, *order_alt, *segs;
-  int *seg_begin, *seg_end, *kept_base, *kept_count, *kept_pos, *merge_count;
-  void *recs;
-  double *acc;
-  void *grid_entries;
-  uint32_t *oversize;
-  int *firstsup;
   void *cub_tmp;
   size_t cub_bytes, total;
 };
 
-static OpLayout op_layout(void *scratch, int n, bool weighted, int D, bool sort) {
+static size_t cub_sort_bytes(int n, int end_bit) {
+  size_t bytes = 0;
+  cub::DoubleBuffer<unsigned long long> k(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, n, 0, end_bit, nullptr);
+  return bytes;
+}
+
+static SortLayout sort_layout(void *scratch, int n) {
   Carver c(scratch);
-  OpLayout L{};
+  SortLayout L{};
   const int nn = n > 0 ? n : 1;
   L.keys = c.take<unsigned long long>(nn);
   L.keys_alt = c.take<unsigned long long>(nn);
   L.order = c.take<uint32_t>(nn);
   L.order_alt = c.take<uint32_t>(nn);
   L.segs = c.take<uint32_t>(nn);
-  L.seg_begin = c.take<int>(4);
-  L.seg_end = L.seg_begin ? L.seg_begin + 1 : nullptr;
-  L.kept_base = L.seg_begin ? L.seg_begin + 2 : nullptr;
-  L.kept_count = L.seg_begin ? L.seg_begin + 3 : nullptr;
-  L.kept_pos = c.take<int>(nn);
-  L.recs = c.take<unsigned char>(static_cast<size_t>(nn) * (weighted ? sizeof(WRec) : sizeof(HardRec)));
-  L.acc = nullptr; L.merge_count = nullptr;
-  if (weighted) {
-    L.acc = c.take<double>(static_cast<size_t>(nn) * D);
-    L.merge_count = c.take<int>(nn);
-  }
-  L.grid_entries = c.take<GridEntry>(nn);
-  L.oversize = c.take<uint32_t>(nn);
-  L.firstsup = weighted ? c.take<int>(nn) : nullptr;
-  L.cub_bytes = sort ? cub_sort_bytes(nn, 64) : 0;
+  L.cub_bytes = cub_sort_bytes(nn, 64);
   L.cub_tmp = c.take<unsigned char>(L.cub_bytes ? L.cub_bytes : 1);
   L.total = align_up(c.used, 256);
   return L;
@@ -1556,12 +1806,15 @@ static OpLayout op_layout(void *scratch, int n, bool weighted, int D, bool sort)
 
 }  // namespace rv3d
 
-extern "C" size_t rv3d_nms_rotated_scratch_bytes(int32_t n) { return op_layout(nullptr, n, false, 0, true).total; }
+extern "C" size_t rv3d_nms_rotated_scratch_bytes(int32_t n) {
+  const int nn = n > 0 ? n : 1;
+  return nms_layout(nullptr, make_plan(nn, 1, nn, nn, nn, false, 0), true, false).total;
+}
 
 extern "C" int rv3d_nms_rotated(const float *boxes, const float *scores, int32_t n, float iou_threshold,
                                 int64_t *keep, int32_t *n_keep, void *scratch, size_t scratch_bytes,
                                 rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(n >= 0 && n_keep && scratch);
+  RV3D_CHECK_ARG(n >= 0 && n < (1 << 20) && n_keep && scratch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n == 0) {
     RV3D_CHECK_CUDA(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), s));
@@ -1569,39 +1822,38 @@ extern "C" int rv3d_nms_rotated(const float *boxes, const float *scores, int32_t
   }
   RV3D_CHECK_ARG(boxes && scores && keep);
   if (!aligned(scratch, 256)) return RV3D_ERR_ALIGN;
-  const OpLayout L = op_layout(scratch, n, false, 0, true);
+  const NmsPlan pl = make_plan(n, 1, n, n, n, false, 0);
+  const NmsLayout L = nms_layout(scratch, pl, true, false);
   if (scratch_bytes < L.total) return RV3D_ERR_SCRATCH;
+  RV3D_CHECK_CUDA(cudaMemsetAsync(L.hist, 0, L.zero_bytes, s));
+  if (L.heads_g) RV3D_CHECK_CUDA(cudaMemsetAsync(L.heads_g, 0xFF, L.heads_bytes, s));
   const int idx_bits = bits_for(n);
-  score_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scores, n, idx_bits, L.keys, L.order);
+  score_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(scores, n, idx_bits, L.keys_own, L.n_dev);
   RV3D_CHECK_LAUNCH();
-  cub::DoubleBuffer<unsigned long long> kb(L.keys, L.keys_alt);
-  cub::DoubleBuffer<uint32_t> vb(L.order, L.order_alt);
-  size_t cub_bytes = L.cub_bytes;
-  RV3D_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(L.cub_tmp, cub_bytes, kb, vb, n, 0, 32 + idx_bits, s));
-  const uint32_t *order = vb.Current();
-  hard_recs_from_boxes5_kernel<<<ceil_div(n, 256), 256, 0, s>>>(boxes, order, n, 0.01745329251,
-                                                                static_cast<HardRec *>(L.recs));
-  RV3D_CHECK_LAUNCH();
-  single_segment_kernel<<<1, 1, 0, s>>>(n, L.seg_begin, L.seg_end, L.kept_base);
-  RV3D_CHECK_LAUNCH();
-  NmsArgs a{};
-  a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
-  a.num_pre = n; a.num_post = n; a.thr = iou_threshold; a.mthr = 0.f; a.prune = iou_threshold >= 0.f ? 1 : 0;
-  a.kept_pos = L.kept_pos; a.kept_count = L.kept_count;
-  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
-  const int rc = launch_nms_segments<HardRec, false>(a, 1, n, s);
+  const KeyGeom g{idx_bits, 32, pl.nb};
+  BinMapArg bma{};
+  int rc = launch_bucketing(L.keys_own, L.n_dev, pl, L, g, false, 0, 0, bma, s);
   if (rc != RV3D_OK) return rc;
-  keep_indices_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.kept_pos, L.kept_count, order, keep, n_keep);
+  scatter_records_kernel<false><<<stride_grid(n), 256, 0, s>>>(L.keys_own, RecFromBoxes5{boxes}, L.n_dev, n, g, bma, 1, L.hist,
+                                                               L.bin_start, L.seg_begin, L.recs, L.skey, L.src, nullptr);
+  RV3D_CHECK_LAUNCH();
+  const NmsArgs a = base_args(pl, L, n, n, iou_threshold, 0.f, false, 0, nullptr);
+  rc = launch_nms_segments<HardRec, false>(a, pl, s);
+  if (rc != RV3D_OK) return rc;
+  keep_indices_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.kept_pos, L.kept_count, L.src, keep, n_keep);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
 
-extern "C" size_t rv3d_wnms_scratch_bytes(int32_t n, int32_t d) { return op_layout(nullptr, n, true, d, false).total; }
+extern "C" size_t rv3d_wnms_scratch_bytes(int32_t n, int32_t d) {
+  const int nn = n > 0 ? n : 1;
+  return nms_layout(nullptr, make_plan(nn, 1, nn, nn, nn, true, d > 0 ? d : 1), false, false).total;
+}
 
 extern "C" int rv3d_wnms(const float *boxes, const float *data, int32_t n, int32_t d, float nms_threshold,
                          float merge_threshold, float *output, int64_t *keep, int64_t *count, int32_t *n_out,
                          void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(n >= 0 && d >= 1 && d <= kMaxD && n_out && scratch);
+  RV3D_CHECK_ARG(n >= 0 && n < (1 << 20) && d >= 1 && d <= kMaxD && n_out && scratch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (n == 0) {
     RV3D_CHECK_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
@@ -1609,24 +1861,21 @@ extern "C" int rv3d_wnms(const float *boxes, const float *data, int32_t n, int32
   }
   RV3D_CHECK_ARG(boxes && data && output && keep && count);
   if (!aligned(scratch, 256)) return RV3D_ERR_ALIGN;
-  const OpLayout L = op_layout(scratch, n, true, d, false);
+  const NmsPlan pl = make_plan(n, 1, n, n, n, true, d);
+  const NmsLayout L = nms_layout(scratch, pl, false, false);
   if (scratch_bytes < L.total) return RV3D_ERR_SCRATCH;
+  RV3D_CHECK_CUDA(cudaMemsetAsync(L.hist, 0, L.zero_bytes, s));
+  if (L.heads_g) RV3D_CHECK_CUDA(cudaMemsetAsync(L.heads_g, 0xFF, L.heads_bytes, s));
   w_recs_from_boxes5_kernel<<<ceil_div(n, 256), 256, 0, s>>>(boxes, n, static_cast<WRec *>(L.recs));
   RV3D_CHECK_LAUNCH();
-  single_segment_kernel<<<1, 1, 0, s>>>(n, L.seg_begin, L.seg_end, L.kept_base);
+  single_segment_kernel<<<1, 1, 0, s>>>(n, L.seg_begin, L.seg_count);
   RV3D_CHECK_LAUNCH();
-  RV3D_CHECK_CUDA(cudaMemsetAsync(L.acc, 0, sizeof(double) * static_cast<size_t>(n) * d, s));
-  RV3D_CHECK_CUDA(cudaMemsetAsync(L.merge_count, 0, sizeof(int) * static_cast<size_t>(n), s));
   RV3D_CHECK_CUDA(cudaMemsetAsync(output, 0, sizeof(float) * static_cast<size_t>(n) * d, s));  // nms.py:155,173
   RV3D_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int64_t) * static_cast<size_t>(n), s));
-  NmsArgs a{};
-  a.recs = L.recs; a.seg_begin = L.seg_begin; a.seg_end = L.seg_end; a.kept_base = L.kept_base;
-  a.num_pre = n; a.num_post = n; a.thr = nms_threshold; a.mthr = merge_threshold;
-  a.prune = (nms_threshold >= 0.f && merge_threshold >= 0.f) ? 1 : 0;
-  a.kept_pos = L.kept_pos; a.kept_count = L.kept_count; a.data = data; a.D = d; a.acc = L.acc;
-  a.merge_count = L.merge_count;
-  a.grid_entries = L.grid_entries; a.oversize = L.oversize; a.firstsup = L.firstsup;
-  const int rc = launch_nms_segments<WRec, true>(a, 1, n, s);
+  NmsArgs a = base_args(pl, L, n, n, nms_threshold, merge_threshold, true, 0, nullptr);
+  a.presorted = 1; a.bin_start = nullptr; a.skey = nullptr; a.gorder = nullptr;   // the caller sorted (nms.py:148-154)
+  a.data = data;
+  const int rc = launch_nms_segments<WRec, true>(a, pl, s);
   if (rc != RV3D_OK) return rc;
   wnms_finalize_kernel<<<ceil_div(n, 256), 256, 0, s>>>(L.kept_pos, L.kept_count, L.acc, L.merge_count, data, d,
                                                         output, keep, count, n_out);
@@ -1658,9 +1907,20 @@ extern "C" int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float
   return RV3D_OK;
 }
 
-extern "C" size_t rv3d_pack_candidates_scratch_bytes(int32_t n) { return op_layout(nullptr, n, false, 0, true).total; }
+extern "C" int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold,
+                                   int8_t *decision, float *approx, float *exact, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0);
+  if (n == 0) return RV3D_OK;
+  RV3D_CHECK_ARG(boxes_a && boxes_b && decision && approx && exact && n < (int64_t(1) << 37));
+  pair_decisions_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(boxes_a, boxes_b, n, iou_threshold,
+                                                                                       decision, approx, exact);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
 
-extern "C" int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t n, int32_t batch,
+extern "C" size_t rv3d_pack_candidates_scratch_bytes(int32_t n) { return sort_layout(nullptr, n).total; }
+
+extern "C" int rv3d_pack_candidates(const uint64_t *keys, const float *boxes, int32_t n, int32_t batch,
                                     int32_t total_classes, int32_t total_candidates, int32_t score_bits, float *out_params,
                                     float *out_scores, int64_t *out_categories, int64_t *out_batch, void *scratch,
                                     size_t scratch_bytes, rv3d_stream_t stream) {
@@ -1669,11 +1929,11 @@ extern "C" int rv3d_pack_candidates(uint64_t *keys, const float *boxes, int32_t 
   if (n == 0) return RV3D_OK;
   RV3D_CHECK_ARG(keys && boxes && out_params && out_scores && out_categories && out_batch);
   if (!aligned(scratch, 256) || !aligned(boxes, 16)) return RV3D_ERR_ALIGN;
-  const OpLayout L = op_layout(scratch, n, false, 0, true);
+  const SortLayout L = sort_layout(scratch, n);
   if (scratch_bytes < L.total) return RV3D_ERR_SCRATCH;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int idx_bits = bits_for(total_candidates);
-  remap_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(reinterpret_cast<unsigned long long *>(keys), n, idx_bits, score_bits,
+  remap_keys_kernel<<<ceil_div(n, 256), 256, 0, s>>>(reinterpret_cast<const unsigned long long *>(keys), n, idx_bits, score_bits,
                                                      total_classes, L.keys, L.order, L.segs);
   RV3D_CHECK_LAUNCH();
   cub::DoubleBuffer<unsigned long long> kb(L.keys, L.keys_alt);

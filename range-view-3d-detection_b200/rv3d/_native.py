@@ -17,6 +17,7 @@ COL_LIBRARY, COL_CONVERTER, COL_CONVERTER_UNIFORM = 0, 1, 2
 SCORE_BITS_DECODE = 31   # include/rv3d.h RV3D_SCORE_BITS_DECODE
 F32, F16, BF16 = 0, 1, 2
 NMS_HARD, NMS_WEIGHTED = 0, 1
+NMS_EXACT_ONLY = 1
 OUT_QUAT, OUT_YAW = 0, 1
 
 
@@ -47,10 +48,12 @@ class DecodeParams(C.Structure):
 class NmsParams(C.Structure):
     _fields_ = [("batch", C.c_int32), ("total_classes", C.c_int32), ("total_candidates", C.c_int32),
                 ("num_pre_nms", C.c_int32), ("num_post_nms", C.c_int32), ("mode", C.c_int32),
-                ("iou_threshold", C.c_float), ("merge_threshold", C.c_float), ("n_candidates", C.c_int32),
+                ("iou_threshold", C.c_float), ("merge_threshold", C.c_float), ("capacity", C.c_int32),
                 ("out_capacity", C.c_int32), ("out_layout", C.c_int32), ("score_bits", C.c_int32),
+                ("score_lo", C.c_float), ("score_hi", C.c_float), ("flags", C.c_int32),
                 ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_capacity", C.c_int32),
-                ("sweep_offset", C.c_int32), ("peer_rows", C.c_void_p * 8)]
+                ("sweep_offset", C.c_int32), ("peer_seq", C.c_uint32), ("reserved", C.c_int32),
+                ("peer_rows", C.c_void_p * 8), ("host_count", C.c_void_p)]
 
 
 class Rv3dError(RuntimeError):
@@ -77,7 +80,9 @@ _SIGNATURES = {
     "rv3d_decode_compact": (C.c_int, [C.POINTER(DecodeParams), _P, _P, _P, _P, _P, _P, _P, _P]),
     "rv3d_compact_candidates": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F, _I32, _I32, _P, _P, _P, _P]),
     "rv3d_nms_scratch_bytes": (_SZ, [C.POINTER(NmsParams)]),
-    "rv3d_nms": (C.c_int, [C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "rv3d_nms": (C.c_int, [C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "rv3d_peer_wait": (C.c_int, [_P, _I32, _I32, C.c_uint32, _P]),
+    "rv3d_pair_decisions": (C.c_int, [_P, _P, _I64, _F, _P, _P, _P, _P]),
     "rv3d_nms_rotated_scratch_bytes": (_SZ, [_I32]),
     "rv3d_nms_rotated": (C.c_int, [_P, _P, _I32, _F, _P, _P, _P, _SZ, _P]),
     "rv3d_wnms_scratch_bytes": (_SZ, [_I32, _I32]),

@@ -95,13 +95,75 @@ def new_candidates(ws: Workspace, batch: int, total_classes: int, total_candidat
     return Candidates(keys, boxes, counter, batch, total_classes, total_candidates, score_bits)
 
 
+class Detections:
+    """Result of a suppression call that has only been ENQUEUED: padded device buffers plus the detection count, which
+    stays on the device (and in one int of mapped pinned host memory the pack kernel also writes) until somebody asks.
+    Nothing here synchronises; ``result()`` is the one place the host waits (on an event, for this call only).
+
+    The buffers are allocated per call, so results of earlier calls are never overwritten by later ones."""
+
+    def __init__(self, params: torch.Tensor, scores: torch.Tensor, categories: torch.Tensor, batch_index: torch.Tensor,
+                 count: torch.Tensor, host_count: torch.Tensor, stream: torch.cuda.Stream):
+        self.params, self.scores, self.categories, self.batch_index = params, scores, categories, batch_index
+        self.count, self.host_count = count, host_count      # device (1,) i32; pinned host (1,) i32
+        self.event = None
+        if not torch.cuda.is_current_stream_capturing():
+            self.event = torch.cuda.Event()
+            self.event.record(stream)
+        self._stream = stream
+
+    def wait(self) -> int:
+        """Host waits for this call (event, not a device-wide sync) and returns the number of detections."""
+        if self.event is not None:
+            self.event.synchronize()
+        else:                          # enqueued under graph capture: the caller replays the graph, then asks
+            self._stream.synchronize()
+        return int(self.host_count[0])
+
+    def result(self, dtype: Optional[torch.dtype] = None):
+        """-> (params (M,10|7), scores (M,), categories (M,), batch_index (M,)), exact size; empty: the reference's
+        (0, W), (0,1), (0,1), (0,1) shapes (math/ops/nms.py:250-253)."""
+        m = self.wait()
+        dt = dtype or self.params.dtype
+        if m == 0:
+            e = torch.empty((0,), dtype=dt, device=self.params.device)
+            return torch.empty((0, self.params.shape[1]), dtype=dt, device=self.params.device), e.view(0, 1), e.view(0, 1), e.view(0, 1)
+        return self.params[:m].to(dt), self.scores[:m].to(dt), self.categories[:m].to(dt), self.batch_index[:m].to(dt)
+
+
 _NMS_PARAMS: Dict[Tuple, "N.NmsParams"] = {}
 
 
-def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_nms: int, iou_threshold: float,
+class _HostCounts:
+    """Ring of mapped pinned host ints the pack kernel stores detection counts to (cudaHostAlloc memory is
+    device-accessible under unified addressing; the pointer is the same on both sides)."""
+
+    def __init__(self, slots: int = 64):
+        self.buf = torch.zeros(slots, dtype=torch.int32).pin_memory()
+        self.next = 0
+
+    def take(self) -> torch.Tensor:
+        i = self.next
+        self.next = (i + 1) % self.buf.numel()
+        return self.buf[i:i + 1]
+
+
+_HOST_COUNTS: Optional[_HostCounts] = None
+
+
+def _host_count_slot() -> torch.Tensor:
+    global _HOST_COUNTS
+    if _HOST_COUNTS is None:
+        _HOST_COUNTS = _HostCounts()
+    return _HOST_COUNTS.take()
+
+
+def run_nms(ws: Workspace, cand: Candidates, num_pre_nms: int, num_post_nms: int, iou_threshold: float,
             mode: str, layout: int, merge_threshold: float = 0.5, stats: Optional[torch.Tensor] = None,
-            peer=None, peer_slot: int = 0, sweep_offset: int = 0):
-    """-> (params (M,10|7) f32, scores (M,) f32, categories (M,) f32, batch_index (M,) f32).
+            peer=None, peer_slot: int = 0, sweep_offset: int = 0, peer_seq: int = 0,
+            score_range: Tuple[float, float] = (0.0, 0.0), exact_only: bool = False) -> Detections:
+    """Enqueue score bucketing + NMS + pack on the current stream -> ``Detections`` (lazy; no host read, no sync: the
+    candidate count is read on the device from ``cand.counter``).
     ``peer`` (rv3d.distributed.PeerGather): also store the detections into every rank's gather buffer from inside the
     pack kernel (slot ``peer_slot``, sweep indices shifted by ``sweep_offset``)."""
     mode = mode.upper()                                                      # nms.py:207
@@ -109,17 +171,19 @@ def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_
         raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")   # nms.py:239-240
     dev = cand.keys.device
     S = cand.batch * cand.total_classes
-    cap = min(n, S * int(num_post_nms))
+    capacity = cand.keys.numel()
+    cap = max(min(capacity, S * int(min(num_post_nms, 2 ** 31 - 1))), 1)
     width = 10 if layout == N.OUT_QUAT else 7
-    out_params = ws.get("out_params", (max(cap, 1), width), torch.float32, dev)
-    out_scores = ws.get("out_scores", (max(cap, 1),), torch.float32, dev)
-    out_cats = ws.get("out_cats", (max(cap, 1),), torch.float32, dev)
-    out_batch = ws.get("out_batch", (max(cap, 1),), torch.float32, dev)
-    out_count = ws.get("out_count", (1,), torch.int32, dev)
-    # This runs right after the host has read the candidate count, i.e. with the GPU idle: the parameter block is
-    # cached per configuration and only its count-dependent fields are refreshed.
-    pkey = (cand.batch, cand.total_classes, cand.total_candidates, int(num_pre_nms), int(num_post_nms), mode,
-            float(iou_threshold), float(merge_threshold), layout, cand.score_bits)
+    # one fresh allocation per call (the caching allocator makes it a pointer bump): results never alias a later call's
+    buf = torch.empty((cap * (width + 3) + 1,), dtype=torch.float32, device=dev)
+    out_params = buf[: cap * width].view(cap, width)
+    out_scores = buf[cap * width: cap * (width + 1)]
+    out_cats = buf[cap * (width + 1): cap * (width + 2)]
+    out_batch = buf[cap * (width + 2): cap * (width + 3)]
+    out_count = buf[cap * (width + 3):].view(torch.int32)
+    host_count = _host_count_slot()
+    pkey = (cand.batch, cand.total_classes, cand.total_candidates, capacity, int(num_pre_nms), int(num_post_nms), mode,
+            float(iou_threshold), float(merge_threshold), layout, cand.score_bits, tuple(score_range), bool(exact_only))
     p = _NMS_PARAMS.get(pkey)
     if p is None:
         p = N.NmsParams()
@@ -129,23 +193,26 @@ def run_nms(ws: Workspace, cand: Candidates, n: int, num_pre_nms: int, num_post_
         # nms.py:44 hands detectron2 an f32 tensor; nms.py:101-107 hands TorchEx python floats -> C float
         p.iou_threshold = threshold_as(torch.float32, float(iou_threshold))
         p.merge_threshold = float(merge_threshold)
+        p.capacity, p.out_capacity = capacity, cap
         p.out_layout, p.score_bits = layout, cand.score_bits
+        p.score_lo, p.score_hi = float(score_range[0]), float(score_range[1])
+        p.flags = N.NMS_EXACT_ONLY if exact_only else 0
+        p.scratch_bytes = N.lib().rv3d_nms_scratch_bytes(p)
         if len(_NMS_PARAMS) > 64:
             _NMS_PARAMS.clear()
         _NMS_PARAMS[pkey] = p
-    p.n_candidates, p.out_capacity = n, cap
-    p.peer_world = 0
+    p.host_count = host_count.data_ptr()
+    p.peer_world, p.peer_seq = 0, 0
     if peer is not None:
         if layout != N.OUT_QUAT:
             raise ValueError("the fused gather carries params(10) rows (RangeDecoder.decode layout)")
         p.peer_world, p.peer_rank, p.peer_capacity, p.sweep_offset = peer.world, peer.rank, peer.capacity, int(sweep_offset)
+        p.peer_seq = int(peer_seq)
         for q, addr in enumerate(peer.slot_ptrs(peer_slot)):
             p.peer_rows[q] = addr
     lib = N.lib()
-    need = lib.rv3d_nms_scratch_bytes(p)
-    work = ws.bytes("nms_scratch", need, dev)
-    N.check(lib.rv3d_nms(p, ptr(cand.keys), ptr(cand.boxes), ptr(out_params), ptr(out_scores), ptr(out_cats),
-                         ptr(out_batch), ptr(out_count), ptr(stats), ptr(work), work.numel(), stream_ptr(dev)),
-            "rv3d_nms")
-    m = int(out_count.item())                                                # host read #2 (stream sync)
-    return out_params[:m], out_scores[:m], out_cats[:m], out_batch[:m]
+    work = ws.bytes("nms_scratch", p.scratch_bytes, dev)
+    N.check(lib.rv3d_nms(p, ptr(cand.keys), ptr(cand.boxes), ptr(cand.counter), ptr(out_params), ptr(out_scores),
+                         ptr(out_cats), ptr(out_batch), ptr(out_count), ptr(stats), ptr(work), work.numel(),
+                         stream_ptr(dev)), "rv3d_nms")
+    return Detections(out_params, out_scores, out_cats, out_batch, out_count, host_count, torch.cuda.current_stream(dev))

@@ -17,15 +17,20 @@ __all__ = ["batched_multiclass_nms", "hard_multiclass_nms", "weighted_multiclass
 _WS = Workspace()
 
 
-def _compact(cuboids: Tensor, scores: Tensor, categories: Tensor, min_confidence: Optional[float]) -> Tuple[Candidates, int]:
+def _compact(cuboids: Tensor, scores: Tensor, categories: Tensor, min_confidence: Optional[float],
+             total_classes: Optional[int] = None) -> Candidates:
     dev = require_cuda(cuboids, scores, categories)
     B, K, P = cuboids.shape
     if P != 7:
         raise ValueError("cuboids must be (B,K,7) [x,y,z,l,w,h,yaw]")
     cats = categories.reshape(B, K).to(torch.int64).contiguous()
-    total_classes = int(cats.max().item()) + 1 if cats.numel() else 1
-    if cats.numel() and int(cats.min().item()) < 0:
-        raise ValueError("negative category index")
+    if total_classes is None:
+        # the reference discovers the classes with torch.unique (nms.py:22), i.e. a host read; callers that know the
+        # class count pass `total_classes` and stay sync-free
+        lo, hi = (int(v) for v in torch.stack([cats.min(), cats.max()]).tolist()) if cats.numel() else (0, 0)
+        if lo < 0:
+            raise ValueError("negative category index")
+        total_classes = hi + 1
     cand = new_candidates(_WS, B, total_classes, max(K, 1), dev)
     sc = scores.reshape(B, K)
     thr = 0.0 if min_confidence is None else threshold_as(sc.dtype, min_confidence)
@@ -33,7 +38,7 @@ def _compact(cuboids: Tensor, scores: Tensor, categories: Tensor, min_confidence
                                             B, K, total_classes, thr, int(min_confidence is not None),
                                             cand.keys.numel(), ptr(cand.keys), ptr(cand.boxes), ptr(cand.counter),
                                             stream_ptr(dev)), "rv3d_compact_candidates")
-    return cand, cand.count()
+    return cand
 
 
 def batched_multiclass_nms(cuboids: Tensor, scores: Tensor, categories: Tensor, num_pre_nms: int, num_post_nms: int,
@@ -44,20 +49,22 @@ def batched_multiclass_nms(cuboids: Tensor, scores: Tensor, categories: Tensor, 
     mode = nms_mode.upper()
     if mode not in ("HARD", "WEIGHTED"):
         raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
-    cand, n = _compact(cuboids, scores, categories, min_confidence)
-    if n == 0:                                                                # nms.py:250-253
+    cand = _compact(cuboids, scores, categories, min_confidence)
+    det = run_nms(_WS, cand, num_pre_nms, num_post_nms, iou_threshold, mode, N.OUT_YAW)
+    if det.wait() == 0:                                                       # nms.py:250-253
         return (cuboids.new_empty((0, cuboids.shape[-1])), scores.new_empty((0, 1)),
                 categories.new_empty((0, 1)), categories.new_empty((0, 1)))
-    p, s, c, b = run_nms(_WS, cand, n, num_pre_nms, num_post_nms, iou_threshold, mode, N.OUT_YAW)
+    p, s, c, b = det.result()
     return p.to(cuboids.dtype), s.to(scores.dtype), c.to(scores.dtype), b.to(scores.dtype)
 
 
 def _per_sweep(cuboids_i, scores_i, categories_i, iou_threshold, num_pre_nms, num_post_nms, mode):
     if cuboids_i.shape[0] == 0:
         return cuboids_i.new_empty((0, 7)), scores_i.new_empty((0,)), scores_i.new_empty((0,))
-    cand, n = _compact(cuboids_i[None], scores_i[None], categories_i[None], None)
-    p, s, c, _ = run_nms(_WS, cand, n, num_pre_nms, num_post_nms, iou_threshold, mode, N.OUT_YAW)
-    return p.to(cuboids_i.dtype), s.to(scores_i.dtype), c.to(scores_i.dtype)
+    cand = _compact(cuboids_i[None], scores_i[None], categories_i[None], None)
+    det = run_nms(_WS, cand, num_pre_nms, num_post_nms, iou_threshold, mode, N.OUT_YAW)
+    m = det.wait()
+    return det.params[:m].to(cuboids_i.dtype), det.scores[:m].to(scores_i.dtype), det.categories[:m].to(scores_i.dtype)
 
 
 def hard_multiclass_nms(cuboids_i: Tensor, scores_i: Tensor, categories_i: Tensor, iou_threshold: float,

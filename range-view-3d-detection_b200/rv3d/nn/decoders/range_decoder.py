@@ -27,9 +27,8 @@ def _mask_u8(mask: Tensor) -> Tensor:
         return mask.contiguous().view(torch.uint8)
     if mask.dtype == torch.uint8:
         return mask.contiguous()
-    if mask.is_floating_point():
-        raise TypeError("rv3d: `mask` must be a bool / uint8 validity mask (the reference builds it as "
-                        "`range > 0`, prototype/loader.py:645-650)")
+    # the reference multiplies the scores by the mask whatever its dtype (range_decoder.py:50); the library takes the
+    # validity form (the reference builds it as `range > 0`, prototype/loader.py:645-650): a 0 / 1 mask of any dtype
     return (mask != 0).contiguous().view(torch.uint8)
 
 
@@ -121,6 +120,30 @@ class RangeDecoder:
                     "rv3d_decode_compact")
         return cand
 
+    def decode_async(self, multiscale_outputs: Dict[Union[int, str], Dict[Any, Any]],
+                     post_processing_config: Mapping[str, Any], task_config: Mapping[Any, Sequence[str]],
+                     gather=None, stats: Tensor = None, **kwargs: Any):
+        """The whole decode + NMS + pack step ENQUEUED on the current stream -> ``rv3d._pipeline.Detections`` (padded
+        device buffers + the detection count on the device).  No host read, no synchronisation, fixed launch geometry:
+        the call can be captured in a CUDA graph together with the rasterizer and replayed.  This is what removes the
+        reference's host sync per sweep and per class (math/ops/nms.py:210-215, :22-23).
+
+        ``gather=(PeerGather, slot, sweep_offset[, seq])``: the pack kernel also stores this rank's detections into
+        every rank's gather buffer (rv3d.distributed.PeerGather)."""
+        mode = str(post_processing_config["nms_mode"]).upper()
+        if mode not in ("HARD", "WEIGHTED"):
+            raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
+        cand = self.candidates(multiscale_outputs, post_processing_config, task_config)
+        thr = float(post_processing_config["min_confidence"])
+        score_range = (max(thr, 0.0), 1.0) if thr < 1.0 else (0.0, 0.0)     # sigmoid * mask lies in [0, 1]
+        peer_kw = {}
+        if gather is not None:
+            peer_kw = dict(peer=gather[0], peer_slot=gather[1], sweep_offset=gather[2],
+                           peer_seq=gather[3] if len(gather) > 3 else 0)
+        return run_nms(self._ws, cand, post_processing_config["num_pre_nms"], post_processing_config["num_post_nms"],
+                       post_processing_config["nms_threshold"], mode, N.OUT_QUAT, stats=stats, score_range=score_range,
+                       exact_only=bool(kwargs.get("exact_only", False)), **peer_kw)
+
     def decode(self, multiscale_outputs: Dict[Union[int, str], Dict[Any, Any]],
                post_processing_config: Mapping[str, Any], task_config: Mapping[Any, Sequence[str]],
                use_nms: bool = True, **kwargs: Any) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
@@ -128,30 +151,25 @@ class RangeDecoder:
         (params (K,10) [x,y,z,l,w,h,qw,qx,qy,qz], scores (K,), categories (K,), batch_index (K,)).
         With NMS, categories / batch_index are float32 (math/ops/nms.py:51,242); without, int64.
 
-        Multi-GPU extra (not in the reference): ``gather=(PeerGather, slot, sweep_offset)`` makes the pack kernel also
-        store this rank's detections into every rank's gather buffer (rv3d.distributed.PeerGather); the caller then
-        calls ``PeerGather.arrive_and_wait()``."""
+        The returned tensors have their exact size, which only the device knows: with NMS the host waits ONCE, after
+        every kernel of the step has been enqueued, on the event of this call (``decode_async`` + ``Detections.result``);
+        callers that can work with padded buffers use ``decode_async`` and never wait.  The tensors are owned by the
+        caller (a later call does not overwrite them).
+
+        Multi-GPU extra (not in the reference): ``gather=(PeerGather, slot, sweep_offset)``, see ``decode_async``."""
         gather = kwargs.pop("gather", None)
+        exact_only = bool(kwargs.pop("exact_only", False))
         del kwargs                                                         # tools/benchmark.py passes data=
         first = next(iter(multiscale_outputs.values()))
         dt = first[next(iter(task_config.keys()))]["logits"].dtype
+        if use_nms:
+            return self.decode_async(multiscale_outputs, post_processing_config, task_config, gather=gather,
+                                     exact_only=exact_only).result(dt)
+        if gather is not None:
+            raise ValueError("gather= needs use_nms=True (the fused gather lives in the NMS pack kernel)")
         cand = self.candidates(multiscale_outputs, post_processing_config, task_config)
         n = cand.count()
         dev = cand.keys.device
-        if use_nms:
-            if n == 0:
-                mode = str(post_processing_config["nms_mode"]).upper()
-                if mode not in ("HARD", "WEIGHTED"):
-                    raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
-                if gather is not None:
-                    gather[0].write_empty(gather[1])
-                e = torch.empty((0,), dtype=dt, device=dev)
-                return torch.empty((0, 10), dtype=dt, device=dev), e.view(0, 1), e.view(0, 1), e.view(0, 1)
-            peer_kw = {} if gather is None else dict(peer=gather[0], peer_slot=gather[1], sweep_offset=gather[2])
-            params, scores, cats, bidx = run_nms(
-                self._ws, cand, n, post_processing_config["num_pre_nms"], post_processing_config["num_post_nms"],
-                post_processing_config["nms_threshold"], str(post_processing_config["nms_mode"]), N.OUT_QUAT, **peer_kw)
-            return params.to(dt), scores.to(dt), cats.to(dt), bidx.to(dt)
         params = torch.empty((n, 10), dtype=torch.float32, device=dev)
         scores = torch.empty((n,), dtype=torch.float32, device=dev)
         cats = torch.empty((n,), dtype=torch.int64, device=dev)

@@ -43,7 +43,7 @@ def test_argument_validation_without_gpu():
     assert L.rv3d_num_candidates(parts, 64, 2650) == 275648
     assert L.rv3d_num_candidates(N.make_partitions([], [], []), 64, 1800) == 64 * 1800
     q = N.NmsParams()
-    assert L.rv3d_nms(q, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert L.rv3d_nms(q, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
 
 
 def test_python_mirror_signatures():
