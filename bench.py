@@ -2,18 +2,26 @@
 """bench.py -- sweeps/sec of the rasterize -> decode -> NMS path on B200 (BASELINE.json's metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nms-mode HARD|WEIGHTED]
+                    [--no-extras] [--global-batch G]
 
-One "step" = one pass of the hot path over one batch of synthetic sweeps:
-rasterize B raw sweeps (N points each -> 64 x W range image), then RangeDecoder.decode of B sets of
-dense head outputs (sigmoid/max/threshold/sample_by_range/box decode/NMS).  Workload at N=1:
-BASELINE.json configs[1], Waymo shape, B=16.  With N>1 (torchrun, one rank per GPU) every rank runs
-its own B sweeps (weak scaling) and the step ends with the path's one collective, a gather of the
-detections.
+One "step" = one pass of the hot path over one batch of synthetic sweeps: rasterize B raw sweeps
+(N points each -> 64 x W range image), then RangeDecoder.decode of B sets of dense head outputs (sigmoid / max /
+threshold / sample_by_range / box decode / NMS).  Workload at N=1: BASELINE.json configs[1], Waymo shape, B=16.
+With N>1 (torchrun, one rank per GPU) every rank runs its own B sweeps (weak scaling) and the step ends with the
+path's one exchange, a gather of the detections, fused into the NMS pack kernel.
 
-The JSON line's `value` is measured with inputs resident in HBM; `e2e` goes through the same public
-API from pinned HOST buffers (H2D of every input + D2H of the detections inside the timed region).
-`--impl reference` times the reference's CPU path (oracle port: /root/reference does not exist on the
-GPU box, and its third-party natives are not installable) on the host cores.
+How the numbers are taken:
+  value      the step's public calls (rv3d.math.range_view.rasterize_sweeps + RangeDecoder.decode_async) are captured
+             ONCE in a CUDA graph -- the step has no host read, so it replays as is -- and replayed K times with
+             inputs resident in HBM; per-step CUDA events on the replay stream, 256 MiB L2 flush between steps.
+  roofline   rasterize and decode_compact replayed as graphs of their own, timed with CUDA events;
+             achieved = SURVEY 8d algorithmic bytes / that time, peak = MEASURED_PEAKS.json.
+  e2e        the same calls, eager, from pinned HOST buffers: H2D of every input (double-buffered on a copy
+             stream), the step, D2H of the detections (on a second copy stream), every step; wall clock.
+  extras     BASELINE configs 1, 3, 4 (and 5 at N>1) and the reference's own batch-1 latency protocol
+             (tools/benchmark.py:231-238), a few steps each, in the same JSON line under "extra".
+`--impl reference` times the reference's CPU path (oracle port: /root/reference does not exist on the GPU box, and
+its third-party natives are not installable) on the host cores.
 """
 from __future__ import annotations
 
@@ -41,6 +49,10 @@ WORKLOADS = {
     # name: (points per sweep, H, W, classes, objects per sweep, identity row map?)
     "waymo": (180_000, 64, 2650, 3, 96, True),
     "av2": (100_000, 64, 1800, 26, 64, False),
+    # BASELINE config 4: the same sweeps rasterized / decoded at three widths
+    "w900": (100_000, 64, 900, 3, 64, True),
+    "w1800": (100_000, 64, 1800, 3, 64, True),
+    "w3600": (100_000, 64, 3600, 3, 64, True),
 }
 PP = {"num_pre_nms": 50000, "num_post_nms": 1000, "nms_threshold": 0.3, "min_confidence": 0.1}  # range_view.yaml:43-47
 SBR = ([0, 15, 30], [15, 30, math.inf], [8, 2, 1])                                              # range_view.yaml:133-135
@@ -58,20 +70,22 @@ def make_inputs(shape: str, batch: int, seed0: int, fp_rate: float = None):
 def algorithmic_bytes(shape: str, batch: int, survivors: int, head_bytes: int = 4):
     """rasterize reads N*(16+1) B and writes 7*H*W*4 B per sweep; decode reads
     H*W*(4*(C+8+3)+1) B per sweep (dense count: every input once) and writes 40 B per survivor.
-    (`head_bytes` = 2 with --head-dtype f16: logits and regressands in half precision, cart stays float32.)"""
+    (`head_bytes` = 2 with f16 heads: logits and regressands in half precision, cart stays float32.)"""
     n, H, W, C, _, _ = WORKLOADS[shape]
     raster = batch * (n * 17 + 7 * H * W * 4)
     decode = batch * (H * W * (head_bytes * (C + 8) + 4 * 3 + 1)) + 40 * survivors
     return raster, decode
 
 
-def ncu_traffic(args, batch: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of scatter + resolve + decode_compact, per step, from the
-    one `ncu --set full` capture of the default workload (profiles/r01_ncu_full_final.md); other workloads were
-    not captured -> None."""
-    if args.shape == "waymo" and batch == 16:
-        return int((70.651 + 0.346 + 67.777 + 35.712 + 154.737 + 20.664) * 1e6)
-    return None
+def ncu_traffic(shape: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of scatter + resolve + decode_compact per step, from the committed
+    `ncu --set full` capture of the default workload (profiles/traffic.json, written by tools/ncu_summary.py from the
+    .ncu-rep); other workloads were not captured -> None."""
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        return int(t["bytes_per_step"]) if (t.get("shape"), t.get("batch")) == (shape, batch) else None
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 # --------------------------------------------------------------------------------------- #
@@ -146,6 +160,19 @@ def cpu_step(sweep, head1, mapping, shape: str, nms_mode: str, pool: ThreadPoolE
             "total_s": t3 - t0, "kept": kept, "survivors": int(live.sum())}
 
 
+def cpu_baseline_record(stages, cores: int, shape: str):
+    """`stages`: list of cpu_step results -> the cpu_baseline object (value = sweeps/s of the whole path; the NMS share is
+    stated because the restated detectron2 CPU NMS dominates it -- a path the reference itself runs on the GPU)."""
+    tot = float(np.mean([s["total_s"] for s in stages]))
+    sm = {k: float(np.mean([s[k] for s in stages])) for k in ("rasterize_ms", "decode_ms", "nms_ms")}
+    return {"value": 1.0 / tot, "unit": "sweeps/s", "cores": cores, "kind": "port",
+            "sample": f"1 {shape}-shaped sweep per step ({WORKLOADS[shape][0]} pts, 64x{WORKLOADS[shape][2]}, "
+                      f"{stages[-1]['survivors']} candidates >= 0.1): numpy rasterize + serial z-buffer (1 thread), torch-CPU "
+                      f"decode ({cores} threads), C rotated NMS (1 thread per class, greedy scan stopped at num_post_nms kept)",
+            "stage_ms": sm, "nms_share": sm["nms_ms"] / (tot * 1e3),
+            "sweeps_per_s_rasterize_decode_only": 1e3 / (sm["rasterize_ms"] + sm["decode_ms"])}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,16 +188,12 @@ def run_reference(args):
     stages = [cpu_step(sweeps[0], head, mapping, args.shape, args.nms_mode, pool) for _ in range(args.steps)]
     dt = time.perf_counter() - t0
     value = args.steps / dt
-    sample = (f"1 {args.shape}-shaped sweep per step ({WORKLOADS[args.shape][0]} pts, 64x{WORKLOADS[args.shape][2]}, "
-              f"{stages[-1]['survivors']} candidates >= 0.1): numpy rasterize + serial z-buffer (1 thread), torch-CPU "
-              f"decode ({cores} threads), C rotated NMS (1 thread per class, greedy scan stopped at num_post_nms kept)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             # the CUDA arm's config; each step here is a bounded sample of it (1 of the batch's sweeps, see `sample`)
             "config": dict(workload_config(args, args.batch), l2="n/a (host arm)", sample_per_step="1 sweep"),
-            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": "port", "sample": sample,
-                             "stage_ms": {k: float(np.mean([s[k] for s in stages])) for k in ("rasterize_ms", "decode_ms", "nms_ms")}},
+            "cpu_baseline": dict(cpu_baseline_record(stages, cores, args.shape), value=value),
             "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -207,11 +230,194 @@ def bind_to_gpu_numa_node(index: int) -> str:
 # --------------------------------------------------------------------------------------- #
 # the CUDA arm                                                                             #
 # --------------------------------------------------------------------------------------- #
+class HotPath:
+    """One configured instance of the path: resident inputs + the public calls of a step (nothing else)."""
+
+    def __init__(self, shape, batch, dev, nms_mode, head_dtype="f32", fp_rate=None, gen_batch=None, peer=None, rank=0,
+                 inputs=None):
+        from rv3d.constants import ROW_MAPPING_64
+        from rv3d.math.range_view import pack_sweeps
+        from rv3d.nn.decoders.range_decoder import RangeDecoder
+        self.shape, self.B, self.dev, self.peer, self.rank = shape, batch, dev, peer, rank
+        n, H, W, C, M, ident = WORKLOADS[shape]
+        self.H, self.W, self.C = H, W, C
+        g = min(gen_batch or batch, batch)
+        # weak scaling: every rank gets the SAME synthetic sweeps, so the per-GPU work is identical at every N (NMS time is
+        # data dependent; with different seeds the max over ranks would measure the unluckiest seed, not the scaling)
+        self.sweeps, head, self.mapping = inputs if inputs is not None else make_inputs(shape, g, 1000, fp_rate)
+        if head_dtype == "f16":   # the reference's own eval_precision = 16 operating point (range_view.yaml:26, detector.py:329-333)
+            head = dict(head, logits=head["logits"].half(), regressands=head["regressands"].half())
+        self.head_host = head
+        self.pts_h, self.las_h, self.cnt_h = pack_sweeps(self.sweeps, dev, pin=True)
+        self.head_h = {k: v.pin_memory() for k, v in head.items()}
+        rep = batch // g
+
+        def tile(t):
+            t = t.to(dev)
+            return t.repeat(rep, *([1] * (t.dim() - 1))) if rep > 1 else t
+
+        self.pts, self.las, self.cnt = tile(self.pts_h), tile(self.las_h), tile(self.cnt_h)
+        self.hd = {k: tile(v) for k, v in self.head_h.items()}
+        self.row_map = torch.as_tensor((np.arange(H) if ident else ROW_MAPPING_64).astype(np.int32), device=dev)
+        self.pp = dict(PP, nms_mode=nms_mode)
+        self.tasks = {0: [f"c{i}" for i in range(C)]}
+        self.dec = RangeDecoder(True, True, *SBR)
+        self.image = torch.empty((batch, 7, H, W), dtype=torch.float32, device=dev)
+        self.rws = torch.empty(batch * H * W * 8, dtype=torch.uint8, device=dev)
+        self.stats = torch.zeros(24, dtype=torch.int64, device=dev)
+
+    @staticmethod
+    def ms_of(h):
+        return {1: {"cart": h["cart"], "mask": h["mask"], 0: {"logits": h["logits"], "regressands": h["regressands"]}}}
+
+    # ---- the calls a user makes ----
+    def rasterize(self, p=None, l=None, c=None):
+        from rv3d.math.range_view import rasterize_sweeps
+        return rasterize_sweeps(self.pts if p is None else p, self.las if l is None else l, self.cnt if c is None else c,
+                                self.row_map, synth.LIDAR_OFFSET, self.H, self.W, out=self.image, workspace=self.rws)
+
+    def decode(self, h=None, stats=None):
+        gather = self.peer.flagged(self.rank * self.B) if self.peer is not None else None
+        return self.dec.decode_async(self.ms_of(self.hd if h is None else h), self.pp, self.tasks, gather=gather, stats=stats)
+
+    def step(self, p=None, l=None, c=None, h=None, stats=None):
+        self.rasterize(p, l, c)
+        return self.decode(h, stats)
+
+
+def capture(fn, dev):
+    """fn() enqueues work through the public API; -> (graph, fn's return value).  The workspaces were sized by an eager
+    warm-up call before: nothing allocates from the default pool while capturing."""
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.graph(g, stream=s):
+        out = fn()
+    torch.cuda.current_stream(dev).wait_stream(s)
+    return g, out
+
+
+def replay_timed(graphs, steps, flush, barrier=None):
+    """Replays the graph(s) back to back `steps` times; events around each one on the current stream, L2 flush between
+    steps.  -> (per-step ms array per graph, wall seconds per step)."""
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(graphs) + 1)] for _ in range(steps)]
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        if flush is not None:
+            flush.zero_()
+        ev[k][0].record()
+        for i, g in enumerate(graphs):
+            g.replay()
+            ev[k][i + 1].record()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps
+    return [np.array([e[i].elapsed_time(e[i + 1]) for e in ev]) for i in range(len(graphs))], wall
+
+
+def run_extras(args, dev, flush, cores_all):
+    """BASELINE configs 1, 3, 4 and the batch-1 latency protocol: small, bounded legs, each through the public API."""
+    from rv3d.math.ops.nms import batched_multiclass_nms
+    steps = max(3, min(args.steps, 10))
+    extra = {}
+
+    def graph_leg(hp):
+        hp.step(); hp.step()
+        torch.cuda.synchronize()
+        g, det = capture(hp.step, dev)
+        for _ in range(3):
+            g.replay()
+        (t,), _ = replay_timed([g], steps, flush)
+        return float(np.mean(t)), int(det.wait())
+
+    # ---- config 1: AV2-shaped sweeps, standard rotated NMS; CPU figure beside it ----
+    hp = HotPath("av2", 16, dev, "HARD", fp_rate=args.fp_rate)
+    ms, ndet = graph_leg(hp)
+    rec = {"workload": "av2-shaped (100000 pts, 64x1800, 26 classes) batch 16, HARD NMS", "ms_per_step": ms,
+           "sweeps_per_s": 16 / (ms * 1e-3), "detections_per_step": ndet, "steps": steps}
+    if not args.no_cpu_baseline:
+        import oracle  # noqa: F401
+        os.sched_setaffinity(0, cores_all)
+        torch.set_num_threads(len(cores_all))
+        pool = ThreadPoolExecutor(max_workers=len(cores_all))
+        h1 = {k: v[:1] for k, v in hp.head_host.items()}
+        cpu_step(hp.sweeps[0], h1, hp.mapping, "av2", "HARD", pool)
+        r = cpu_step(hp.sweeps[0], h1, hp.mapping, "av2", "HARD", pool)
+        rec["cpu_reference_port"] = dict(cpu_baseline_record([r], len(cores_all), "av2"))
+    extra["config1_av2_hard"] = rec
+    del hp
+
+    # ---- config 3: weighted NMS stress, 200 k candidates of one class in one sweep ----
+    cub, sc, ca = synth.make_nms_candidates(1, 200_000, 1, 256, seed=123, spread=75.0, frac_clustered=0.97)
+    sc = 0.1 + 0.9 * sc
+    cub, sc, ca = cub.to(dev), sc.to(dev), ca.to(dev)
+    for mode in ("WEIGHTED", "HARD"):
+        for _ in range(3):
+            out = batched_multiclass_nms(cub, sc, ca, 200_000, 1000, 0.3, 0.1, mode)
+        ts = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = batched_multiclass_nms(cub, sc, ca, 200_000, 1000, 0.3, 0.1, mode)   # includes its one host wait
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        extra[f"config3_stress_200k_{mode.lower()}"] = {
+            "workload": "1 sweep, 1 class, 200000 candidates >= 0.1 around 256 objects, num_pre_nms 200000, num_post_nms 1000",
+            "ms_per_call": float(np.median(ts)) * 1e3, "candidates_per_s": 200_000 / float(np.median(ts)), "kept": int(out[1].shape[0]),
+            "protocol": "sync-bracketed wall clock around batched_multiclass_nms (public call)",
+            "torchex": "TorchEx is not installable here (no network): keep-set / merged rows are compared against the "
+                       "oracle in tests/test_gpu_nms.py::test_config3_weighted_stress_200k; the reference kernel would "
+                       "build two 200000 x 3125 u64 masks (10 GB) and scan them on the host"}
+    del cub, sc, ca
+
+    # ---- config 4: multi-resolution range images 64 x {900, 1800, 3600}, batch 64 ----
+    base = None
+    for name in ("w900", "w1800", "w3600"):
+        if base is None:
+            base = [synth.make_points(WORKLOADS[name][0], 64, 1000 + s) for s in range(8)]
+        n, H, W, C, M, _ = WORKLOADS[name]
+        head = synth.make_head_outputs(8, C, H, W, seed=1000, n_objects=M, fp_rate=FP_RATE if args.fp_rate is None else args.fp_rate,
+                                       distinct_scores=False)
+        hp = HotPath(name, 64, dev, "HARD", gen_batch=8, inputs=(base, head, np.arange(H)))
+        ms, ndet = graph_leg(hp)
+        extra[f"config4_{name}"] = {"workload": f"{n} pts -> 64x{W}, 3 classes, batch 64 (8 distinct sweeps tiled 8x), HARD NMS",
+                                    "ms_per_step": ms, "sweeps_per_s": 64 / (ms * 1e-3), "detections_per_step": ndet, "steps": steps}
+        del hp
+
+    # ---- batch-1 latency, the reference's protocol (tools/benchmark.py:231-238: sync, perf_counter, call, sync; warm-up 5) ----
+    hp = HotPath("waymo", 1, dev, "HARD", fp_rate=args.fp_rate)
+
+    def bench(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    ms1 = hp.ms_of(hp.hd)
+    for _ in range(5):
+        hp.rasterize(); hp.dec.decode(ms1, hp.pp, hp.tasks, use_nms=True)
+    t_r = [bench(hp.rasterize) for _ in range(20)]
+    t_d = [bench(lambda: hp.dec.decode(ms1, hp.pp, hp.tasks, use_nms=True)) for _ in range(20)]
+    g, det = capture(hp.step, dev)
+    for _ in range(3):
+        g.replay()
+    (t,), _ = replay_timed([g], 20, flush)
+    extra["batch1_latency"] = {"workload": "1 waymo-shaped sweep, HARD NMS", "protocol": "tools/benchmark.py:231-238 (sync-bracketed wall clock, warm-up 5)",
+                               "rasterize_ms": float(np.mean(t_r)), "decoder_ms": float(np.mean(t_d)),
+                               "total_ms": float(np.mean(t_r) + np.mean(t_d)), "fps": 1e3 / float(np.mean(t_r) + np.mean(t_d)),
+                               "graph_replay_ms_device": float(np.mean(t)), "detections": int(det.wait())}
+    return extra
+
+
 def run_ours(args):
     import torch.distributed as dist
     from rv3d.distributed import PeerGather, gather_detections_fixed, pack_rows
-    from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
-    from rv3d.nn.decoders.range_decoder import RangeDecoder
     from rv3d import _native as N
     from rv3d._pipeline import run_nms
 
@@ -232,70 +438,29 @@ def run_ours(args):
 
     B = args.batch
     n, H, W, C, M, ident = WORKLOADS[args.shape]
-    # weak scaling: every rank gets the SAME synthetic sweeps, so the per-GPU work is identical at every N (NMS time is
-    # data dependent; with different seeds the max over ranks would measure the unluckiest seed, not the scaling)
-    sweeps, head, mapping = make_inputs(args.shape, B, 1000, args.fp_rate)
-    if args.head_dtype == "f16":   # exploration: the reference's own eval_precision = 16 operating point (range_view.yaml:26,
-        head = dict(head, logits=head["logits"].half(), regressands=head["regressands"].half())   # detector.py:329-333)
-    pts_h, las_h, cnt_h = pack_sweeps(sweeps, dev, pin=True)
-    head_h = {k: v.pin_memory() for k, v in head.items()}
-    from rv3d.constants import ROW_MAPPING_64
-    row_map = torch.as_tensor((np.arange(H) if ident else ROW_MAPPING_64).astype(np.int32), device=dev)
-    pp = dict(PP, nms_mode=args.nms_mode)
-    tasks = {0: [f"c{i}" for i in range(C)]}
-    dec = RangeDecoder(True, True, *SBR)
-
-    # resident copies
-    pts, las, cnt = pts_h.to(dev), las_h.to(dev), cnt_h.to(dev)
-    hd = {k: v.to(dev) for k, v in head_h.items()}
-    image = torch.empty((B, 7, H, W), dtype=torch.float32, device=dev)
-    rws = torch.empty(B * H * W * 8, dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stats = torch.zeros(24, dtype=torch.int64, device=dev)
-
     gather_cap = B * C * PP["num_post_nms"]
-
-    def ms_of(h):
-        return {1: {"cart": h["cart"], "mask": h["mask"], 0: {"logits": h["logits"], "regressands": h["regressands"]}}}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # the path's one exchange step (N > 1): detections go into every rank's gather buffer from inside the NMS pack
-    # kernel (peer-memory stores over NVLink + a device-side barrier); NCCL all_gather only if symmetric memory is
-    # not available on the box
+    # kernel (peer-memory stores over NVLink, per-slot sequence flags); NCCL all_gather only if symmetric memory is not
+    # available on the box
     peer, gather_kind = None, "none (1 GPU)"
     if world > 1:
         try:
             peer = PeerGather(gather_cap, dev)
-            gather_kind = "peer-memory stores fused into the pack kernel + device-side barrier"
+            gather_kind = "peer-memory stores fused into the pack kernel + per-slot sequence flags (no barrier kernel)"
         except Exception as exc:   # noqa: BLE001
             gather_kind = f"nccl all_gather_into_tensor (symmetric memory unavailable: {type(exc).__name__})"
-    step_no = [0]
+    hp = HotPath(args.shape, B, dev, args.nms_mode, args.head_dtype, args.fp_rate, peer=peer, rank=rank)
 
-    def step(p, l, c, h, evs=None):
-        rasterize_sweeps(p, l, c, row_map, synth.LIDAR_OFFSET, H, W, out=image, workspace=rws)
-        if evs: evs[1].record()
-        cand = dec.candidates(ms_of(h), pp, tasks)
-        if evs: evs[2].record()
-        ncand = cand.count()
-        slot = step_no[0] & 1
-        step_no[0] += 1
-        kw = dict(peer=peer, peer_slot=slot, sweep_offset=rank * B) if peer is not None else {}
-        if peer is not None:
-            peer.begin(slot)
-        out = run_nms(dec._ws, cand, ncand, pp["num_pre_nms"], pp["num_post_nms"], pp["nms_threshold"], pp["nms_mode"],
-                      N.OUT_QUAT, stats=stats, **kw) if ncand else None
-        if out is None:
-            e = torch.empty((0,), device=dev)
-            out = (torch.empty((0, 10), device=dev), e, e, e)
-            if peer is not None:
-                peer.write_empty(slot)
-        if peer is not None:
-            peer.publish(slot)        # barrier over the ranks on a side stream: overlaps the next step's rasterize + decode
-            rows = peer.rows(slot)    # complete once peer.wait(slot) has passed
-        elif world > 1:
-            rows = gather_detections_fixed(pack_rows(*out, batch_offset=rank * B), gather_cap)
-        else:
-            rows = out
-        return ncand, out, rows
+    def full_step():
+        det = hp.step(stats=hp.stats)
+        if world > 1 and peer is None:
+            m = det.params.shape[0]
+            rows = torch.zeros((m, 13), dtype=torch.float32, device=dev)   # padded rows; counts travel in the block header
+            rows[:, 0] = det.batch_index + float(rank * B); rows[:, 1] = det.categories; rows[:, 2] = det.scores; rows[:, 3:] = det.params
+            gather_detections_fixed(rows[:gather_cap], gather_cap)
+        return det
 
     def barrier():
         if world > 1:
@@ -306,104 +471,165 @@ def run_ours(args):
     clk = ClockSampler(local, enabled=(rank == 0))
     clk.__enter__()
     for _ in range(max(args.warmup, 3)):
-        step(pts, las, cnt, hd)
-    if world > 1 and peer is None:   # NCCL sets its channels up lazily: establish the gather's path before timing
-        _, out0, _ = step(pts, las, cnt, hd)
-        for _ in range(10):
-            gather_detections_fixed(pack_rows(*out0, batch_offset=rank * B), gather_cap)
+        det = full_step()
     barrier()
 
-    # ---------------- resident timing: K steps, per-step CUDA events, L2 flushed between steps -----------
-    stats.zero_()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    ncand = ndet = 0
+    # ---------------- resident timing: the step as ONE CUDA graph, K replays, per-step events, L2 flush between ----------
+    g_step, det = capture(full_step, dev)
+    for _ in range(max(args.warmup, 3)):
+        g_step.replay()
     barrier()
-    t_wall = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record()
-        ncand, out, _ = step(pts, las, cnt, hd, ev[k])
-        if peer is not None and k == args.steps - 1:
-            peer.wait((step_no[0] - 1) & 1)      # the last step's gather is inside the timed region too
-        ev[k][3].record()
-        ndet = out[0].shape[0]
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    t_step = np.array([e[0].elapsed_time(e[3]) for e in ev])
-    t_raster = np.array([e[0].elapsed_time(e[1]) for e in ev])
-    t_decode = np.array([e[1].elapsed_time(e[2]) for e in ev])
-    t_nms = np.array([e[2].elapsed_time(e[3]) for e in ev])
+    hp.stats.zero_()
+    (t_step,), wall = replay_timed([g_step], args.steps, flush, barrier if world > 1 else None)
+    if peer is not None:
+        peer.sync_steps()      # replays advance the device-side step counter; capturing advanced only the host's
+    st = (hp.stats.cpu().numpy() / args.steps).tolist()
+    ndet = det.wait()
+    ncand = int(hp.dec._ws.get("counter", (1,), torch.int32, dev).item())
     total_ms = torch.tensor([t_step.sum()], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * B * args.steps / (total_ms * 1e-3)
-    st = (stats.cpu().numpy() / args.steps).tolist()
+
+    # ---------------- N > 1: the gathered rows equal the concatenation of every rank's local output ----------------
+    gather_ok = None
+    if peer is not None:
+        det = full_step()
+        peer.wait_published()
+        torch.cuda.synchronize()
+        got = PeerGather.unpack_rows(peer.rows_published())
+        m = det.wait()
+        mine = pack_rows(det.params[:m], det.scores[:m], det.categories[:m], det.batch_index[:m], batch_offset=rank * B)
+        from rv3d.distributed import gather_detections
+        want = gather_detections(mine)
+        ok = torch.tensor([int(got.shape == want.shape and torch.equal(got, want))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_ok = bool(ok.item())
+
+    # ---------------- stage graphs: rasterize | decode_compact | bucketing + NMS + pack (roofline, breakdown) -------------
+    hp1 = hp if peer is None else HotPath(args.shape, B, dev, args.nms_mode, args.head_dtype, args.fp_rate,
+                                          inputs=(hp.sweeps, hp.head_host, hp.mapping))
+    cand_box = {}
+
+    def stage_decode():
+        cand_box["c"] = hp1.dec.candidates(hp1.ms_of(hp1.hd), hp1.pp, hp1.tasks)
+
+    def stage_nms():
+        return run_nms(hp1.dec._ws, cand_box["c"], PP["num_pre_nms"], PP["num_post_nms"], PP["nms_threshold"], args.nms_mode,
+                       N.OUT_QUAT, score_range=(PP["min_confidence"], 1.0))
+
+    hp1.rasterize(); stage_decode(); stage_nms()
+    torch.cuda.synchronize()
+    g_r, _ = capture(hp1.rasterize, dev)
+    g_d, _ = capture(stage_decode, dev)
+    g_n, _ = capture(stage_nms, dev)
+    for _ in range(3):
+        g_r.replay(); g_d.replay(); g_n.replay()
+    (t_raster, t_decode, t_nms), _ = replay_timed([g_r, g_d, g_n], args.steps, flush)
 
     # ---------------- e2e: pinned host inputs -> H2D -> path -> D2H of the detections, every step --------
-    copy_stream = torch.cuda.Stream(dev)
-    bufs = [dict(pts=torch.empty_like(pts), las=torch.empty_like(las), cnt=torch.empty_like(cnt),
-                 head={k: torch.empty_like(v) for k, v in hd.items()}, ready=torch.cuda.Event(), free=torch.cuda.Event())
-            for _ in range(2)]
-    h2d = pts_h.numel() * 4 + las_h.numel() + cnt_h.numel() * 4 + sum(v.numel() * v.element_size() for v in head_h.values())
-    out_h = torch.empty(world * (gather_cap + 1) * 16, dtype=torch.float32).pin_memory()
+    def e2e_leg(hpx, steps):
+        copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        bufs = [dict(pts=torch.empty_like(hpx.pts), las=torch.empty_like(hpx.las), cnt=torch.empty_like(hpx.cnt),
+                     head={k: torch.empty_like(v) for k, v in hpx.hd.items()}, ready=torch.cuda.Event(), free=torch.cuda.Event())
+                for _ in range(2)]
+        h2d = (hpx.pts_h.numel() * 4 + hpx.las_h.numel() + hpx.cnt_h.numel() * 4 +
+               sum(v.numel() * v.element_size() for v in hpx.head_h.values()))
+        rows_per_rank = (gather_cap + 1) * 16 if peer is not None else gather_cap * 13 + 1
+        out_h = [torch.empty((world if (peer is not None and rank == 0) else 1) * rows_per_rank, dtype=torch.float32).pin_memory()
+                 for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    def upload(slot):
-        b = bufs[slot]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(b["free"])
-            b["pts"].copy_(pts_h, non_blocking=True); b["las"].copy_(las_h, non_blocking=True)
-            b["cnt"].copy_(cnt_h, non_blocking=True)
-            for k2, v in head_h.items():
-                b["head"][k2].copy_(v, non_blocking=True)
-            b["ready"].record(copy_stream)
-
-    def e2e_run(steps):
-        cur = torch.cuda.current_stream(dev)
-        for b in bufs:
-            b["free"].record(cur)
-        d2h = 0
-        upload(0)
-        for k in range(steps):
-            slot = k & 1
-            if k + 1 < steps:
-                upload(slot ^ 1)          # next step's inputs cross PCIe while this step computes
-            cur.wait_event(bufs[slot]["ready"])
+        def upload(slot):
             b = bufs[slot]
-            # the calls a user makes: rv3d.math.range_view.rasterize_sweeps + RangeDecoder.decode
-            rasterize_sweeps(b["pts"], b["las"], b["cnt"], row_map, synth.LIDAR_OFFSET, H, W, out=image, workspace=rws)
-            if peer is not None:
-                slot = step_no[0] & 1
-                step_no[0] += 1
-                peer.begin(slot)
-                out = dec.decode(ms_of(b["head"]), pp, tasks, gather=(peer, slot, rank * B))
-                b["free"].record(cur)
-                peer.publish(slot)
-                peer.wait(slot)
-                # every rank holds the full gather on the device; the host copy is the whole set on rank 0 and the
-                # rank's own detections elsewhere (the reference's ranks each write only their own sweeps' files)
-                rows = peer.rows(slot).flatten(0, 1) if rank == 0 else peer.rows(slot)[rank]
-            else:
-                out = dec.decode(ms_of(b["head"]), pp, tasks)
-                b["free"].record(cur)
-                rows = pack_rows(*out, batch_offset=rank * B)
-                if world > 1:
-                    rows = gather_detections_fixed(rows, gather_cap).flatten(0, 1)
-            out_h[: rows.numel()].view(rows.shape).copy_(rows, non_blocking=True)
-            d2h = rows.numel() * 4 + 8   # rows + the two device counters read by the host
-        return d2h
+            with torch.cuda.stream(copy_in):
+                copy_in.wait_event(b["free"])
+                b["pts"].copy_(hpx.pts_h, non_blocking=True); b["las"].copy_(hpx.las_h, non_blocking=True)
+                b["cnt"].copy_(hpx.cnt_h, non_blocking=True)
+                for k2, v in hpx.head_h.items():
+                    b["head"][k2].copy_(v, non_blocking=True)
+                b["ready"].record(copy_in)
 
-    e2e_run(2)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = e2e_run(args.steps)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(e2e_s.item())
+        def run(nsteps):
+            cur = torch.cuda.current_stream(dev)
+            for b in bufs:
+                b["free"].record(cur)
+            d2h = 0
+            upload(0)
+            for k in range(nsteps):
+                slot = k & 1
+                if k + 1 < nsteps:
+                    upload(slot ^ 1)          # next step's inputs cross PCIe while this step computes
+                cur.wait_event(bufs[slot]["ready"])
+                b = bufs[slot]
+                # the calls a user makes: rv3d.math.range_view.rasterize_sweeps + RangeDecoder.decode_async
+                det = hpx.step(b["pts"], b["las"], b["cnt"], b["head"])
+                b["free"].record(cur)
+                if peer is not None:
+                    peer.wait_published()
+                    # every rank holds the full gather on the device; the host copy is the whole set on rank 0 and the
+                    # rank's own detections elsewhere (the reference's ranks each write only their own sweeps' files)
+                    src = peer.rows_published().flatten() if rank == 0 else peer.rows_published()[rank].flatten()
+                else:
+                    src = det.buffer                     # padded detections + the count, one block
+                done[slot].record(cur)
+                with torch.cuda.stream(copy_out):        # the download overlaps the next step's kernels
+                    copy_out.wait_event(done[slot])
+                    out_h[slot][: src.numel()].copy_(src, non_blocking=True)
+                    src.record_stream(copy_out)
+                d2h = src.numel() * 4
+            cur.wait_stream(copy_out)
+            return d2h
+
+        run(2)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = run(steps)
+        barrier()
+        secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        secs = float(secs.item())
+        return {"value": world * hpx.B * steps / secs, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "h2d_gbs_per_gpu": h2d * steps / secs / 1e9,
+                "note": "host buffers pinned; upload double-buffered on a copy stream, download on a second one"}
+
+    e2e = e2e_leg(hp, args.steps)
+    e2e_f16 = None
+    if args.head_dtype == "f32":
+        hp16 = HotPath(args.shape, B, dev, args.nms_mode, "f16", args.fp_rate, peer=peer, rank=rank,
+                       inputs=(hp.sweeps, hp.head_host, hp.mapping))
+        hp16.step(); hp16.step()
+        e2e_f16 = e2e_leg(hp16, args.steps)
+        e2e_f16["note"] = ("second record: logits / regressands in float16 (the reference's own eval_precision 16 operating point, "
+                           "detector.py:329-333), cart float32; " + e2e_f16["note"])
+        del hp16
     clk.__exit__()
     clocks = clk.summary()
+
+    extra = {}
+    if world > 1 and args.global_batch and peer is not None:
+        # BASELINE config 5: a fixed global batch sharded over the ranks (strong scaling of one big batch)
+        Bg = args.global_batch // world
+        peer5 = PeerGather(Bg * C * PP["num_post_nms"], dev)
+        hp5 = HotPath(args.shape, Bg, dev, args.nms_mode, args.head_dtype, args.fp_rate, gen_batch=B, peer=peer5, rank=rank,
+                      inputs=(hp.sweeps, hp.head_host, hp.mapping))
+        hp5.step(); hp5.step()
+        barrier()
+        g5, _ = capture(hp5.step, dev)
+        peer5.sync_steps()
+        for _ in range(2):
+            g5.replay()
+        (t5,), _ = replay_timed([g5], 5, flush, barrier)
+        t5 = torch.tensor([t5.sum()], dtype=torch.float64, device=dev)
+        dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        extra["config5_global_batch"] = {"global_batch": Bg * world, "batch_per_gpu": Bg, "steps": 5,
+                                         "ms_per_step": float(t5.item()) / 5, "sweeps_per_s": Bg * world * 5 / (float(t5.item()) * 1e-3),
+                                         "note": f"waymo shape, {B} distinct sweeps tiled to {Bg} per rank, detections gathered by the fused peer stores"}
+        del hp5, peer5
+    if world == 1 and not args.no_extras:
+        extra.update(run_extras(args, dev, flush, all_cpus))
 
     if rank == 0:
         raster_b, decode_b = algorithmic_bytes(args.shape, B, ncand, 2 if args.head_dtype == "f16" else 4)
@@ -415,6 +641,7 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         rd_ms = float(np.mean(t_raster) + np.mean(t_decode))
         achieved = (raster_b + decode_b) / (rd_ms * 1e-3) / 1e9
+        S = B * C
         line = {
             "metric": METRIC, "value": value, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -422,54 +649,56 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, B), detection_gather=gather_kind,
                            per_rank_data="identical synthetic sweeps on every rank (seed 1000)", host_affinity=numa,
-                           head_dtype=args.head_dtype),
-            "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            # own kernels per step: raster scatter + resolve, decode_compact, iota, prepare_records, nms_segment, pack
-            # (+ kept_scan above 512 segments); the CUB sort passes and memsets are not counted
-            "gpu_launches": (7 if B * C <= 512 else 8) * args.steps,
+                           head_dtype=args.head_dtype,
+                           timed_region="one CUDA-graph replay of rasterize_sweeps + RangeDecoder.decode_async per step (no host read inside the step)"),
+            "e2e": e2e,
+            # own kernels per step: raster scatter + resolve, decode_compact, hist, bin_scan, scatter_records, nms_pull, pack
+            # (+ kept_scan above 512 segments, + the peer wait at N > 1); memsets are not counted
+            "gpu_launches": (8 + (1 if S > 512 else 0) + (1 if peer is not None else 0)) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernels": "rasterize (scatter+resolve) + decode_compact", "achieved": achieved,
                          "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args, B),
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.shape, B),
                          "algorithmic_bytes": {"rasterize": raster_b, "decode": decode_b},
                          "rasterize_gbs": raster_b / (float(np.mean(t_raster)) * 1e-3) / 1e9,
                          "decode_gbs": decode_b / (float(np.mean(t_decode)) * 1e-3) / 1e9,
-                         # the stage that dominates the step, for completeness: it reads each candidate's key + box once
-                         # and writes the detections (NMS is latency / issue bound, an HBM fraction says
-                         # little about it -- its work units are under "nms")
+                         "timing": "each stage replayed as its own CUDA graph, CUDA events on the replay stream, L2 flushed per step",
+                         # the suppression stage, for completeness: it reads each candidate's key + box once and writes the
+                         # detections (NMS is latency / issue bound, an HBM fraction says little -- work units under "nms")
                          "nms_stage": {"bound": "hbm", "algorithmic_bytes": int(ncand) * 40 + int(ndet) * 52,
                                        "achieved": (int(ncand) * 40 + int(ndet) * 52) / (float(np.mean(t_nms)) * 1e-3) / 1e9,
                                        "frac": (int(ncand) * 40 + int(ndet) * 52) / (float(np.mean(t_nms)) * 1e-3) / 1e9 / peak,
-                                       "note": "sort + nms_segment_kernel + pack; not HBM-bound (ncu: DRAM 0.6 %, IPC 1.4)"}},
+                                       "note": "score bucketing + nms_pull_kernel + pack; not HBM-bound"}},
             "stage_ms": {"rasterize": float(np.mean(t_raster)), "decode_compact": float(np.mean(t_decode)),
-                         "sort+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": t_wall / args.steps * 1e3},
-            # work units of the suppression stage (device counters of nms_segment_kernel, averaged over the timed steps)
-            "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "segments": B * C,
-                    "iou_evals_per_step": st[0], "kept_per_step": st[1], "frontier_rounds_per_step": st[2],
-                    "circle_tests_per_step": st[3],
-                    "pairs_above_thr_per_step": float(stats[18].item()) / args.steps,
-                    "approx_iou_per_step": float(stats[19].item()) / args.steps,
-                    # leader CTAs' cycles per phase: build, frontier load, frontier pairs, greedy, kill scan, IoU, publish, sync
-                    "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]]
-                                              + [round(float(stats[i].item()) / args.steps / 1e6, 3) for i in (20, 21)],
-                    "slowest_segment_mcycles": round(float(stats[10].item()) / 1e6, 3),
-                    "largest_segment": int(stats[11].item()),
-                    "slowest_segment_phase_kcycles": [int(x) // 1000 for x in stats[12:18].tolist()]},
+                         "bucketing+nms+pack": float(np.mean(t_nms)), "wall_per_step_incl_flush": wall * 1e3,
+                         "flush_ms_note": "wall includes the 256 MiB flush memset (~0.04 ms); host launch cost per step = one graph launch"},
+            # work units of the suppression stage (device counters of nms_pull_kernel, averaged over the timed steps)
+            "nms": {"candidates_per_step": int(ncand), "detections_per_step": int(ndet), "segments": S,
+                    "candidates_consumed_per_step": st[20], "exact_iou_per_step": st[0], "approx_iou_per_step": st[19],
+                    "kept_per_step": st[1], "frontier_rounds_per_step": st[2], "circle_tests_per_step": st[3],
+                    "pairs_above_thr_per_step": st[18],
+                    # cycles summed over the segments' CTAs per phase: window sort, pull walk, pull IoU, frontier pairs, greedy, publish
+                    "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]],
+                    "slowest_segment_mcycles": round(float(hp.stats[10].item()) / 1e6, 3),
+                    "largest_segment": int(hp.stats[11].item()),
+                    "slowest_segment_phase_kcycles": [int(x) // 1000 for x in hp.stats[12:18].tolist()]},
         }
+        if e2e_f16 is not None:
+            line["e2e_f16_heads"] = e2e_f16
+        if gather_ok is not None:
+            line["gather_ok"] = gather_ok
         if world == 1 and not args.no_cpu_baseline and args.head_dtype == "f32":
             import oracle  # noqa: F401
             os.sched_setaffinity(0, all_cpus)          # the CPU baseline gets every host core again
             cores = len(all_cpus)
             torch.set_num_threads(cores)
             pool = ThreadPoolExecutor(max_workers=cores)
-            h1 = {k: v[:1] for k, v in head.items()}
-            cpu_step(sweeps[0], h1, mapping, args.shape, args.nms_mode, pool)        # JIT / page-in
-            r = cpu_step(sweeps[0], h1, mapping, args.shape, args.nms_mode, pool)
-            line["cpu_baseline"] = {
-                "value": 1.0 / r["total_s"], "unit": "sweeps/s", "cores": cores, "kind": "port",
-                "sample": f"1 sweep of the same workload ({r['survivors']} candidates): numpy rasterize + serial z-buffer "
-                          f"(1 thread), torch-CPU decode ({cores} threads), C rotated NMS (1 thread per class)",
-                "stage_ms": {k: r[k] for k in ("rasterize_ms", "decode_ms", "nms_ms")}}
+            h1 = {k: v[:1] for k, v in hp.head_host.items()}
+            cpu_step(hp.sweeps[0], h1, hp.mapping, args.shape, args.nms_mode, pool)        # JIT / page-in
+            rs = [cpu_step(hp.sweeps[0], h1, hp.mapping, args.shape, args.nms_mode, pool) for _ in range(3)]
+            line["cpu_baseline"] = cpu_baseline_record(rs, cores, args.shape)
+        if extra:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -482,10 +711,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shape", default="waymo", choices=list(WORKLOADS))
+    ap.add_argument("--shape", default="waymo", choices=["waymo", "av2"])
     ap.add_argument("--batch", type=int, default=16, help="sweeps per GPU per step")
     ap.add_argument("--nms-mode", default="HARD", choices=["HARD", "WEIGHTED"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE config 1 / 3 / 4 and batch-1 latency legs")
+    ap.add_argument("--global-batch", type=int, default=512,
+                    help="N > 1: also time BASELINE config 5, this many sweeps sharded over the ranks (0 = skip)")
     ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"],
                     help="exploration only: f16 = half-precision logits / regressands next to float32 cart (autocast); "
                          "the CPU baseline leg is skipped")

@@ -240,14 +240,20 @@ typedef struct {
    * ALSO stores every detection as a 16-float row [sweep + sweep_offset, class, score, 0, x,y,z,l, w,h,qw,qx,
    * qy,qz,0,0] into slot `peer_rank` of each rank's (peer_world, peer_capacity + 1, 16) f32 buffer, row 0 of
    * the slot being [rows written, rows kept, seq, 0], with plain 16-byte stores through peer-mapped (NVLink)
-   * pointers.  peer_seq == 0: the caller orders readers behind the writers (a device-side barrier over the
-   * ranks).  peer_seq != 0: the last pack block to finish publishes the header with uint32 `peer_seq` in its
-   * third word behind a system-scope fence; readers wait for it with rv3d_peer_wait -- no barrier kernel.
+   * pointers.  peer_seq == NULL: the caller picked the slot (peer_rows point at it) and orders readers behind the
+   * writers itself (a device-side barrier over the ranks).  peer_seq != NULL (device u32, this rank's count of
+   * published steps): step k = *peer_seq + 1 is written to slot k & 1 at peer_rows[q] + slot * peer_slot_stride
+   * floats; the last pack block to finish publishes the header with k in its third word behind a system-scope
+   * fence and sets *peer_seq = k.  Readers wait with rv3d_peer_wait -- no barrier kernel, and since slot and
+   * sequence number are read from device memory the step replays unchanged inside a CUDA graph.  The caller waits
+   * for step k - 1 (rv3d_peer_wait) before enqueueing step k's rv3d_nms and consumes a step's rows on the same
+   * stream before the next one: then no writer overtakes a reader of the slot it reuses.
    * RV3D_OUT_QUAT only.  peer_world == 0: off. */
   int32_t peer_world, peer_rank, peer_capacity, sweep_offset;
-  uint32_t peer_seq;
   int32_t reserved;
   float *peer_rows[RV3D_MAX_PEERS];
+  uint32_t *peer_seq;
+  int64_t peer_slot_stride;
   int32_t *host_count;       /* optional HOST pointer (mapped pinned memory, device-accessible): the detection count
                                 is also stored there, so a caller waiting on an event can read it without a copy */
 } rv3d_nms_params;
@@ -269,9 +275,11 @@ int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys, const float *boxes,
              float *out_params, float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
              int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
 
-/* Consumer side of the peer_seq protocol: enqueue a wait until every rank's header in THIS rank's slot buffer
- * `rows` ((world, peer_capacity + 1, 16) f32) carries `seq`. */
-int rv3d_peer_wait(const float *rows, int32_t world, int32_t peer_capacity, uint32_t seq, rv3d_stream_t stream);
+/* Consumer side of the peer_seq protocol: with k = *seq (device; the steps this rank has published), enqueue a wait
+ * until every rank's header in slot k & 1 of THIS rank's buffer `rows` ((2, world, peer_capacity + 1, 16) f32, slots
+ * `slot_stride` floats apart) carries a sequence number >= k. */
+int rv3d_peer_wait(const float *rows, int64_t slot_stride, int32_t world, int32_t peer_capacity, const uint32_t *seq,
+                   rv3d_stream_t stream);
 
 /* detectron2-style entry: boxes (N,5) f32 (xc,yc,w,h,angle_deg), scores (N,) f32 ->
  * keep (N,) i64 original indices in score order, *n_keep device i32.
@@ -300,11 +308,12 @@ int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b, int64_t n
 int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int32_t aligned,
                          float *out, rv3d_stream_t stream);
 
-/* Test hook for the two-stage IoU comparison of the NMS kernels: aligned pairs of (N,5) f32 boxes (xc, yc, w, h,
- * angle in degrees) -> decision (N,) i8 (2: skipped by the upper bound, +1 / -1: decided by the approximate IoU,
- * 0: sent to the exact routine), approx (N,) f32, exact (N,) f32 (the bit-exact routine's value). */
-int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold, int8_t *decision,
-                        float *approx, float *exact, rv3d_stream_t stream);
+/* Test hook for the two-stage IoU comparison of the NMS kernels: aligned pairs of (N,5) f32 boxes -- routine 0:
+ * (xc, yc, w, h, angle in degrees), the hard mode's detectron2-style routine; routine 1: (x1, y1, x2, y2, ry), the
+ * weighted mode's iou_bev -- -> decision (N,) i8 (2: skipped by the upper bound, +1 / -1: decided by the approximate
+ * IoU, 0: sent to the exact routine), approx (N,) f32, exact (N,) f32 (the bit-exact routine's value). */
+int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold, int32_t routine,
+                        int8_t *decision, float *approx, float *exact, rv3d_stream_t stream);
 
 /* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
 int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);

@@ -1200,8 +1200,13 @@ struct PackArgs {
   // fused gather: every rank's buffer is (world, peer_capacity + 1, 16) f32; this rank writes slot `peer_rank` of each
   int n_peers, peer_rank, peer_capacity, sweep_offset;
   float *peer_rows[RV3D_MAX_PEERS];
-  uint32_t peer_seq;      // > 0: after its rows, the LAST block to finish stores this sequence number into the header
-  int *done_ticket;       // (zeroed per call) of slot `peer_rank` on every rank, behind a system-scope fence
+  // sequence-flag protocol (peer_seq != null): *peer_seq = steps this rank has published.  Step k = *peer_seq + 1 goes
+  // to slot k & 1 (peer_rows[q] + slot * peer_slot_stride); after its rows, the LAST block to finish stores k into the
+  // header of slot `peer_rank` on every rank behind a system-scope fence, then sets *peer_seq = k.  Everything a
+  // replayed CUDA graph needs (slot, sequence number) is read from device memory.
+  uint32_t *peer_seq;
+  long long peer_slot_stride;
+  int *done_ticket;       // zeroed per call
 };
 
 __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
@@ -1217,6 +1222,12 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
   int off, total = 0;
   const bool first = blockIdx.x == 0 && blockIdx.y == 0;
   const bool need_total = first || (a.n_peers > 0 && a.peer_seq);
+  uint32_t step = 0;
+  size_t slot_off = 0;
+  if (a.n_peers > 0 && a.peer_seq) {
+    step = *reinterpret_cast<volatile uint32_t *>(a.peer_seq) + 1u;   // only the last block advances it, after every block has read it
+    slot_off = static_cast<size_t>(step & 1u) * static_cast<size_t>(a.peer_slot_stride);
+  }
   if (a.fused_scan) {
     int part = 0, tot = 0;
     const int upto = need_total ? a.n_segments : seg;
@@ -1283,7 +1294,7 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
       const float4 r1 = make_float4(p[0], p[1], p[2], p[3]);
       const float4 r2 = make_float4(p[4], p[5], static_cast<float>(qc), 0.f);
       const float4 r3 = make_float4(0.f, static_cast<float>(qs), 0.f, 0.f);
-      const size_t at = (static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) + 1 + row) * 16;
+      const size_t at = slot_off + (static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) + 1 + row) * 16;
       // consecutive lanes start at different peers, so a warp's stores fan out over all NVLink ports at once
       for (int qq = 0; qq < a.n_peers; ++qq) {
         const int q = (qq + threadIdx.x) % a.n_peers;
@@ -1293,7 +1304,7 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
     }
   }
   if (a.n_peers > 0) {
-    const size_t hdr = static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) * 16;
+    const size_t hdr = slot_off + static_cast<size_t>(a.peer_rank) * (a.peer_capacity + 1) * 16;
     if (!a.peer_seq) {
       if (first && threadIdx.x == 0) {   // header row: [rows written, rows kept]; the caller orders readers (barrier)
         const float4 h = make_float4(static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity),
@@ -1307,25 +1318,32 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a) {
       __syncthreads();
       if (threadIdx.x == 0) s_last = (atomicAdd(a.done_ticket, 1) == static_cast<int>(gridDim.x * gridDim.y) - 1) ? 1 : 0;
       __syncthreads();
-      if (s_last && threadIdx.x < a.n_peers) {
-        __threadfence_system();
-        volatile float *h = a.peer_rows[threadIdx.x] + hdr;
-        h[0] = static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity);
-        h[1] = static_cast<float>(total);
-        __threadfence_system();
-        reinterpret_cast<volatile uint32_t *>(h)[2] = a.peer_seq;
+      if (s_last) {
+        if (threadIdx.x < a.n_peers) {
+          __threadfence_system();
+          volatile float *h = a.peer_rows[threadIdx.x] + hdr;
+          h[0] = static_cast<float>(total < a.peer_capacity ? total : a.peer_capacity);
+          h[1] = static_cast<float>(total);
+          __threadfence_system();
+          reinterpret_cast<volatile uint32_t *>(h)[2] = step;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(a.peer_seq) = step;
       }
     }
   }
 }
 
-// consumer side of the sequence-flag protocol: spin until every rank's header in THIS rank's buffer carries `seq`
-__global__ void wait_peer_seq_kernel(const float *__restrict__ rows, int world, int peer_capacity, uint32_t seq) {
+// consumer side of the sequence-flag protocol: k = *seq steps published by this rank so far; spin until every rank's
+// header in slot k & 1 of THIS rank's buffer carries a sequence number >= k (k == 0: nothing to wait for)
+__global__ void wait_peer_seq_kernel(const float *__restrict__ rows, long long slot_stride, int world, int peer_capacity,
+                                     const uint32_t *__restrict__ seq) {
+  const uint32_t k = *reinterpret_cast<const volatile uint32_t *>(seq);
   const int q = threadIdx.x;
-  if (q < world) {
-    const volatile uint32_t *h =
-        reinterpret_cast<const volatile uint32_t *>(rows + static_cast<size_t>(q) * (peer_capacity + 1) * 16);
-    while (h[2] != seq) __nanosleep(64);
+  if (q < world && k != 0u) {
+    const volatile uint32_t *h = reinterpret_cast<const volatile uint32_t *>(
+        rows + static_cast<size_t>(k & 1u) * static_cast<size_t>(slot_stride) + static_cast<size_t>(q) * (peer_capacity + 1) * 16);
+    while (static_cast<int32_t>(h[2] - k) < 0) __nanosleep(64);
   }
   __threadfence_system();
 }
@@ -1596,7 +1614,7 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys_in, const
   pa.out_params = out_params; pa.out_scores = out_scores; pa.out_cats = out_categories; pa.out_batch = out_batch;
   pa.out_count = out_count;
   pa.n_peers = p->peer_world; pa.peer_rank = p->peer_rank; pa.peer_capacity = p->peer_capacity; pa.sweep_offset = p->sweep_offset;
-  pa.peer_seq = p->peer_seq; pa.done_ticket = L.ticket + 1;
+  pa.peer_seq = p->peer_seq; pa.peer_slot_stride = p->peer_slot_stride; pa.done_ticket = L.ticket + 1;
   for (int q = 0; q < p->peer_world; ++q) pa.peer_rows[q] = p->peer_rows[q];
   {
     const int per_seg = p->num_post_nms < pl.kc ? p->num_post_nms : pl.kc;
@@ -1607,9 +1625,10 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys_in, const
   return RV3D_OK;
 }
 
-extern "C" int rv3d_peer_wait(const float *rows, int32_t world, int32_t peer_capacity, uint32_t seq, rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(rows && world > 0 && world <= RV3D_MAX_PEERS && peer_capacity > 0 && seq != 0);
-  wait_peer_seq_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(rows, world, peer_capacity, seq);
+extern "C" int rv3d_peer_wait(const float *rows, int64_t slot_stride, int32_t world, int32_t peer_capacity,
+                              const uint32_t *seq, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(rows && world > 0 && world <= RV3D_MAX_PEERS && peer_capacity > 0 && seq && slot_stride >= 0);
+  wait_peer_seq_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(rows, slot_stride, world, peer_capacity, seq);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
@@ -1720,25 +1739,31 @@ box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__re
 // boxes (N,5) f32 (xc, yc, w, h, angle in degrees, detectron2 convention), aligned pairs.
 // decision[i]: 2 = skipped by the upper bound (certainly <= thr), +1 / -1 = decided by the approximate IoU
 // (above / not above), 0 = sent to the exact routine;  approx[i] / exact[i]: the two IoU values.
-__global__ void __launch_bounds__(128)
-pair_decisions_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t n, float thr,
-                      int8_t *__restrict__ decision, float *__restrict__ approx, float *__restrict__ exact) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float *a = A + i * 5, *b = B + i * 5;
-  const HardRec ra = make_hard_rec(a[0], a[1], a[2], a[3], a[4], 0.01745329251);
-  const HardRec rb = make_hard_rec(b[0], b[1], b[2], b[3], b[4], 0.01745329251);
+template <typename Rec>
+__device__ __forceinline__ void decide_pair(const Rec &ra, const Rec &rb, float thr, int8_t &decision, float &ap, float &ex) {
   const Obb oa = obb_of(ra), ob = obb_of(rb);
   int d = 0;
-  float ap = CUDART_NAN_F;
+  ap = CUDART_NAN_F;
   if (!iou_may_exceed(ra, rb, thr)) d = 2;
   else if (obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
     ap = approx_iou(oa, ob);
     d = decide_vs(ap, thr);
   }
-  decision[i] = static_cast<int8_t>(d);
-  approx[i] = ap;
-  exact[i] = rot_iou(ra, rb);
+  decision = static_cast<int8_t>(d);
+  ex = pair_iou(ra, rb);
+}
+
+__global__ void __launch_bounds__(128)
+pair_decisions_kernel(const float *__restrict__ A, const float *__restrict__ B, int64_t n, float thr, int routine,
+                      int8_t *__restrict__ decision, float *__restrict__ approx, float *__restrict__ exact) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *a = A + i * 5, *b = B + i * 5;
+  if (routine == 0)
+    decide_pair(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 0.01745329251), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 0.01745329251),
+                thr, decision[i], approx[i], exact[i]);
+  else
+    decide_pair(make_w_rec(a[0], a[1], a[2], a[3], a[4]), make_w_rec(b[0], b[1], b[2], b[3], b[4]), thr, decision[i], approx[i], exact[i]);
 }
 
 // threshold-only branch: rows ordered by (sweep, candidate index)
@@ -1908,12 +1933,12 @@ extern "C" int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float
 }
 
 extern "C" int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold,
-                                   int8_t *decision, float *approx, float *exact, rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(n >= 0);
+                                   int32_t routine, int8_t *decision, float *approx, float *exact, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && (routine == 0 || routine == 1));
   if (n == 0) return RV3D_OK;
   RV3D_CHECK_ARG(boxes_a && boxes_b && decision && approx && exact && n < (int64_t(1) << 37));
   pair_decisions_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(boxes_a, boxes_b, n, iou_threshold,
-                                                                                       decision, approx, exact);
+                                                                                       routine, decision, approx, exact);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }

@@ -52,8 +52,9 @@ class NmsParams(C.Structure):
                 ("out_capacity", C.c_int32), ("out_layout", C.c_int32), ("score_bits", C.c_int32),
                 ("score_lo", C.c_float), ("score_hi", C.c_float), ("flags", C.c_int32),
                 ("peer_world", C.c_int32), ("peer_rank", C.c_int32), ("peer_capacity", C.c_int32),
-                ("sweep_offset", C.c_int32), ("peer_seq", C.c_uint32), ("reserved", C.c_int32),
-                ("peer_rows", C.c_void_p * 8), ("host_count", C.c_void_p)]
+                ("sweep_offset", C.c_int32), ("reserved", C.c_int32),
+                ("peer_rows", C.c_void_p * 8), ("peer_seq", C.c_void_p), ("peer_slot_stride", C.c_int64),
+                ("host_count", C.c_void_p)]
 
 
 class Rv3dError(RuntimeError):
@@ -81,8 +82,8 @@ _SIGNATURES = {
     "rv3d_compact_candidates": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _F, _I32, _I32, _P, _P, _P, _P]),
     "rv3d_nms_scratch_bytes": (_SZ, [C.POINTER(NmsParams)]),
     "rv3d_nms": (C.c_int, [C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "rv3d_peer_wait": (C.c_int, [_P, _I32, _I32, C.c_uint32, _P]),
-    "rv3d_pair_decisions": (C.c_int, [_P, _P, _I64, _F, _P, _P, _P, _P]),
+    "rv3d_peer_wait": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "rv3d_pair_decisions": (C.c_int, [_P, _P, _I64, _F, _I32, _P, _P, _P, _P]),
     "rv3d_nms_rotated_scratch_bytes": (_SZ, [_I32]),
     "rv3d_nms_rotated": (C.c_int, [_P, _P, _I32, _F, _P, _P, _P, _SZ, _P]),
     "rv3d_wnms_scratch_bytes": (_SZ, [_I32, _I32]),

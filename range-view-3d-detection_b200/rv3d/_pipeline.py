@@ -103,9 +103,10 @@ class Detections:
     The buffers are allocated per call, so results of earlier calls are never overwritten by later ones."""
 
     def __init__(self, params: torch.Tensor, scores: torch.Tensor, categories: torch.Tensor, batch_index: torch.Tensor,
-                 count: torch.Tensor, host_count: torch.Tensor, stream: torch.cuda.Stream):
+                 count: torch.Tensor, host_count: torch.Tensor, stream: torch.cuda.Stream, buffer: Optional[torch.Tensor] = None):
         self.params, self.scores, self.categories, self.batch_index = params, scores, categories, batch_index
         self.count, self.host_count = count, host_count      # device (1,) i32; pinned host (1,) i32
+        self.buffer = buffer                                 # the one f32 block all of the above are views of (count last)
         self.event = None
         if not torch.cuda.is_current_stream_capturing():
             self.event = torch.cuda.Event()
@@ -117,7 +118,7 @@ class Detections:
         if self.event is not None:
             self.event.synchronize()
         else:                          # enqueued under graph capture: the caller replays the graph, then asks
-            self._stream.synchronize()
+            torch.cuda.synchronize(self.params.device)
         return int(self.host_count[0])
 
     def result(self, dtype: Optional[torch.dtype] = None):
@@ -202,17 +203,23 @@ def run_nms(ws: Workspace, cand: Candidates, num_pre_nms: int, num_post_nms: int
             _NMS_PARAMS.clear()
         _NMS_PARAMS[pkey] = p
     p.host_count = host_count.data_ptr()
-    p.peer_world, p.peer_seq = 0, 0
+    p.peer_world, p.peer_seq, p.peer_slot_stride = 0, None, 0
     if peer is not None:
         if layout != N.OUT_QUAT:
             raise ValueError("the fused gather carries params(10) rows (RangeDecoder.decode layout)")
         p.peer_world, p.peer_rank, p.peer_capacity, p.sweep_offset = peer.world, peer.rank, peer.capacity, int(sweep_offset)
-        p.peer_seq = int(peer_seq)
-        for q, addr in enumerate(peer.slot_ptrs(peer_slot)):
-            p.peer_rows[q] = addr
+        if peer_seq:     # sequence-flag protocol: slot and step number are read from device memory by the pack kernel
+            p.peer_seq, p.peer_slot_stride = peer.seq.data_ptr(), peer.slot_bytes // 4
+            for q, addr in enumerate(peer.slot_ptrs(0)):
+                p.peer_rows[q] = addr
+        else:
+            for q, addr in enumerate(peer.slot_ptrs(peer_slot)):
+                p.peer_rows[q] = addr
     lib = N.lib()
     work = ws.bytes("nms_scratch", p.scratch_bytes, dev)
+    if peer is not None and peer_seq:
+        peer.wait_published()     # step k - 1 has arrived everywhere before step k reuses the other slot (overlaps the decode)
     N.check(lib.rv3d_nms(p, ptr(cand.keys), ptr(cand.boxes), ptr(cand.counter), ptr(out_params), ptr(out_scores),
                          ptr(out_cats), ptr(out_batch), ptr(out_count), ptr(stats), ptr(work), work.numel(),
                          stream_ptr(dev)), "rv3d_nms")
-    return Detections(out_params, out_scores, out_cats, out_batch, out_count, host_count, torch.cuda.current_stream(dev))
+    return Detections(out_params, out_scores, out_cats, out_batch, out_count, host_count, torch.cuda.current_stream(dev), buf)

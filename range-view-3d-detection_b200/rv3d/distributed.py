@@ -105,6 +105,9 @@ class PeerGather:
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.slot_bytes = self.world * (self.capacity + 1) * self.ROW16 * 4
+        # sequence-flag protocol: this rank's count of published steps, advanced by the pack kernel itself
+        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        self.steps = 0
         self.hdl.barrier()
 
     def slot_ptrs(self, slot: int):
@@ -153,13 +156,47 @@ class PeerGather:
         if self._published[slot % self.slots]:
             torch.cuda.current_stream(self.buf.device).wait_event(self._done[slot % self.slots])
 
+    # ---- sequence-flag form (slots == 2): no barrier kernel, no host-side slot bookkeeping, graph-replayable ----
+    #   decode_async(..., gather=self.flagged(sweep_offset))   the pack kernel writes step k = seq + 1 into slot k & 1 of
+    #                                                          every rank and publishes k in the slot headers
+    #   wait_published()   enqueue a wait until every rank's step `seq` has arrived in THIS rank's buffer.  Call it before
+    #                      the next step's NMS (it then overlaps the next rasterize + decode) and before reading rows.
+    def flagged(self, sweep_offset: int = 0):
+        if self.slots != 2:
+            raise ValueError("the sequence-flag protocol alternates between exactly two slots")
+        self.steps += 1
+        return (self, 0, int(sweep_offset), True)
+
+    def wait_published(self) -> None:
+        from . import _native as N
+        from ._util import stream_ptr
+        import ctypes as C
+        N.check(N.lib().rv3d_peer_wait(C.c_void_p(self.buf.data_ptr()), self.slot_bytes // 4, self.world, self.capacity,
+                                       C.c_void_p(self.seq.data_ptr()), stream_ptr(self.buf.device)), "rv3d_peer_wait")
+
+    def sync_steps(self) -> int:
+        """Re-read the device-side step counter (after CUDA-graph replays, which advance it without the host noticing)."""
+        self.steps = int(self.seq.item())
+        return self.steps
+
+    def rows_published(self) -> Tensor:
+        """Rows of the last published step (host-side step count; valid after ``wait_published``)."""
+        return self.buf[self.steps & 1]
+
     def rows(self, slot: int) -> Tensor:
         """(world, capacity + 1, 16): row 0 of each rank's block is [rows written, rows kept, 0, 0]."""
         return self.buf[slot % self.slots]
 
     def unpack(self, slot: int) -> Tensor:
         """-> (M, 13) rows [sweep, class, score, params(10)] of all ranks in rank order (host reads the counts)."""
-        blk = self.rows(slot)
-        counts = blk[:, 0, 0].to(torch.int64).tolist()
+        return self.unpack_rows(self.rows(slot))
+
+    @staticmethod
+    def unpack_rows(blk: Tensor) -> Tensor:
+        head = blk[:, 0, :2].cpu()
+        counts, kept = head[:, 0].to(torch.int64).tolist(), head[:, 1].to(torch.int64).tolist()
+        if any(k > c for c, k in zip(counts, kept)):
+            raise RuntimeError(f"PeerGather: a rank kept {max(kept)} detections but the gather buffer holds "
+                               f"{blk.shape[1] - 1} rows per rank; raise `capacity`")
         cols = [0, 1, 2] + list(range(4, 14))
         return torch.cat([blk[r, 1 : c + 1][:, cols] for r, c in enumerate(counts)], dim=0)
