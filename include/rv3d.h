@@ -215,7 +215,6 @@ int rv3d_compact_candidates(const float *cuboids, const float *scores, const int
 #define RV3D_OUT_QUAT 0
 #define RV3D_OUT_YAW 1
 #define RV3D_MAX_PEERS 8
-#define RV3D_NMS_EXACT_ONLY 1 /* flags: decide every pair with the bit-exact IoU routine (no approximate shortcut) */
 
 typedef struct {
   int32_t batch, total_classes, total_candidates;
@@ -234,7 +233,8 @@ typedef struct {
   float score_lo, score_hi;  /* range the scores are known to lie in (decode: [min_confidence, 1]); only balances the
                                 score bins, any scores stay correct.  score_hi <= score_lo: unknown, the library
                                 reduces min / max on the device first                     */
-  int32_t flags;             /* RV3D_NMS_EXACT_ONLY                                      */
+  int32_t flags;             /* must be 0 (every pair that survives the pruning runs the bit-exact IoU routine;
+                                there is no approximate mode)                              */
   /* Fused detection gather over peer memory (the path's one exchange step, multi-GPU; replaces the per-sweep
    * feather files + dist.barrier() of nn/arch/detector.py:366-380,415-421).  peer_world > 0: the pack kernel
    * ALSO stores every detection as a 16-float row [sweep + sweep_offset, class, score, 0, x,y,z,l, w,h,qw,qx,
@@ -308,12 +308,13 @@ int rv3d_iou3d_aligned(const float *cuboids_a, const float *cuboids_b, int64_t n
 int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int32_t aligned,
                          float *out, rv3d_stream_t stream);
 
-/* Test hook for the two-stage IoU comparison of the NMS kernels: aligned pairs of (N,5) f32 boxes -- routine 0:
- * (xc, yc, w, h, angle in degrees), the hard mode's detectron2-style routine; routine 1: (x1, y1, x2, y2, ry), the
- * weighted mode's iou_bev -- -> decision (N,) i8 (2: skipped by the upper bound, +1 / -1: decided by the approximate
- * IoU, 0: sent to the exact routine), approx (N,) f32, exact (N,) f32 (the bit-exact routine's value). */
+/* Test hook for the pruning the NMS kernels apply in front of the bit-exact IoU routine: aligned pairs of (N,5) f32
+ * boxes -- routine 0: (xc, yc, w, h, angle in degrees), the hard mode's detectron2-style routine; routine 1:
+ * (x1, y1, x2, y2, ry), the weighted mode's iou_bev -- -> decision (N,) i8 (2: stopped by the IoU upper bound, i.e.
+ * treated as "not above the threshold"; 0: sent to the exact routine), bound (N,) f32 (that upper bound), exact (N,)
+ * f32 (the bit-exact routine's value). */
 int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold, int32_t routine,
-                        int8_t *decision, float *approx, float *exact, rv3d_stream_t stream);
+                        int8_t *decision, float *bound, float *exact, rv3d_stream_t stream);
 
 /* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
 int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);

@@ -35,4 +35,31 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   return copysign(a, y);
 }
 
+// hypot(x, y) exactly as the reference's numpy evaluates it: numpy.hypot is libm's hypot, and glibc (>= 2.35; 2.39 in this
+// image) implements it, when no FMA is used, as  h = sqrt(ax^2 + ay^2)  followed by one correction step
+// (sysdeps/ieee754/dbl-64/e_hypot.c `kernel`, after C. Borges, "An Improved Algorithm for hypot(a,b)").  The result is
+// NOT the correctly rounded value (it differs from it in ~0.6 % of the cases), so being bit-exact with the reference
+// means restating it: IEEE add / mul / div / sqrt only, no contraction (the library is built with --fmad=false).
+// oracle/libm_hypot.py holds the same restatement in numpy; tests/test_oracle_golden.py pins it against numpy.hypot.
+// Inputs here are differences of float32-origin values: the scaling branches for |x| > 2^511 or |y| < 2^-459 never apply
+// (y == 0 takes the `ax >= ay / EPS` exit like upstream).
+static __device__ __noinline__ double libm_hypot(double x, double y) {
+  x = fabs(x); y = fabs(y);
+  const double ax = x < y ? y : x, ay = x < y ? x : y;
+  if (ax >= ay / 0x1p-54) return ax + ay;
+  double h = sqrt(ax * ax + ay * ay);
+  double t1, t2;
+  if (h <= 2.0 * ay) {
+    const double delta = h - ay;
+    t1 = ax * (2.0 * delta - ax);
+    t2 = (delta - 2.0 * (ax - ay)) * delta;
+  } else {
+    const double delta = h - ax;
+    t1 = 2.0 * delta * (ax - 2.0 * ay);
+    t2 = (4.0 * delta - ay) * ay + delta * delta;
+  }
+  h -= (t1 + t2) / (2.0 * h);
+  return h;
+}
+
 }  // namespace rv3d

@@ -18,7 +18,7 @@
 //         repeat: take the next window (<= 2048 candidates = whole score bins), sort it exactly in shared
 //                 memory by (score desc, candidate asc);
 //           a. PULL: every window candidate looks up the boxes KEPT so far in a spatial hash of kept boxes
-//              (circle pre-test -> work queue -> approximate / exact IoU on dense lanes) and dies if suppressed;
+//              (circle pre-test -> work queue -> IoU upper bound -> bit-exact IoU on dense lanes) and dies if suppressed;
 //           b. the first kF survivors form a frontier: all pairs inside it -> suppression bit-matrix ->
 //              greedy resolution in rank order -> newly kept boxes join the hash;
 //           c. the remaining survivors pull again, against the NEW kept boxes only; back to b.
@@ -53,6 +53,8 @@ constexpr int kKeptSmem = 2048;      // kept boxes tracked in shared memory when
 constexpr int kBucketsSmem = 4096;   // hash buckets of the kept-box grid (shared-memory form)
 constexpr float kPosCap = 1.0e6f;
 constexpr int kMaxCellsPerQuery = 25;
+constexpr int kFrontBuckets = 1024;   // hash buckets of the per-round frontier grid
+constexpr int kRankSortMax = 48;      // bins up to this size are ordered by rank counting, larger ones by the bitonic network
 
 // ------------------------------------------------------------------------------------------
 // K3: counting sort by (segment, coarse score bin)
@@ -267,7 +269,6 @@ struct NmsArgs {
   int num_pre, num_post;
   float thr, mthr;
   int prune;                      // 0: thresholds < 0 make even disjoint boxes interact -> test every pair
-  int exact_only;                 // 1: never decide a pair with the approximate IoU
   int kept_stride;                // > 0: kept rows of segment s start at s * kept_stride; 0: at seg_begin[s]
   int *kept_pos;                  // [kept_base + i] = position inside the segment
   int *kept_count;                // [s]
@@ -303,78 +304,28 @@ __device__ __forceinline__ float overlap_in_frame(const Obb &a, const Obb &b) {
   const float ov = fminf(ah, dv + ev) - fmaxf(-ah, dv - ev);
   return fmaxf(ou, 0.f) * fmaxf(ov, 0.f);
 }
+// The bound is on the TRUE IoU.  The reference routines work with absolute tolerances (1e-5 on dot products in m^2, 1e-6
+// on cross products), which for boxes of a few decimetres become commensurate with the geometry: there the routine's
+// value can exceed the true IoU by 10 % and more (tests/test_gpu_iou_decisions.py found 0.327 for a true 0.289 on
+// 0.15 m x 0.07 m boxes).  The bound is therefore only trusted when both boxes have extents >= kBoundMinExtent, where
+// those tolerances move the result by < 1e-4 relative; smaller boxes always run the exact routine.
+constexpr float kBoundMinExtent = 0.5f;
 template <typename Rec>
 __device__ __forceinline__ bool iou_may_exceed(const Rec &ra, const Rec &rb, float thr) {
   const Obb a = obb_of(ra), b = obb_of(rb);
+  if (!(fminf(fminf(fabsf(a.w), fabsf(a.h)), fminf(fabsf(b.w), fabsf(b.h))) >= kBoundMinExtent)) return true;
   const float inter = fminf(overlap_in_frame(a, b), overlap_in_frame(b, a));
   const float uni = fabsf(a.w * a.h) + fabsf(b.w * b.h) - inter;
   if (!(uni > 0.f) || !(inter == inter)) return true;  // degenerate / NaN: let the exact routine decide
   return (inter / uni) * 1.02f + 1e-5f >= thr;
 }
 
-// ---- fast approximate IoU (float32 Sutherland-Hodgman clip in box A's frame) --------------------
-// NMS never needs the IoU value, only the comparisons `iou > thr` (and `> merge_thr`).  A pair whose approximate
-// IoU is outside a +-(2 % + 1e-3) band around a threshold is decided without the bit-exact routine; pairs inside
-// the band, and unusual boxes (obb_sane), still run it.  tests/test_gpu_iou_decisions.py measures, over 1e7
-// adversarial pairs, that no decided pair disagrees with the exact routine and reports the smallest margin;
-// rv3d_nms_params.flags & RV3D_NMS_EXACT_ONLY switches the shortcut off.
-__device__ __forceinline__ float approx_iou(const Obb &A, const Obb &B) {
-  const float aw = fabsf(A.w) * 0.5f, ah = fabsf(A.h) * 0.5f, bw = fabsf(B.w) * 0.5f, bh = fabsf(B.h) * 0.5f;
-  const float dx = B.x - A.x, dy = B.y - A.y;
-  const float cx = dx * A.c + dy * A.s, cy = -dx * A.s + dy * A.c;          // B's centre in A's frame
-  const float cd = A.c * B.c + A.s * B.s, sd = A.c * B.s - A.s * B.c;       // B's axis in A's frame
-  const float ux = cd * bw, uy = sd * bw, vx = -sd * bh, vy = cd * bh;
-  float px[10], py[10], qx[10], qy[10];
-  px[0] = cx + ux + vx; py[0] = cy + uy + vy;
-  px[1] = cx - ux + vx; py[1] = cy - uy + vy;
-  px[2] = cx - ux - vx; py[2] = cy - uy - vy;
-  px[3] = cx + ux - vx; py[3] = cy + uy - vy;
-  int n = 4;
-#pragma unroll
-  for (int plane = 0; plane < 4; ++plane) {
-    // planes: x <= aw, -x <= aw, y <= ah, -y <= ah  (coordinate c, sign sg, limit lim)
-    const float sg = (plane & 1) ? -1.f : 1.f;
-    const float lim = (plane < 2) ? aw : ah;
-    int m = 0;
-    float prx = px[n - 1], pry = py[n - 1];
-    float prd = sg * ((plane < 2) ? prx : pry) - lim;     // signed distance, inside when <= 0
-    for (int i = 0; i < n; ++i) {
-      const float cxp = px[i], cyp = py[i];
-      const float cd2 = sg * ((plane < 2) ? cxp : cyp) - lim;
-      if ((cd2 <= 0.f) != (prd <= 0.f)) {
-        const float t = __fdividef(prd, prd - cd2);
-        qx[m] = prx + t * (cxp - prx); qy[m] = pry + t * (cyp - pry); ++m;
-      }
-      if (cd2 <= 0.f) { qx[m] = cxp; qy[m] = cyp; ++m; }
-      prx = cxp; pry = cyp; prd = cd2;
-    }
-    if (m < 3) return 0.f;
-    n = m;
-    for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
-  }
-  float area2 = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const int k = (i + 1 == n) ? 0 : i + 1;
-    area2 += px[i] * py[k] - px[k] * py[i];
-  }
-  const float inter = 0.5f * fabsf(area2);
-  const float uni = 4.f * (aw * ah + bw * bh) - inter;
-  return uni > 0.f ? inter / uni : CUDART_NAN_F;
-}
-
-// boxes the approximate clip is trusted on: extents within [0.05 m, 1e4 m], aspect ratio <= 64, centres within
-// 1e6 m of the origin and within 1e4 m of each other (float32 cancellation in the centre difference)
-__device__ __forceinline__ bool obb_sane(const Obb &o) {
-  const float w = fabsf(o.w), h = fabsf(o.h);
-  const float lo = fminf(w, h), hi = fmaxf(w, h);
-  return lo >= 0.05f && hi <= 1.0e4f && hi <= 64.f * lo && fabsf(o.x) <= kPosCap && fabsf(o.y) <= kPosCap;
-}
-// -1: certainly below / equal, +1: certainly above, 0: too close to call -> exact routine
-__device__ __forceinline__ int decide_vs(float approx, float thr) {
-  if (!(approx == approx)) return 0;
-  const float m = 0.02f * fabsf(thr) + 1e-3f;
-  return approx > thr + m ? 1 : (approx < thr - m ? -1 : 0);
-}
+// There is deliberately NO approximate IoU stage.  Round 1 decided ~98 % of the pairs with a float32 polygon clip and a
+// +-(2 % + 1e-3) band around the threshold; tests/test_gpu_iou_decisions.py showed why that cannot be bit-exact: the
+// detectron2 routine the reference binds is itself irregular -- for some near-parallel pairs its tolerance-based
+// angular sort drops hull points and it returns e.g. 0.133 where the true IoU is 0.307 (and 0.307 with the boxes
+// swapped).  Reproducing the reference's keep-set means reproducing that, so every pair that survives the circle
+// test and the upper bound runs the bit-exact routine.
 
 template <typename Rec, bool kWeighted, int kF>
 __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
@@ -386,14 +337,15 @@ __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   b += kWin;                                                       // walive
   b += sizeof(uint16_t) * kNmsThreads;                             // batch slot -> window index
   b += sizeof(Rec) * kF;                                           // frec
-  b += sizeof(float) * kF * 3;                                     // fx, fy, fr
+  b += sizeof(float4) * kF;                                        // fq
+  b += sizeof(int) * kFrontBuckets + sizeof(uint16_t) * kF;        // fheads, fos
   b += sizeof(uint16_t) * kF;                                      // front_w
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
   b += sizeof(uint32_t) * kQ2Cap;                                  // queue2 (the window sort's keys + indices alias it)
   b += sizeof(uint32_t) * kNmsWarps * kWBuf;                       // per-warp exact-IoU buffers
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
   if (kWeighted) b += sizeof(int) * kWin + kQ2Cap + sizeof(int) * kF; // wfs, qflag, killer
-  if (kept_in_smem) b += sizeof(float4) * kKeptSmem + sizeof(int) * kKeptSmem + sizeof(int) * kBucketsSmem;
+  if (kept_in_smem) b += sizeof(float4) * kKeptSmem + sizeof(int) * kBucketsSmem + sizeof(int) * kKeptSmem;
   return align_up_c(b, 16);
 }
 static_assert(sizeof(unsigned long long) * kWin + sizeof(uint16_t) * kWin <= sizeof(uint32_t) * kQ2Cap, "sort buffers alias the queue");
@@ -461,14 +413,14 @@ __device__ __forceinline__ void cta_bitonic_sort(unsigned long long *keys, V *va
   }
 }
 
-template <typename Rec, bool kWeighted, int kF>
+template <typename Rec, bool kWeighted, int kF, bool kSm>
 __global__ void __launch_bounds__(kNmsThreads, 1)
-nms_pull_kernel(NmsArgs a, int kept_in_smem) {
+nms_pull_kernel(NmsArgs a) {
   constexpr int kFW = kF / 32;   // words per bit-matrix row
   static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0 && kF <= kNmsThreads, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsWarps + 1];
-  __shared__ int s_qn, s_qvalid, s_nk, s_nos;
+  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_nfos;
   __shared__ float s_red[kNmsWarps * 2];
   __shared__ float s_cell[2];   // inv_cell, r_cap
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
@@ -487,10 +439,8 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
   uint32_t *gorder = a.gorder ? a.gorder + beg : nullptr;
   const int kbase = a.kept_stride > 0 ? seg * a.kept_stride : beg;
   int *kept_pos = a.kept_pos + kbase;
-  int *kos = a.kos + kbase;
   const float thr_any = kWeighted ? fminf(a.thr, a.mthr) : a.thr;  // smallest IoU that matters
   const bool prune = a.prune != 0;
-  const bool use_approx = prune && !a.exact_only;
 
   // ---- carve shared memory
   unsigned char *p = smem_raw;
@@ -501,9 +451,9 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
   uint8_t *walive = reinterpret_cast<uint8_t *>(p); p += kWin;
   uint16_t *s_bj = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kNmsThreads;
   Rec *frec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;
-  float *fx = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  float *fy = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
-  float *fr = reinterpret_cast<float *>(p); p += sizeof(float) * kF;
+  float4 *fq = reinterpret_cast<float4 *>(p); p += sizeof(float4) * kF;            // frontier (x, y, padded radius, next in chain)
+  int *fheads = reinterpret_cast<int *>(p); p += sizeof(int) * kFrontBuckets;
+  uint16_t *fos = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kF;     // frontier boxes that are not in the frontier grid
   uint16_t *front_w = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kF;
   uint32_t *sup = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kF * kFW;
   uint32_t *mrg = sup;
@@ -521,16 +471,18 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
     qflag = reinterpret_cast<uint8_t *>(p); p += kQ2Cap;             // per queued pair: bit0 iou > thr, bit1 iou > merge_thr
     killer = reinterpret_cast<int *>(p); p += sizeof(int) * kF;      // frontier box -> rank of its first suppressor
   }
-  // kept boxes: (x, y, padded radius, position) + hash chains; shared memory when num_post_nms is small
-  float4 *kxyr; int *knext, *heads; uint32_t bmask;
-  if (kept_in_smem) {
+  // Kept boxes: a spatial hash with chaining.  Shared-memory form (kSm, num_post_nms <= kKeptSmem): ONE 16-byte entry
+  // per kept box, (x, y, padded radius, next + 1 << 20 | position in the segment), so a chain step is a single LDS.128.
+  // Global form: (x, y, r, position) + a separate next array, for calls that may keep more than kKeptSmem boxes.
+  float4 *kxyr; int *knext = nullptr, *heads, *kos; uint32_t bmask;
+  if (kSm) {
     kxyr = reinterpret_cast<float4 *>(p); p += sizeof(float4) * kKeptSmem;
-    knext = reinterpret_cast<int *>(p); p += sizeof(int) * kKeptSmem;
     heads = reinterpret_cast<int *>(p); p += sizeof(int) * kBucketsSmem;
+    kos = reinterpret_cast<int *>(p); p += sizeof(int) * kKeptSmem;
     bmask = kBucketsSmem - 1;
     for (int i = tid; i < kBucketsSmem; i += kNmsThreads) heads[i] = -1;
   } else {
-    kxyr = a.kxyr_g + kbase; knext = a.knext_g + kbase;
+    kxyr = a.kxyr_g + kbase; knext = a.knext_g + kbase; kos = a.kos + kbase;
     heads = a.heads_g + static_cast<size_t>(seg) * a.n_buckets_g;   // pre-set to -1 by the host (memset 0xFF)
     bmask = static_cast<uint32_t>(a.n_buckets_g - 1);
   }
@@ -539,7 +491,7 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
   if (tid == 0) { s_nos = 0; s_qn = 0; }
   __syncthreads();
 
-  unsigned long long st_iou = 0, st_circle = 0, st_hit = 0, st_approx = 0;   // exact IoUs, circle tests, pairs above thr, approximate IoUs
+  unsigned long long st_iou = 0, st_circle = 0, st_hit = 0, st_bound = 0;   // exact IoUs, circle tests, pairs above thr, upper-bound tests
   // per-phase cycle counters (thread 0, only when stats are requested):
   // [0] window assembly + sort, [1] pull: grid walks, [2] pull: IoU, [3] frontier pairs, [4] greedy, [5] publish (+ weighted merges)
   long long ph[6] = {0, 0, 0, 0, 0, 0};
@@ -555,44 +507,74 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
 
   auto cell_of = [&](float v) -> int { return static_cast<int>(fminf(fmaxf(floorf(v * inv_cell), -32768.f), 32767.f)); };
   auto bucket_of = [&](int ix, int iy) -> uint32_t {
-    return ((static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u)) & bmask;
+    return (static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u);
   };
   auto in_grid = [&](float x, float y, float r) -> bool {
     return (r <= r_cap) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap);   // false for NaN
   };
+  auto kept_entry = [&](int k, float &x, float &y, float &r, int &next) {
+    const float4 q = kxyr[k];
+    x = q.x; y = q.y; r = q.z;
+    if (kSm) next = static_cast<int>(__float_as_uint(q.w) >> 20) - 1;
+    else next = knext[k];
+  };
+  auto kept_position = [&](int k) -> int {
+    const uint32_t w = __float_as_uint(kxyr[k].w);
+    return static_cast<int>(kSm ? (w & 0xfffffu) : w);
+  };
+  // does the circle (x, y, r) touch (qx, qy, qr)?  (the pads of iou.cuh padded_radius make "no" exact)
+  auto touches = [&](float x, float y, float r, float qx, float qy, float qr) -> bool {
+    const float dx = qx - x, dy = qy - y, rr = qr + r;
+    return dx * dx + dy * dy <= rr * rr;
+  };
 
-  // Every kept box k >= since whose padded circle can touch (x, y, r): fn(k, kx, ky, kr).  Chains are newest-first
-  // (insertion prepends, kept indices only grow), so a walk stops at the first index below `since`.
+  // Query window of a box in cell coordinates; false -> the caller scans everything (pruning off, a radius that is
+  // infinite or covers too many cells).  NaN boxes never interact: `skip`.
+  auto query_cells = [&](float x, float y, float r, int &ix0, int &ix1, int &iy0, int &iy1, bool &skip) -> bool {
+    skip = false;
+    if (!prune) return false;
+    if (!(x == x) || !(y == y) || !(r == r)) { skip = true; return false; }   // its circle test is false against anything
+    const float reach = r + r_cap;
+    if (!(reach <= kPosCap) || !(fabsf(x) <= kPosCap) || !(fabsf(y) <= kPosCap)) return false;
+    ix0 = cell_of(x - reach); ix1 = cell_of(x + reach); iy0 = cell_of(y - reach); iy1 = cell_of(y + reach);
+    return (ix1 - ix0 + 1) * (iy1 - iy0 + 1) <= kMaxCellsPerQuery;
+  };
+
+  // Every kept box k >= since whose padded circle touches (x, y, r): fn(k).  Chains are newest-first (insertion
+  // prepends, kept indices only grow), so a walk stops at the first index below `since`.  The circle test comes
+  // first; only a hit pays for the check that the entry really belongs to the queried cell (cells share buckets, and a
+  // box visited through two cells of the window must not count twice).
   auto for_each_near = [&](float x, float y, float r, int since, auto &&fn) {
-    const int hi = kept;
-    bool brute = !prune;
     int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
-    if (!brute) {
-      if (!(x == x) || !(y == y) || !(r == r)) return;          // NaN never interacts (its circle test is false)
-      const float reach = r + r_cap;
-      if (!(reach <= kPosCap) || !(fabsf(x) <= kPosCap) || !(fabsf(y) <= kPosCap)) brute = true;
-      else {
-        ix0 = cell_of(x - reach); ix1 = cell_of(x + reach); iy0 = cell_of(y - reach); iy1 = cell_of(y + reach);
-        if ((ix1 - ix0 + 1) * (iy1 - iy0 + 1) > kMaxCellsPerQuery) brute = true;
+    bool skip;
+    if (!query_cells(x, y, r, ix0, ix1, iy0, iy1, skip)) {
+      if (skip) return;
+      for (int k = since; k < kept; ++k) {
+        const float4 q = kxyr[k];
+        ++st_circle;
+        if (!prune || touches(x, y, r, q.x, q.y, q.z)) fn(k);
       }
-    }
-    if (brute) {
-      for (int k = since; k < hi; ++k) { const float4 q = kxyr[k]; fn(k, q.x, q.y, q.z); }
       return;
     }
     for (int iy = iy0; iy <= iy1; ++iy)
       for (int ix = ix0; ix <= ix1; ++ix) {
-        int k = heads[bucket_of(ix, iy)];
+        int k = heads[bucket_of(ix, iy) & bmask];
         while (k >= since) {
-          const float4 q = kxyr[k];
-          if (cell_of(q.x) == ix && cell_of(q.y) == iy) fn(k, q.x, q.y, q.z);   // other cells share the bucket
-          k = knext[k];
+          float qx, qy, qr; int next;
+          kept_entry(k, qx, qy, qr, next);
+          ++st_circle;
+          if (touches(x, y, r, qx, qy, qr) && cell_of(qx) == ix && cell_of(qy) == iy) fn(k);
+          k = next;
         }
       }
     const int nos = s_nos;
     for (int o = 0; o < nos; ++o) {
       const int k = kos[o];
-      if (k >= since) { const float4 q = kxyr[k]; fn(k, q.x, q.y, q.z); }
+      if (k >= since) {
+        const float4 q = kxyr[k];
+        ++st_circle;
+        if (touches(x, y, r, q.x, q.y, q.z)) fn(k);
+      }
     }
   };
 
@@ -610,30 +592,19 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
     atomicAdd(a.merge_count + kbase + slot, 1);
   };
 
-  // bound -> approximate -> exact for ONE pair, in place (overflow paths; divergent, so only a fallback)
+  // bound -> exact for ONE pair, in place (overflow paths; divergent, so only a fallback)
   auto classify_pair = [&](const Rec &ra, const Rec &rb, bool &above, bool &above_m) {
-    int d1 = 0, d2 = 0;
-    if (prune) {
-      if (!iou_may_exceed(ra, rb, thr_any)) { above = false; above_m = false; return; }
-      const Obb oa = obb_of(ra), ob = obb_of(rb);
-      if (use_approx && obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
-        const float ap = approx_iou(oa, ob);
-        ++st_approx;
-        d1 = decide_vs(ap, a.thr);
-        d2 = kWeighted ? decide_vs(ap, a.mthr) : 1;
-      }
-    }
-    if (d1 != 0 && d2 != 0) { above = d1 > 0; above_m = kWeighted && d2 > 0; return; }
+    if (prune && !iou_may_exceed(ra, rb, thr_any)) { above = false; above_m = false; return; }
     const float iou = pair_iou(ra, rb);
     ++st_iou;
     above = iou > a.thr;
     above_m = kWeighted && iou > a.mthr;
   };
 
-  // Two-stage evaluation of a queue of pairs, warp-converged: every lane classifies its pair with the
-  // approximate IoU; the few undecided pairs are compacted per warp (wbuf) so that the exact routine
-  // always runs on (nearly) full warps.  get(q, ra, rb) loads the pair, emit(q, above_thr, above_mthr)
-  // consumes the two comparisons.
+  // Evaluation of a queue of pairs, warp-converged: every lane tests its pair against the cheap upper bound; the
+  // pairs that may exceed a threshold are compacted per warp (wbuf) so that the bit-exact routine always runs on
+  // (nearly) full warps.  get(q, ra, rb) loads the pair, emit(q, above_thr, above_mthr) consumes the two comparisons
+  // (only called for pairs that reach the exact routine: a pair stopped by the bound is below both thresholds).
   auto eval_queue = [&](int qn, auto &&get, auto &&emit) {
     int nbuf = 0;   // warp-uniform
     auto exact32 = [&](int count) {
@@ -652,26 +623,19 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
     for (int q0 = wid * 32; q0 < qn_pad; q0 += kNmsThreads) {   // each warp owns 32 consecutive entries per pass
       __syncwarp();
       const int q = q0 + lane;
-      bool undecided = false;
+      bool pending = false;
       if (q < qn) {
-        Rec ra, rb;
-        get(q, ra, rb);
-        const Obb oa = obb_of(ra), ob = obb_of(rb);
-        int d1 = 0, d2 = 0;
-        if (prune && !iou_may_exceed(ra, rb, thr_any)) {
-          d1 = -1; d2 = -1;                       // even the upper bound stays below both thresholds
-        } else if (use_approx && obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
-          const float ap = approx_iou(oa, ob);
-          ++st_approx;
-          d1 = decide_vs(ap, a.thr);
-          d2 = kWeighted ? decide_vs(ap, a.mthr) : 1;
+        pending = true;
+        if (prune) {
+          Rec ra, rb;
+          get(q, ra, rb);
+          ++st_bound;
+          pending = iou_may_exceed(ra, rb, thr_any);
         }
-        if (d1 != 0 && d2 != 0) emit(q, d1 > 0, kWeighted && d2 > 0);
-        else undecided = true;
       }
-      const uint32_t m = __ballot_sync(0xffffffffu, undecided);
+      const uint32_t m = __ballot_sync(0xffffffffu, pending);
       if (m) {
-        if (undecided) wbuf[nbuf + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(q);
+        if (pending) wbuf[nbuf + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(q);
         nbuf += __popc(m);
         if (nbuf >= 32) {
           exact32(32);
@@ -685,10 +649,12 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
   };
 
   // ---- PULL: the candidates list[0, ns) (window indices, rank order) against the kept boxes [since, kept).
-  // One candidate per thread: count its circle hits, block scan, write the (candidate, kept) pairs to the queue
-  // at the scanned offsets, evaluate the queue on dense lanes.  A batch whose pairs do not fit the queue is cut at
-  // the last thread that fits (the hits are a prefix sum, so the threads that fit form a prefix of the batch).
+  // One candidate per thread: walk the grid once (the first kPullCache hits stay in registers), block scan of the hit
+  // counts, write the (candidate, kept) pairs to the queue at the scanned offsets, evaluate the queue on dense lanes.
+  // A batch whose pairs do not fit the queue is cut at the last thread that fits (the offsets are a prefix sum, so the
+  // threads that fit form a prefix of the batch).
   // merges_only: the scan is over (weighted, num_post_nms reached) -- candidates only contribute to merge sets.
+  constexpr int kPullCache = 4;
   auto pull = [&](const uint16_t *list, int ns, int since, bool merges_only) {
     if (since >= kept || ns <= 0) return;
     int bi = 0;
@@ -696,14 +662,16 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       const int t = bi + tid;
       const bool active = t < ns;
       int j = 0, pos = 0, cnt = 0;
+      int hk[kPullCache];
       float x = 0.f, y = 0.f, r = 0.f;
       if (active) {
         j = list[t];
         pos = static_cast<int>(wpos[j]);
         x = rec_cx(recs[pos]); y = rec_cy(recs[pos]); r = recs[pos].r;
-        for_each_near(x, y, r, since, [&](int, float kx, float ky, float kr) {
-          ++st_circle;
-          if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+        for_each_near(x, y, r, since, [&](int k) {
+#pragma unroll
+          for (int c = 0; c < kPullCache; ++c)
+            if (cnt == c) hk[c] = k;
           ++cnt;
         });
       }
@@ -714,41 +682,42 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       if (tid == 0) s_qn = 0;
       __syncthreads();
       if (m == 0) {
-        // the first candidate alone overflows the queue: thread 0 evaluates its pairs in place, in kept order
+        // the first candidate alone overflows the queue: thread 0 evaluates its pairs in place
         if (tid == 0) {
           const Rec rj = recs[pos];
           int fs = 0x7fffffff;
-          for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
-            if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
+          for_each_near(x, y, r, since, [&](int k) {
             if (!kWeighted && fs != 0x7fffffff) return;
             bool above, above_m;
-            classify_pair(recs[__float_as_int(kxyr[k].w)], rj, above, above_m);
+            classify_pair(recs[kept_position(k)], rj, above, above_m);
             if (above && k < fs) fs = k;
           });
           if (kWeighted) {
-            for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
+            for_each_near(x, y, r, since, [&](int k) {
               if (k > fs) return;
-              if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
               bool above, above_m;
-              classify_pair(recs[__float_as_int(kxyr[k].w)], rj, above, above_m);
+              classify_pair(recs[kept_position(k)], rj, above, above_m);
               if (above_m) accumulate(k, pos);
             });
           }
           if (fs != 0x7fffffff) { walive[j] = 0; ++st_hit; }
         }
-        m = 1;
         __syncthreads();
-        bi += m;
+        bi += 1;
         continue;
       }
       if (ok) {
         s_bj[tid] = static_cast<uint16_t>(j);
         if (kWeighted) wfs[j] = 0x7fffffff;
-        int w = off;
-        for_each_near(x, y, r, since, [&](int k, float kx, float ky, float kr) {
-          if (prune) { const float dx = kx - x, dy = ky - y, rr = kr + r; if (!(dx * dx + dy * dy <= rr * rr)) return; }
-          queue2[w++] = (static_cast<uint32_t>(tid) << 20) | static_cast<uint32_t>(k);
-        });
+        const uint32_t tag = static_cast<uint32_t>(tid) << 20;
+        if (cnt <= kPullCache) {
+#pragma unroll
+          for (int c = 0; c < kPullCache; ++c)
+            if (c < cnt) queue2[off + c] = tag | static_cast<uint32_t>(hk[c]);
+        } else {
+          int w = off;
+          for_each_near(x, y, r, since, [&](int k) { queue2[w++] = tag | static_cast<uint32_t>(k); });
+        }
         if (tid == m - 1) s_qn = off + cnt;   // ok threads are exactly tid < m
       }
       __syncthreads();
@@ -756,7 +725,7 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       const int qn = s_qn;
       auto get = [&](int q, Rec &ra, Rec &rb) {
         const uint32_t e = queue2[q];
-        ra = recs[__float_as_int(kxyr[e & 0xfffffu].w)];   // the kept box ranks higher: box1 of the routine
+        ra = recs[kept_position(static_cast<int>(e & 0xfffffu))];   // the kept box ranks higher: box1 of the routine
         rb = recs[wpos[s_bj[e >> 20]]];
       };
       if (!kWeighted) {
@@ -765,6 +734,8 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
         });
         __syncthreads();
       } else {
+        for (int q = tid; q < qn; q += kNmsThreads) qflag[q] = 0;
+        __syncthreads();
         // pass 1: the two comparisons of every queued pair; each candidate's FIRST suppressor
         eval_queue(qn, get, [&](int q, bool above, bool above_m) {
           qflag[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
@@ -827,15 +798,16 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
         break;
       }
       if (bin_cur >= a.nb) return 0;
-      const int base = s_bins[bin_cur];
-      int lo = bin_cur, hi = a.nb;           // largest b with s_bins[b] - base <= kWin (every thread, same result)
+      const int b0 = bin_cur;
+      const int base = s_bins[b0];
+      int lo = b0, hi = a.nb;                // largest b with s_bins[b] - base <= kWin (every thread, same result)
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (s_bins[mid] - base <= kWin) lo = mid; else hi = mid - 1;
       }
-      if (lo == bin_cur) {
+      if (lo == b0) {
         // this bin alone exceeds a window (massively tied / saturated scores): sort it once through global memory
-        const int m = s_bins[bin_cur + 1] - base;
+        const int m = s_bins[b0 + 1] - base;
         for (int t = tid; t < m; t += kNmsThreads) gorder[base + t] = static_cast<uint32_t>(base + t);
         __syncthreads();
         cta_bitonic_sort(skey + base, gorder + base, m);
@@ -849,10 +821,31 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       // the order inside the window only matters when candidates are consumed in rank order (need_order) or the
       // num_pre_nms cut falls inside it
       if (need_order || rank_base + wn > n_use) {
-        for (int t = tid; t < wn; t += kNmsThreads) { wkey[t] = skey[base + t]; widx[t] = static_cast<uint16_t>(t); }
-        __syncthreads();
-        cta_bitonic_sort(wkey, widx, wn);
-        for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(base + widx[t]);
+        for (int t = tid; t < wn; t += kNmsThreads) wkey[t] = skey[base + t];
+        // The bins are already in rank order: only the order INSIDE each bin is missing.  Small bins (the rule): every
+        // element counts the smaller keys of its own bin and goes straight to its place -- no dependent exchanges.
+        // A bin above kRankSortMax sends the whole window to the bitonic network instead.
+        bool big = false;
+        for (int b = b0 + tid; b < lo; b += kNmsThreads) big |= (s_bins[b + 1] - s_bins[b]) > kRankSortMax;
+        if (!__syncthreads_or(big)) {
+          for (int t = tid; t < wn; t += kNmsThreads) {
+            int bl = b0, bh = lo - 1;        // the bin of element t: largest b with s_bins[b] - base <= t
+            while (bl < bh) {
+              const int mid = (bl + bh + 1) >> 1;
+              if (s_bins[mid] - base <= t) bl = mid; else bh = mid - 1;
+            }
+            const int e0 = s_bins[bl] - base, e1 = s_bins[bl + 1] - base;
+            const unsigned long long mine = wkey[t];
+            int rank = 0;
+            for (int e = e0; e < e1; ++e) rank += wkey[e] < mine ? 1 : 0;
+            wpos[e0 + rank] = static_cast<uint32_t>(base + t);
+          }
+        } else {
+          for (int t = tid; t < wn; t += kNmsThreads) widx[t] = static_cast<uint16_t>(t);
+          __syncthreads();
+          cta_bitonic_sort(wkey, widx, wn);
+          for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(base + widx[t]);
+        }
       } else {
         for (int t = tid; t < wn; t += kNmsThreads) wpos[t] = static_cast<uint32_t>(base + t);
       }
@@ -866,7 +859,7 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
     const int wn = next_window(true);
     if (wn <= 0) break;
     if (!geom_set) {
-      // cell size of the kept-box grid from the padded radii of the first (top-scored) window
+      // cell size of the grids from the padded radii of the first (top-scored) window
       float sr = 0.f, sc = 0.f;
       for (int t = tid; t < wn; t += kNmsThreads) {
         const float r = recs[wpos[t]].r;
@@ -879,8 +872,8 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
         float tr = 0.f, tc = 0.f;
         for (int w = 0; w < kNmsWarps; ++w) { tr += s_red[w]; tc += s_red[kNmsWarps + w]; }
         const float mr = tc > 0.f ? tr / tc : 1.f;
-        s_cell[1] = 2.0f * mr;                                             // r_cap: larger kept boxes go to the oversize list
-        s_cell[0] = 1.0f / fminf(fmaxf(3.0f * mr, 1e-3f), 1.0e5f);         // cell = mean radius + r_cap: a typical query spans 3 x 3 cells
+        s_cell[1] = 3.0f * mr;                                             // r_cap: larger boxes go to the oversize lists
+        s_cell[0] = 1.0f / fminf(fmaxf(4.0f * mr, 1e-3f), 1.0e5f);         // cell = mean radius + r_cap: a typical query spans 3 x 3 cells
       }
       __syncthreads();
       inv_cell = s_cell[0]; r_cap = s_cell[1];
@@ -902,86 +895,90 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       }
       if (ns == 0) break;
       ++rounds;
-      // ================= b. frontier = the first nf survivors; all pairs inside it =================
+      // ================= b. frontier = the first nf survivors; interacting pairs inside it =================
       const int nf = min(kF, ns);
-      if (tid < nf) {
-        const int j = list[tid];
-        const Rec r = recs[wpos[j]];
-        frec[tid] = r;
-        fx[tid] = rec_cx(r); fy[tid] = rec_cy(r); fr[tid] = r.r;
-        front_w[tid] = static_cast<uint16_t>(j);
-        keptrank[tid] = -1;
-      }
+      for (int i = tid; i < kFrontBuckets; i += kNmsThreads) fheads[i] = -1;
       for (int i = tid; i < nf * kFW; i += kNmsThreads) {
         sup[i] = 0u;
         if (kWeighted) mrg[i] = 0u;
       }
       if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
-      if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
+      if (tid == 0) { s_qn = 0; s_nfos = 0; }
+      float mx = 0.f, my = 0.f, mrad = 0.f;
+      if (tid < nf) {
+        const int j = list[tid];
+        const Rec r = recs[wpos[j]];
+        frec[tid] = r;
+        mx = rec_cx(r); my = rec_cy(r); mrad = r.r;
+        front_w[tid] = static_cast<uint16_t>(j);
+        keptrank[tid] = -1;
+      }
+      __syncthreads();
+      // frontier grid: same cells as the kept grid, chains of frontier slots
+      if (tid < nf) {
+        int next = -1;
+        if (prune) {
+          if (in_grid(mx, my, mrad)) next = atomicExch(&fheads[bucket_of(cell_of(mx), cell_of(my)) & (kFrontBuckets - 1)], tid);
+          else fos[atomicAdd(&s_nfos, 1)] = static_cast<uint16_t>(tid);
+        }
+        fq[tid] = make_float4(mx, my, mrad, __int_as_float(next));
+      }
       __syncthreads();
       {
         auto mark = [&](int i, int j, bool above, bool above_m) {
           if (above) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
           if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
         };
-        // Rows of the upper-triangular pair matrix are dealt round-robin to the warps (row i costs nf - i tests):
-        // warp per row, lanes over the columns j > i, circle test -> work queue.  One queue reservation per ROW:
-        // lane b keeps the hit mask of the row's b-th 32-column batch, the warp reserves the row's total once.  A
-        // row that does not fit waits for the next drain: reservations are handed out in order, so everything
-        // before the first refused one (s_qvalid) is written and everything after it is refused too.
-        int i = wid;
-        for (;;) {
-          while (i < nf - 1) {
-            const float xi = fx[i], yi = fy[i], ri = fr[i];
-            uint32_t mymask = 0;
-            for (int jb = i + 1, b = 0; jb < nf; jb += 32, ++b) {
-              const int j = jb + lane;
-              bool hit = false;
-              if (j < nf) {
+        // thread i collects the frontier boxes j > i whose circles touch its own: the cells around it, plus the
+        // frontier's oversize list; (i, j) goes to the work queue (in place if the queue is full: marking is
+        // order-independent)
+        if (tid < nf) {
+          const int i = tid;
+          auto offer = [&](int j) {
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < kQ2Cap) { queue2[slot] = static_cast<uint32_t>((i << 10) | j); return; }
+            bool above, above_m;
+            classify_pair(frec[i], frec[j], above, above_m);
+            mark(i, j, above, above_m);
+          };
+          int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
+          bool skip;
+          if (!query_cells(mx, my, mrad, ix0, ix1, iy0, iy1, skip)) {
+            if (!skip)
+              for (int j = i + 1; j < nf; ++j) {
+                const float4 q = fq[j];
                 ++st_circle;
-                hit = true;
-                if (prune) {
-                  const float dx = xi - fx[j], dy = yi - fy[j], rr = ri + fr[j];
-                  hit = dx * dx + dy * dy <= rr * rr;   // the IoU bound runs later, on dense lanes (eval_queue)
+                if (!prune || touches(mx, my, mrad, q.x, q.y, q.z)) offer(j);
+              }
+          } else {
+            for (int iy = iy0; iy <= iy1; ++iy)
+              for (int ix = ix0; ix <= ix1; ++ix) {
+                int j = fheads[bucket_of(ix, iy) & (kFrontBuckets - 1)];
+                while (j >= 0) {
+                  const float4 q = fq[j];
+                  ++st_circle;
+                  if (j > i && touches(mx, my, mrad, q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) offer(j);
+                  j = __float_as_int(q.w);
                 }
               }
-              const uint32_t m = __ballot_sync(0xffffffffu, hit);
-              if (lane == b) mymask = m;
-            }
-            const int mine = __popc(mymask);
-            int incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-              const int v = __shfl_up_sync(0xffffffffu, incl, d);
-              if (lane >= d) incl += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total) {
-              int base = 0;
-              if (lane == 0) base = atomicAdd(&s_qn, total);
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (base + total > kQ2Cap) {
-                if (lane == 0) atomicMin(&s_qvalid, base);
-                break;   // this row is redone after the drain
+            const int nfos = s_nfos;
+            for (int o = 0; o < nfos; ++o) {
+              const int j = fos[o];
+              if (j > i) {
+                const float4 q = fq[j];
+                ++st_circle;
+                if (touches(mx, my, mrad, q.x, q.y, q.z)) offer(j);
               }
-              int slot = base + incl - mine;
-              const int j0 = i + 1 + 32 * lane;
-              for (uint32_t m = mymask; m; m &= m - 1)
-                queue2[slot++] = static_cast<uint32_t>((i << 10) | (j0 + __ffs(m) - 1));
             }
-            i += kNmsWarps;
           }
-          const int more = __syncthreads_or(i < nf - 1);
-          eval_queue(min(s_qn, s_qvalid),
-                     [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
-                     [&](int q, bool above, bool above_m) {
-                       mark(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
-                     });
-          __syncthreads();
-          if (!more) break;
-          if (tid == 0) { s_qn = 0; s_qvalid = kQ2Cap; }
-          __syncthreads();
         }
+        __syncthreads();
+        eval_queue(min(s_qn, kQ2Cap),
+                   [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
+                   [&](int q, bool above, bool above_m) {
+                     mark(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
+                   });
+        __syncthreads();
       }
       lap(3);
       // ================= greedy resolution of the frontier =================
@@ -1063,10 +1060,16 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
         const int pos = static_cast<int>(wpos[front_w[fi]]);
         const int k = kept + tid;
         kept_pos[k] = pos;
-        const float x = fx[fi], y = fy[fi], r = fr[fi];
-        kxyr[k] = make_float4(x, y, r, __int_as_float(pos));
-        if (in_grid(x, y, r)) knext[k] = atomicExch(&heads[bucket_of(cell_of(x), cell_of(y))], k);
+        const float4 q = fq[fi];
+        int next = -1;
+        if (in_grid(q.x, q.y, q.z)) next = atomicExch(&heads[bucket_of(cell_of(q.x), cell_of(q.y)) & bmask], k);
         else kos[atomicAdd(&s_nos, 1)] = k;
+        if (kSm) {
+          kxyr[k] = make_float4(q.x, q.y, q.z, __uint_as_float((static_cast<uint32_t>(next + 1) << 20) | static_cast<uint32_t>(pos)));
+        } else {
+          kxyr[k] = make_float4(q.x, q.y, q.z, __int_as_float(pos));
+          knext[k] = next;
+        }
       }
       if (kWeighted) {
         // merge sets inside the frontier: candidate j joins every kept i < j with iou > merge_thr that comes no
@@ -1139,13 +1142,13 @@ nms_pull_kernel(NmsArgs a, int kept_in_smem) {
       st_iou += __shfl_xor_sync(0xffffffffu, st_iou, o);
       st_circle += __shfl_xor_sync(0xffffffffu, st_circle, o);
       st_hit += __shfl_xor_sync(0xffffffffu, st_hit, o);
-      st_approx += __shfl_xor_sync(0xffffffffu, st_approx, o);
+      st_bound += __shfl_xor_sync(0xffffffffu, st_bound, o);
     }
     if (lane == 0) {
       atomicAdd(a.stats + 0, st_iou);
       atomicAdd(a.stats + 3, st_circle);
       atomicAdd(a.stats + 18, st_hit);
-      atomicAdd(a.stats + 19, st_approx);
+      atomicAdd(a.stats + 19, st_bound);
     }
     if (tid == 0) {
       atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept));
@@ -1472,16 +1475,20 @@ static int stride_grid(int cap) {
   return want < most ? want : most;
 }
 
-template <typename Rec, bool kWeighted>
-static int launch_nms_segments(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s) {
+template <typename Rec, bool kWeighted, bool kSm>
+static int launch_nms_kernel(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s) {
   constexpr int kF = Frontier<kWeighted>::kF;
-  const size_t smem = nms_smem_bytes<Rec, kWeighted, kF>(pl.kept_in_smem);
+  const size_t smem = nms_smem_bytes<Rec, kWeighted, kF>(kSm);
   if (smem > 220 * 1024) return RV3D_ERR_ARG;
-  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_pull_kernel<Rec, kWeighted, kF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(nms_smem_bytes<Rec, kWeighted, kF>(true))));
-  nms_pull_kernel<Rec, kWeighted, kF><<<pl.S, kNmsThreads, smem, s>>>(a, pl.kept_in_smem ? 1 : 0);
+  RV3D_CHECK_CUDA(cudaFuncSetAttribute(nms_pull_kernel<Rec, kWeighted, kF, kSm>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  nms_pull_kernel<Rec, kWeighted, kF, kSm><<<pl.S, kNmsThreads, smem, s>>>(a);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
+}
+template <typename Rec, bool kWeighted>
+static int launch_nms_segments(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s) {
+  return pl.kept_in_smem ? launch_nms_kernel<Rec, kWeighted, true>(a, pl, s) : launch_nms_kernel<Rec, kWeighted, false>(a, pl, s);
 }
 
 // hist -> bin_scan -> (caller's scatter) : shared front of every sorted entry point
@@ -1521,7 +1528,7 @@ static NmsArgs base_args(const NmsPlan &pl, const NmsLayout &L, int num_pre, int
   a.bin_start = L.bin_start; a.nb = pl.nb; a.presorted = 0;
   a.num_pre = num_pre; a.num_post = num_post; a.thr = thr; a.mthr = mthr;
   a.prune = (thr >= 0.f && (!weighted || mthr >= 0.f)) ? 1 : 0;
-  a.exact_only = (flags & RV3D_NMS_EXACT_ONLY) ? 1 : 0;
+  (void)flags;
   a.kept_stride = pl.kept_stride; a.kept_pos = L.kept_pos; a.kept_count = L.kept_count;
   a.kxyr_g = L.kxyr_g; a.knext_g = L.knext_g; a.heads_g = L.heads_g; a.n_buckets_g = pl.n_buckets_g; a.kos = L.kos;
   a.data = L.data; a.D = pl.D; a.acc = L.acc; a.merge_count = L.merge_count;
@@ -1735,21 +1742,17 @@ box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__re
   out[t] = rot_iou(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 1.0), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 1.0));
 }
 
-// The approximate-vs-exact decision of the NMS kernels, exposed for tests/test_gpu_iou_decisions.py:
-// boxes (N,5) f32 (xc, yc, w, h, angle in degrees, detectron2 convention), aligned pairs.
-// decision[i]: 2 = skipped by the upper bound (certainly <= thr), +1 / -1 = decided by the approximate IoU
-// (above / not above), 0 = sent to the exact routine;  approx[i] / exact[i]: the two IoU values.
+// The pruning decision of the NMS kernels, exposed for tests/test_gpu_iou_decisions.py: aligned pairs.
+// decision[i]: 2 = stopped by the upper bound (the kernels treat the pair as "not above the threshold" without running
+// the exact routine), 0 = sent to the exact routine;  bound[i]: the upper bound on the IoU the kernels compare with the
+// threshold (NaN when it is not trusted);  exact[i]: the bit-exact routine's value.
 template <typename Rec>
-__device__ __forceinline__ void decide_pair(const Rec &ra, const Rec &rb, float thr, int8_t &decision, float &ap, float &ex) {
+__device__ __forceinline__ void decide_pair(const Rec &ra, const Rec &rb, float thr, int8_t &decision, float &bound, float &ex) {
   const Obb oa = obb_of(ra), ob = obb_of(rb);
-  int d = 0;
-  ap = CUDART_NAN_F;
-  if (!iou_may_exceed(ra, rb, thr)) d = 2;
-  else if (obb_sane(oa) && obb_sane(ob) && fabsf(oa.x - ob.x) <= 1.0e4f && fabsf(oa.y - ob.y) <= 1.0e4f) {
-    ap = approx_iou(oa, ob);
-    d = decide_vs(ap, thr);
-  }
-  decision = static_cast<int8_t>(d);
+  const float inter = fminf(overlap_in_frame(oa, ob), overlap_in_frame(ob, oa));
+  const float uni = fabsf(oa.w * oa.h) + fabsf(ob.w * ob.h) - inter;
+  bound = (!(uni > 0.f) || !(inter == inter)) ? CUDART_NAN_F : (inter / uni) * 1.02f + 1e-5f;
+  decision = static_cast<int8_t>(iou_may_exceed(ra, rb, thr) ? 0 : 2);
   ex = pair_iou(ra, rb);
 }
 

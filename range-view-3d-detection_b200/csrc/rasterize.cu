@@ -19,6 +19,7 @@
 // K1  (scatter): 1 thread / point, float4 load, fp64 index math, atomicMin.u64 (REDG).
 // K1b (resolve): 1 thread / pixel, reads the key, gathers the winning point, recomputes its
 //                spherical coordinates and writes the 7 channel planes coalesced.
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -53,13 +54,30 @@ __device__ __forceinline__ double column_of(double az, const RasterArgs &a) {
   return fmin(fmax(c, 0.0), nb - 1.0);  // np.clip(col, 0, W-1)
 }
 
-// sqrt(x^2 + y^2 (+ z^2)) in fp64.  The coordinates come from float32 storage (|v| < 3.4e38), so the
-// squares can neither overflow nor lose range in fp64 and the scaling that makes libm's hypot expensive
-// (~100 instructions) is unnecessary.  The result is within ~1 ulp(fp64) of numpy's
-// hypot(hypot(x, y), z); after the single cast to float32 the two agree except on a 2^-28 fraction of
-// values (the same order as the difference between two libms), which the tests allow for (1 f32 ulp).
+// Radius of a point, bit-compatible with the reference where it matters.  The reference computes
+// r = hypot(hypot(x, y), z) with numpy / libm (numpy/conversions.py:61-62); the z-buffer then only looks at
+// float32(r), at the comparison r < float32(r) (the class bit of pack_key) and at r < min_distance.  The fast form
+// sqrt(x^2 + y^2), sqrt(hxy^2 + z^2) is within a few fp64 ulps of libm's value, so those three outcomes can only
+// differ when r lies within a few ulps of a float32 value, of a midpoint between two float32 values, or of
+// min_distance.  Exactly then (about 1e-6 of the points) the radius is recomputed with the restatement of libm's hypot
+// (fastmath.cuh libm_hypot): pixel assignment and the range channel are bit-exact by construction, not with
+// probability 1 - 2^-28.
 __device__ __forceinline__ double norm2d(double x, double y) { return sqrt(x * x + y * y); }
-__device__ __forceinline__ double norm_hz(double hxy, double z) { return sqrt(hxy * hxy + z * z); }
+__device__ __forceinline__ bool near_f32_decision(double r, double min_distance) {
+  const float m = __double2float_rn(r);
+  const double md = static_cast<double>(m);
+  const double up = static_cast<double>(__uint_as_float(__float_as_uint(m) + 1u));   // m > 0, finite
+  const double dn = static_cast<double>(__uint_as_float(__float_as_uint(m) - 1u));
+  const double tol = r * 4.0e-15;                                                     // ~18 fp64 ulps
+  return fabs(r - md) <= tol || fabs(r - 0.5 * (md + up)) <= tol || fabs(r - 0.5 * (md + dn)) <= tol ||
+         fabs(r - min_distance) <= tol;
+}
+// one fp64 sqrt in the common case: sqrt(x^2 + y^2 + z^2) is within ~4 fp64 ulps of hypot(hypot(x, y), z)
+__device__ __forceinline__ double radius_of(double cx, double cy, double cz, double min_distance) {
+  double r = sqrt((cx * cx + cy * cy) + cz * cz);
+  if (r > 0.0 && r < 3.0e38 && near_f32_decision(r, min_distance)) r = libm_hypot(libm_hypot(cx, cy), cz);
+  return r;
+}
 
 // Column of a point without the fp64 atan2 in the common case: float32 atan2f of the (rounded) offsets
 // is within 1e-6 rad of the fp64 azimuth (2 ulp of atan2f at |az| <= pi = 4.8e-7, plus 0.6e-7 from
@@ -93,8 +111,7 @@ __device__ __forceinline__ void scatter_point(const RasterArgs &a, int b, int i,
   const double cx = static_cast<double>(p.x) - a.ox;  // range_view.py:29
   const double cy = static_cast<double>(p.y) - a.oy;
   const double cz = static_cast<double>(p.z) - a.oz;
-  const double hxy = norm2d(cx, cy);
-  const double r = norm_hz(hxy, cz);
+  const double r = radius_of(cx, cy, cz, a.min_distance);
   // z_buffer: `d < min_distance -> continue`, then `d < buffer` with buffer starting at +inf;
   // NaN and +inf never write.
   if (!(r >= a.min_distance) || !(r < CUDART_INF)) return;
@@ -143,11 +160,12 @@ __device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned 
     const double cx = static_cast<double>(p.x) - a.ox;
     const double cy = static_cast<double>(p.y) - a.oy;
     const double cz = static_cast<double>(p.z) - a.oz;
-    const double hxy = norm2d(cx, cy);
+    const double hxy = norm2d(cx, cy);                // planar radius: inclination channel only (1-ulp bar)
+    const double r = radius_of(cx, cy, cz, a.min_distance);
     // features are snapshotted BEFORE the in-place azimuth rescale (range_view.py:33, H3)
     o.az = static_cast<float>(fast_atan2(cy, cx));    // fastmath.cuh: <= 1 ulp of fp64 before the cast
     o.inc = static_cast<float>(fast_atan2(cz, hxy));
-    o.rr = static_cast<float>(norm_hz(hxy, cz));
+    o.rr = static_cast<float>(r);                     // bit-exact with the reference's float32(hypot(hypot(x, y), z))
     o.x = p.x; o.y = p.y; o.z = p.z; o.it = p.w;
   }
   return o;
@@ -214,10 +232,10 @@ __global__ void cart_to_sph_kernel(const double *__restrict__ cart, double *__re
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double x = cart[3 * i], y = cart[3 * i + 1], z = cart[3 * i + 2];
-  const double hxy = hypot(x, y);
+  const double hxy = libm_hypot(x, y);   // bit-compatible with numpy.hypot (fastmath.cuh)
   sph[3 * i] = atan2(y, x);
   sph[3 * i + 1] = atan2(z, hxy);
-  sph[3 * i + 2] = hypot(hxy, z);
+  sph[3 * i + 2] = libm_hypot(hxy, z);
 }
 
 __global__ void rv_coordinates_kernel(double *__restrict__ sph, const int64_t *__restrict__ laser,
@@ -344,16 +362,39 @@ extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, 
   const size_t need = rv3d_rasterize_scratch_bytes(p);
   if (scratch_bytes < need) return RV3D_ERR_SCRATCH;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const RasterArgs a = make_args(p);
+  RasterArgs a = make_args(p);
   auto *keys = static_cast<unsigned long long *>(scratch);
-  RV3D_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, need, s));
-  dim3 g1(ceil_div(p->max_points, 256 * kScatterPerThread), p->batch);
-  raster_scatter_kernel<<<g1, 256, 0, s>>>(a, reinterpret_cast<const float4 *>(points), laser, n_points,
-                                           laser_mapping, keys);
-  RV3D_CHECK_LAUNCH();
-  dim3 g2(ceil_div(static_cast<int64_t>(p->height) * p->width, 256), p->batch);
-  raster_resolve_kernel<<<g2, 256, 0, s>>>(a, reinterpret_cast<const float4 *>(points), keys, image, winner);
-  RV3D_CHECK_LAUNCH();
+  // The batch is processed in chunks of sweeps whose points + keys fit the L2 comfortably (B200: 126 MB in two
+  // halves): the keys a chunk's scatter writes and the points it streams are still resident when its resolve pass
+  // reads the keys back and gathers the winning points, instead of coming from DRAM a second time.
+  const int64_t HW = static_cast<int64_t>(p->height) * p->width;
+  const int64_t per_sweep = static_cast<int64_t>(p->max_points) * 17 + HW * 8;
+  int64_t budget = int64_t(36) << 20;
+  if (const char *e = getenv("RV3D_RASTER_CHUNK_MB")) {   // experiments only; 0 = one chunk
+    const long v = atol(e);
+    budget = v > 0 ? (int64_t(v) << 20) : (int64_t(1) << 62);
+  }
+  int chunk = static_cast<int>(budget / (per_sweep > 0 ? per_sweep : 1));
+  if (chunk < 1) chunk = 1;
+  if (chunk > p->batch) chunk = p->batch;
+  // equal-sized chunks (16 sweeps, room for 8 -> 8 + 8, not 8 + 8 + 0; 20 sweeps, room for 8 -> 7 + 7 + 6)
+  const int n_chunks = (p->batch + chunk - 1) / chunk;
+  chunk = (p->batch + n_chunks - 1) / n_chunks;
+  for (int b0 = 0; b0 < p->batch; b0 += chunk) {
+    const int nb = p->batch - b0 < chunk ? p->batch - b0 : chunk;
+    a.B = nb;
+    unsigned long long *k = keys + static_cast<size_t>(b0) * HW;
+    const float4 *pts = reinterpret_cast<const float4 *>(points) + static_cast<size_t>(b0) * p->max_points;
+    RV3D_CHECK_CUDA(cudaMemsetAsync(k, 0xFF, static_cast<size_t>(nb) * HW * sizeof(unsigned long long), s));
+    dim3 g1(ceil_div(p->max_points, 256 * kScatterPerThread), nb);
+    raster_scatter_kernel<<<g1, 256, 0, s>>>(a, pts, laser + static_cast<size_t>(b0) * p->max_points, n_points + b0,
+                                             laser_mapping, k);
+    RV3D_CHECK_LAUNCH();
+    dim3 g2(ceil_div(HW, 256), nb);
+    raster_resolve_kernel<<<g2, 256, 0, s>>>(a, pts, k, image + static_cast<size_t>(b0) * 7 * HW,
+                                             winner ? winner + static_cast<size_t>(b0) * HW : nullptr);
+    RV3D_CHECK_LAUNCH();
+  }
   return RV3D_OK;
 }
 

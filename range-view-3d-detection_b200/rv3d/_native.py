@@ -17,7 +17,6 @@ COL_LIBRARY, COL_CONVERTER, COL_CONVERTER_UNIFORM = 0, 1, 2
 SCORE_BITS_DECODE = 31   # include/rv3d.h RV3D_SCORE_BITS_DECODE
 F32, F16, BF16 = 0, 1, 2
 NMS_HARD, NMS_WEIGHTED = 0, 1
-NMS_EXACT_ONLY = 1
 OUT_QUAT, OUT_YAW = 0, 1
 
 

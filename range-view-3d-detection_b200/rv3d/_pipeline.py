@@ -162,7 +162,7 @@ def _host_count_slot() -> torch.Tensor:
 def run_nms(ws: Workspace, cand: Candidates, num_pre_nms: int, num_post_nms: int, iou_threshold: float,
             mode: str, layout: int, merge_threshold: float = 0.5, stats: Optional[torch.Tensor] = None,
             peer=None, peer_slot: int = 0, sweep_offset: int = 0, peer_seq: int = 0,
-            score_range: Tuple[float, float] = (0.0, 0.0), exact_only: bool = False) -> Detections:
+            score_range: Tuple[float, float] = (0.0, 0.0)) -> Detections:
     """Enqueue score bucketing + NMS + pack on the current stream -> ``Detections`` (lazy; no host read, no sync: the
     candidate count is read on the device from ``cand.counter``).
     ``peer`` (rv3d.distributed.PeerGather): also store the detections into every rank's gather buffer from inside the
@@ -184,7 +184,7 @@ def run_nms(ws: Workspace, cand: Candidates, num_pre_nms: int, num_post_nms: int
     out_count = buf[cap * (width + 3):].view(torch.int32)
     host_count = _host_count_slot()
     pkey = (cand.batch, cand.total_classes, cand.total_candidates, capacity, int(num_pre_nms), int(num_post_nms), mode,
-            float(iou_threshold), float(merge_threshold), layout, cand.score_bits, tuple(score_range), bool(exact_only))
+            float(iou_threshold), float(merge_threshold), layout, cand.score_bits, tuple(score_range))
     p = _NMS_PARAMS.get(pkey)
     if p is None:
         p = N.NmsParams()
@@ -197,7 +197,7 @@ def run_nms(ws: Workspace, cand: Candidates, num_pre_nms: int, num_post_nms: int
         p.capacity, p.out_capacity = capacity, cap
         p.out_layout, p.score_bits = layout, cand.score_bits
         p.score_lo, p.score_hi = float(score_range[0]), float(score_range[1])
-        p.flags = N.NMS_EXACT_ONLY if exact_only else 0
+        p.flags = 0
         p.scratch_bytes = N.lib().rv3d_nms_scratch_bytes(p)
         if len(_NMS_PARAMS) > 64:
             _NMS_PARAMS.clear()

@@ -142,7 +142,7 @@ class RangeDecoder:
                            peer_seq=gather[3] if len(gather) > 3 else 0)
         return run_nms(self._ws, cand, post_processing_config["num_pre_nms"], post_processing_config["num_post_nms"],
                        post_processing_config["nms_threshold"], mode, N.OUT_QUAT, stats=stats, score_range=score_range,
-                       exact_only=bool(kwargs.get("exact_only", False)), **peer_kw)
+                       **peer_kw)
 
     def decode(self, multiscale_outputs: Dict[Union[int, str], Dict[Any, Any]],
                post_processing_config: Mapping[str, Any], task_config: Mapping[Any, Sequence[str]],
@@ -158,13 +158,11 @@ class RangeDecoder:
 
         Multi-GPU extra (not in the reference): ``gather=(PeerGather, slot, sweep_offset)``, see ``decode_async``."""
         gather = kwargs.pop("gather", None)
-        exact_only = bool(kwargs.pop("exact_only", False))
         del kwargs                                                         # tools/benchmark.py passes data=
         first = next(iter(multiscale_outputs.values()))
         dt = first[next(iter(task_config.keys()))]["logits"].dtype
         if use_nms:
-            return self.decode_async(multiscale_outputs, post_processing_config, task_config, gather=gather,
-                                     exact_only=exact_only).result(dt)
+            return self.decode_async(multiscale_outputs, post_processing_config, task_config, gather=gather).result(dt)
         if gather is not None:
             raise ValueError("gather= needs use_nms=True (the fused gather lives in the NMS pack kernel)")
         cand = self.candidates(multiscale_outputs, post_processing_config, task_config)

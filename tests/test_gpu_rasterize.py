@@ -1,6 +1,7 @@
 """CUDA rasterizer (through the C ABI) vs the golden vectors minted from the verbatim reference
-and vs the CPU oracle on seeded inputs.  Bar: winner map and x/y/z/intensity channels bit-exact;
-az / inc / range channels within 1 float32 ulp (device libm vs host libm in fp64, then one cast)."""
+and vs the CPU oracle on seeded inputs.  Bar: winner map, x/y/z/intensity AND range channels bit-exact (the radius
+is libm's hypot restated wherever a last bit could matter); az / inc within 1 float32 ulp (device atan2 vs host libm
+in fp64, then one cast)."""
 import numpy as np
 import pytest
 import torch
@@ -35,8 +36,10 @@ def _check_image(img, ref):
     assert img.shape == ref.shape and img.dtype == np.float32
     # x, y, z, intensity: copies of the winning point -> the pixel assignment is bit-exact
     assert np.array_equal(img[3:].view(np.uint32), ref[3:].view(np.uint32))
-    d = _ulp_diff(img[:3], ref[:3])
-    assert d.max() <= 1, f"az/inc/range differ by {d.max()} ulp"
+    assert np.array_equal(img[2].view(np.uint32), ref[2].view(np.uint32)), \
+        f"range channel: {(img[2] != ref[2]).sum()} pixels differ"
+    d = _ulp_diff(img[:2], ref[:2])
+    assert d.max() <= 1, f"az/inc differ by {d.max()} ulp"
     return int((d > 0).sum())
 
 
@@ -59,6 +62,55 @@ def test_full_size_vs_oracle(shape, seed):
     img, win = _run(xyz, inten, laser, mapping, synth.LIDAR_OFFSET, H, W)
     assert np.array_equal(win, ref_win)          # bit-exact pixel assignment
     _check_image(img, ref_img)
+
+
+def test_zbuffer_f32_distances_golden():
+    """The all-float32 flavour (float32 offset -> float32 distances and features, numpy/conversions.py:118-127 with a
+    float32 `distances`): rv3d_zbuffer's float32 path against the golden image minted from the verbatim reference."""
+    from rv3d.math.numpy.conversions import z_buffer
+    g = np.load(GOLDEN / "raster_f32.npz")
+    H, W = int(g["H"]), int(g["W"])
+    xyz, off = g["xyz"], g["offset"]
+    assert off.dtype == np.float32
+    cart = xyz - off                                                       # float32 arithmetic, like the reference
+    sph = oracle.cart_to_sph(cart)
+    assert sph.dtype == np.float32
+    feats = np.concatenate([sph, xyz, g["intensity"].reshape(-1, 1)], axis=1).T.copy()
+    hyb = oracle.build_range_view_coordinates(cart, sph, g["laser"].astype(np.int64), g["mapping"], H, W)
+    idx = np.ascontiguousarray(hyb[:, :2].T.astype(int))
+    dist = np.ascontiguousarray(hyb[:, 2])
+    assert dist.dtype == np.float32 and feats.dtype == np.float32
+    img, win = z_buffer(idx, dist, feats, H, W, return_winner=True)
+    ref_img, ref_win = oracle.z_buffer(idx, dist, feats, H, W, return_winner=True)
+    assert np.array_equal(np.asarray(win), ref_win)
+    assert np.array_equal(np.asarray(img).view(np.uint32), g["image"].view(np.uint32))
+
+
+def test_radius_decision_points_are_exact():
+    """Radii engineered to sit within a few fp64 ulps of a float32 value / of a midpoint between two float32 values /
+    of min_distance: there sqrt(x^2 + y^2 + z^2) and the reference's hypot(hypot(x, y), z) round differently, and the
+    winner (class bit of the z-buffer key), the range channel and the min_distance cut depend on the last bit."""
+    rng = np.random.default_rng(11)
+    off = np.array([1.356, 0.0, 1.726])
+    n = 400_000
+    # many points per pixel with nearly equal radii: one laser row, a few columns
+    az = rng.uniform(0.30, 0.31, n)
+    r = np.float32(rng.uniform(1.0, 60.0, n))
+    r[: n // 4] = np.float32(1.0) + np.float32(rng.integers(-3, 4, n // 4)) * np.spacing(np.float32(1.0))
+    xyz = np.stack([r * np.cos(az), r * np.sin(az), 0.05 * r], 1) + off
+    xyz = xyz.astype(np.float32)
+    inten = rng.random(n).astype(np.float32)
+    laser = np.zeros(n, np.uint8)
+    ref_img, ref_win = oracle.build_range_view(xyz, inten, laser, np.arange(4), off, num_lasers=4, width=1800,
+                                               n_azimuth_bins=1800, return_winner=True)
+    img, win = _run(xyz, inten, laser, np.arange(4), off, 4, 1800)
+    assert np.array_equal(win, ref_win)
+    _check_image(img, ref_img)
+    # the sweep really contains decision points where the two radius formulas differ after the float32 cast
+    c = xyz.astype(np.float64) - off
+    fast = np.sqrt(np.sqrt(c[:, 0] ** 2 + c[:, 1] ** 2) ** 2 + c[:, 2] ** 2)
+    ref = np.hypot(np.hypot(c[:, 0], c[:, 1]), c[:, 2])
+    assert (fast != ref).mean() > 0.05
 
 
 def test_h2_order_dependence():

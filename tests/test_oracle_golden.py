@@ -100,3 +100,21 @@ def test_subsample_range_view_matches_reference():
         assert np.array_equal(f.numpy(), g[f"{ds}_{stride}_{mode}_f"])
         assert np.array_equal(m.numpy(), g[f"{ds}_{stride}_{mode}_m"])
         assert np.array_equal(c.numpy(), g[f"{ds}_{stride}_{mode}_c"])
+
+
+def test_libm_hypot_restatement():
+    """The restatement of glibc's hypot the CUDA rasterizer uses near float32 decision points == numpy.hypot, bit for
+    bit, on the value ranges the path meets (differences of float32 coordinates and float64 sensor offsets), including
+    the exits for y == 0 and |y| << |x|."""
+    from oracle.libm_hypot import libm_hypot
+    rng = np.random.default_rng(5)
+    n = 2_000_000
+    x = rng.uniform(-250, 250, n).astype(np.float32).astype(np.float64) - 1.356
+    y = rng.uniform(-250, 250, n).astype(np.float32).astype(np.float64)
+    z = rng.uniform(-30, 30, n).astype(np.float32).astype(np.float64) - 1.726
+    y[:1000] = 0.0; x[1000:2000] = 0.0; y[2000:3000] = x[2000:3000]; y[3000:4000] *= 1e-17; x[4000:5000] *= 1e-3
+    h = np.hypot(x, y)
+    assert np.array_equal(libm_hypot(x, y).view(np.uint64), h.view(np.uint64))
+    assert np.array_equal(libm_hypot(h, z).view(np.uint64), np.hypot(h, z).view(np.uint64))
+    # and it is NOT simply sqrt(x^2 + y^2): the correction step matters
+    assert (np.sqrt(x * x + y * y) != h).mean() > 0.05
