@@ -283,6 +283,7 @@ struct NmsArgs {
   double *acc;                    // [(kept_base + i) * D + c]: c < D-1 weighted sums, c = D-1 weight sum
   int *merge_count;               // [kept_base + i]
   unsigned long long *stats;
+  float rcap_mult, cell_mult;     // grid geometry in units of the mean padded radius
 };
 
 // ---- cheap, safe upper bound on the IoU (separating axes + projected overlap) -----------------
@@ -343,13 +344,11 @@ __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
   b += sizeof(uint32_t) * kQ2Cap;                                  // queue2 (the window sort's keys + indices alias it)
   b += sizeof(uint32_t) * kNmsWarps * kWBuf;                       // per-warp exact-IoU buffers
-  b += sizeof(int) * 1024 + sizeof(uint16_t) * kNmsThreads;        // pcnt, s_perm
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
   if (kWeighted) b += sizeof(int) * kWin + kQ2Cap + sizeof(int) * kF; // wfs, qflag, killer
   if (kept_in_smem) b += sizeof(float4) * kKeptSmem + sizeof(int) * kBucketsSmem + sizeof(int) * kKeptSmem;
   return align_up_c(b, 16);
 }
-static_assert(kNmsWarps * kWBuf >= kNmsThreads && 1024 % kNmsThreads == 0, "hcnt aliases the eval buffers");
 static_assert(sizeof(unsigned long long) * kWin + sizeof(uint16_t) * kWin <= sizeof(uint32_t) * kQ2Cap, "sort buffers alias the queue");
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total) {
@@ -425,7 +424,7 @@ nms_pull_kernel(NmsArgs a) {
   __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_nfos;
   __shared__ float s_red[kNmsWarps * 2];
   __shared__ float s_cell[2];   // inv_cell, r_cap
-  __shared__ uint32_t s_haspred[kFW], s_removed[kFW], s_killed[kFW];
+  __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
 
   const int seg = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -463,10 +462,7 @@ nms_pull_kernel(NmsArgs a) {
   uint32_t *queue2 = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kQ2Cap;
   unsigned long long *wkey = reinterpret_cast<unsigned long long *>(queue2);        // window sort only
   uint16_t *widx = reinterpret_cast<uint16_t *>(wkey + kWin);
-  uint32_t *wbuf_base = reinterpret_cast<uint32_t *>(p);
-  uint32_t *wbuf = wbuf_base + wid * kWBuf; p += sizeof(uint32_t) * kNmsWarps * kWBuf;
-  int *pcnt = reinterpret_cast<int *>(p); p += sizeof(int) * 1024;                // counting sort of a batch by cell
-  uint16_t *s_perm = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kNmsThreads;
+  uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * kNmsWarps * kWBuf;
   uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
   int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
   p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
@@ -556,6 +552,7 @@ nms_pull_kernel(NmsArgs a) {
       if (skip) return;
       for (int k = since; k < kept; ++k) {
         const float4 q = kxyr[k];
+        ++st_circle;
         if (!prune || touches(x, y, r, q.x, q.y, q.z)) fn(k);
       }
       return;
@@ -566,6 +563,7 @@ nms_pull_kernel(NmsArgs a) {
         while (k >= since) {
           float qx, qy, qr; int next;
           kept_entry(k, qx, qy, qr, next);
+          ++st_circle;
           if (touches(x, y, r, qx, qy, qr) && cell_of(qx) == ix && cell_of(qy) == iy) fn(k);
           k = next;
         }
@@ -575,6 +573,7 @@ nms_pull_kernel(NmsArgs a) {
       const int k = kos[o];
       if (k >= since) {
         const float4 q = kxyr[k];
+        ++st_circle;
         if (touches(x, y, r, q.x, q.y, q.z)) fn(k);
       }
     }
@@ -657,80 +656,35 @@ nms_pull_kernel(NmsArgs a) {
   // threads that fit form a prefix of the batch).
   // merges_only: the scan is over (weighted, num_post_nms reached) -- candidates only contribute to merge sets.
   constexpr int kPullCache = 4;
-  // Walks are assigned to threads in CELL order (counting sort of the batch by the cell of the query's centre): the
-  // lanes of a warp then walk the same or neighbouring chains and stay converged.  In rank order the warp pays, for
-  // every cell of the window, the longest chain any of its 32 unrelated queries meets -- measured 6x the useful work.
-  // fq[slot] holds the batch's queries; -> s_perm[t] = the slot thread t works on.
-  auto build_perm = [&](int nq) {
-    for (int i = tid; i < 1024; i += kNmsThreads) pcnt[i] = 0;
-    __syncthreads();
-    int key = 0;
-    if (tid < nq) {
-      const float4 q = fq[tid];
-      key = ((cell_of(q.y) & 31) << 5) | (cell_of(q.x) & 31);
-      atomicAdd(&pcnt[key], 1);
-    }
-    __syncthreads();
-    {
-      constexpr int kPer = 1024 / kNmsThreads;
-      int c[kPer], sum = 0;
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) { c[k] = pcnt[tid * kPer + k]; sum += c[k]; }
-      int total;
-      int off = block_exclusive_scan(sum, s_warp, total);
-#pragma unroll
-      for (int k = 0; k < kPer; ++k) { pcnt[tid * kPer + k] = off; off += c[k]; }
-    }
-    __syncthreads();
-    if (tid < nq) s_perm[atomicAdd(&pcnt[key], 1)] = static_cast<uint16_t>(tid);
-    __syncthreads();
-  };
-  int *hcnt = reinterpret_cast<int *>(wbuf_base);            // per-slot hit count, then queue offset (the eval buffers are idle during walks)
-
   auto pull = [&](const uint16_t *list, int ns, int since, bool merges_only) {
     if (since >= kept || ns <= 0) return;
     int bi = 0;
     while (bi < ns) {
-      const int nb = min(kNmsThreads, ns - bi);
-      if (tid < nb) {
-        const int j = list[bi + tid];
-        const int pos = static_cast<int>(wpos[j]);
-        s_bj[tid] = static_cast<uint16_t>(j);
-        fq[tid] = make_float4(rec_cx(recs[pos]), rec_cy(recs[pos]), recs[pos].r, 0.f);
-      }
-      __syncthreads();
-      build_perm(nb);
-      // thread t works on batch slot s_perm[t]
-      const int slot = tid < nb ? static_cast<int>(s_perm[tid]) : -1;
-      int cnt = 0;
+      const int t = bi + tid;
+      const bool active = t < ns;
+      int j = 0, pos = 0, cnt = 0;
       int hk[kPullCache];
       float x = 0.f, y = 0.f, r = 0.f;
-      if (slot >= 0) {
-        const float4 q = fq[slot];
-        x = q.x; y = q.y; r = q.z;
+      if (active) {
+        j = list[t];
+        pos = static_cast<int>(wpos[j]);
+        x = rec_cx(recs[pos]); y = rec_cy(recs[pos]); r = recs[pos].r;
         for_each_near(x, y, r, since, [&](int k) {
 #pragma unroll
           for (int c = 0; c < kPullCache; ++c)
             if (cnt == c) hk[c] = k;
           ++cnt;
         });
-        hcnt[slot] = cnt;
       }
-      __syncthreads();
-      // offsets in SLOT (= rank) order, so that a batch that does not fit is cut at a rank
       int total;
-      const int mine = tid < nb ? hcnt[tid] : 0;
-      const int off = block_exclusive_scan(mine, s_warp, total);
-      const bool ok = tid < nb && (off + mine <= kQ2Cap);
-      const int m = __syncthreads_count(ok);       // slots [0, m) fit
-      if (tid < nb) hcnt[tid] = off;
+      const int off = block_exclusive_scan(cnt, s_warp, total);
+      const bool ok = active && (off + cnt <= kQ2Cap);
+      int m = __syncthreads_count(ok);
       if (tid == 0) s_qn = 0;
       __syncthreads();
       if (m == 0) {
-        // the first candidate alone overflows the queue: one thread evaluates its pairs in place
-        if (slot == 0) {
-          const int j = s_bj[0];
-          const int pos = static_cast<int>(wpos[j]);
+        // the first candidate alone overflows the queue: thread 0 evaluates its pairs in place
+        if (tid == 0) {
           const Rec rj = recs[pos];
           int fs = 0x7fffffff;
           for_each_near(x, y, r, since, [&](int k) {
@@ -753,20 +707,20 @@ nms_pull_kernel(NmsArgs a) {
         bi += 1;
         continue;
       }
-      if (slot >= 0 && slot < m) {
-        if (kWeighted) wfs[s_bj[slot]] = 0x7fffffff;
-        const uint32_t tag = static_cast<uint32_t>(slot) << 20;
-        const int off_s = hcnt[slot];
+      if (ok) {
+        s_bj[tid] = static_cast<uint16_t>(j);
+        if (kWeighted) wfs[j] = 0x7fffffff;
+        const uint32_t tag = static_cast<uint32_t>(tid) << 20;
         if (cnt <= kPullCache) {
 #pragma unroll
           for (int c = 0; c < kPullCache; ++c)
-            if (c < cnt) queue2[off_s + c] = tag | static_cast<uint32_t>(hk[c]);
+            if (c < cnt) queue2[off + c] = tag | static_cast<uint32_t>(hk[c]);
         } else {
-          int w = off_s;
+          int w = off;
           for_each_near(x, y, r, since, [&](int k) { queue2[w++] = tag | static_cast<uint32_t>(k); });
         }
+        if (tid == m - 1) s_qn = off + cnt;   // ok threads are exactly tid < m
       }
-      if (tid == m - 1) s_qn = off + mine;
       __syncthreads();
       lap(1);
       const int qn = s_qn;
@@ -919,8 +873,8 @@ nms_pull_kernel(NmsArgs a) {
         float tr = 0.f, tc = 0.f;
         for (int w = 0; w < kNmsWarps; ++w) { tr += s_red[w]; tc += s_red[kNmsWarps + w]; }
         const float mr = tc > 0.f ? tr / tc : 1.f;
-        s_cell[1] = 3.0f * mr;                                             // r_cap: larger boxes go to the oversize lists
-        s_cell[0] = 1.0f / fminf(fmaxf(4.0f * mr, 1e-3f), 1.0e5f);         // cell = mean radius + r_cap: a typical query spans 3 x 3 cells
+        s_cell[1] = a.rcap_mult * mr;                                      // r_cap: larger boxes go to the oversize lists
+        s_cell[0] = 1.0f / fminf(fmaxf(a.cell_mult * mr, 1e-3f), 1.0e5f);  // cell = mean radius + r_cap: a typical query spans 3 x 3 cells
       }
       __syncthreads();
       inv_cell = s_cell[0]; r_cap = s_cell[1];
@@ -929,128 +883,58 @@ nms_pull_kernel(NmsArgs a) {
     for (int t = tid; t < wn; t += kNmsThreads) { surv_a[t] = static_cast<uint16_t>(t); walive[t] = 1; }
     __syncthreads();
     lap(0);
-    uint16_t *list = surv_a;
-    int ns = wn;
-    // Every candidate of this window meets the boxes kept BEFORE the window, kept[0, K0), in one pull of the whole
-    // window; the boxes kept while the window is being consumed, kept[K0, ...), it meets at its own round.
-    const int K0 = kept;
-    if (K0 > 0) {
-      pull(list, ns, 0, false);
-      ns = compact(list, ns, surv_b);
-      list = surv_b;
-    }
-    while (ns > 0) {
+    uint16_t *list = surv_a, *other = surv_b;
+    int ns = wn, since = 0;
+
+    while (true) {
+      // ================= a / c. pull against the kept boxes [since, kept), drop the suppressed =================
+      if (since < kept) {
+        pull(list, ns, since, false);
+        const int ns2 = compact(list, ns, other);
+        uint16_t *tmp = list; list = other; other = tmp;
+        ns = ns2;
+      }
+      if (ns == 0) break;
       ++rounds;
-      // ================= round: the next nf survivors form a frontier.  ONE enumeration + ONE evaluation settles both
-      // what the kept boxes of this window's earlier rounds do to them and what they do to each other ==============
-      int nf = min(kF, ns);
+      // ================= b. frontier = the first nf survivors; interacting pairs inside it =================
+      const int nf = min(kF, ns);
       for (int i = tid; i < kFrontBuckets; i += kNmsThreads) fheads[i] = -1;
-      if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; s_killed[tid] = 0u; }
-      if (tid == 0) { s_qn = 0; s_nfos = 0; }
-      if (tid < nf) {
-        const int j = list[tid];
-        const Rec r = recs[wpos[j]];
-        frec[tid] = r;
-        fq[tid] = make_float4(rec_cx(r), rec_cy(r), r.r, __int_as_float(-1));
-        front_w[tid] = static_cast<uint16_t>(j);
-        keptrank[tid] = -1;
-        if (kWeighted) killer[tid] = 0x7fffffff;   // until the greedy step: first suppressor among kept[K0, kept)
-      }
-      __syncthreads();
-      build_perm(nf);
-      // thread t works on frontier slot s_perm[t] (cell order, see build_perm)
-      const int my_slot = tid < nf ? static_cast<int>(s_perm[tid]) : -1;
-      float mx = 0.f, my = 0.f, mrad = 0.f;
-      if (my_slot >= 0) { const float4 q = fq[my_slot]; mx = q.x; my = q.y; mrad = q.z; }
-      int n_pull = 0;
-      if (kept > K0) {
-        // ---- (frontier box, kept box of this window) pairs first, at scanned queue offsets: they must all fit (the
-        // weighted mode needs every comparison of a box before it can merge), so a frontier whose pairs overflow the
-        // queue is cut at the last box (in rank order) that fits
-        int cnt = 0;
-        int hk[kPullCache];
-        if (my_slot >= 0) {
-          for_each_near(mx, my, mrad, K0, [&](int k) {
-#pragma unroll
-            for (int c = 0; c < kPullCache; ++c)
-              if (cnt == c) hk[c] = k;
-            ++cnt;
-          });
-          hcnt[my_slot] = cnt;
-        }
-        __syncthreads();
-        int total;
-        const int mine = tid < nf ? hcnt[tid] : 0;
-        const int off = block_exclusive_scan(mine, s_warp, total);
-        const bool ok = tid < nf && (off + mine <= kQ2Cap / 2);
-        const int m = __syncthreads_count(ok);      // slots [0, m) fit
-        if (tid < nf) hcnt[tid] = off;
-        __syncthreads();
-        if (m == 0) {
-          // the first box alone overflows: it is settled in place by one thread and forms a frontier of one
-          if (my_slot == 0) {
-            const int mpos = static_cast<int>(wpos[front_w[0]]);
-            int fs = 0x7fffffff;
-            for_each_near(mx, my, mrad, K0, [&](int k) {
-              if (!kWeighted && fs != 0x7fffffff) return;
-              bool above, above_m;
-              classify_pair(recs[kept_position(k)], frec[0], above, above_m);
-              if (above && k < fs) fs = k;
-            });
-            if (kWeighted)
-              for_each_near(mx, my, mrad, K0, [&](int k) {
-                if (k > fs) return;
-                bool above, above_m;
-                classify_pair(recs[kept_position(k)], frec[0], above, above_m);
-                if (above_m) accumulate(k, mpos);
-              });
-            if (fs != 0x7fffffff) { s_killed[0] = 1u; ++st_hit; }
-          }
-          nf = 1;
-        } else {
-          nf = m;
-          if (my_slot >= 0 && my_slot < m) {
-            const uint32_t tag = 0x80000000u | (static_cast<uint32_t>(my_slot) << 20);
-            const int off_s = hcnt[my_slot];
-            if (cnt <= kPullCache) {
-#pragma unroll
-              for (int c = 0; c < kPullCache; ++c)
-                if (c < cnt) queue2[off_s + c] = tag | static_cast<uint32_t>(hk[c]);
-            } else {
-              int w = off_s;
-              for_each_near(mx, my, mrad, K0, [&](int k) { queue2[w++] = tag | static_cast<uint32_t>(k); });
-            }
-          }
-          if (tid == m - 1) s_qn = off + mine;
-        }
-        __syncthreads();
-        n_pull = s_qn;
-      }
       for (int i = tid; i < nf * kFW; i += kNmsThreads) {
         sup[i] = 0u;
         if (kWeighted) mrg[i] = 0u;
       }
-      if (kWeighted)
-        for (int q = tid; q < n_pull; q += kNmsThreads) qflag[q] = 0;
-      __syncthreads();
-      // frontier grid: same cells as the kept grid, chains of frontier slots
-      if (tid < nf && prune) {
-        const float4 q = fq[tid];
-        if (in_grid(q.x, q.y, q.z)) fq[tid].w = __int_as_float(atomicExch(&fheads[bucket_of(cell_of(q.x), cell_of(q.y)) & (kFrontBuckets - 1)], tid));
-        else fos[atomicAdd(&s_nfos, 1)] = static_cast<uint16_t>(tid);
+      if (tid < kFW) { s_haspred[tid] = 0u; s_removed[tid] = 0u; }
+      if (tid == 0) { s_qn = 0; s_nfos = 0; }
+      float mx = 0.f, my = 0.f, mrad = 0.f;
+      if (tid < nf) {
+        const int j = list[tid];
+        const Rec r = recs[wpos[j]];
+        frec[tid] = r;
+        mx = rec_cx(r); my = rec_cy(r); mrad = r.r;
+        front_w[tid] = static_cast<uint16_t>(j);
+        keptrank[tid] = -1;
       }
       __syncthreads();
-      lap(1);
+      // frontier grid: same cells as the kept grid, chains of frontier slots
+      if (tid < nf) {
+        int next = -1;
+        if (prune) {
+          if (in_grid(mx, my, mrad)) next = atomicExch(&fheads[bucket_of(cell_of(mx), cell_of(my)) & (kFrontBuckets - 1)], tid);
+          else fos[atomicAdd(&s_nfos, 1)] = static_cast<uint16_t>(tid);
+        }
+        fq[tid] = make_float4(mx, my, mrad, __int_as_float(next));
+      }
+      __syncthreads();
       {
         auto mark = [&](int i, int j, bool above, bool above_m) {
           if (above) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
           if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
         };
-        // ---- pairs inside the frontier: thread i collects the boxes j > i whose circles touch its own (the cells
-        // around it + the frontier's oversize list) behind the kept pairs in the queue (in place if the queue is
-        // full: marking is order-independent)
-        if (my_slot >= 0 && my_slot < nf) {
-          const int i = my_slot;
+        // thread i collects the frontier boxes j > i whose circles touch its own: the cells around it, plus the
+        // frontier's oversize list; (i, j) goes to the work queue (in place if the queue is full: marking is
+        // order-independent)
+        if (tid < nf) {
+          const int i = tid;
           auto offer = [&](int j) {
             const int slot = atomicAdd(&s_qn, 1);
             if (slot < kQ2Cap) { queue2[slot] = static_cast<uint32_t>((i << 10) | j); return; }
@@ -1064,6 +948,7 @@ nms_pull_kernel(NmsArgs a) {
             if (!skip)
               for (int j = i + 1; j < nf; ++j) {
                 const float4 q = fq[j];
+                ++st_circle;
                 if (!prune || touches(mx, my, mrad, q.x, q.y, q.z)) offer(j);
               }
           } else {
@@ -1072,6 +957,7 @@ nms_pull_kernel(NmsArgs a) {
                 int j = fheads[bucket_of(ix, iy) & (kFrontBuckets - 1)];
                 while (j >= 0) {
                   const float4 q = fq[j];
+                  ++st_circle;
                   if (j > i && touches(mx, my, mrad, q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) offer(j);
                   j = __float_as_int(q.w);
                 }
@@ -1081,50 +967,21 @@ nms_pull_kernel(NmsArgs a) {
               const int j = fos[o];
               if (j > i) {
                 const float4 q = fq[j];
+                ++st_circle;
                 if (touches(mx, my, mrad, q.x, q.y, q.z)) offer(j);
               }
             }
           }
         }
         __syncthreads();
-        lap(3);
-        // ---- one evaluation of both kinds of pairs
         eval_queue(min(s_qn, kQ2Cap),
-                   [&](int q, Rec &ra, Rec &rb) {
-                     const uint32_t e = queue2[q];
-                     if (e & 0x80000000u) { ra = recs[kept_position(static_cast<int>(e & 0xfffffu))]; rb = frec[(e >> 20) & 1023u]; }
-                     else { ra = frec[e >> 10]; rb = frec[e & 1023u]; }
-                   },
+                   [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
                    [&](int q, bool above, bool above_m) {
-                     const uint32_t e = queue2[q];
-                     if (e & 0x80000000u) {
-                       const int i = static_cast<int>((e >> 20) & 1023u);
-                       if (!kWeighted) {
-                         if (above) { ++st_hit; atomicOr(&s_killed[i >> 5], 1u << (i & 31)); }
-                       } else {
-                         qflag[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
-                         if (above) atomicMin(&killer[i], static_cast<int>(e & 0xfffffu));
-                       }
-                     } else {
-                       mark(static_cast<int>(e >> 10), static_cast<int>(e & 1023u), above, above_m);
-                     }
+                     mark(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
                    });
         __syncthreads();
-        if (kWeighted && n_pull > 0) {
-          // merges into the kept boxes up to and including a box's first suppressor; a suppressed box is out of the
-          // frontier's greedy step (and of its merge sets: marked by killer = -1 below)
-          for (int q = tid; q < n_pull; q += kNmsThreads) {
-            const uint32_t e = queue2[q];
-            const int i = static_cast<int>((e >> 20) & 1023u), k = static_cast<int>(e & 0xfffffu);
-            const int fs = killer[i];
-            if (k > fs) continue;
-            if (qflag[q] & 2u) accumulate(k, static_cast<int>(wpos[front_w[i]]));
-            if (k == fs) { ++st_hit; atomicOr(&s_killed[i >> 5], 1u << (i & 31)); }
-          }
-          __syncthreads();
-        }
       }
-      lap(2);
+      lap(3);
       // ================= greedy resolution of the frontier =================
       // Boxes that no earlier frontier box can suppress (empty column in `sup`) are kept outright, in
       // parallel; only the rest needs the dependent scan, done by one warp.
@@ -1139,7 +996,7 @@ nms_pull_kernel(NmsArgs a) {
         const int w = tid & (kFW - 1);
         uint32_t rm = 0u;
         for (int i = tid / kFW; i < nf; i += kNmsThreads / kFW)
-          if (!(((s_haspred[i >> 5] | s_killed[i >> 5]) >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
+          if (!((s_haspred[i >> 5] >> (i & 31)) & 1u)) rm |= sup[i * kFW + w];   // rows of the free boxes
         if (rm) atomicOr(&s_removed[w], rm);
       }
       __syncthreads();
@@ -1149,9 +1006,9 @@ nms_pull_kernel(NmsArgs a) {
         if (lane < kFW) {
           const int lo = lane << 5;
           valid = (nf >= lo + 32) ? 0xffffffffu : (nf <= lo ? 0u : ((1u << (nf - lo)) - 1u));
-          removed = s_removed[lane] | s_killed[lane];   // suppressed by a kept box of an earlier round: never kept
-          pending = valid & s_haspred[lane];            // must be visited in rank order
-          keptm = valid & ~s_haspred[lane] & ~s_killed[lane];
+          removed = s_removed[lane];
+          pending = valid & s_haspred[lane];       // must be visited in rank order
+          keptm = valid & ~s_haspred[lane];
         }
         while (true) {
           const uint32_t cand = pending & ~removed;
@@ -1221,7 +1078,7 @@ nms_pull_kernel(NmsArgs a) {
         // = min rank over the kept rows that contain it; (2) each kept row queues itself and the boxes of its merge
         // row that it reaches no later than their first suppressor; (3) the queue is accumulated one pair per lane.
         if (tid == 0) s_qn = 0;
-        if (tid < nf) killer[tid] = ((s_killed[tid >> 5] >> (tid & 31)) & 1u) ? -1 : 0x7fffffff;   // -1: gone before this frontier's first box
+        if (tid < nf) killer[tid] = 0x7fffffff;
         __syncthreads();
         if (tid < nk) {
           const int i = keptf[tid];
@@ -1251,16 +1108,18 @@ nms_pull_kernel(NmsArgs a) {
       }
       __syncthreads();
       lap(5);
+      since = kept;
       kept += nk;
       list += nf;
       ns -= nf;
       // nms.py:53-56: only the first num_post_nms kept survive, so the scan can stop there
       if (kept >= a.num_post) { done = true; break; }
+      if (ns == 0) break;
     }
     if (kWeighted && done) {
-      // the survivors behind the last frontier still owe the boxes kept in this window their merge contributions
-      // (they have met the boxes kept before the window already)
-      pull(list, ns, K0, true);
+      // the survivors behind the last frontier still owe the last kept boxes their merge contributions
+      // (they have met the kept boxes below `since` already)
+      pull(list, ns, since, true);
     }
     rank_base += wn;
   }
@@ -1675,6 +1534,9 @@ static NmsArgs base_args(const NmsPlan &pl, const NmsLayout &L, int num_pre, int
   a.kxyr_g = L.kxyr_g; a.knext_g = L.knext_g; a.heads_g = L.heads_g; a.n_buckets_g = pl.n_buckets_g; a.kos = L.kos;
   a.data = L.data; a.D = pl.D; a.acc = L.acc; a.merge_count = L.merge_count;
   a.stats = reinterpret_cast<unsigned long long *>(stats);
+  a.rcap_mult = 2.0f; a.cell_mult = 3.0f;   // measured sweep (profiles/r02_nms_geometry.md): r_cap 2, cell 3 mean radii
+  if (const char *e = getenv("RV3D_NMS_RCAP")) { const float v = static_cast<float>(atof(e)); if (v > 0.f) a.rcap_mult = v; }   // experiments only
+  if (const char *e = getenv("RV3D_NMS_CELL")) { const float v = static_cast<float>(atof(e)); if (v > 0.f) a.cell_mult = v; }
   return a;
 }
 
