@@ -364,15 +364,16 @@ extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RasterArgs a = make_args(p);
   auto *keys = static_cast<unsigned long long *>(scratch);
-  // The batch is processed in chunks of sweeps whose points + keys fit the L2 comfortably (B200: 126 MB in two
-  // halves): the keys a chunk's scatter writes and the points it streams are still resident when its resolve pass
-  // reads the keys back and gathers the winning points, instead of coming from DRAM a second time.
+  // Measured and dropped (profiles/r02_raster_chunks.md): processing the batch in L2-sized chunks of sweeps (scatter +
+  // resolve per chunk, so that the keys and points a resolve pass gathers are still L2-resident) is SLOWER at every chunk
+  // size -- 85 us for one chunk, 97 / 120 / 167 us for 36 / 24 / 12 MB chunks at B = 16 Waymo: the half-size kernels lose
+  // more to their tails than the gathers win.  The chunk loop stays for experiments (RV3D_RASTER_CHUNK_MB).
   const int64_t HW = static_cast<int64_t>(p->height) * p->width;
   const int64_t per_sweep = static_cast<int64_t>(p->max_points) * 17 + HW * 8;
-  int64_t budget = int64_t(36) << 20;
-  if (const char *e = getenv("RV3D_RASTER_CHUNK_MB")) {   // experiments only; 0 = one chunk
+  int64_t budget = int64_t(1) << 62;
+  if (const char *e = getenv("RV3D_RASTER_CHUNK_MB")) {
     const long v = atol(e);
-    budget = v > 0 ? (int64_t(v) << 20) : (int64_t(1) << 62);
+    if (v > 0) budget = int64_t(v) << 20;
   }
   int chunk = static_cast<int>(budget / (per_sweep > 0 ? per_sweep : 1));
   if (chunk < 1) chunk = 1;

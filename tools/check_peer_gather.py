@@ -57,8 +57,49 @@ def main():
     peer.wait(pending[0])
     assert torch.equal(peer.unpack(pending[0]), pending[1])
     dist.barrier()
+    # sequence-flag form: no barrier kernel; slot and step number live in device memory, so the step also replays as a
+    # CUDA graph.  Different data every step; one rank goes empty once; consumers wait with wait_published().
+    torch.cuda.synchronize()
+    peer2 = PeerGather(B * C * pp["num_post_nms"], dev)
+    for step in range(6):
+        head = synth.make_head_outputs(B, C, 16, 256, seed=1000 + 100 * step + rank, n_objects=8)
+        if step == 2 and rank == 0:
+            head["logits"].fill_(-20.0)
+        det = dec.decode_async(ms_outputs(to_dev(head, dev)), pp, tasks, gather=peer2.flagged(rank * B))
+        peer2.wait_published()
+        out = det.result()
+        torch.cuda.synchronize()
+        got = PeerGather.unpack_rows(peer2.rows_published())
+        ref = gather_detections(pack_rows(*out, batch_offset=rank * B))
+        assert got.shape == ref.shape and torch.equal(got, ref), f"flagged step {step}: rows differ"
+    # the same step captured once and replayed on fresh data
+    hd = to_dev(synth.make_head_outputs(B, C, 16, 256, seed=5000 + rank, n_objects=8), dev)
+    dec.decode_async(ms_outputs(hd), pp, tasks, gather=peer2.flagged(rank * B))        # warm the workspaces
+    torch.cuda.synchronize()
+    dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(g, stream=side):
+        det = dec.decode_async(ms_outputs(hd), pp, tasks, gather=peer2.flagged(rank * B))
+    torch.cuda.current_stream().wait_stream(side)
+    for step in range(4):
+        new = to_dev(synth.make_head_outputs(B, C, 16, 256, seed=6000 + 100 * step + rank, n_objects=8), dev)
+        for k in hd:
+            hd[k].copy_(new[k])
+        g.replay()
+        peer2.wait_published()
+        torch.cuda.synchronize()
+        peer2.sync_steps()
+        m = det.wait()
+        mine = pack_rows(det.params[:m], det.scores[:m], det.categories[:m], det.batch_index[:m], batch_offset=rank * B)
+        got = PeerGather.unpack_rows(peer2.rows_published())
+        ref = gather_detections(mine)
+        assert got.shape == ref.shape and torch.equal(got, ref), f"graph replay {step}: rows differ"
+    dist.barrier()
     if rank == 0:
-        print(f"peer gather ok: world {world}, {got.shape[0]} rows in the last step", flush=True)
+        print(f"peer gather ok: world {world}, {got.shape[0]} rows in the last step (barrier, pipelined, sequence-flag and "
+              f"graph-replay forms)", flush=True)
     dist.destroy_process_group()
 
 
