@@ -316,6 +316,15 @@ int rv3d_box_iou_rotated(const float *boxes_a, int64_t n, const float *boxes_b, 
 int rv3d_pair_decisions(const float *boxes_a, const float *boxes_b, int64_t n, float iou_threshold, int32_t routine,
                         int8_t *decision, float *bound, float *exact, rv3d_stream_t stream);
 
+/* Test hooks for the fast math the rasterizer / decoder use in place of libm (csrc/fastmath.cuh): out[i] =
+ * op 0: fast_atan2(a[i], b[i]); 1: fast_exp(a[i]); 2: fast_sqrt(a[i]); 3: (double)atan2f_lite((float)a[i], (float)b[i]).
+ * rv3d_debug_column: per point (n, 4) f32, col_fast = the float32 azimuth-bin decision of the scatter kernel, or
+ * -1 - c when it declined and the fp64 fallback answered c; col_exact = the reference's arithmetic with libm atan2
+ * (numpy/conversions.py:30-35 / converters/av2/utils.py:133-137).  Every decided point must agree. */
+int rv3d_debug_fastmath(int32_t op, const double *a, const double *b, double *out, int64_t n, rv3d_stream_t stream);
+int rv3d_debug_column(const rv3d_raster_params *p, const float *points, int64_t n, int32_t *col_fast,
+                      int32_t *col_exact, rv3d_stream_t stream);
+
 /* yaw (N,) f32 -> quat (N,4) f32 (qw,qx,qy,qz) = (cos(yaw/2),0,0,sin(yaw/2)) (SO3.py:122-134). */
 int rv3d_yaw_to_quat(const float *yaw, float *quat, int64_t n, rv3d_stream_t stream);
 

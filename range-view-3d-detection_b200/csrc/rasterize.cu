@@ -19,6 +19,7 @@
 // K1  (scatter): 1 thread / point, float4 load, fp64 index math, atomicMin.u64 (REDG).
 // K1b (resolve): 1 thread / pixel, reads the key, gathers the winning point, recomputes its
 //                spherical coordinates and writes the 7 channel planes coalesced.
+#include <cmath>
 #include <cstdlib>
 #include <math_constants.h>
 
@@ -29,20 +30,13 @@ namespace rv3d {
 
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
-__device__ __forceinline__ unsigned long long pack_key(double d, uint32_t i) {
-  const float m = __double2float_rn(d);
-  const uint32_t cls = (d < static_cast<double>(m)) ? 0u : 1u;
-  const uint32_t low = cls ? (0x80000000u | i) : (~i & 0x7fffffffu);
-  return (static_cast<unsigned long long>(__float_as_uint(m)) << 32) | low;
-}
-__device__ __forceinline__ uint32_t key_index(unsigned long long key) {
-  const uint32_t low = static_cast<uint32_t>(key);
-  return (low & 0x80000000u) ? (low & 0x7fffffffu) : (~low & 0x7fffffffu);
-}
-
 struct RasterArgs {
-  int32_t B, max_points, H, W, az_bins, num_lasers, col_mode;
+  int32_t B, max_points, H, W, az_bins, num_lasers, col_mode, fast_col;
   double ox, oy, oz, min_distance, bin_scale;  // bin_scale = az_bins / tau (computed on the host in double)
+  // float32 side of the azimuth-bin fast path (make_args)
+  float ox_hi, ox_lo, oy_hi, oy_lo;   // lidar offset as hi + lo float32 pairs
+  float min_xy, scale_hi, scale_lo;   // smallest |cx| + |cy| the float32 offsets resolve; bin_scale as hi + lo
+  float frac0, sgn, col0, half_minus_band, col_max;
 };
 
 // azimuth -> column, both formulas, in fp64 with round-half-even (np.round == rint)
@@ -54,103 +48,151 @@ __device__ __forceinline__ double column_of(double az, const RasterArgs &a) {
   return fmin(fmax(c, 0.0), nb - 1.0);  // np.clip(col, 0, W-1)
 }
 
-// Radius of a point, bit-compatible with the reference where it matters.  The reference computes
-// r = hypot(hypot(x, y), z) with numpy / libm (numpy/conversions.py:61-62); the z-buffer then only looks at
-// float32(r), at the comparison r < float32(r) (the class bit of pack_key) and at r < min_distance.  The fast form
-// sqrt(x^2 + y^2), sqrt(hxy^2 + z^2) is within a few fp64 ulps of libm's value, so those three outcomes can only
-// differ when r lies within a few ulps of a float32 value, of a midpoint between two float32 values, or of
-// min_distance.  Exactly then (about 1e-6 of the points) the radius is recomputed with the restatement of libm's hypot
-// (fastmath.cuh libm_hypot): pixel assignment and the range channel are bit-exact by construction, not with
-// probability 1 - 2^-28.
-__device__ __forceinline__ double norm2d(double x, double y) { return sqrt(x * x + y * y); }
-__device__ __forceinline__ bool near_f32_decision(double r, double min_distance) {
-  const float m = __double2float_rn(r);
-  const double md = static_cast<double>(m);
-  const double up = static_cast<double>(__uint_as_float(__float_as_uint(m) + 1u));   // m > 0, finite
-  const double dn = static_cast<double>(__uint_as_float(__float_as_uint(m) - 1u));
-  const double tol = r * 4.0e-15;                                                     // ~18 fp64 ulps
-  return fabs(r - md) <= tol || fabs(r - 0.5 * (md + up)) <= tol || fabs(r - 0.5 * (md + dn)) <= tol ||
-         fabs(r - min_distance) <= tol;
-}
-// one fp64 sqrt in the common case: sqrt(x^2 + y^2 + z^2) is within ~4 fp64 ulps of hypot(hypot(x, y), z)
-__device__ __forceinline__ double radius_of(double cx, double cy, double cz, double min_distance) {
-  double r = sqrt((cx * cx + cy * cy) + cz * cz);
-  if (r > 0.0 && r < 3.0e38 && near_f32_decision(r, min_distance)) r = libm_hypot(libm_hypot(cx, cy), cz);
-  return r;
-}
-
-// Column of a point without the fp64 atan2 in the common case: float32 atan2f of the (rounded) offsets
-// is within 1e-6 rad of the fp64 azimuth (2 ulp of atan2f at |az| <= pi = 4.8e-7, plus 0.6e-7 from
-// rounding the two arguments), i.e. within `band` = 2e-6 * bin_scale azimuth bins (2x safety).  If the
-// pre-rounding column value is farther than `band` from a rounding boundary (x.5), the float32 path
-// rounds to the same integer as the fp64 path; otherwise (~0.2 % of the points) the fp64 path runs.
-__device__ __forceinline__ double column_of_fast(double cx, double cy, const RasterArgs &a) {
-  const float az32 = atan2f(static_cast<float>(cy), static_cast<float>(cx));
-  const double t = (static_cast<double>(az32) + CUDART_PI) * a.bin_scale;
+// The exact column of a point whose float32 estimate was too close to a bin boundary (~0.2 % of the points): fp64
+// table atan2 (fastmath.cuh, <= 2 ulp: 1e-12 bins) unless THAT lands within 1e-7 bins of a boundary; then libm.
+static __device__ __noinline__ int column_exact(double cx, double cy, RasterArgs a) {
   const double nb = static_cast<double>(a.az_bins);
+  const double t = (fast_atan2(cy, cx) + CUDART_PI) * a.bin_scale;
   const double pre = (a.col_mode == RV3D_COL_LIBRARY) ? ((nb - t) - 1.0) : t;   // value handed to rint()
-  const double fl = floor(pre);
-  const double band = 2.0e-6 * a.bin_scale + 1e-9;
-  if (fabs((pre - fl) - 0.5) > band && cx == cx && cy == cy) {
+  if (fabs((pre - floor(pre)) - 0.5) > 1.0e-7) {
     const double r = rint(pre);
     const double c = (a.col_mode == RV3D_COL_LIBRARY) ? r : (nb - r);
-    return fmin(fmax(c, 0.0), nb - 1.0);
+    return static_cast<int>(fmin(fmax(c, 0.0), nb - 1.0));
   }
-  return column_of(atan2(cy, cx), a);
+  return static_cast<int>(column_of(atan2(cy, cx), a));
+}
+
+// Column of a point in float32, with a proof obligation instead of an fp64 atan2.  With v = az * bin_scale (bins from
+// the -x axis ... ) both reference formulas are `integer - k + rint(z)`-shaped once k = rint(v) is split off:
+//   library    rint((nb - (az + pi) s) - 1) = (nb/2 - 1) - v   = B_i - k + rint(B_f - res)
+//   converter  nb - rint((az + pi) s)       = nb - (nb/2 + v)  = (nb - H_i) - k - rint(H_f + res)
+// (res = v - k in [-0.5, 0.5]; B_i + B_f = nb/2 - 1, H_i + H_f = nb/2, fractional parts 0 or 0.5; pi * bin_scale = nb/2
+// to 1e-13 bins).  az comes from atan2f_lite on float32 copies of the offsets (|error| < 5e-7 rad in total, measured:
+// tests/test_gpu_fastmath.py), res from one FMA against the hi + lo split of bin_scale (no cancellation error), so the
+// float32 z is within `band` = 2e-6 rad * bin_scale + 2e-6 bins of the fp64 value: when z is farther than that from a
+// rounding boundary both paths round to the same integer.  Returns false when it cannot promise that.
+__device__ __forceinline__ bool column_fast(const RasterArgs &a, float x32, float y32, int &col) {
+  const float mag = fabsf(x32) + fabsf(y32);
+  const float az = atan2f_lite(y32, x32);
+  const float kMagic = 12582912.0f;                      // 1.5 * 2^23: (v + kMagic) - kMagic == rintf(v) for |v| < 2^22
+  const float kf = (az * a.scale_hi + kMagic) - kMagic;
+  float res = fmaf(az, a.scale_hi, -kf);
+  res = fmaf(az, a.scale_lo, res);
+  const float z = fmaf(-a.sgn, res, a.frac0);            // in [-0.5, 1.0]
+  const float rz = z > 0.5f ? 1.0f : 0.0f;
+  float c = (a.col0 - kf) + a.sgn * rz;
+  c = fminf(fmaxf(c, 0.0f), a.col_max);                  // np.clip(col, 0, n_azimuth_bins - 1)
+  col = __float_as_int(c + kMagic) - 0x4B400000;
+  return fabsf(z - rz) < a.half_minus_band && mag >= a.min_xy && mag < 1.0e30f;   // NaN fails every test
+}
+
+// Radius of a point, bit-compatible with the reference where it matters.  The reference computes
+// r = hypot(hypot(x, y), z) with numpy / libm (numpy/conversions.py:61-62); the z-buffer then only looks at
+// float32(r), at the comparison r < float32(r) (the class bit of the key) and at r < min_distance.  The fast form
+// sqrt(x^2 + y^2 + z^2) (fastmath.cuh fast_sqrt) is within a few fp64 ulps of libm's value, so those three outcomes
+// can only differ when r lies within a few ulps of a float32 value, of a midpoint between two float32 values, or of
+// min_distance.  Exactly then (about 1e-6 of the points) the radius is recomputed with the restatement of libm's hypot
+// (fastmath.cuh libm_hypot): pixel assignment and the range channel are bit-exact by construction.
+// The float32 neighbourhood test and the rounding itself are integer operations on the fp64 bit pattern: the low 29
+// mantissa bits of r are its position between two float32 values (0 = exact, 2^28 = midpoint).
+constexpr uint32_t kUlpBand = 64;   // fp64 ulps; fast_sqrt of the fused sum of squares vs hypot(hypot()): <= ~6
+
+__device__ __forceinline__ unsigned long long pack_key_bits(uint32_t f32_bits, uint32_t cls, uint32_t i) {
+  const uint32_t low = cls ? (0x80000000u | i) : (~i & 0x7fffffffu);
+  return (static_cast<unsigned long long>(f32_bits) << 32) | low;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(double d, uint32_t i) {
+  const float m = __double2float_rn(d);
+  return pack_key_bits(__float_as_uint(m), (d < static_cast<double>(m)) ? 0u : 1u, i);
+}
+__device__ __forceinline__ uint32_t key_index(unsigned long long key) {
+  const uint32_t low = static_cast<uint32_t>(key);
+  return (low & 0x80000000u) ? (low & 0x7fffffffu) : (~low & 0x7fffffffu);
+}
+
+// the reference's own arithmetic for the few points the fast forms cannot decide; returns kEmptyKey for "no write"
+static __device__ __noinline__ unsigned long long key_exact(double cx, double cy, double cz, double min_distance, uint32_t i) {
+  const double r = libm_hypot(libm_hypot(cx, cy), cz);
+  // z_buffer: `d < min_distance -> continue`, then `d < buffer` with buffer starting at +inf; NaN and +inf never write
+  if (!(r >= min_distance) || !(r < CUDART_INF)) return kEmptyKey;
+  return pack_key(r, i);
 }
 
 // Two points per thread, every load issued before the first use: the kernel is a latency-bound stream
-// (laser byte -> branch -> float4 -> ~150 dependent fp64 instructions -> one L2 atomic), so the memory-level
-// parallelism per thread is what sets its speed.
+// (laser byte + float4 -> ~100 dependent instructions -> one L2 atomic), so the memory-level parallelism per thread
+// is what sets its speed.
 constexpr int kScatterPerThread = 2;
 
 __device__ __forceinline__ void scatter_point(const RasterArgs &a, int b, int i, int l, float4 p,
-                                              const int32_t *__restrict__ laser_mapping,
-                                              unsigned long long *__restrict__ keys) {
+                                              const int32_t *s_map, unsigned long long *__restrict__ keys) {
   if (l >= a.num_lasers) return;  // range_view.py:23-26
   const double cx = static_cast<double>(p.x) - a.ox;  // range_view.py:29
   const double cy = static_cast<double>(p.y) - a.oy;
   const double cz = static_cast<double>(p.z) - a.oz;
-  const double r = radius_of(cx, cy, cz, a.min_distance);
-  // z_buffer: `d < min_distance -> continue`, then `d < buffer` with buffer starting at +inf;
-  // NaN and +inf never write.
-  if (!(r >= a.min_distance) || !(r < CUDART_INF)) return;
-  const double col = column_of_fast(cx, cy, a);
-  const int row = a.H - laser_mapping[l] - 1;  // conversions.py:37
-  const long long pix = static_cast<long long>(row) * a.W + static_cast<long long>(col);
+  // ---- radius -> (float32 bits, class bit)
+  const double s = fma(cx, cx, fma(cy, cy, cz * cz));
+  unsigned long long key;
+  bool decided = false;
+  if (fast_sqrt_ok(s)) {
+    const double r = fast_sqrt(s);
+    const double diff = r - a.min_distance;
+    const uint32_t lo = static_cast<uint32_t>(__double2loint(r));
+    const uint32_t lo29 = lo & 0x1FFFFFFFu;
+    const bool near_f32 = ((lo29 + kUlpBand) & 0x0FFFFFFFu) <= 2u * kUlpBand;          // exact value or midpoint
+    const bool near_min = fabs(diff) <= r * (static_cast<double>(kUlpBand) * 0x1p-52);
+    if (!near_f32 && !near_min) {
+      if (diff < 0.0) return;                                                          // d < min_distance
+      const uint32_t up = lo29 > 0x10000000u ? 1u : 0u;                                // round to nearest: up => r < float32(r)
+      const uint32_t bits = (((static_cast<uint32_t>(__double2hiint(r)) - 0x38000000u) << 3) | (lo >> 29)) + up;
+      key = pack_key_bits(bits, up ^ 1u, static_cast<uint32_t>(i));
+      decided = true;
+    }
+  }
+  if (!decided) {
+    key = key_exact(cx, cy, cz, a.min_distance, static_cast<uint32_t>(i));
+    if (key == kEmptyKey) return;
+  }
+  // ---- column
+  int col;
+  const float x32 = (p.x - a.ox_hi) - a.ox_lo, y32 = (p.y - a.oy_hi) - a.oy_lo;
+  if (!a.fast_col || !column_fast(a, x32, y32, col)) col = column_exact(cx, cy, a);
+  const int row = a.H - s_map[l] - 1;  // conversions.py:37
+  const long long pix = static_cast<long long>(row) * a.W + col;
   if (pix < 0 || pix >= static_cast<long long>(a.H) * a.W) return;
-  atomicMin(keys + static_cast<size_t>(b) * a.H * a.W + pix, pack_key(r, static_cast<uint32_t>(i)));
+  atomicMin(keys + static_cast<size_t>(b) * a.H * a.W + pix, key);
 }
 
 __global__ void __launch_bounds__(256)
 raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uint8_t *__restrict__ laser,
                       const int32_t *__restrict__ n_points, const int32_t *__restrict__ laser_mapping,
                       unsigned long long *__restrict__ keys) {
+  __shared__ int32_t s_map[256];
+  if (threadIdx.x < a.num_lasers) s_map[threadIdx.x] = laser_mapping[threadIdx.x];
   const int b = blockIdx.y;
   const int n = n_points[b];
   const int i0 = blockIdx.x * (blockDim.x * kScatterPerThread) + threadIdx.x;
-  if (i0 >= n) return;
   int l[kScatterPerThread];
   float4 p[kScatterPerThread];
   const uint64_t keep = l2_policy_evict_last();   // resolve gathers the winners from these lines: keep them in L2
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
     const int i = i0 + u * blockDim.x;
-    const size_t gi = static_cast<size_t>(b) * a.max_points + (i < n ? i : i0);
+    const size_t gi = static_cast<size_t>(b) * a.max_points + (i < n ? i : 0);
     l[u] = laser[gi];
     p[u] = ldg_f4_hint(points + gi, keep);
   }
+  __syncthreads();
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
     const int i = i0 + u * blockDim.x;
-    if (i < n) scatter_point(a, b, i, l[u], p[u], laser_mapping, keys);
+    if (i < n) scatter_point(a, b, i, l[u], p[u], s_map, keys);
   }
 }
 
-// K1b: one pixel per thread.  The kernel is bound by the rate at which an SM can keep random 32-byte sector
-// gathers in flight (key -> winning point; synthetic sweeps are in random point order, the worst case), not
-// by instruction issue: four pixels per thread with all gathers issued up front and 16-byte plane stores
-// measured SLOWER (46.5 vs 43.1 us at B = 16 Waymo: 76 registers, 33 % occupancy), so the simple form stays.
+// K1b: one pixel per thread: key -> winning point (a random 16-byte gather; synthetic sweeps are in random point
+// order, the worst case) -> azimuth / inclination in fp64 -> 7 coalesced plane stores.  The range channel is NOT
+// recomputed: the key's high word is float32(r) of the winner, bit for bit (scatter_point).
 struct PixelOut { float az, inc, rr, x, y, z, it; int32_t w; };
 
 __device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned long long key, float4 p) {
@@ -160,12 +202,12 @@ __device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned 
     const double cx = static_cast<double>(p.x) - a.ox;
     const double cy = static_cast<double>(p.y) - a.oy;
     const double cz = static_cast<double>(p.z) - a.oz;
-    const double hxy = norm2d(cx, cy);                // planar radius: inclination channel only (1-ulp bar)
-    const double r = radius_of(cx, cy, cz, a.min_distance);
+    const double s2 = fma(cx, cx, cy * cy);
+    const double hxy = fast_sqrt_ok(s2) ? fast_sqrt(s2) : sqrt(s2);   // planar radius: inclination channel only (1-ulp bar)
     // features are snapshotted BEFORE the in-place azimuth rescale (range_view.py:33, H3)
-    o.az = static_cast<float>(fast_atan2(cy, cx));    // fastmath.cuh: <= 1 ulp of fp64 before the cast
+    o.az = static_cast<float>(fast_atan2(cy, cx));    // fastmath.cuh: <= 2 ulp of fp64 before the cast
     o.inc = static_cast<float>(fast_atan2(cz, hxy));
-    o.rr = static_cast<float>(r);                     // bit-exact with the reference's float32(hypot(hypot(x, y), z))
+    o.rr = __uint_as_float(static_cast<uint32_t>(key >> 32));   // == float32(hypot(hypot(x, y), z)), see scatter_point
     o.x = p.x; o.y = p.y; o.z = p.z; o.it = p.w;
   }
   return o;
@@ -331,13 +373,68 @@ subsample_range_view_kernel(const float *__restrict__ rv, const uint8_t *__restr
   o_mask[static_cast<size_t>(b) * HWo + o] = m ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// test hooks: the fast math routines and the rasterizer's float32 column decision, exposed so the GPU suite can
+// measure their error / check the proof obligation directly (tests/test_gpu_fastmath.py)
+// ---------------------------------------------------------------------------------------------
+__global__ void debug_fastmath_kernel(int op, const double *__restrict__ a, const double *__restrict__ b,
+                                      double *__restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b ? b[i] : 0.0;
+  double r;
+  switch (op) {
+    case 0: r = fast_atan2(x, y); break;
+    case 1: r = fast_exp(x); break;
+    case 2: r = fast_sqrt_ok(x) ? fast_sqrt(x) : sqrt(x); break;
+    default: r = static_cast<double>(atan2f_lite(static_cast<float>(x), static_cast<float>(y))); break;
+  }
+  out[i] = r;
+}
+
+__global__ void debug_column_kernel(RasterArgs a, const float4 *__restrict__ points, int64_t n,
+                                    int32_t *__restrict__ col_fast, int32_t *__restrict__ col_exact) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = points[i];
+  const double cx = static_cast<double>(p.x) - a.ox, cy = static_cast<double>(p.y) - a.oy;
+  const float x32 = (p.x - a.ox_hi) - a.ox_lo, y32 = (p.y - a.oy_hi) - a.oy_lo;
+  int col = -1;
+  const bool ok = a.fast_col && column_fast(a, x32, y32, col);
+  col_fast[i] = ok ? col : -1 - column_exact(cx, cy, a);      // undecided: -1 - (the two-level fallback's answer)
+  col_exact[i] = static_cast<int>(column_of(atan2(cy, cx), a));   // the reference's arithmetic, libm atan2
+}
+
+static void split_f32(double v, float &hi, float &lo) {
+  hi = static_cast<float>(v);
+  lo = static_cast<float>(v - static_cast<double>(hi));
+}
+
 static RasterArgs make_args(const rv3d_raster_params *p) {
-  RasterArgs a;
+  RasterArgs a{};
   a.B = p->batch; a.max_points = p->max_points; a.H = p->height; a.W = p->width;
   a.az_bins = p->azimuth_bins; a.num_lasers = p->num_lasers; a.col_mode = p->col_mode;
   a.ox = p->lidar_offset[0]; a.oy = p->lidar_offset[1]; a.oz = p->lidar_offset[2];
   a.min_distance = p->min_distance;
   a.bin_scale = static_cast<double>(p->azimuth_bins) / 6.283185307179586;  // n_azimuth_bins / math.tau
+  // float32 column path (column_fast): constants of `col0 - k + sgn * rint(frac0 - sgn * res)`
+  const double nb = static_cast<double>(p->azimuth_bins);
+  const double base = (p->col_mode == RV3D_COL_LIBRARY) ? nb / 2.0 - 1.0 : nb / 2.0;   // B = nb/2 - 1 | H = nb/2
+  const double base_i = std::floor(base);
+  split_f32(a.ox, a.ox_hi, a.ox_lo);
+  split_f32(a.oy, a.oy_hi, a.oy_lo);
+  split_f32(a.bin_scale, a.scale_hi, a.scale_lo);
+  a.frac0 = static_cast<float>(base - base_i);                                          // 0 or 0.5
+  a.sgn = (p->col_mode == RV3D_COL_LIBRARY) ? 1.0f : -1.0f;
+  a.col0 = static_cast<float>((p->col_mode == RV3D_COL_LIBRARY) ? base_i : nb - base_i);
+  a.col_max = static_cast<float>(nb - 1.0);
+  const double band = 2.0e-6 * a.bin_scale + 2.0e-6;                                    // bins
+  a.half_minus_band = static_cast<float>(0.5 - band);
+  // below this |cx| + |cy| the residual of the float32 hi + lo offsets (2^-48 relative) is no longer negligible
+  a.min_xy = static_cast<float>(std::fmax(1.0e-30, (std::fabs(a.ox) + std::fabs(a.oy)) * 0x1p-18));
+  const bool finite_off = std::isfinite(a.ox) && std::isfinite(a.oy) && std::fabs(a.ox) < 1e30 && std::fabs(a.oy) < 1e30;
+  a.fast_col = (p->azimuth_bins <= (1 << 20) && band < 0.25 && finite_off) ? 1 : 0;
   return a;
 }
 
@@ -498,6 +595,27 @@ extern "C" int rv3d_subsample_range_view(const float *range_view, const uint8_t 
   dim3 grid(ceil_div(static_cast<int64_t>(height) * Wo, 256), batch);
   subsample_range_view_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       range_view, mask, cart, channels, height, width, Wo, x_stride, pad, pad_mode, out_range_view, out_mask, out_cart);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_debug_fastmath(int32_t op, const double *a, const double *b, double *out, int64_t n,
+                                   rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(op >= 0 && op <= 3 && n >= 0 && (n == 0 || (a && out)) && (b || op == 1 || op == 2 || n == 0));
+  if (n == 0) return RV3D_OK;
+  debug_fastmath_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(op, a, b, out, n);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_debug_column(const rv3d_raster_params *p, const float *points, int64_t n, int32_t *col_fast,
+                                 int32_t *col_exact, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && n >= 0 && p->azimuth_bins > 0 && (n == 0 || (points && col_fast && col_exact)));
+  RV3D_CHECK_ARG(p->col_mode == RV3D_COL_LIBRARY || p->col_mode == RV3D_COL_CONVERTER);
+  if (n == 0) return RV3D_OK;
+  if (!aligned(points, 16)) return RV3D_ERR_ALIGN;
+  debug_column_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      make_args(p), reinterpret_cast<const float4 *>(points), n, col_fast, col_exact);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }

@@ -83,6 +83,8 @@ _SIGNATURES = {
     "rv3d_nms": (C.c_int, [C.POINTER(NmsParams), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "rv3d_peer_wait": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "rv3d_pair_decisions": (C.c_int, [_P, _P, _I64, _F, _I32, _P, _P, _P, _P]),
+    "rv3d_debug_fastmath": (C.c_int, [_I32, _P, _P, _P, _I64, _P]),
+    "rv3d_debug_column": (C.c_int, [C.POINTER(RasterParams), _P, _I64, _P, _P, _P]),
     "rv3d_nms_rotated_scratch_bytes": (_SZ, [_I32]),
     "rv3d_nms_rotated": (C.c_int, [_P, _P, _I32, _F, _P, _P, _P, _SZ, _P]),
     "rv3d_wnms_scratch_bytes": (_SZ, [_I32, _I32]),

@@ -15,7 +15,7 @@ def main(path, want="", top=40):
     i = 0
     while i < len(rows):
         r = rows[i]
-        if r and r[0] == "File Name":
+        if r and r[0] in ("File Name", "File Path"):
             cur_file = r[1]
         elif r and r[0] == "Line No" and len(r) > 8:
             hdr = r
@@ -23,7 +23,7 @@ def main(path, want="", top=40):
             ws = hdr.index("Warp Stall Sampling (All Samples)")
             j = i + 1
             line = None
-            while j < len(rows) and rows[j] and rows[j][0] not in ("File Name", "Line No"):
+            while j < len(rows) and rows[j] and rows[j][0] not in ("File Name", "File Path", "Line No"):
                 q = rows[j]
                 if q[0].strip() and len(q) > ie:   # a CUDA source line (its SASS rows follow, line no empty)
                     line = int(q[0])
