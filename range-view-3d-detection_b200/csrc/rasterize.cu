@@ -119,80 +119,114 @@ static __device__ __noinline__ unsigned long long key_exact(double cx, double cy
   return pack_key(r, i);
 }
 
-// Two points per thread, every load issued before the first use: the kernel is a latency-bound stream
-// (laser byte + float4 -> ~100 dependent instructions -> one L2 atomic), so the memory-level parallelism per thread
-// is what sets its speed.
-constexpr int kScatterPerThread = 2;
+// Four points per thread.  (1) Every load is issued before the first use.  (2) The common path of a point is
+// BRANCH-FREE (eval_point: ~100 instructions ending in a state flag), so the compiler interleaves the four independent
+// dependency chains -- with one point at a time a warp waited ~10 cycles between instructions on fp64 latencies
+// (ncu r02c: stall_wait 2.8 + long_scoreboard 3.1 per issue at 43 % occupancy).  (3) The rare exits -- radius within 64
+// fp64 ulps of a float32 decision point, azimuth within 2e-6 rad of a bin boundary (~0.2 % of the points), a row outside
+// the image -- are flagged and handled after the straight-line part by out-of-line routines that restate the
+// reference's own arithmetic.
+constexpr int kScatterThreads = 128;
+constexpr int kScatterPerThread = 4;
+enum : uint32_t { kPtDrop = 0u, kPtReady = 1u, kPtSlowKey = 2u, kPtSlowCol = 4u, kPtSlowRow = 8u };
 
-__device__ __forceinline__ void scatter_point(const RasterArgs &a, int b, int i, int l, float4 p,
-                                              const int32_t *s_map, unsigned long long *__restrict__ keys) {
-  if (l >= a.num_lasers) return;  // range_view.py:23-26
+struct PointEval {
+  unsigned long long key;
+  uint32_t pix, state;
+  int row;
+};
+
+__device__ __forceinline__ PointEval eval_point(const RasterArgs &a, int i, int l, float4 p, const int32_t *s_map) {
+  PointEval e;
   const double cx = static_cast<double>(p.x) - a.ox;  // range_view.py:29
   const double cy = static_cast<double>(p.y) - a.oy;
   const double cz = static_cast<double>(p.z) - a.oz;
   // ---- radius -> (float32 bits, class bit)
   const double s = fma(cx, cx, fma(cy, cy, cz * cz));
-  unsigned long long key;
-  bool decided = false;
-  if (fast_sqrt_ok(s)) {
-    const double r = fast_sqrt(s);
-    const double diff = r - a.min_distance;
-    const uint32_t lo = static_cast<uint32_t>(__double2loint(r));
-    const uint32_t lo29 = lo & 0x1FFFFFFFu;
-    const bool near_f32 = ((lo29 + kUlpBand) & 0x0FFFFFFFu) <= 2u * kUlpBand;          // exact value or midpoint
-    const bool near_min = fabs(diff) <= r * (static_cast<double>(kUlpBand) * 0x1p-52);
-    if (!near_f32 && !near_min) {
-      if (diff < 0.0) return;                                                          // d < min_distance
-      const uint32_t up = lo29 > 0x10000000u ? 1u : 0u;                                // round to nearest: up => r < float32(r)
-      const uint32_t bits = (((static_cast<uint32_t>(__double2hiint(r)) - 0x38000000u) << 3) | (lo >> 29)) + up;
-      key = pack_key_bits(bits, up ^ 1u, static_cast<uint32_t>(i));
-      decided = true;
-    }
-  }
-  if (!decided) {
-    key = key_exact(cx, cy, cz, a.min_distance, static_cast<uint32_t>(i));
-    if (key == kEmptyKey) return;
-  }
+  const double r = fast_sqrt(s);                                                       // garbage unless fast_sqrt_ok(s)
+  const double diff = r - a.min_distance;
+  const uint32_t lo = static_cast<uint32_t>(__double2loint(r));
+  const uint32_t lo29 = lo & 0x1FFFFFFFu;
+  const bool near_f32 = ((lo29 + kUlpBand) & 0x0FFFFFFFu) <= 2u * kUlpBand;            // exact value or midpoint
+  const bool near_min = fabs(diff) <= r * (static_cast<double>(kUlpBand) * 0x1p-52);
+  const bool key_ok = fast_sqrt_ok(s) && !near_f32 && !near_min;
+  const uint32_t up = lo29 > 0x10000000u ? 1u : 0u;                                    // round to nearest: up => r < float32(r)
+  const uint32_t bits = (((static_cast<uint32_t>(__double2hiint(r)) - 0x38000000u) << 3) | (lo >> 29)) + up;
+  e.key = pack_key_bits(bits, up ^ 1u, static_cast<uint32_t>(i));
   // ---- column
   int col;
   const float x32 = (p.x - a.ox_hi) - a.ox_lo, y32 = (p.y - a.oy_hi) - a.oy_lo;
-  if (!a.fast_col || !column_fast(a, x32, y32, col)) col = column_exact(cx, cy, a);
-  const int row = a.H - s_map[l] - 1;  // conversions.py:37
-  const long long pix = static_cast<long long>(row) * a.W + col;
-  if (pix < 0 || pix >= static_cast<long long>(a.H) * a.W) return;
-  atomicMin(keys + static_cast<size_t>(b) * a.H * a.W + pix, key);
+  const bool col_ok = column_fast(a, x32, y32, col) && a.fast_col;
+  // ---- row, raveled index row * W + col (col may exceed W when azimuth_bins > W: the reference ravels the same way)
+  e.row = a.H - s_map[l & 255] - 1;  // conversions.py:37
+  const bool row_ok = static_cast<uint32_t>(e.row) < static_cast<uint32_t>(a.H);
+  e.pix = static_cast<uint32_t>(e.row) * a.W + col;                                    // H * W < 2^31 (checked on the host)
+  // z_buffer: `d < min_distance -> continue`
+  const bool drop = (l >= a.num_lasers) || (key_ok && diff < 0.0) || (key_ok && col_ok && row_ok && e.pix >= static_cast<uint32_t>(a.H * a.W));
+  e.state = drop ? kPtDrop : ((key_ok && col_ok && row_ok) ? kPtReady : ((key_ok ? 0u : kPtSlowKey) | (col_ok ? 0u : kPtSlowCol) | (row_ok ? 0u : kPtSlowRow)));
+  return e;
 }
 
-__global__ void __launch_bounds__(256)
+// the flagged points: the reference's arithmetic where the fast form declined
+static __device__ __noinline__ void finish_point_slow(RasterArgs a, int i, float4 p, PointEval e, unsigned long long *keys) {
+  const double cx = static_cast<double>(p.x) - a.ox, cy = static_cast<double>(p.y) - a.oy, cz = static_cast<double>(p.z) - a.oz;
+  unsigned long long key = e.key;
+  if (e.state & kPtSlowKey) {
+    key = key_exact(cx, cy, cz, a.min_distance, static_cast<uint32_t>(i));
+    if (key == kEmptyKey) return;
+  }
+  int col;
+  const float x32 = (p.x - a.ox_hi) - a.ox_lo, y32 = (p.y - a.oy_hi) - a.oy_lo;
+  if ((e.state & kPtSlowCol) || !a.fast_col || !column_fast(a, x32, y32, col)) col = column_exact(cx, cy, a);
+  const long long p64 = static_cast<long long>(e.row) * a.W + col;
+  if (p64 < 0 || p64 >= static_cast<long long>(a.H) * a.W) return;
+  atomicMin(keys + p64, key);
+}
+
+__global__ void __launch_bounds__(kScatterThreads, 7)
 raster_scatter_kernel(RasterArgs a, const float4 *__restrict__ points, const uint8_t *__restrict__ laser,
                       const int32_t *__restrict__ n_points, const int32_t *__restrict__ laser_mapping,
                       unsigned long long *__restrict__ keys) {
   __shared__ int32_t s_map[256];
-  if (threadIdx.x < a.num_lasers) s_map[threadIdx.x] = laser_mapping[threadIdx.x];
+  for (int t = threadIdx.x; t < 256; t += kScatterThreads) s_map[t] = t < a.num_lasers ? laser_mapping[t] : 0;
   const int b = blockIdx.y;
   const int n = n_points[b];
-  const int i0 = blockIdx.x * (blockDim.x * kScatterPerThread) + threadIdx.x;
+  const int i0 = blockIdx.x * (kScatterThreads * kScatterPerThread) + threadIdx.x;
+  const float4 *pts = points + static_cast<size_t>(b) * a.max_points;
+  const uint8_t *las = laser + static_cast<size_t>(b) * a.max_points;
   int l[kScatterPerThread];
   float4 p[kScatterPerThread];
   const uint64_t keep = l2_policy_evict_last();   // resolve gathers the winners from these lines: keep them in L2
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
-    const int i = i0 + u * blockDim.x;
-    const size_t gi = static_cast<size_t>(b) * a.max_points + (i < n ? i : 0);
-    l[u] = laser[gi];
-    p[u] = ldg_f4_hint(points + gi, keep);
+    const int i = i0 + u * kScatterThreads;
+    const int gi = i < n ? i : 0;
+    l[u] = las[gi];
+    p[u] = ldg_f4_hint(pts + gi, keep);
   }
   __syncthreads();
+  unsigned long long *k = keys + static_cast<size_t>(b) * a.H * a.W;
+  PointEval e[kScatterPerThread];
 #pragma unroll
   for (int u = 0; u < kScatterPerThread; ++u) {
-    const int i = i0 + u * blockDim.x;
-    if (i < n) scatter_point(a, b, i, l[u], p[u], s_map, keys);
+    e[u] = eval_point(a, i0 + u * kScatterThreads, l[u], p[u], s_map);
+    if (i0 + u * kScatterThreads >= n) e[u].state = kPtDrop;
+  }
+#pragma unroll
+  for (int u = 0; u < kScatterPerThread; ++u) {
+    if (e[u].state == kPtReady) atomicMin(k + e[u].pix, e[u].key);
+    else if (e[u].state != kPtDrop) finish_point_slow(a, i0 + u * kScatterThreads, p[u], e[u], k);
   }
 }
 
-// K1b: one pixel per thread: key -> winning point (a random 16-byte gather; synthetic sweeps are in random point
-// order, the worst case) -> azimuth / inclination in fp64 -> 7 coalesced plane stores.  The range channel is NOT
-// recomputed: the key's high word is float32(r) of the winner, bit for bit (scatter_point).
+// K1b: key -> winning point (a random 16-byte gather; synthetic sweeps are in random point order, the worst case) ->
+// azimuth / inclination in fp64 -> 7 coalesced plane stores.  The range channel is NOT recomputed: the key's high word
+// is float32(r) of the winner, bit for bit (scatter_point).  The kernel is bound by the latency of its two dependent
+// loads (ncu: 53 % of the stall samples on the gather and its first use at one pixel per thread), so a thread owns
+// four pixels, reads the four keys, then issues the four gathers unconditionally (an empty pixel gathers point 0 and
+// ignores it) before any arithmetic.
+constexpr int kResolvePx = 4;
+constexpr int kResolveThreads = 128;
 struct PixelOut { float az, inc, rr, x, y, z, it; int32_t w; };
 
 __device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned long long key, float4 p) {
@@ -213,27 +247,41 @@ __device__ __forceinline__ PixelOut resolve_pixel(const RasterArgs &a, unsigned 
   return o;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kResolveThreads, 8)
 raster_resolve_kernel(RasterArgs a, const float4 *__restrict__ points, const unsigned long long *__restrict__ keys,
                       float *__restrict__ image, int32_t *__restrict__ winner) {
   const int b = blockIdx.y;
   const int HW = a.H * a.W;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= HW) return;
-  const unsigned long long key = keys[static_cast<size_t>(b) * HW + pix];
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (key != kEmptyKey) p = __ldg(points + static_cast<size_t>(b) * a.max_points + key_index(key));
-  const PixelOut o = resolve_pixel(a, key, p);
-  float *out = image + static_cast<size_t>(b) * 7 * HW + pix;
+  const int pix0 = blockIdx.x * (kResolveThreads * kResolvePx) + threadIdx.x;
+  const unsigned long long *kb = keys + static_cast<size_t>(b) * HW;
+  const float4 *pts = points + static_cast<size_t>(b) * a.max_points;
+  unsigned long long key[kResolvePx];
+  float4 p[kResolvePx];
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j) {
+    const int pix = pix0 + j * kResolveThreads;
+    key[j] = pix < HW ? __ldg(kb + pix) : kEmptyKey;
+  }
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j)
+    p[j] = ldg_stream_f4(pts + (key[j] != kEmptyKey ? key_index(key[j]) : 0u));
   const uint64_t stream = l2_policy_evict_first();   // the 76 MB image must not push the points out of L2
-  st_f_hint(out + 0 * static_cast<size_t>(HW), o.az, stream);
-  st_f_hint(out + 1 * static_cast<size_t>(HW), o.inc, stream);
-  st_f_hint(out + 2 * static_cast<size_t>(HW), o.rr, stream);
-  st_f_hint(out + 3 * static_cast<size_t>(HW), o.x, stream);
-  st_f_hint(out + 4 * static_cast<size_t>(HW), o.y, stream);
-  st_f_hint(out + 5 * static_cast<size_t>(HW), o.z, stream);
-  st_f_hint(out + 6 * static_cast<size_t>(HW), o.it, stream);
-  if (winner) winner[static_cast<size_t>(b) * HW + pix] = o.w;
+  float *out = image + static_cast<size_t>(b) * 7 * HW;
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j) {
+    const int pix = pix0 + j * kResolveThreads;
+    if (pix >= HW) break;
+    const PixelOut o = resolve_pixel(a, key[j], p[j]);
+    float *q = out + pix;
+    st_f_hint(q, o.az, stream);
+    st_f_hint(q + HW, o.inc, stream);
+    st_f_hint(q + 2 * HW, o.rr, stream);
+    st_f_hint(q + 3 * HW, o.x, stream);
+    st_f_hint(q + 4 * HW, o.y, stream);
+    st_f_hint(q + 5 * HW, o.z, stream);
+    st_f_hint(q + 6 * HW, o.it, stream);
+    if (winner) winner[static_cast<size_t>(b) * HW + pix] = o.w;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -484,12 +532,12 @@ extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, 
     unsigned long long *k = keys + static_cast<size_t>(b0) * HW;
     const float4 *pts = reinterpret_cast<const float4 *>(points) + static_cast<size_t>(b0) * p->max_points;
     RV3D_CHECK_CUDA(cudaMemsetAsync(k, 0xFF, static_cast<size_t>(nb) * HW * sizeof(unsigned long long), s));
-    dim3 g1(ceil_div(p->max_points, 256 * kScatterPerThread), nb);
-    raster_scatter_kernel<<<g1, 256, 0, s>>>(a, pts, laser + static_cast<size_t>(b0) * p->max_points, n_points + b0,
-                                             laser_mapping, k);
+    dim3 g1(ceil_div(p->max_points, kScatterThreads * kScatterPerThread), nb);
+    raster_scatter_kernel<<<g1, kScatterThreads, 0, s>>>(a, pts, laser + static_cast<size_t>(b0) * p->max_points, n_points + b0,
+                                                         laser_mapping, k);
     RV3D_CHECK_LAUNCH();
-    dim3 g2(ceil_div(HW, 256), nb);
-    raster_resolve_kernel<<<g2, 256, 0, s>>>(a, pts, k, image + static_cast<size_t>(b0) * 7 * HW,
+    dim3 g2(ceil_div(HW, kResolveThreads * kResolvePx), nb);
+    raster_resolve_kernel<<<g2, kResolveThreads, 0, s>>>(a, pts, k, image + static_cast<size_t>(b0) * 7 * HW,
                                              winner ? winner + static_cast<size_t>(b0) * HW : nullptr);
     RV3D_CHECK_LAUNCH();
   }
