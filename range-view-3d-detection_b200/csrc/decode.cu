@@ -21,6 +21,8 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "fastmath.cuh"
 
@@ -73,29 +75,47 @@ __device__ __forceinline__ void decode_box(const float (&reg)[8], const float (&
                                            double (&out)[7]) {
   double ox = reg[0], oy = reg[1];
   const double oz = reg[2];
-  double yaw = fast_atan2(static_cast<double>(reg[6]), static_cast<double>(reg[7]));  // :136 (fastmath.cuh: <= 1 ulp)
+  const double sy = reg[6], cyw = reg[7];
   const double cx = cart[0], cy = cart[1], cz = cart[2];
+  double yaw;
   if (az_inv) {                                                                    // :79-107
-    const double phi = fast_atan2(cy, cx);
-    // cos / sin of atan2(cy, cx) are cx / h and cy / h (one reciprocal instead of a sincos); degenerate or
-    // non-finite rays take the library path
+    // cos / sin of phi = atan2(cy, cx) are cx / h and cy / h (one reciprocal square root instead of a sincos);
+    // degenerate or non-finite rays take the library path
     const double h2 = cx * cx + cy * cy;
     double s, c;
     if (h2 > 1e-60 && h2 < 1e60) {
-      const double rh = 1.0 / sqrt(h2);
+      double rh = rsqrt_seed(h2);                  // 1 / sqrt(h2): MUFU seed + two Newton steps (<= 1 ulp)
+      double e = fma(-h2 * rh, rh, 1.0);
+      rh = fma(0.5 * rh, e, rh);
+      e = fma(-h2 * rh, rh, 1.0);
+      rh = fma(0.5 * rh, e, rh);
       c = cx * rh; s = cy * rh;
     } else {
-      sincos(phi, &s, &c);
+      sincos(atan2(cy, cx), &s, &c);
     }
     const double x = c * ox - s * oy;
     const double y = s * ox + c * oy;
     ox = x; oy = y;
-    yaw += phi;
+    // yaw = atan2(sy, cyw) + atan2(cy, cx) (:136, :104) with ONE arctangent: the sum of the two angles is the angle of
+    // the product of the two complex numbers, up to a multiple of 2 pi that the signs of the two angles determine
+    // (both in [0, pi] -> sum in [0, 2 pi]; both negative -> [-2 pi, 0); mixed -> (-pi, pi)).  Next to the branch cut
+    // of the merged arctangent (|Y| tiny against |X|) rounding could pick the wrong sheet: those take the two-call form.
+    const double Y = fma(sy, cx, cyw * cy), X = fma(cyw, cx, -(sy * cy));
+    if (fabs(Y) > 1.0e-9 * fabs(X)) {
+      const double m = fast_atan2(Y, X);
+      const bool n1 = __double2hiint(sy) < 0, n2 = __double2hiint(cy) < 0;   // sign bits: atan2(-0, .) is negative too
+      double wrap = 0.0;
+      if (!n1 && !n2 && m < 0.0) wrap = 6.283185307179586;
+      if (n1 && n2 && m > 0.0) wrap = -6.283185307179586;
+      yaw = m + wrap;
+    } else {
+      yaw = fast_atan2(sy, cyw) + fast_atan2(cy, cx);
+    }
+  } else {
+    yaw = fast_atan2(sy, cyw);                                                     // :136 (fastmath.cuh: <= 2 ulp)
   }
   out[0] = cx + ox; out[1] = cy + oy; out[2] = cz + oz;                            // :142
-  out[3] = exp(static_cast<double>(reg[3]));                                       // :132
-  out[4] = exp(static_cast<double>(reg[4]));
-  out[5] = exp(static_cast<double>(reg[5]));
+  fast_exp3(static_cast<double>(reg[3]), static_cast<double>(reg[4]), static_cast<double>(reg[5]), out[3], out[4], out[5]);  // :132
   out[6] = yaw;
 }
 
@@ -212,6 +232,8 @@ struct KeyPack {
 struct DecodeArgs {
   int B, C, H, W, az_inv, cat_off, cand_off, total_classes, capacity;
   float thr;
+  float inv_w;  // 1 / W (row of a tile's first pixel; corrected by one step on the device)
+  float x_lo;   // conservative logit bound: sigmoid_T(x) >= thr implies x >= x_lo (logit_lower_bound)
   KeyPack kp;
   PartArgs pa;
 };
@@ -228,6 +250,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA prefetch of a contiguous span into L2 (no shared memory, no completion to wait for; SASS: UBLKPF)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
@@ -274,21 +300,57 @@ static size_t decode_smem_bytes(int C, int tile, size_t elem, size_t cart_elem) 
   size_t b = static_cast<size_t>(C) * tile * elem + static_cast<size_t>(3) * tile * cart_elem;   // logit and cart planes (regressands are gathered)
   b += tile;                                              // mask
   b = align_up(b, 16);
-  b += static_cast<size_t>(tile) * (2 + 2 + 1 + 2 + 2 + 4 + 4);   // q_pix, q_meta, q_emit, q_h, q_w, q_score, q_off
+  b += static_cast<size_t>(tile) * (4 + 2 + 2 + 2 + 1 + 1);   // q_score, q_pix, q2_t, q2_off, q_cls, q_emit
   return align_up(b, 16) + 64;
 }
 
+// Running max over the classes for 4 consecutive pixels (first index wins ties; NaN never becomes the max).
+//   runner   max logit among the classes BEFORE the winner (for the first-index tie check of the score phase)
+//   nansum   sum of the logits: NaN iff some logit is NaN (or +inf and -inf meet) -- one FADD per (pixel, class)
+//            instead of a comparison + predicate merge; the rare NaN sum is re-examined exactly by the caller
+// kC > 0: class count known at compile time (fully unrolled, everything stays in registers / predicates).
+template <typename T, int kC, int kTile>
+__device__ __forceinline__ void class_max(const T *s_logits, int lp0, int C, float (&best)[4], float (&runner)[4],
+                                          float (&nansum)[4], int (&cls)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { best[j] = -CUDART_INF_F; runner[j] = -CUDART_INF_F; nansum[j] = 0.f; cls[j] = 0; }
+  const int n = kC > 0 ? kC : C;
+#pragma unroll
+  for (int c = 0; c < n; ++c) {
+    float v[4];
+    Sm<T>::four(s_logits + c * kTile + lp0, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      nansum[j] += v[j];
+      const bool gt = v[j] > best[j];
+      runner[j] = gt ? best[j] : runner[j];
+      cls[j] = gt ? c : cls[j];
+      best[j] = gt ? v[j] : best[j];
+    }
+  }
+}
+
+constexpr int kRegParts = 4;   // partitions whose constants a thread keeps in registers (more: shared memory)
+
 // One CTA per tile of kTile consecutive pixels of one sweep, kTile / 4 threads.
-//   stage   the logit, cart and mask planes' slices of the tile are brought into shared memory: with kBulk,
-//           C + 4 TMA 1-D bulk copies issued by one thread, completion on an mbarrier (no registers, no
-//           per-thread loads; several resident CTAs overlap each other's copies and math); without
-//           (unaligned shapes) plain cooperative loads into the same layout.  The 8 regressand planes are
-//           NOT staged: only live pixels need them, phase B gathers them (8 independent loads per pixel),
-//           which halves the tile's shared memory (more resident CTAs) and, at realistic candidate
-//           densities, skips most of their bytes.
-//   phase A / scan / phase B   as described at the top of this file, reading shared memory only.
+//   stage    the logit, cart and mask planes' slices of the tile are brought into shared memory: with kBulk,
+//            C + 4 TMA 1-D bulk copies issued by one thread, completion on an mbarrier (no registers, no
+//            per-thread loads; several resident CTAs overlap each other's copies and math); without
+//            (unaligned shapes) plain cooperative loads into the same layout.  The 8 regressand planes are
+//            NOT staged: only emitting pixels need them, the last phase gathers them (8 independent loads per pixel).
+//   filter   every thread owns 4 consecutive pixels: running max over the classes (first index wins, NaN kills the
+//            pixel like torch.max) and ONE comparison against a conservative logit bound x_lo (sigmoid_T(x) >= thr
+//            implies x >= x_lo, computed on the host with slack for the float32 / half rounding).  Survivors go to
+//            queue 1 (warp-aggregated shared-memory reservation).  Nothing else runs on sparse lanes: with one
+//            pixel in three alive, a per-pixel branch costs the whole warp its full price (ncu r02a: sigmoid +
+//            threshold + partition + stride tests were 36 % of the kernel's instructions at 30 % lane use).
+//   score    dense lanes over queue 1: float32 sigmoid the way the reference's CUDA path rounds it, exact threshold,
+//            first-index tie check, sample_by_range partition bits from ||cart||, column-stride test.
+//   scan     block scan of (emitting pixels, emitted rows); ONE global atomicAdd per tile reserves the output rows;
+//            emitting pixels are compacted again (queue 2) so the fp64 decode also runs on dense lanes.
+//   decode   fp64 decode (3 exp, 2 atan2, rotation) of queue 2, 1..n_partitions (key, box) rows each.
 template <typename T, typename TC, int kTile, bool kBulk>
-__global__ void __launch_bounds__(kTile / kPxPerThread)
+__global__ void __launch_bounds__(kTile / kPxPerThread, kTile == 512 ? 9 : 12)
 decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__restrict__ reg,
                       const TC *__restrict__ cart, const uint8_t *__restrict__ mask,
                       unsigned long long *__restrict__ out_keys, float *__restrict__ out_boxes,
@@ -297,7 +359,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ uint32_t s_scan[kWarps];
-  __shared__ uint32_t s_base, s_total_live;
+  __shared__ uint32_t s_base, s_total_live, s_q1n;
   __shared__ __align__(8) uint64_t s_bar;
   // partition constants out of the kernel-parameter bank (dynamic indexing there costs uniform moves)
   __shared__ float s_lower[RV3D_MAX_PARTITIONS], s_upper[RV3D_MAX_PARTITIONS];
@@ -307,6 +369,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   const int b = blockIdx.y;
   const int HW = a.H * a.W;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
   const int blk0 = blockIdx.x * kTile;
   const int npx = min(kTile, HW - blk0);
 
@@ -315,21 +378,21 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   TC *s_cart = reinterpret_cast<TC *>(s_logits + static_cast<size_t>(a.C) * kTile);   // C * kTile * sizeof(T) is a multiple of 16
   uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cart + 3 * kTile);
   unsigned char *qp = dsm + align_up_c(static_cast<size_t>(a.C) * kTile * sizeof(T) + 3 * kTile * sizeof(TC) + kTile, 16);
-  float *q_score = reinterpret_cast<float *>(qp);                    // score of live pixel t
-  uint32_t *q_off = reinterpret_cast<uint32_t *>(q_score + kTile);   // exclusive emit offset inside the block
-  uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_off + kTile);     // local pixel id of live pixel t
-  uint16_t *q_meta = q_pix + kTile;                                  // class index within the task
-  uint8_t *q_emit = reinterpret_cast<uint8_t *>(q_meta + kTile);     // partition bit-mask
-  uint16_t *q_h = reinterpret_cast<uint16_t *>(q_emit + kTile);      // image row / column of live pixel t
-  uint16_t *q_w = q_h + kTile;
+  float *q_score = reinterpret_cast<float *>(qp);                    // queue 1: score of entry t
+  uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_score + kTile);   // queue 1: local pixel id
+  uint16_t *q2_t = q_pix + kTile;                                    // queue 2: queue-1 entry of emitting pixel u
+  uint16_t *q2_off = q2_t + kTile;                                   // queue 2: exclusive row offset inside the block
+  uint8_t *q_cls = reinterpret_cast<uint8_t *>(q2_off + kTile);      // queue 1: class index within the task (C <= 128 checked on the host)
+  uint8_t *q_emit = q_cls + kTile;                                   // queue 1: partition bit-mask
 
   if (tid < RV3D_MAX_PARTITIONS) {
     s_lower[tid] = a.pa.lower[tid]; s_upper[tid] = a.pa.upper[tid]; s_rate[tid] = a.pa.rate[tid];
     s_shift[tid] = a.pa.shift[tid]; s_magic[tid] = a.pa.magic[tid]; s_off[tid] = a.pa.off[tid]; s_wsub[tid] = a.pa.wsub[tid];
   }
+  if (tid == 0) s_q1n = 0u;
   const int n_parts = a.pa.n;
 
-  const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;   // regressands: gathered in phase B for the live pixels only
+  const T *rg = reg + static_cast<size_t>(b) * 8 * HW + blk0;   // regressands: gathered in the decode phase for the emitting pixels only
 
   // ---------------- stage the tile ----------------
   {
@@ -343,7 +406,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
         const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
         const uint32_t cplane = static_cast<uint32_t>(npx) * sizeof(TC);
         mbar_expect_tx(&s_bar, plane * a.C + cplane * 3 + npx);
-        for (int c = 0; c < a.C; ++c) bulk_g2s(s_logits + static_cast<size_t>(c) * kTile, lg + static_cast<size_t>(c) * HW, plane, &s_bar);
+        for (int c = 0; c < a.C; ++c) bulk_g2s(s_logits + c * kTile, lg + static_cast<size_t>(c) * HW, plane, &s_bar);
         for (int k = 0; k < 3; ++k) bulk_g2s(s_cart + k * kTile, ct + static_cast<size_t>(k) * HW, cplane, &s_bar);
         bulk_g2s(s_mask, mk, npx, &s_bar);
       }
@@ -359,92 +422,137 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     }
   }
 
-  // ---------------- phase A: class max over the staged logits ----------------
-  const int lp0 = tid * kPxPerThread;          // first local pixel of this thread
-  const int row0 = (blk0 + lp0) / a.W;         // one division per thread; (row, col) advance incrementally
-  const int col0 = (blk0 + lp0) - row0 * a.W;
-  float best[kPxPerThread], runner[kPxPerThread];   // runner = max logit among the classes before `cls`
-  int cls[kPxPerThread];
-  bool bad[kPxPerThread];
+  // ---------------- filter: class max + conservative logit bound ----------------
+  const bool zero_passes = 0.0f >= a.thr;
+  {
+    const int lp0 = tid * kPxPerThread;          // first local pixel of this thread
+    float best[kPxPerThread], runner[kPxPerThread], nansum[kPxPerThread];
+    int cls[kPxPerThread];
+    if (a.C == 3) class_max<T, 3, kTile>(s_logits, lp0, 3, best, runner, nansum, cls);
+    else class_max<T, 0, kTile>(s_logits, lp0, a.C, best, runner, nansum, cls);
+    const uchar4 m4 = *reinterpret_cast<const uchar4 *>(s_mask + lp0);
+    const uint32_t mbits = (m4.x ? 1u : 0u) | (m4.y ? 2u : 0u) | (m4.z ? 4u : 0u) | (m4.w ? 8u : 0u);
+    uint32_t maybe = 0u;
 #pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) { best[j] = -CUDART_INF_F; runner[j] = -CUDART_INF_F; cls[j] = 0; bad[j] = false; }
-#pragma unroll 4
-  for (int c = 0; c < a.C; ++c) {
-    float v[4];
-    Sm<T>::four(s_logits + static_cast<size_t>(c) * kTile + lp0, v);
+    for (int j = 0; j < kPxPerThread; ++j) {
+      bool bad = false;
+      if (nansum[j] != nansum[j]) {             // rare: a NaN logit, or infinities of both signs
+        for (int c = 0; c < a.C; ++c) {
+          const float x = Sm<T>::one(s_logits + c * kTile + lp0 + j);
+          bad |= (x != x);
+        }
+      }
+      // a masked pixel scores sigmoid * 0 == 0 for every class: it survives only when 0 >= thr
+      const bool pass = zero_passes || (((mbits >> j) & 1u) && best[j] >= a.x_lo);
+      if ((lp0 + j < npx) && !bad && pass) maybe |= 1u << j;
+      // bit 7 of the queued class: an earlier class may round to the same float32 sigmoid (checked in the score phase)
+      if (cls[j] > 0 && (best[j] >= 15.f || runner[j] > best[j] - 1.0f)) cls[j] |= 0x80;
+    }
+    // warp-aggregated reservation in queue 1 (the order of the queue is irrelevant: every row carries its own key)
+    const uint32_t cnt = __popc(maybe);
+    uint32_t incl = cnt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bad[j] |= (v[j] != v[j]);
-      if (v[j] > best[j]) { runner[j] = best[j]; best[j] = v[j]; cls[j] = c; }
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t wbase = 0u;
+    if (lane == 31 && incl) wbase = atomicAdd(&s_q1n, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    uint32_t pos = wbase + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < kPxPerThread; ++j) {
+      if (maybe & (1u << j)) {
+        q_pix[pos] = static_cast<uint16_t>(lp0 + j);
+        q_cls[pos] = static_cast<uint8_t>(cls[j]);
+        ++pos;
+      }
     }
   }
-  const uchar4 m4 = *reinterpret_cast<const uchar4 *>(s_mask + lp0);
-  const uint32_t mbits = (m4.x ? 1u : 0u) | (m4.y ? 2u : 0u) | (m4.z ? 4u : 0u) | (m4.w ? 8u : 0u);
+  __syncthreads();
+  const uint32_t n1 = s_q1n;
+  // The decode phase gathers the 8 regressand planes of the emitting pixels; when a good part of the tile is still
+  // alive, one thread asks the TMA unit to pull the tile's slices of those planes into L2 now, so that the gathers
+  // (a dependent DRAM round trip per warp otherwise: ncu r02f long_scoreboard 3.4 per issue) find them there.
+  if (kBulk && tid == 0 && n1 * 8u >= static_cast<uint32_t>(kTile)) {
+    const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
+    for (int k = 0; k < 8; ++k) bulk_prefetch_l2(rg + static_cast<size_t>(k) * HW, plane);
+  }
+  // (row, col) of the tile's first pixel: float reciprocal + one correction step instead of an integer division
+  int row0b = __float2int_rz(__int2float_rn(blk0) * a.inv_w);
+  int col0b = blk0 - row0b * a.W;
+  if (col0b < 0) { col0b += a.W; --row0b; }
+  if (col0b >= a.W) { col0b -= a.W; ++row0b; }
 
-  // score + threshold + partition test
-  float score[kPxPerThread];
-  uint32_t emit[kPxPerThread];
+  // ---------------- score: exact sigmoid / threshold / first index / partition / stride, dense lanes ----------------
   uint32_t n_live = 0, n_emit = 0;
-  const bool zero_passes = 0.0f >= a.thr;
-  float cx[4], cy[4], cz[4];
-  Sm<TC>::four(s_cart + lp0, cx);
-  Sm<TC>::four(s_cart + kTile + lp0, cy);
-  Sm<TC>::four(s_cart + 2 * kTile + lp0, cz);
+  // partition constants of the first kRegParts partitions in registers (unused slots never match)
+  float plo[kRegParts], phi[kRegParts];
+  int prate[kRegParts], pshift[kRegParts];
+  uint32_t pmagic[kRegParts];
 #pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) {
-    emit[j] = 0;
-    score[j] = 0.f;
-    if (lp0 + j >= npx || bad[j]) continue;
-    if (mbits & (1u << j)) {
-      score[j] = sigmoid_t<T>(best[j]);
-      // torch.max returns the FIRST index attaining the max of the float32 scores: an earlier
-      // class with a smaller logit can round to the same float32 sigmoid (always when saturated)
-      if (cls[j] > 0 && score[j] >= a.thr && (best[j] >= 15.f || runner[j] > best[j] - 1.0f)) {
-        for (int c = 0; c < cls[j]; ++c) {
-          const float x = Sm<T>::one(s_logits + static_cast<size_t>(c) * kTile + lp0 + j);
-          if ((best[j] >= 15.f || x > best[j] - 1.0f) && sigmoid_t<T>(x) == score[j]) { cls[j] = c; break; }
+  for (int i = 0; i < kRegParts; ++i) {
+    const bool on = i < n_parts;
+    plo[i] = on ? s_lower[i] : CUDART_INF_F; phi[i] = on ? s_upper[i] : -CUDART_INF_F;
+    prate[i] = on ? s_rate[i] : 1; pshift[i] = on ? s_shift[i] : 0; pmagic[i] = on ? s_magic[i] : 0u;
+  }
+  for (uint32_t t = tid; t < n1; t += kThreads) {
+    const int lp = q_pix[t];
+    const int qc = q_cls[t];
+    int cls = qc & 0x7f;
+    float score = 0.f;
+    if (s_mask[lp]) {
+      const float best = Sm<T>::one(s_logits + cls * kTile + lp);
+      score = sigmoid_t<T>(best);
+      // torch.max returns the FIRST index attaining the max of the float32 scores: an earlier class with a smaller
+      // logit can round to the same float32 sigmoid (always when saturated)
+      if ((qc & 0x80) && score >= a.thr) {
+        for (int c = 0; c < cls; ++c) {
+          const float x = Sm<T>::one(s_logits + c * kTile + lp);
+          if ((best >= 15.f || x > best - 1.0f) && sigmoid_t<T>(x) == score) { cls = c; break; }
         }
       }
     } else {
-      cls[j] = 0;  // sigmoid * 0 == 0 for every class -> argmax 0
+      cls = 0;  // sigmoid * 0 == 0 for every class -> argmax 0
     }
-    if (!(score[j] >= a.thr || zero_passes)) continue;
-    if (n_parts == 0) {
-      if (score[j] >= a.thr) emit[j] = 1u;
-    } else {
-      // bit i of part_in: the pixel's range lies in partition i; the column-stride test comes below
-      // cart.norm(dim=1) accumulates in float32 and rounds to cart's dtype; the bounds are a float32 tensor
-      const float d = Ld<TC>::round_f32(norm3(cx[j], cy[j], cz[j]));
-      uint32_t part_in = 0u;
-      for (int i = 0; i < n_parts; ++i) part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
-      emit[j] = score[j] >= a.thr ? part_in : 0u;
-      if (zero_passes) emit[j] = (1u << n_parts) - 1u;     // 0 >= thr: out-of-partition copies survive with score 0
+    uint32_t emit = 0u;
+    if (score >= a.thr || zero_passes) {
+      if (n_parts == 0) {
+        emit = score >= a.thr ? 1u : 0u;
+      } else {
+        // bit i of part_in: the pixel's range lies in partition i
+        // cart.norm(dim=1) accumulates in float32 and rounds to cart's dtype; the bounds are a float32 tensor
+        const float d = Ld<TC>::round_f32(norm3(Sm<TC>::one(s_cart + lp), Sm<TC>::one(s_cart + kTile + lp),
+                                                Sm<TC>::one(s_cart + 2 * kTile + lp)));
+        int w = col0b + lp;
+        while (w >= a.W) w -= a.W;
+        uint32_t part_in = 0u, stride_ok = 0u;
+#pragma unroll
+        for (int i = 0; i < kRegParts; ++i) {
+          part_in |= ((d > plo[i]) && (d <= phi[i])) ? (1u << i) : 0u;
+          // column stride: partition i keeps the columns w with w % rate_i == 0
+          stride_ok |= (w - fast_div(w, pshift[i], pmagic[i]) * prate[i]) ? 0u : (1u << i);
+        }
+        for (int i = kRegParts; i < n_parts; ++i) {
+          part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
+          stride_ok |= (w - fast_div(w, s_shift[i], s_magic[i]) * s_rate[i]) ? 0u : (1u << i);
+        }
+        emit = score >= a.thr ? part_in : 0u;
+        if (zero_passes) emit = (1u << n_parts) - 1u;       // 0 >= thr: out-of-partition copies survive with score 0
+        emit &= stride_ok;
+      }
     }
-  }
-  if (n_parts > 0) {
-    // column stride: partition i keeps the columns w with w % rate_i == 0
-    int wj[kPxPerThread];
-#pragma unroll
-    for (int j = 0; j < kPxPerThread; ++j) { wj[j] = col0 + j; if (wj[j] >= a.W) wj[j] -= a.W; }   // W >= 4: one wrap at most
-    for (int i = 0; i < n_parts; ++i) {
-      const int sh = s_shift[i], rate = s_rate[i];
-      const uint32_t mg = s_magic[i];
-#pragma unroll
-      for (int j = 0; j < kPxPerThread; ++j)
-        if (wj[j] - fast_div(wj[j], sh, mg) * rate) emit[j] &= ~(1u << i);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) {
-    n_live += emit[j] ? 1u : 0u;
-    n_emit += __popc(emit[j]);
+    q_cls[t] = static_cast<uint8_t>(cls);
+    q_emit[t] = static_cast<uint8_t>(emit);
+    q_score[t] = score;
+    n_live += emit ? 1u : 0u;
+    n_emit += __popc(emit);
   }
 
   // ---------------- block scan of (live, emit) packed as hi16 | lo16 ----------------
   // per block: live <= 512, emit <= 512 * 8 -> both fit 16 bits, no carry between the halves
   const uint32_t mine = (n_live << 16) | n_emit;
   uint32_t incl = mine;
-  const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -469,35 +577,30 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     }
   }
   __syncthreads();
-  const uint32_t excl = s_scan[wid] + (incl - mine);
-  uint32_t live_pos = excl >> 16, emit_pos = excl & 0xffffu;
-#pragma unroll
-  for (int j = 0; j < kPxPerThread; ++j) {
-    if (!emit[j]) continue;
-    q_pix[live_pos] = static_cast<uint16_t>(lp0 + j);
-    q_meta[live_pos] = static_cast<uint16_t>(cls[j]);
-    {
-      const bool wrap = col0 + j >= a.W;
-      q_h[live_pos] = static_cast<uint16_t>(row0 + (wrap ? 1 : 0));
-      q_w[live_pos] = static_cast<uint16_t>(col0 + j - (wrap ? a.W : 0));
+  {
+    const uint32_t excl = s_scan[wid] + (incl - mine);
+    uint32_t live_pos = excl >> 16, emit_pos = excl & 0xffffu;
+    for (uint32_t t = tid; t < n1; t += kThreads) {     // the same entries, in the same order, as the score loop
+      const uint32_t e = q_emit[t];
+      if (!e) continue;
+      q2_t[live_pos] = static_cast<uint16_t>(t);
+      q2_off[live_pos] = static_cast<uint16_t>(emit_pos);
+      ++live_pos;
+      emit_pos += __popc(e);
     }
-    q_emit[live_pos] = static_cast<uint8_t>(emit[j]);
-    q_score[live_pos] = score[j];
-    q_off[live_pos] = emit_pos;
-    ++live_pos;
-    emit_pos += __popc(emit[j]);
   }
   __syncthreads();
   const uint32_t total_live = s_total_live;
   const uint32_t base = s_base;
 
-  // ---------------- phase B: dense-lane fp64 decode of the live pixels ----------------
-  for (uint32_t t = tid; t < total_live; t += kThreads) {
+  // ---------------- decode: dense-lane fp64 decode of the emitting pixels ----------------
+  for (uint32_t u = tid; u < total_live; u += kThreads) {
+    const int t = q2_t[u];
     const int lp = q_pix[t];
     const int p = blk0 + lp;
     float r[8], c[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(rg + static_cast<size_t>(k) * HW + lp);   // 8 independent loads in flight
+    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(rg + (static_cast<uint32_t>(k) * static_cast<uint32_t>(HW) + lp));   // 8 independent loads in flight (7 * H * W < 2^32: host check)
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[k] = Sm<TC>::one(s_cart + k * kTile + lp);
     double o[7];
@@ -506,10 +609,11 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     float box[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) box[k] = static_cast<float>(Ld<T>::cast(o[k]));
-    const uint32_t seg = static_cast<uint32_t>(b) * a.total_classes + q_meta[t] + a.cat_off;
-    const int h = q_h[t], w = q_w[t];   // (row, col) computed incrementally in phase A
+    const uint32_t seg = static_cast<uint32_t>(b) * a.total_classes + q_cls[t] + a.cat_off;
+    int h = row0b, w = col0b + lp;
+    while (w >= a.W) { w -= a.W; ++h; }
     uint32_t e = q_emit[t];
-    uint32_t row = base + q_off[t];
+    uint32_t row = base + q2_off[u];
     const float sc = q_score[t];
     while (e) {
       const int i = __ffs(e) - 1;
@@ -520,9 +624,12 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
         cand = p;
       } else {
         cand = s_off[i] + h * s_wsub[i] + fast_div(w, s_shift[i], s_magic[i]);
-        // the partition that does not contain the pixel contributes score 0 (only when 0 >= thr)
-        const float d = Ld<TC>::round_f32(norm3(c[0], c[1], c[2]));
-        if (!((d > s_lower[i]) && (d <= s_upper[i]))) s_out = 0.0f;
+        // the partition that does not contain the pixel contributes score 0 (only when 0 >= thr: otherwise a
+        // pixel only emits into partitions that contain it)
+        if (zero_passes) {
+          const float d = Ld<TC>::round_f32(norm3(c[0], c[1], c[2]));
+          if (!((d > s_lower[i]) && (d <= s_upper[i]))) s_out = 0.0f;
+        }
       }
       if (row < static_cast<uint32_t>(a.capacity)) {
         out_keys[row] = a.kp.make_nonneg(seg, s_out, cand + a.cand_off);
@@ -678,18 +785,36 @@ extern "C" int rv3d_sample_by_range(const float *scores, const int64_t *categori
   return RV3D_OK;
 }
 
+// Smallest logit that can still reach the confidence threshold: sigmoid_T(x) >= thr  =>  x >= logit_lower_bound.
+// sigmoid_T is the float32 evaluation rounded to the tensor dtype (relative error < 1e-6 + half an ulp of T), so the
+// bound is the exact logit of a threshold lowered by that much and then some; it only has to be conservative -- every
+// pixel that passes it gets the exact test.
+static float logit_lower_bound(float thr, int32_t dtype) {
+  if (!(thr > 0.0f)) return -INFINITY;            // 0 >= thr (or NaN): nothing is filtered here
+  const double rel = dtype == RV3D_F32 ? 1.0e-5 : (dtype == RV3D_F16 ? 2.0e-3 : 1.6e-2);
+  const double t = static_cast<double>(thr) * (1.0 - rel) - 1.0e-6;
+  if (t <= 0.0) return -INFINITY;
+  if (t >= 1.0) return INFINITY;                  // thr > 1: no sigmoid reaches it
+  const double x = std::log(t / (1.0 - t));
+  return static_cast<float>(x - 1.0e-4 * (1.0 + std::fabs(x)));
+}
+
 extern "C" int rv3d_decode_compact(const rv3d_decode_params *p, const void *logits, const void *regressands,
                                    const void *cart, const uint8_t *mask, uint64_t *out_keys, float *out_boxes,
                                    int32_t *counter, rv3d_stream_t stream) {
   RV3D_CHECK_ARG(p && logits && regressands && cart && mask && out_keys && out_boxes && counter);
   RV3D_CHECK_ARG(p->batch > 0 && p->n_classes > 0 && p->height > 0 && p->width > 0 && p->capacity >= 0);
   RV3D_CHECK_ARG(parts_ok(&p->parts) && p->total_classes >= p->category_offset + p->n_classes);
-  RV3D_CHECK_ARG(static_cast<int64_t>(p->height) * p->width < (int64_t(1) << 30));
+  RV3D_CHECK_ARG(static_cast<int64_t>(p->height) * p->width < (int64_t(1) << 29));   // 32-bit element offsets over the 8 regressand planes
   if (!aligned(out_boxes, 16) || !aligned(out_keys, 8)) return RV3D_ERR_ALIGN;
   DecodeArgs a;
   a.B = p->batch; a.C = p->n_classes; a.H = p->height; a.W = p->width; a.az_inv = p->azimuth_invariant;
   a.cat_off = p->category_offset; a.cand_off = p->candidate_offset; a.total_classes = p->total_classes;
   a.capacity = p->capacity; a.thr = p->min_confidence;
+  a.x_lo = logit_lower_bound(p->min_confidence, p->dtype);
+  a.inv_w = 1.0f / static_cast<float>(p->width);
+  RV3D_CHECK_ARG(p->height < (1 << 22));   // row estimate from a float32 quotient is within one of the true row
+  RV3D_CHECK_ARG(p->n_classes <= 128);   // queue 1 keeps the class in 7 bits
   a.pa = make_parts(&p->parts, p->height, p->width);
   RV3D_CHECK_ARG(p->total_candidates >= p->candidate_offset + a.pa.off[a.pa.n]);
   a.kp.idx_bits = bits_for(p->total_candidates);

@@ -71,8 +71,7 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
 // exp(x) = 2^(k/64) * e^r,  k = round(64 x / ln 2),  r = x - k ln2/64 (two-constant reduction), |r| <= ln2/128:
 //   e^r = 1 + r + r^2 (1/2 + r/6 + r^2/24 + r^3/120)   (next term 3.4e-17 relative)
 // 2^((k mod 64)/64) from a 64-entry table, 2^(k div 64) added to the exponent field (|x| < 700: always normal).
-__device__ __forceinline__ double fast_exp(double x) {
-  if (!(fabs(x) < 700.0)) return exp(x);          // overflow / underflow / NaN: libm
+__device__ __forceinline__ double fast_exp_core(double x) {   // |x| < 700
   const double d = fma(x, 92.33248261689366, 0x1.8p52);   // 64 / ln 2; integer k in the low word (two's complement)
   const int k = __double2loint(d);
   const double kd = d - 0x1.8p52;
@@ -86,6 +85,18 @@ __device__ __forceinline__ double fast_exp(double x) {
   const double t = kExp2Table[k & 63];
   const double v = fma(t, em1, t);
   return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
+__device__ __forceinline__ double fast_exp(double x) {
+  if (!(fabs(x) < 700.0)) return exp(x);          // overflow / underflow / NaN: libm
+  return fast_exp_core(x);
+}
+// three at once (the decoder's l, w, h): one range test, three independent chains for the scheduler to interleave
+__device__ __forceinline__ void fast_exp3(double x0, double x1, double x2, double &e0, double &e1, double &e2) {
+  if (!(fmax(fmax(fabs(x0), fabs(x1)), fabs(x2)) < 700.0) || x0 != x0 || x1 != x1 || x2 != x2) {
+    e0 = exp(x0); e1 = exp(x1); e2 = exp(x2);
+    return;
+  }
+  e0 = fast_exp_core(x0); e1 = fast_exp_core(x1); e2 = fast_exp_core(x2);
 }
 
 // sqrt(s) to <= 2 fp64 ulps for 2^-200 <= s < 2^200 (callers guard): RSQ64H seed + two coupled Newton steps + one
