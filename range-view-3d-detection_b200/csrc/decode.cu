@@ -177,6 +177,46 @@ static PartArgs make_parts(const rv3d_partitions *p, int H, int W) {
   return a;
 }
 
+// The first kRegParts partitions in the form the decode kernel's filter phase wants them (registers, no branches):
+//   * range test on the SUM OF SQUARES: d = fl(sqrtf(s)) is monotone in s, so `d > lower` and `d <= upper` are
+//     `s > S(lower)` and `s <= S(upper)` with S(b) = the largest float whose correctly rounded square root is <= b
+//     (found on the host by stepping through neighbouring floats; CUDA's sqrtf under --prec-sqrt=true and glibc's are
+//     both correctly rounded).  No square root per pixel, bit-identical decisions.  Float32 cart only.
+//   * column stride for 4 consecutive columns w0 .. w0+3 at once: with n = (-w0) mod rate the multiples of `rate` among
+//     them are the set bits of (pattern << n) & 0xF, pattern = {bit k*rate : k*rate < 4}.
+constexpr int kRegParts = 4;
+struct FilterParts {
+  float s_lo[kRegParts], s_hi[kRegParts];
+  float lower[kRegParts], upper[kRegParts];
+  int rate[kRegParts], shift[kRegParts];
+  uint32_t magic[kRegParts], pattern[kRegParts];
+};
+
+static float sumsq_bound(float b) {
+  if (b != b) return b;                         // NaN: every comparison fails, like the reference's
+  if (b < 0.0f) return -1.0f;                   // no norm is <= b
+  if (std::isinf(b)) return b;
+  double sq = static_cast<double>(b) * static_cast<double>(b);
+  float s = sq >= 3.4028234663852886e38 ? 3.4028234663852886e38f : static_cast<float>(sq);
+  while (s > 0.0f && std::sqrt(s) > b) s = std::nextafterf(s, -INFINITY);
+  while (s < 3.4028234663852886e38f && std::sqrt(std::nextafterf(s, INFINITY)) <= b) s = std::nextafterf(s, INFINITY);
+  return s;
+}
+
+static FilterParts make_filter_parts(const PartArgs &pa) {
+  FilterParts f{};
+  for (int i = 0; i < kRegParts; ++i) {
+    const bool on = i < pa.n;
+    f.lower[i] = on ? pa.lower[i] : INFINITY; f.upper[i] = on ? pa.upper[i] : -INFINITY;   // unused slots never match
+    f.s_lo[i] = on ? sumsq_bound(pa.lower[i]) : INFINITY; f.s_hi[i] = on ? sumsq_bound(pa.upper[i]) : -INFINITY;
+    f.rate[i] = on ? pa.rate[i] : 1; f.shift[i] = on ? pa.shift[i] : 0; f.magic[i] = on ? pa.magic[i] : 0u;
+    uint32_t pat = 0u;
+    for (int k = 0; on && k * pa.rate[i] < 4; ++k) pat |= 1u << (k * pa.rate[i]);
+    f.pattern[i] = pat;
+  }
+  return f;
+}
+
 // ||cart||_2 in float32, the way torch's CPU / CUDA vector_norm reduces three floats
 __device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf((x * x + y * y) + z * z); }
 
@@ -236,6 +276,7 @@ struct DecodeArgs {
   float x_lo;   // conservative logit bound: sigmoid_T(x) >= thr implies x >= x_lo (logit_lower_bound)
   KeyPack kp;
   PartArgs pa;
+  FilterParts fp;
 };
 
 // ---- TMA 1-D bulk copy + mbarrier (inline PTX; SASS: UBLKCP / SYNCS) ---------------------------
@@ -300,7 +341,7 @@ static size_t decode_smem_bytes(int C, int tile, size_t elem, size_t cart_elem) 
   size_t b = static_cast<size_t>(C) * tile * elem + static_cast<size_t>(3) * tile * cart_elem;   // logit and cart planes (regressands are gathered)
   b += tile;                                              // mask
   b = align_up(b, 16);
-  b += static_cast<size_t>(tile) * (4 + 2 + 2 + 2 + 1 + 1);   // q_score, q_pix, q2_t, q2_off, q_cls, q_emit
+  b += static_cast<size_t>(tile) * (4 + 2 + 1 + 1);   // q_score, q_pix, q_cls, q_emit
   return align_up(b, 16) + 64;
 }
 
@@ -330,7 +371,6 @@ __device__ __forceinline__ void class_max(const T *s_logits, int lp0, int C, flo
   }
 }
 
-constexpr int kRegParts = 4;   // partitions whose constants a thread keeps in registers (more: shared memory)
 
 // One CTA per tile of kTile consecutive pixels of one sweep, kTile / 4 threads.
 //   stage    the logit, cart and mask planes' slices of the tile are brought into shared memory: with kBulk,
@@ -359,7 +399,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ uint32_t s_scan[kWarps];
-  __shared__ uint32_t s_base, s_total_live, s_q1n;
+  __shared__ uint32_t s_base, s_q1n;
   __shared__ __align__(8) uint64_t s_bar;
   // partition constants out of the kernel-parameter bank (dynamic indexing there costs uniform moves)
   __shared__ float s_lower[RV3D_MAX_PARTITIONS], s_upper[RV3D_MAX_PARTITIONS];
@@ -378,12 +418,10 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   TC *s_cart = reinterpret_cast<TC *>(s_logits + static_cast<size_t>(a.C) * kTile);   // C * kTile * sizeof(T) is a multiple of 16
   uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cart + 3 * kTile);
   unsigned char *qp = dsm + align_up_c(static_cast<size_t>(a.C) * kTile * sizeof(T) + 3 * kTile * sizeof(TC) + kTile, 16);
-  float *q_score = reinterpret_cast<float *>(qp);                    // queue 1: score of entry t
-  uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_score + kTile);   // queue 1: local pixel id
-  uint16_t *q2_t = q_pix + kTile;                                    // queue 2: queue-1 entry of emitting pixel u
-  uint16_t *q2_off = q2_t + kTile;                                   // queue 2: exclusive row offset inside the block
-  uint8_t *q_cls = reinterpret_cast<uint8_t *>(q2_off + kTile);      // queue 1: class index within the task (C <= 128 checked on the host)
-  uint8_t *q_emit = q_cls + kTile;                                   // queue 1: partition bit-mask
+  float *q_score = reinterpret_cast<float *>(qp);                    // queue: score of entry t
+  uint16_t *q_pix = reinterpret_cast<uint16_t *>(q_score + kTile);   // queue: local pixel id
+  uint8_t *q_cls = reinterpret_cast<uint8_t *>(q_pix + kTile);       // queue: class index within the task (C <= 128 checked on the host)
+  uint8_t *q_emit = q_cls + kTile;                                   // queue: partition bit-mask
 
   if (tid < RV3D_MAX_PARTITIONS) {
     s_lower[tid] = a.pa.lower[tid]; s_upper[tid] = a.pa.upper[tid]; s_rate[tid] = a.pa.rate[tid];
@@ -422,7 +460,13 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     }
   }
 
-  // ---------------- filter: class max + conservative logit bound ----------------
+  // (row, col) of the tile's first pixel: float reciprocal + one correction step instead of an integer division
+  int row0b = __float2int_rz(__int2float_rn(blk0) * a.inv_w);
+  int col0b = blk0 - row0b * a.W;
+  if (col0b < 0) { col0b += a.W; --row0b; }
+  if (col0b >= a.W) { col0b -= a.W; ++row0b; }
+
+  // ---------------- filter: class max, conservative logit bound, partition / stride mask ----------------
   const bool zero_passes = 0.0f >= a.thr;
   {
     const int lp0 = tid * kPxPerThread;          // first local pixel of this thread
@@ -448,7 +492,68 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       // bit 7 of the queued class: an earlier class may round to the same float32 sigmoid (checked in the score phase)
       if (cls[j] > 0 && (best[j] >= 15.f || runner[j] > best[j] - 1.0f)) cls[j] |= 0x80;
     }
-    // warp-aggregated reservation in queue 1 (the order of the queue is irrelevant: every row carries its own key)
+    // sample_by_range for the pixels that may pass: bit i of emit = the pixel's range lies in partition i (or 0 >= thr,
+    // where out-of-partition copies survive with score 0) AND its column is a multiple of rate_i.  A pixel whose mask
+    // comes out empty can never produce a row, whatever its exact score: it leaves here, on the 4-pixels-per-thread
+    // lanes, before the sigmoid (at the bench workload 95 % of the pixels pass the threshold but 2 in 3 are strided out).
+    uint32_t emit[kPxPerThread];
+#pragma unroll
+    for (int j = 0; j < kPxPerThread; ++j) emit[j] = n_parts == 0 ? 1u : 0u;
+    if (maybe && n_parts > 0) {
+      float cxv[4], cyv[4], czv[4];
+      Sm<TC>::four(s_cart + lp0, cxv);
+      Sm<TC>::four(s_cart + kTile + lp0, cyv);
+      Sm<TC>::four(s_cart + 2 * kTile + lp0, czv);
+      int w0 = col0b + lp0;
+      while (w0 >= a.W) w0 -= a.W;
+      // stride masks of the 4 columns, 4 bits per partition (FilterParts); a thread whose pixels straddle the end of
+      // an image row (one in W / 4) tests its columns one by one instead
+      const bool straddle = w0 + (kPxPerThread - 1) >= a.W;
+      uint32_t M = 0u;
+#pragma unroll
+      for (int i = 0; i < kRegParts; ++i) {
+        const int R = a.fp.rate[i];
+        const int r0 = a.fp.shift[i] >= 0 ? (w0 & (R - 1)) : (w0 - static_cast<int>(__umulhi(static_cast<uint32_t>(w0), a.fp.magic[i])) * R);
+        const int n = r0 ? R - r0 : 0;
+        M |= (n < 4 ? ((a.fp.pattern[i] << n) & 0xFu) : 0u) << (4 * i);
+      }
+#pragma unroll
+      for (int j = 0; j < kPxPerThread; ++j) {
+        uint32_t part_in = 0u, stride_ok;
+        if (sizeof(TC) == 4) {
+          const float ss = (cxv[j] * cxv[j] + cyv[j] * cyv[j]) + czv[j] * czv[j];   // norm3 without its square root (FilterParts)
+#pragma unroll
+          for (int i = 0; i < kRegParts; ++i) part_in |= ((ss > a.fp.s_lo[i]) && (ss <= a.fp.s_hi[i])) ? (1u << i) : 0u;
+        } else {
+          // cart.norm(dim=1) accumulates in float32 and rounds to cart's dtype; the bounds are a float32 tensor
+          const float d = Ld<TC>::round_f32(norm3(cxv[j], cyv[j], czv[j]));
+#pragma unroll
+          for (int i = 0; i < kRegParts; ++i) part_in |= ((d > a.fp.lower[i]) && (d <= a.fp.upper[i])) ? (1u << i) : 0u;
+        }
+        if (!straddle) {
+          const uint32_t x = (M >> j) & 0x1111u;
+          stride_ok = (x | (x >> 3) | (x >> 6) | (x >> 9)) & 0xFu;
+        } else {
+          int w = w0 + j;
+          if (w >= a.W) w -= a.W;
+          stride_ok = 0u;
+          for (int i = 0; i < n_parts && i < kRegParts; ++i)
+            stride_ok |= (w - fast_div(w, s_shift[i], s_magic[i]) * s_rate[i]) ? 0u : (1u << i);
+        }
+        if (n_parts > kRegParts) {                 // partitions beyond the register set: the plain form
+          const float d = Ld<TC>::round_f32(norm3(cxv[j], cyv[j], czv[j]));
+          int w = w0 + j;
+          if (w >= a.W) w -= a.W;
+          for (int i = kRegParts; i < n_parts; ++i) {
+            part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
+            stride_ok |= (w - fast_div(w, s_shift[i], s_magic[i]) * s_rate[i]) ? 0u : (1u << i);
+          }
+        }
+        emit[j] = (zero_passes ? ((1u << n_parts) - 1u) : part_in) & stride_ok;
+        if (!emit[j]) maybe &= ~(1u << j);
+      }
+    }
+    // warp-aggregated reservation in the queue (its order is irrelevant: every row carries its own key)
     const uint32_t cnt = __popc(maybe);
     uint32_t incl = cnt;
 #pragma unroll
@@ -465,6 +570,7 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
       if (maybe & (1u << j)) {
         q_pix[pos] = static_cast<uint16_t>(lp0 + j);
         q_cls[pos] = static_cast<uint8_t>(cls[j]);
+        q_emit[pos] = static_cast<uint8_t>(emit[j]);
         ++pos;
       }
     }
@@ -478,24 +584,9 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     const uint32_t plane = static_cast<uint32_t>(npx) * sizeof(T);
     for (int k = 0; k < 8; ++k) bulk_prefetch_l2(rg + static_cast<size_t>(k) * HW, plane);
   }
-  // (row, col) of the tile's first pixel: float reciprocal + one correction step instead of an integer division
-  int row0b = __float2int_rz(__int2float_rn(blk0) * a.inv_w);
-  int col0b = blk0 - row0b * a.W;
-  if (col0b < 0) { col0b += a.W; --row0b; }
-  if (col0b >= a.W) { col0b -= a.W; ++row0b; }
 
-  // ---------------- score: exact sigmoid / threshold / first index / partition / stride, dense lanes ----------------
-  uint32_t n_live = 0, n_emit = 0;
-  // partition constants of the first kRegParts partitions in registers (unused slots never match)
-  float plo[kRegParts], phi[kRegParts];
-  int prate[kRegParts], pshift[kRegParts];
-  uint32_t pmagic[kRegParts];
-#pragma unroll
-  for (int i = 0; i < kRegParts; ++i) {
-    const bool on = i < n_parts;
-    plo[i] = on ? s_lower[i] : CUDART_INF_F; phi[i] = on ? s_upper[i] : -CUDART_INF_F;
-    prate[i] = on ? s_rate[i] : 1; pshift[i] = on ? s_shift[i] : 0; pmagic[i] = on ? s_magic[i] : 0u;
-  }
+  // ---------------- score: exact sigmoid / threshold / first index, dense lanes ----------------
+  uint32_t n_emit = 0;
   for (uint32_t t = tid; t < n1; t += kThreads) {
     const int lp = q_pix[t];
     const int qc = q_cls[t];
@@ -515,44 +606,19 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     } else {
       cls = 0;  // sigmoid * 0 == 0 for every class -> argmax 0
     }
-    uint32_t emit = 0u;
-    if (score >= a.thr || zero_passes) {
-      if (n_parts == 0) {
-        emit = score >= a.thr ? 1u : 0u;
-      } else {
-        // bit i of part_in: the pixel's range lies in partition i
-        // cart.norm(dim=1) accumulates in float32 and rounds to cart's dtype; the bounds are a float32 tensor
-        const float d = Ld<TC>::round_f32(norm3(Sm<TC>::one(s_cart + lp), Sm<TC>::one(s_cart + kTile + lp),
-                                                Sm<TC>::one(s_cart + 2 * kTile + lp)));
-        int w = col0b + lp;
-        while (w >= a.W) w -= a.W;
-        uint32_t part_in = 0u, stride_ok = 0u;
-#pragma unroll
-        for (int i = 0; i < kRegParts; ++i) {
-          part_in |= ((d > plo[i]) && (d <= phi[i])) ? (1u << i) : 0u;
-          // column stride: partition i keeps the columns w with w % rate_i == 0
-          stride_ok |= (w - fast_div(w, pshift[i], pmagic[i]) * prate[i]) ? 0u : (1u << i);
-        }
-        for (int i = kRegParts; i < n_parts; ++i) {
-          part_in |= ((d > s_lower[i]) && (d <= s_upper[i])) ? (1u << i) : 0u;
-          stride_ok |= (w - fast_div(w, s_shift[i], s_magic[i]) * s_rate[i]) ? 0u : (1u << i);
-        }
-        emit = score >= a.thr ? part_in : 0u;
-        if (zero_passes) emit = (1u << n_parts) - 1u;       // 0 >= thr: out-of-partition copies survive with score 0
-        emit &= stride_ok;
-      }
-    }
+    uint32_t emit = q_emit[t];
+    if (!(score >= a.thr)) emit = 0u;             // 0 >= thr: every score (>= 0) passes
     q_cls[t] = static_cast<uint8_t>(cls);
     q_emit[t] = static_cast<uint8_t>(emit);
     q_score[t] = score;
-    n_live += emit ? 1u : 0u;
     n_emit += __popc(emit);
   }
 
-  // ---------------- block scan of (live, emit) packed as hi16 | lo16 ----------------
-  // per block: live <= 512, emit <= 512 * 8 -> both fit 16 bits, no carry between the halves
-  const uint32_t mine = (n_live << 16) | n_emit;
-  uint32_t incl = mine;
+  // ---------------- block scan of the emitted rows ----------------
+  // Every warp adds up the warp totals itself: no serial warp-0 step, one barrier.  The ONE global atomicAdd per tile
+  // that reserves the block's output rows is issued by thread 0 right after that barrier; a thread decodes the queue
+  // entries it scored, so no shared-memory hand-over is needed in between.
+  uint32_t incl = n_emit;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -560,47 +626,26 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
   }
   if (lane == 31) s_scan[wid] = incl;
   __syncthreads();
-  if (wid == 0) {
-    const uint32_t v = lane < kWarps ? s_scan[lane] : 0u;
-    uint32_t inc2 = v;
+  uint32_t before = 0u, total = 0u;
 #pragma unroll
-    for (int o = 1; o < kWarps; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
-      if (lane >= o) inc2 += t;
-    }
-    if (lane < kWarps) s_scan[lane] = inc2 - v;  // exclusive warp offsets
-    if (lane == kWarps - 1) {
-      const uint32_t total_emit = inc2 & 0xffffu;
-      s_total_live = inc2 >> 16;
-      // ONE global atomic per tile reserves the block's output rows
-      s_base = total_emit ? static_cast<uint32_t>(atomicAdd(counter, static_cast<int>(total_emit))) : 0u;
-    }
+  for (int w = 0; w < kWarps; ++w) {
+    const uint32_t v = s_scan[w];
+    before += w < wid ? v : 0u;
+    total += v;
   }
+  if (tid == 0) s_base = total ? static_cast<uint32_t>(atomicAdd(counter, static_cast<int>(total))) : 0u;
   __syncthreads();
-  {
-    const uint32_t excl = s_scan[wid] + (incl - mine);
-    uint32_t live_pos = excl >> 16, emit_pos = excl & 0xffffu;
-    for (uint32_t t = tid; t < n1; t += kThreads) {     // the same entries, in the same order, as the score loop
-      const uint32_t e = q_emit[t];
-      if (!e) continue;
-      q2_t[live_pos] = static_cast<uint16_t>(t);
-      q2_off[live_pos] = static_cast<uint16_t>(emit_pos);
-      ++live_pos;
-      emit_pos += __popc(e);
-    }
-  }
-  __syncthreads();
-  const uint32_t total_live = s_total_live;
-  const uint32_t base = s_base;
+  uint32_t row = s_base + before + (incl - n_emit);
 
   // ---------------- decode: dense-lane fp64 decode of the emitting pixels ----------------
-  for (uint32_t u = tid; u < total_live; u += kThreads) {
-    const int t = q2_t[u];
+  for (uint32_t t = tid; t < n1; t += kThreads) {
+    uint32_t e = q_emit[t];
+    if (!e) continue;                              // failed the exact threshold (only pixels inside the bound's slack)
     const int lp = q_pix[t];
     const int p = blk0 + lp;
     float r[8], c[3];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(rg + (static_cast<uint32_t>(k) * static_cast<uint32_t>(HW) + lp));   // 8 independent loads in flight (7 * H * W < 2^32: host check)
+    for (int k = 0; k < 8; ++k) r[k] = Ld<T>::one(rg + static_cast<size_t>(k) * HW + lp);   // 8 independent loads in flight
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[k] = Sm<TC>::one(s_cart + k * kTile + lp);
     double o[7];
@@ -612,8 +657,6 @@ decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__res
     const uint32_t seg = static_cast<uint32_t>(b) * a.total_classes + q_cls[t] + a.cat_off;
     int h = row0b, w = col0b + lp;
     while (w >= a.W) { w -= a.W; ++h; }
-    uint32_t e = q_emit[t];
-    uint32_t row = base + q2_off[u];
     const float sc = q_score[t];
     while (e) {
       const int i = __ffs(e) - 1;
@@ -816,6 +859,7 @@ extern "C" int rv3d_decode_compact(const rv3d_decode_params *p, const void *logi
   RV3D_CHECK_ARG(p->height < (1 << 22));   // row estimate from a float32 quotient is within one of the true row
   RV3D_CHECK_ARG(p->n_classes <= 128);   // queue 1 keeps the class in 7 bits
   a.pa = make_parts(&p->parts, p->height, p->width);
+  a.fp = make_filter_parts(a.pa);
   RV3D_CHECK_ARG(p->total_candidates >= p->candidate_offset + a.pa.off[a.pa.n]);
   a.kp.idx_bits = bits_for(p->total_candidates);
   a.kp.score_bits = RV3D_SCORE_BITS_DECODE;   // sigmoid * mask is never negative
