@@ -579,9 +579,15 @@ def run_ours(args):
     g_r, _ = capture(hp1.rasterize, dev)
     g_d, _ = capture(stage_decode, dev)
     g_n, _ = capture(stage_nms, dev)
+
+    def stage_raster_decode():
+        hp1.rasterize(); stage_decode()
+
+    g_rd, _ = capture(stage_raster_decode, dev)   # the roofline pair as ONE graph: one launch, no gap between the two stages
     for _ in range(3):
-        g_r.replay(); g_d.replay(); g_n.replay()
+        g_r.replay(); g_d.replay(); g_n.replay(); g_rd.replay()
     (t_raster, t_decode, t_nms), _ = replay_timed([g_r, g_d, g_n], args.steps, flush)
+    (t_rd,), _ = replay_timed([g_rd], args.steps, flush)
 
     # ---------------- e2e: pinned host inputs -> H2D -> path -> D2H of the detections, every step --------
     def e2e_leg(hpx, steps):
@@ -694,7 +700,7 @@ def run_ours(args):
         except (OSError, ValueError):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        rd_ms = float(np.mean(t_raster) + np.mean(t_decode))
+        rd_ms = float(np.mean(t_rd))
         achieved = (raster_b + decode_b) / (rd_ms * 1e-3) / 1e9
         S = B * C
         single = {"value": value, "ms_per_step": total_ms / args.steps, "ms_per_step_median_rank0": float(np.median(t_step)),
@@ -729,7 +735,10 @@ def run_ours(args):
                          "algorithmic_bytes": {"rasterize": raster_b, "decode": decode_b},
                          "rasterize_gbs": raster_b / (float(np.mean(t_raster)) * 1e-3) / 1e9,
                          "decode_gbs": decode_b / (float(np.mean(t_decode)) * 1e-3) / 1e9,
-                         "timing": "each stage replayed as its own CUDA graph, CUDA events on the replay stream, L2 flushed per step",
+                         "timing": ("achieved / frac: rasterize + decode_compact replayed as ONE CUDA graph (memset of the z-keys, scatter, resolve, "
+                                    "counter fill, decode_compact), CUDA events on the replay stream around the replay, L2 flushed before every "
+                                    "replay; rasterize_gbs / decode_gbs: each stage as its own graph (each pays its own graph launch)"),
+                         "ms": rd_ms,
                          # the suppression stage, for completeness: it reads each candidate's key + box once and writes the
                          # detections (NMS is latency / issue bound, an HBM fraction says little -- work units under "nms")
                          "nms_stage": {"bound": "hbm", "algorithmic_bytes": int(ncand) * 40 + int(ndet) * 52,

@@ -7,16 +7,11 @@
 //   math/ops/nms.py:212-215             min-confidence gather
 //   math/linalg/lie/SO3.py:122-134      yaw_to_quat
 //
-// K2 (decode_compact) is one pass over the head outputs:
-//   phase A  every thread owns 4 consecutive pixels: float4 loads of the C logit planes + mask,
-//            running max (first index wins ties, NaN kills the pixel like torch.max would),
-//            correctly-rounded float32 sigmoid of the winner, threshold; for pixels that pass,
-//            the range-partition / column-stride test of sample_by_range on ||cart||.
-//   scan     block-wide exclusive scan of (live pixels, emitted candidates); ONE global atomicAdd
-//            per 1024 pixels reserves the output rows.
-//   phase B  live pixels are compacted into a shared-memory queue so the fp64 decode
-//            (3 exp, 2 atan2, sincos) runs with dense lanes instead of ~20 %-full warps;
-//            each live pixel writes 1..n_partitions (key, box) rows.
+// K2 (decode_compact) is one pass over the head outputs, one CTA per tile of 512 pixels (phases described at the
+// kernel): TMA-staged logits / cart / mask -> class max + conservative logit bound + sample_by_range mask on the
+// 4-pixels-per-thread lanes -> exact float32 sigmoid / threshold / first-index check on dense lanes -> block scan,
+// ONE global atomicAdd per tile -> fp64 box decode (csrc/fastmath.cuh) of the emitting pixels on dense lanes,
+// 1..n_partitions (key, box) rows each.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -380,15 +375,17 @@ __device__ __forceinline__ void class_max(const T *s_logits, int lp0, int C, flo
 //            NOT staged: only emitting pixels need them, the last phase gathers them (8 independent loads per pixel).
 //   filter   every thread owns 4 consecutive pixels: running max over the classes (first index wins, NaN kills the
 //            pixel like torch.max) and ONE comparison against a conservative logit bound x_lo (sigmoid_T(x) >= thr
-//            implies x >= x_lo, computed on the host with slack for the float32 / half rounding).  Survivors go to
-//            queue 1 (warp-aggregated shared-memory reservation).  Nothing else runs on sparse lanes: with one
-//            pixel in three alive, a per-pixel branch costs the whole warp its full price (ncu r02a: sigmoid +
-//            threshold + partition + stride tests were 36 % of the kernel's instructions at 30 % lane use).
-//   score    dense lanes over queue 1: float32 sigmoid the way the reference's CUDA path rounds it, exact threshold,
-//            first-index tie check, sample_by_range partition bits from ||cart||, column-stride test.
-//   scan     block scan of (emitting pixels, emitted rows); ONE global atomicAdd per tile reserves the output rows;
-//            emitting pixels are compacted again (queue 2) so the fp64 decode also runs on dense lanes.
-//   decode   fp64 decode (3 exp, 2 atan2, rotation) of queue 2, 1..n_partitions (key, box) rows each.
+//            implies x >= x_lo, computed on the host with slack for the float32 / half rounding); for threads with a
+//            survivor, the sample_by_range mask of the 4 pixels (FilterParts: range test on the sum of squares, stride
+//            test for 4 columns at once).  Pixels that may pass AND can emit go to the queue (warp-aggregated
+//            shared-memory reservation).  No sigmoid, no square root, no division on these sparse lanes: with one pixel
+//            in three alive a per-pixel branch costs the whole warp its full price (ncu r02a: sigmoid + threshold +
+//            partition + stride tests were 36 % of the kernel's instructions at 30 % lane use).
+//   score    dense lanes over the queue: float32 sigmoid the way the reference's CUDA path rounds it, exact threshold,
+//            first-index tie check (only where the filter flagged a close runner-up).
+//   scan     block scan of the emitted rows; ONE global atomicAdd per tile reserves the output rows.
+//   decode   every thread decodes the queue entries it scored: fp64 decode (3 exp, 1-2 atan2, rotation), 1..n_partitions
+//            (key, box) rows each.
 template <typename T, typename TC, int kTile, bool kBulk>
 __global__ void __launch_bounds__(kTile / kPxPerThread, kTile == 512 ? 9 : 12)
 decode_compact_kernel(DecodeArgs a, const T *__restrict__ logits, const T *__restrict__ reg,
