@@ -121,6 +121,13 @@ typedef struct {
 } rv3d_inputs_params;
 int rv3d_range_view_inputs(const rv3d_inputs_params *p, const float *image, float *features, float *cart,
                            uint8_t *mask, rv3d_stream_t stream);
+/* The same assembly fused into the rasterizer (raw sweeps -> network inputs in one scatter + one resolve pass; the
+ * 7-plane range image is never materialised).  `p` as in rv3d_rasterize, `ip` as in rv3d_range_view_inputs with
+ * ip->batch / height / width equal to p's; results are identical to rv3d_rasterize followed by rv3d_range_view_inputs. */
+int rv3d_rasterize_inputs(const rv3d_raster_params *p, const rv3d_inputs_params *ip, const float *points,
+                          const uint8_t *laser, const int32_t *n_points, const int32_t *laser_mapping,
+                          float *features, float *cart, uint8_t *mask, void *scratch, size_t scratch_bytes,
+                          rv3d_stream_t stream);
 /* subsample_range_view alone (prototype/loader.py:792-815) on already assembled tensors:
  * range_view (B,C,H,W) f32, mask (B,1,H,W) u8, cart (B,3,H,W) f32 -> the same three, padded and strided. */
 int rv3d_subsample_range_view(const float *range_view, const uint8_t *mask, const float *cart, int32_t batch,

@@ -423,6 +423,74 @@ subsample_range_view_kernel(const float *__restrict__ rv, const uint8_t *__restr
 
 
 // ---------------------------------------------------------------------------------------------
+// rasterize straight into the network's inputs: K1b with the loader's assembly folded in.  One
+// thread per OUTPUT pixel (after padding / striding): key -> winning point -> only the channels the feature list
+// asks for (the two fp64 arctangents are skipped when neither azimuth nor inclination is a feature, the usual
+// case), tanh / mask / zero padding applied on the way out.  The 7-plane image is never written or re-read.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kResolveThreads, 8)
+raster_resolve_inputs_kernel(RasterArgs a, InputsArgs ia, int need_angles, const float4 *__restrict__ points,
+                             const unsigned long long *__restrict__ keys, float *__restrict__ features,
+                             float *__restrict__ cart, uint8_t *__restrict__ mask) {
+  const int b = blockIdx.y;
+  const int HW = a.H * a.W, HWo = ia.H * ia.Wo;
+  const int o0 = blockIdx.x * (kResolveThreads * kResolvePx) + threadIdx.x;
+  const unsigned long long *kb = keys + static_cast<size_t>(b) * HW;
+  const float4 *pts = points + static_cast<size_t>(b) * a.max_points;
+  unsigned long long key[kResolvePx];
+  float4 p[kResolvePx];
+  bool inside[kResolvePx];
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j) {
+    const int o = o0 + j * kResolveThreads;
+    key[j] = kEmptyKey;
+    inside[j] = false;
+    if (o < HWo) {
+      const int h = o / ia.Wo, wo = o - h * ia.Wo;
+      int w = wo * ia.stride - ia.pad;                      // column in the unpadded image
+      inside[j] = true;
+      if (w < 0 || w >= ia.W) {
+        if (ia.mode == RV3D_PAD_CIRCULAR) { w %= ia.W; if (w < 0) w += ia.W; }
+        else inside[j] = false;                             // constant (zero) padding
+      }
+      if (inside[j]) key[j] = __ldg(kb + h * ia.W + w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j)
+    p[j] = ldg_stream_f4(pts + (key[j] != kEmptyKey ? key_index(key[j]) : 0u));
+#pragma unroll
+  for (int j = 0; j < kResolvePx; ++j) {
+    const int o = o0 + j * kResolveThreads;
+    if (o >= HWo) break;
+    float ch[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (key[j] != kEmptyKey) {
+      if (need_angles) {
+        const PixelOut px = resolve_pixel(a, key[j], p[j]);
+        ch[0] = px.az; ch[1] = px.inc;
+      }
+      ch[2] = __uint_as_float(static_cast<uint32_t>(key[j] >> 32));
+      ch[3] = p[j].x; ch[4] = p[j].y; ch[5] = p[j].z; ch[6] = p[j].w;
+    }
+    const bool valid = inside[j] && ch[2] > 0.0f;           // mask = range > 0 (loader.py:645-650)
+    for (int f = 0; f < ia.F; ++f) {
+      float v = 0.f;
+      if (inside[j]) {
+        const int c = ia.ch[f];
+        v = c == 0 ? ch[0] : c == 1 ? ch[1] : c == 2 ? ch[2] : c == 3 ? ch[3] : c == 4 ? ch[4] : c == 5 ? ch[5] : ch[6];
+        if (c == ia.tanh_ch) v = tanhf(v);                  // Waymo: intensity.tanh() (loader.py:625-626)
+        v = valid ? v : v * 0.0f;                           // range_view *= mask (loader.py:808)
+      }
+      features[(static_cast<size_t>(b) * ia.F + f) * HWo + o] = v;
+    }
+    cart[(static_cast<size_t>(b) * 3 + 0) * HWo + o] = inside[j] ? ch[3] : 0.f;
+    cart[(static_cast<size_t>(b) * 3 + 1) * HWo + o] = inside[j] ? ch[4] : 0.f;
+    cart[(static_cast<size_t>(b) * 3 + 2) * HWo + o] = inside[j] ? ch[5] : 0.f;
+    mask[static_cast<size_t>(b) * HWo + o] = valid ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // test hooks: the fast math routines and the rasterizer's float32 column decision, exposed so the GPU suite can
 // measure their error / check the proof obligation directly (tests/test_gpu_fastmath.py)
 // ---------------------------------------------------------------------------------------------
@@ -495,52 +563,82 @@ extern "C" size_t rv3d_rasterize_scratch_bytes(const rv3d_raster_params *p) {
   return static_cast<size_t>(p->batch) * p->height * p->width * sizeof(unsigned long long);
 }
 
-extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, const uint8_t *laser,
-                              const int32_t *n_points, const int32_t *laser_mapping, float *image,
-                              int32_t *winner, void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
-  RV3D_CHECK_ARG(p && points && laser && n_points && laser_mapping && image && scratch);
+// memset of the z-keys + K1 for the whole batch; shared by rv3d_rasterize and rv3d_rasterize_inputs
+static int launch_scatter(const rv3d_raster_params *p, const RasterArgs &a, const float *points, const uint8_t *laser,
+                          const int32_t *n_points, const int32_t *laser_mapping, unsigned long long *keys, cudaStream_t s) {
+  const int64_t HW = static_cast<int64_t>(p->height) * p->width;
+  RV3D_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, static_cast<size_t>(p->batch) * HW * sizeof(unsigned long long), s));
+  dim3 g1(ceil_div(p->max_points, kScatterThreads * kScatterPerThread), p->batch);
+  raster_scatter_kernel<<<g1, kScatterThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(points), laser, n_points,
+                                                       laser_mapping, keys);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+static int check_raster_args(const rv3d_raster_params *p, const void *points, const void *scratch, size_t scratch_bytes) {
   RV3D_CHECK_ARG(p->batch > 0 && p->max_points > 0 && p->height > 0 && p->width > 0 && p->azimuth_bins > 0);
   RV3D_CHECK_ARG(p->num_lasers > 0 && p->num_lasers <= 256 && p->reserved == 0);
   RV3D_CHECK_ARG(p->col_mode == RV3D_COL_LIBRARY || p->col_mode == RV3D_COL_CONVERTER);
   RV3D_CHECK_ARG(static_cast<int64_t>(p->height) * p->width < (int64_t(1) << 31));
   if (!aligned(points, 16) || !aligned(scratch, 8)) return RV3D_ERR_ALIGN;
-  const size_t need = rv3d_rasterize_scratch_bytes(p);
-  if (scratch_bytes < need) return RV3D_ERR_SCRATCH;
+  if (scratch_bytes < rv3d_rasterize_scratch_bytes(p)) return RV3D_ERR_SCRATCH;
+  return RV3D_OK;
+}
+
+// Measured and dropped (profiles/r02_raster_chunks.md): processing the batch in L2-sized chunks of sweeps (scatter +
+// resolve per chunk, so that the keys and points a resolve pass gathers are still L2-resident) is SLOWER at every chunk
+// size -- the half-size kernels lose more to their tails and launch gaps than the gathers win.
+extern "C" int rv3d_rasterize(const rv3d_raster_params *p, const float *points, const uint8_t *laser,
+                              const int32_t *n_points, const int32_t *laser_mapping, float *image,
+                              int32_t *winner, void *scratch, size_t scratch_bytes, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && points && laser && n_points && laser_mapping && image && scratch);
+  if (const int st = check_raster_args(p, points, scratch, scratch_bytes)) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  RasterArgs a = make_args(p);
+  const RasterArgs a = make_args(p);
   auto *keys = static_cast<unsigned long long *>(scratch);
-  // Measured and dropped (profiles/r02_raster_chunks.md): processing the batch in L2-sized chunks of sweeps (scatter +
-  // resolve per chunk, so that the keys and points a resolve pass gathers are still L2-resident) is SLOWER at every chunk
-  // size -- 85 us for one chunk, 97 / 120 / 167 us for 36 / 24 / 12 MB chunks at B = 16 Waymo: the half-size kernels lose
-  // more to their tails than the gathers win.  The chunk loop stays for experiments (RV3D_RASTER_CHUNK_MB).
+  if (const int st = launch_scatter(p, a, points, laser, n_points, laser_mapping, keys, s)) return st;
   const int64_t HW = static_cast<int64_t>(p->height) * p->width;
-  const int64_t per_sweep = static_cast<int64_t>(p->max_points) * 17 + HW * 8;
-  int64_t budget = int64_t(1) << 62;
-  if (const char *e = getenv("RV3D_RASTER_CHUNK_MB")) {
-    const long v = atol(e);
-    if (v > 0) budget = int64_t(v) << 20;
+  dim3 g2(ceil_div(HW, kResolveThreads * kResolvePx), p->batch);
+  raster_resolve_kernel<<<g2, kResolveThreads, 0, s>>>(a, reinterpret_cast<const float4 *>(points), keys, image, winner);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+static int make_inputs_args(const rv3d_inputs_params *p, InputsArgs &a) {
+  RV3D_CHECK_ARG(p->batch > 0 && p->height > 0 && p->width > 0 && p->x_stride > 0 && p->pad >= 0);
+  RV3D_CHECK_ARG(p->pad_mode == RV3D_PAD_CIRCULAR || p->pad_mode == RV3D_PAD_CONSTANT);
+  RV3D_CHECK_ARG(p->n_features >= 0 && p->n_features <= 8 && p->tanh_channel >= -1 && p->tanh_channel < 7);
+  RV3D_CHECK_ARG(p->pad_mode != RV3D_PAD_CIRCULAR || p->pad <= p->width);   // torch's circular pad limit
+  a = InputsArgs{};
+  a.B = p->batch; a.H = p->height; a.W = p->width; a.stride = p->x_stride; a.pad = p->pad; a.mode = p->pad_mode;
+  a.Wo = (p->width + 2 * p->pad + p->x_stride - 1) / p->x_stride;
+  a.F = p->n_features; a.tanh_ch = p->tanh_channel;
+  for (int f = 0; f < a.F; ++f) {
+    RV3D_CHECK_ARG(p->feature_channel[f] >= 0 && p->feature_channel[f] < 7);
+    a.ch[f] = p->feature_channel[f];
   }
-  int chunk = static_cast<int>(budget / (per_sweep > 0 ? per_sweep : 1));
-  if (chunk < 1) chunk = 1;
-  if (chunk > p->batch) chunk = p->batch;
-  // equal-sized chunks (16 sweeps, room for 8 -> 8 + 8, not 8 + 8 + 0; 20 sweeps, room for 8 -> 7 + 7 + 6)
-  const int n_chunks = (p->batch + chunk - 1) / chunk;
-  chunk = (p->batch + n_chunks - 1) / n_chunks;
-  for (int b0 = 0; b0 < p->batch; b0 += chunk) {
-    const int nb = p->batch - b0 < chunk ? p->batch - b0 : chunk;
-    a.B = nb;
-    unsigned long long *k = keys + static_cast<size_t>(b0) * HW;
-    const float4 *pts = reinterpret_cast<const float4 *>(points) + static_cast<size_t>(b0) * p->max_points;
-    RV3D_CHECK_CUDA(cudaMemsetAsync(k, 0xFF, static_cast<size_t>(nb) * HW * sizeof(unsigned long long), s));
-    dim3 g1(ceil_div(p->max_points, kScatterThreads * kScatterPerThread), nb);
-    raster_scatter_kernel<<<g1, kScatterThreads, 0, s>>>(a, pts, laser + static_cast<size_t>(b0) * p->max_points, n_points + b0,
-                                                         laser_mapping, k);
-    RV3D_CHECK_LAUNCH();
-    dim3 g2(ceil_div(HW, kResolveThreads * kResolvePx), nb);
-    raster_resolve_kernel<<<g2, kResolveThreads, 0, s>>>(a, pts, k, image + static_cast<size_t>(b0) * 7 * HW,
-                                             winner ? winner + static_cast<size_t>(b0) * HW : nullptr);
-    RV3D_CHECK_LAUNCH();
-  }
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_rasterize_inputs(const rv3d_raster_params *p, const rv3d_inputs_params *ip, const float *points,
+                                     const uint8_t *laser, const int32_t *n_points, const int32_t *laser_mapping,
+                                     float *features, float *cart, uint8_t *mask, void *scratch, size_t scratch_bytes,
+                                     rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(p && ip && points && laser && n_points && laser_mapping && features && cart && mask && scratch);
+  if (const int st = check_raster_args(p, points, scratch, scratch_bytes)) return st;
+  RV3D_CHECK_ARG(ip->batch == p->batch && ip->height == p->height && ip->width == p->width);
+  InputsArgs ia;
+  if (const int st = make_inputs_args(ip, ia)) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const RasterArgs a = make_args(p);
+  auto *keys = static_cast<unsigned long long *>(scratch);
+  if (const int st = launch_scatter(p, a, points, laser, n_points, laser_mapping, keys, s)) return st;
+  int need_angles = 0;
+  for (int f = 0; f < ia.F; ++f) need_angles |= (ia.ch[f] == 0 || ia.ch[f] == 1) ? 1 : 0;
+  dim3 g2(ceil_div(static_cast<int64_t>(ia.H) * ia.Wo, kResolveThreads * kResolvePx), p->batch);
+  raster_resolve_inputs_kernel<<<g2, kResolveThreads, 0, s>>>(a, ia, need_angles, reinterpret_cast<const float4 *>(points), keys,
+                                                              features, cart, mask);
+  RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
 
@@ -613,18 +711,8 @@ extern "C" int rv3d_range_view_coordinates(double *sph, const int64_t *laser, co
 extern "C" int rv3d_range_view_inputs(const rv3d_inputs_params *p, const float *image, float *features,
                                       float *cart, uint8_t *mask, rv3d_stream_t stream) {
   RV3D_CHECK_ARG(p && image && features && cart && mask);
-  RV3D_CHECK_ARG(p->batch > 0 && p->height > 0 && p->width > 0 && p->x_stride > 0 && p->pad >= 0);
-  RV3D_CHECK_ARG(p->pad_mode == RV3D_PAD_CIRCULAR || p->pad_mode == RV3D_PAD_CONSTANT);
-  RV3D_CHECK_ARG(p->n_features >= 0 && p->n_features <= 8 && p->tanh_channel >= -1 && p->tanh_channel < 7);
-  RV3D_CHECK_ARG(p->pad_mode != RV3D_PAD_CIRCULAR || p->pad <= p->width);   // torch's circular pad limit
-  InputsArgs a{};
-  a.B = p->batch; a.H = p->height; a.W = p->width; a.stride = p->x_stride; a.pad = p->pad; a.mode = p->pad_mode;
-  a.Wo = (p->width + 2 * p->pad + p->x_stride - 1) / p->x_stride;
-  a.F = p->n_features; a.tanh_ch = p->tanh_channel;
-  for (int f = 0; f < a.F; ++f) {
-    RV3D_CHECK_ARG(p->feature_channel[f] >= 0 && p->feature_channel[f] < 7);
-    a.ch[f] = p->feature_channel[f];
-  }
+  InputsArgs a;
+  if (const int st = make_inputs_args(p, a)) return st;
   dim3 grid(ceil_div(static_cast<int64_t>(a.H) * a.Wo, 256), a.B);
   range_view_inputs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, image, features, cart, mask);
   RV3D_CHECK_LAUNCH();

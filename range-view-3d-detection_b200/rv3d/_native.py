@@ -73,6 +73,7 @@ _SIGNATURES = {
     "rv3d_cart_to_sph": (C.c_int, [_P, _P, _I64, _P]),
     "rv3d_range_view_coordinates": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P]),
     "rv3d_range_view_inputs": (C.c_int, [C.POINTER(InputsParams), _P, _P, _P, _P, _P]),
+    "rv3d_rasterize_inputs": (C.c_int, [C.POINTER(RasterParams), C.POINTER(InputsParams), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "rv3d_subsample_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rv3d_decode_range_view": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "rv3d_num_candidates": (_I64, [C.POINTER(Partitions), _I32, _I32]),

@@ -19,6 +19,29 @@ __all__ = ["build_range_view", "rasterize_sweeps", "pack_sweeps"]
 _RASTER_PARAMS: dict = {}
 
 
+def raster_params(B: int, nmax: int, height: int, width: int, n_azimuth_bins, num_lasers, mapping_len: int, col_mode: str,
+                  lidar_offset: Sequence[float], min_distance: float):
+    """-> (rv3d_raster_params, scratch bytes).  The parameter block (and the scratch size it implies) only depends on shapes
+    and options: built once per key, so that the launch is not waiting on host work every step."""
+    key = (B, nmax, height, width, n_azimuth_bins, num_lasers, mapping_len, col_mode,
+           tuple(float(v) for v in lidar_offset), float(min_distance))
+    hit = _RASTER_PARAMS.get(key)
+    if hit is None:
+        p = N.RasterParams()
+        p.batch, p.max_points, p.height, p.width = B, nmax, height, width
+        p.azimuth_bins = width if n_azimuth_bins is None else n_azimuth_bins
+        p.num_lasers = mapping_len if num_lasers is None else num_lasers
+        if p.num_lasers > mapping_len:
+            raise ValueError("laser_mapping is shorter than num_lasers")
+        p.col_mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
+        p.lidar_offset[:] = [float(v) for v in lidar_offset]
+        p.min_distance = float(min_distance)
+        if len(_RASTER_PARAMS) > 64:
+            _RASTER_PARAMS.clear()
+        hit = _RASTER_PARAMS[key] = (p, N.lib().rv3d_rasterize_scratch_bytes(p))
+    return hit
+
+
 def rasterize_sweeps(points: torch.Tensor, laser: torch.Tensor, n_points: torch.Tensor,
                      laser_mapping: torch.Tensor, lidar_offset: Sequence[float], height: int = 64,
                      width: int = 1800, n_azimuth_bins: Optional[int] = None, num_lasers: Optional[int] = None,
@@ -40,25 +63,8 @@ def rasterize_sweeps(points: torch.Tensor, laser: torch.Tensor, n_points: torch.
     points, laser = points.contiguous(), laser.contiguous()
     B, nmax, _ = points.shape
     lib = N.lib()
-    # the parameter block (and the scratch size it implies) only depends on shapes and options: built once per key,
-    # so that the launch is not waiting on host work every step
-    key = (B, nmax, height, width, n_azimuth_bins, num_lasers, laser_mapping.numel(), col_mode,
-           tuple(float(v) for v in lidar_offset), float(min_distance))
-    hit = _RASTER_PARAMS.get(key)
-    if hit is None:
-        p = N.RasterParams()
-        p.batch, p.max_points, p.height, p.width = B, nmax, height, width
-        p.azimuth_bins = width if n_azimuth_bins is None else n_azimuth_bins
-        p.num_lasers = laser_mapping.numel() if num_lasers is None else num_lasers
-        if p.num_lasers > laser_mapping.numel():
-            raise ValueError("laser_mapping is shorter than num_lasers")
-        p.col_mode = {"library": N.COL_LIBRARY, "converter": N.COL_CONVERTER}[col_mode]
-        p.lidar_offset[:] = [float(v) for v in lidar_offset]
-        p.min_distance = float(min_distance)
-        if len(_RASTER_PARAMS) > 64:
-            _RASTER_PARAMS.clear()
-        hit = _RASTER_PARAMS[key] = (p, lib.rv3d_rasterize_scratch_bytes(p))
-    p, need = hit
+    p, need = raster_params(B, nmax, height, width, n_azimuth_bins, num_lasers, laser_mapping.numel(), col_mode, lidar_offset,
+                            min_distance)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = scratch(need, dev)
     image = out if out is not None else torch.empty((B, 7, height, width), dtype=torch.float32, device=dev)

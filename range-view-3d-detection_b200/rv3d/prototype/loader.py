@@ -10,7 +10,7 @@ from torch import Tensor
 from .. import _native as N
 from .._util import ptr, require_cuda, stream_ptr
 
-__all__ = ["subsample_range_view", "range_view_inputs", "intersection_test", "IMAGE_CHANNELS"]
+__all__ = ["subsample_range_view", "range_view_inputs", "rasterize_inputs", "intersection_test", "IMAGE_CHANNELS"]
 
 # channel order of rv3d.math.range_view images (math/range_view.py:33)
 IMAGE_CHANNELS = ("azimuth", "inclination", "range", "x", "y", "z", "intensity")
@@ -25,6 +25,52 @@ def _pad_for(dataset_name: str, x_stride: int) -> int:
     raise ValueError(f"unknown dataset {dataset_name!r}")
 
 
+def _inputs_params(B: int, H: int, W: int, feature_column_names: Sequence[str], dataset_name: str, x_stride: int, mode: str):
+    if mode not in ("circular", "constant"):
+        raise NotImplementedError(f"padding mode {mode!r}")
+    p = N.InputsParams()
+    p.batch, p.height, p.width = B, H, W
+    p.x_stride, p.pad = int(x_stride), _pad_for(dataset_name, x_stride)
+    p.pad_mode = 0 if mode == "circular" else 1
+    p.n_features = len(feature_column_names)
+    for f, name in enumerate(feature_column_names):
+        p.feature_channel[f] = IMAGE_CHANNELS.index(name)
+    p.tanh_channel = IMAGE_CHANNELS.index("intensity") if dataset_name == "waymo" else -1
+    return p, (W + 2 * p.pad + p.x_stride - 1) // p.x_stride
+
+
+def rasterize_inputs(points: Tensor, laser: Tensor, n_points: Tensor, laser_mapping: Tensor, lidar_offset: Sequence[float],
+                     height: int = 64, width: int = 1800, feature_column_names: Sequence[str] = ("intensity", "range", "x", "y", "z"),
+                     dataset_name: str = "av2", x_stride: int = 1, mode: str = "circular", n_azimuth_bins: int = None,
+                     num_lasers: int = None, col_mode: str = "library", min_distance: float = 1.0,
+                     workspace: Tensor = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Raw sweeps -> (features (B,F,H,Wo), mask (B,1,H,Wo) bool, cart (B,3,H,Wo)) in one scatter + one resolve pass:
+    ``rv3d.math.range_view.rasterize_sweeps`` followed by ``range_view_inputs`` (math/range_view.py:14-44 +
+    prototype/loader.py:623-650, 792-815) without materialising the 7-plane range image in between.  Arguments as in
+    those two functions; results are identical to calling them one after the other."""
+    from ..math.range_view import raster_params
+    dev = require_cuda(points, laser, n_points, laser_mapping)
+    if points.dtype != torch.float32 or points.dim() != 3 or points.shape[-1] != 4:
+        raise ValueError("points must be (B,Nmax,4) float32")
+    if laser.dtype != torch.uint8 or n_points.dtype != torch.int32 or laser_mapping.dtype != torch.int32:
+        raise ValueError("laser must be uint8; n_points and laser_mapping int32")
+    points, laser = points.contiguous(), laser.contiguous()
+    B = points.shape[0]
+    rp, need = raster_params(B, points.shape[1], height, width, n_azimuth_bins, num_lasers, laser_mapping.numel(), col_mode,
+                             lidar_offset, min_distance)
+    ip, wo = _inputs_params(B, height, width, feature_column_names, dataset_name, x_stride, mode)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        from .._util import scratch
+        workspace = scratch(need, dev)
+    features = torch.empty((B, ip.n_features, height, wo), dtype=torch.float32, device=dev)
+    cart = torch.empty((B, 3, height, wo), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, 1, height, wo), dtype=torch.uint8, device=dev)
+    N.check(N.lib().rv3d_rasterize_inputs(rp, ip, ptr(points), ptr(laser), ptr(n_points), ptr(laser_mapping), ptr(features),
+                                          ptr(cart), ptr(mask), ptr(workspace), workspace.numel() * workspace.element_size(),
+                                          stream_ptr(dev)), "rv3d_rasterize_inputs")
+    return features, mask.view(torch.bool), cart
+
+
 def range_view_inputs(image: Tensor, feature_column_names: Sequence[str] = ("intensity", "range", "x", "y", "z"),
                       dataset_name: str = "av2", x_stride: int = 1, mode: str = "circular"
                       ) -> Tuple[Tensor, Tensor, Tensor]:
@@ -34,18 +80,8 @@ def range_view_inputs(image: Tensor, feature_column_names: Sequence[str] = ("int
     dev = require_cuda(image)
     if image.dim() != 4 or image.shape[1] != 7 or image.dtype != torch.float32:
         raise ValueError("image must be (B,7,H,W) float32 as produced by rasterize_sweeps")
-    if mode not in ("circular", "constant"):
-        raise NotImplementedError(f"padding mode {mode!r}")
     B, _, H, W = image.shape
-    p = N.InputsParams()
-    p.batch, p.height, p.width = B, H, W
-    p.x_stride, p.pad = int(x_stride), _pad_for(dataset_name, x_stride)
-    p.pad_mode = 0 if mode == "circular" else 1
-    p.n_features = len(feature_column_names)
-    for f, name in enumerate(feature_column_names):
-        p.feature_channel[f] = IMAGE_CHANNELS.index(name)
-    p.tanh_channel = IMAGE_CHANNELS.index("intensity") if dataset_name == "waymo" else -1
-    wo = (W + 2 * p.pad + p.x_stride - 1) // p.x_stride
+    p, wo = _inputs_params(B, H, W, feature_column_names, dataset_name, x_stride, mode)
     features = torch.empty((B, p.n_features, H, wo), dtype=torch.float32, device=dev)
     cart = torch.empty((B, 3, H, wo), dtype=torch.float32, device=dev)
     mask = torch.empty((B, 1, H, wo), dtype=torch.uint8, device=dev)

@@ -51,3 +51,28 @@ def test_subsample_range_view_drop_in(dataset, stride, mode):
     got = subsample_range_view(feats.to(DEV), mask.to(DEV), cart.to(DEV), dataset, stride, mode)
     for g, r in zip(got, ref):
         assert g.dtype == r.dtype and torch.equal(g.cpu(), r)
+
+
+@pytest.mark.parametrize("dataset,stride,mode,names", [
+    ("av2", 1, "circular", ("intensity", "range", "x", "y", "z")),
+    ("waymo", 4, "circular", ("intensity", "range", "x", "y", "z")),
+    ("waymo", 1, "constant", ("azimuth", "inclination", "range", "intensity")),
+    ("av2", 2, "constant", ("range",)),
+])
+def test_rasterize_inputs_equals_rasterize_then_assemble(dataset, stride, mode, names):
+    """rv3d_rasterize_inputs (raw sweeps -> network inputs, the 7-plane image never written) is bit-identical to
+    rasterize_sweeps followed by range_view_inputs, whose two halves are pinned against the reference separately."""
+    from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
+    from rv3d.prototype.loader import range_view_inputs, rasterize_inputs
+    H, W = 32, 600
+    sweeps = [synth.make_points(n, H, s, extra_laser_frac=0.01) for s, n in ((5, 25_000), (6, 9_000), (7, 0))]
+    sweeps[2] = (np.zeros((0, 3), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.uint8))
+    pts, las, cnt = [t.to(DEV) for t in pack_sweeps(sweeps, DEV)]
+    mapping = torch.arange(H, dtype=torch.int32, device=DEV)
+    img = rasterize_sweeps(pts, las, cnt, mapping, synth.LIDAR_OFFSET, height=H, width=W)
+    want = range_view_inputs(img, names, dataset, stride, mode)
+    got = rasterize_inputs(pts, las, cnt, mapping, synth.LIDAR_OFFSET, height=H, width=W, feature_column_names=names,
+                           dataset_name=dataset, x_stride=stride, mode=mode)
+    for g, w_ in zip(got, want):
+        assert g.shape == w_.shape and g.dtype == w_.dtype and torch.equal(g, w_)
+    assert got[1][2].sum() == 0 and got[1][0].sum() > 0        # the empty sweep has an empty mask

@@ -57,7 +57,8 @@ def main():
     from rv3d.converters.av2 import utils as cu
     from rv3d.math.ops.assignment import box_iou_rotated, compute_classification_targets
     from rv3d.math.ops.coding import decode_range_view
-    from rv3d.prototype.loader import range_view_inputs
+    from rv3d.prototype.loader import range_view_inputs, rasterize_inputs
+    from rv3d.math.range_view import pack_sweeps, rasterize_sweeps
 
     B, H, W = 16, 64, 2650
     # ---- row 1: loader inputs --------------------------------------------------------------
@@ -76,6 +77,21 @@ def main():
         _ = (f[..., ::stride].contiguous(), c[..., ::stride].contiguous(), m[..., ::stride].contiguous())
         cpu = time.perf_counter() - t0
         report(f"range_view_inputs(stride={stride})", ms, alg, B, "sweeps", cpu, 1, "row 1: features/cart/mask assembly + subsample_range_view")
+
+    # raw sweeps -> network inputs: rasterize_sweeps + range_view_inputs (two passes over the 76 MB image) vs the fused entry
+    sweeps = [synth.make_points(180_000, H, 1000 + s_) for s_ in range(B)]
+    pts, las_, cnt = [t.to(DEV) for t in pack_sweeps(sweeps, DEV)]
+    mapping = torch.arange(H, dtype=torch.int32, device=DEV)
+    ws = torch.empty(B * H * W * 8, dtype=torch.uint8, device=DEV)
+    img_out = torch.empty((B, 7, H, W), dtype=torch.float32, device=DEV)
+    for stride in (1, 4):
+        alg = B * (180_000 * 17 + H * ((W + 6) // stride) * (8 * 4 + 1))     # points + laser bytes in, 5 + 3 planes + mask out
+        ms2 = timed(lambda: range_view_inputs(rasterize_sweeps(pts, las_, cnt, mapping, synth.LIDAR_OFFSET, H, W, out=img_out, workspace=ws),
+                                              dataset_name="waymo", x_stride=stride, mode="circular"))
+        report(f"rasterize_sweeps + range_view_inputs(stride={stride})", ms2, alg, B, "sweeps", note="row 1: the unfused pair, bytes of the fused form")
+        ms1 = timed(lambda: rasterize_inputs(pts, las_, cnt, mapping, synth.LIDAR_OFFSET, H, W, dataset_name="waymo", x_stride=stride,
+                                             mode="circular", workspace=ws))
+        report(f"rasterize_inputs(stride={stride})", ms1, alg, B, "sweeps", note="row 1: rasterizer with the loader assembly fused into its resolve pass")
 
     # ---- row 2: sweep preparation -----------------------------------------------------------
     n = 16 * 180_000
