@@ -413,6 +413,20 @@ int rv3d_detection_records(const float *params, const float *scores, const float
                            float max_range_m, int32_t apply_range_filter, rv3d_detection_record *out,
                            int32_t *out_count, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
 
+/* prepare_for_evaluation's `.sort(col("score"), descending=True).unique()` (detector.py:581-584) on a record stream
+ * that is still on the device: records (capacity,) with *count (device i32) live rows -> out: the distinct rows (all
+ * 64 bytes compared) in the order (score descending, then a hash of the row, then input order), *out_count (device
+ * i32).  polars leaves the order after unique() unspecified; the set of rows is what the evaluation consumes. */
+size_t rv3d_records_sort_unique_scratch_bytes(int64_t capacity);
+int rv3d_records_sort_unique(const rv3d_detection_record *records, const int32_t *count, int64_t capacity,
+                             rv3d_detection_record *out, int32_t *out_count, void *scratch, size_t scratch_bytes,
+                             rv3d_stream_t stream);
+/* validation_step's `dts.group_by(["log_id", "timestamp_ns"], maintain_order=True)` (detector.py:366-380) on a record
+ * stream in the decoder's order (batch_index ascending): offsets (batch + 1,) i32, sweep b's records are
+ * [offsets[b], offsets[b + 1]). */
+int rv3d_records_group_offsets(const rv3d_detection_record *records, const int32_t *count, int32_t batch,
+                               int32_t *offsets, rv3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

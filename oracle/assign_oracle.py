@@ -85,3 +85,14 @@ def detection_rows(params, scores, categories, batch_index, timestamps_ns=None, 
         keep = norms.astype(np.float64) <= float(max_range_m)                     # .le(lit(cfg.max_range_m))
         cols = {k: v[keep] for k, v in cols.items()}
     return cols
+
+
+def prepare_for_evaluation_rows(params, scores, categories, batch_index, timestamps_ns, max_range_m):
+    """detector.py:573-584 on the detection frame: range filter, `.sort(score, descending=True)`, `.unique()` -> the set
+    of distinct rows as a list of tuples sorted by score descending (polars leaves the order inside equal scores, and
+    after unique(), unspecified: compare as sets + the score order)."""
+    cols = detection_rows(params, scores, categories, batch_index, timestamps_ns, max_range_m)
+    names = list(cols)
+    rows = {tuple(cols[k][i].item() for k in names) for i in range(len(cols["score"]))}
+    return names, sorted(rows, key=lambda r: -r[names.index("score")])
+

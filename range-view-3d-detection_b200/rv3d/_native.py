@@ -99,6 +99,9 @@ _SIGNATURES = {
     "rv3d_instance_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "rv3d_detection_records_scratch_bytes": (_SZ, [_I64]),
     "rv3d_detection_records": (C.c_int, [_P, _P, _P, _P, _I64, _P, _I32, _F, _I32, _P, _P, _P, _SZ, _P]),
+    "rv3d_records_sort_unique_scratch_bytes": (_SZ, [_I64]),
+    "rv3d_records_sort_unique": (C.c_int, [_P, _P, _I64, _P, _P, _P, _SZ, _P]),
+    "rv3d_records_group_offsets": (C.c_int, [_P, _P, _I32, _P, _P]),
     "rv3d_unmotion_compensate": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
     "rv3d_transform_points": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P]),
     "rv3d_correct_laser_numbers": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P, _P]),

@@ -12,7 +12,8 @@ from ... import _native as N
 from ..._pipeline import cart_as, dtype_code
 from ..._util import ptr, require_cuda, scratch, stream_ptr
 
-__all__ = ["decode_range_view", "build_records", "build_dataframe", "RECORD_DTYPE", "SCHEMA"]
+__all__ = ["decode_range_view", "build_records", "build_records_device", "prepare_for_evaluation", "group_by_sweep",
+           "build_dataframe", "RECORD_DTYPE", "SCHEMA"]
 
 # one detection on the wire (include/rv3d.h rv3d_detection_record, 64 bytes); the fields are the numeric columns of
 # SERIALIZED_SCHEMA (nn/arch/detector.py:45-60) plus batch_index and the range the evaluation filters on
@@ -43,11 +44,11 @@ def decode_range_view(regressands: Tensor, cart: Tensor, enable_azimuth_invarian
     return out
 
 
-def build_records(params: Tensor, scores: Tensor, categories: Tensor, batch_index: Tensor,
-                  timestamps_ns: Optional[Sequence[int]] = None, max_range_m: Optional[float] = None) -> np.ndarray:
-    """The decoder's four outputs -> a numpy structured array of ``RECORD_DTYPE`` rows in the decoder's order, packed
-    (and, with ``max_range_m``, range-filtered like detector.py:573-581) on the device and brought over in ONE copy;
-    the reference reads thirteen columns back one ``.tolist()`` at a time (coding.py:42-57)."""
+def build_records_device(params: Tensor, scores: Tensor, categories: Tensor, batch_index: Tensor,
+                         timestamps_ns: Optional[Sequence[int]] = None, max_range_m: Optional[float] = None):
+    """The decoder's four outputs -> (records (capacity, 64) uint8 CUDA tensor of ``RECORD_DTYPE`` rows in the decoder's
+    order, count (1,) int32 CUDA tensor): packed and, with ``max_range_m``, range-filtered like detector.py:573-581 on the
+    device.  Enqueues work only."""
     dev = require_cuda(params)
     n = params.shape[0]
     if params.dim() != 2 or params.shape[1] != 10:
@@ -68,8 +69,49 @@ def build_records(params: Tensor, scores: Tensor, categories: Tensor, batch_inde
     N.check(lib.rv3d_detection_records(ptr(p), ptr(sc), ptr(ca), ptr(bi), n, ptr(stamps), 0 if stamps is None else stamps.numel(),
                                        float(max_range_m or 0.0), int(max_range_m is not None), ptr(out), ptr(count), ptr(work),
                                        work.numel(), stream_ptr(dev)), "rv3d_detection_records")
+    return out[:max(n, 0)] if n else out[:0], count
+
+
+def build_records(params: Tensor, scores: Tensor, categories: Tensor, batch_index: Tensor,
+                  timestamps_ns: Optional[Sequence[int]] = None, max_range_m: Optional[float] = None) -> np.ndarray:
+    """The decoder's four outputs -> a numpy structured array of ``RECORD_DTYPE`` rows in the decoder's order, packed
+    (and, with ``max_range_m``, range-filtered like detector.py:573-581) on the device and brought over in ONE copy;
+    the reference reads thirteen columns back one ``.tolist()`` at a time (coding.py:42-57)."""
+    rec, count = build_records_device(params, scores, categories, batch_index, timestamps_ns, max_range_m)
     m = int(count.item())
+    return rec[:m].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+
+
+def prepare_for_evaluation(params: Tensor, scores: Tensor, categories: Tensor, batch_index: Tensor,
+                           timestamps_ns: Optional[Sequence[int]], max_range_m: float) -> np.ndarray:
+    """The detection half of ``prepare_for_evaluation`` (nn/arch/detector.py:573-584) without leaving the device: range
+    filter ``||(tx,ty,tz)|| <= max_range_m``, ``.sort(col("score"), descending=True)``, ``.unique()`` -> the distinct rows
+    (all fields compared bit for bit) as ``RECORD_DTYPE``, score descending; ONE copy to the host.  (polars leaves the
+    order of rows with equal scores, and the order after ``unique()``, unspecified; the evaluation consumes the set.)"""
+    rec, count = build_records_device(params, scores, categories, batch_index, timestamps_ns, max_range_m)
+    dev = rec.device
+    cap = rec.shape[0]
+    out = torch.empty((max(cap, 1), 64), dtype=torch.uint8, device=dev)
+    out_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = N.lib()
+    work = scratch(lib.rv3d_records_sort_unique_scratch_bytes(cap), dev)
+    N.check(lib.rv3d_records_sort_unique(ptr(rec) if cap else None, ptr(count), cap, ptr(out), ptr(out_count), ptr(work), work.numel(),
+                                         stream_ptr(dev)), "rv3d_records_sort_unique")
+    m = int(out_count.item())
     return out[:m].cpu().numpy().view(RECORD_DTYPE).reshape(-1)
+
+
+def group_by_sweep(records: Tensor, count: Tensor, batch: int) -> Tensor:
+    """``dts.group_by(["log_id", "timestamp_ns"], maintain_order=True)`` (nn/arch/detector.py:366-380) on a device record
+    stream in the decoder's order: -> offsets (batch + 1,) int32 CUDA tensor, sweep b's records are
+    ``records[offsets[b]:offsets[b + 1]]`` (each slice is what the reference writes to ``<log_id>/<timestamp_ns>.feather``)."""
+    dev = require_cuda(records, count)
+    offsets = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    if records.shape[0] == 0:
+        return offsets.zero_()
+    N.check(N.lib().rv3d_records_group_offsets(ptr(records), ptr(count), int(batch), ptr(offsets), stream_ptr(dev)),
+            "rv3d_records_group_offsets")
+    return offsets
 
 
 def build_dataframe(params: Tensor, scores: Tensor, categories: Tensor, batch_index: Tensor, uuids: Mapping[str, Sequence[Any]],

@@ -56,3 +56,31 @@ def test_build_records_empty():
     from rv3d.math.ops.coding import build_records
     e = torch.empty((0,), device=DEV)
     assert len(build_records(torch.empty((0, 10), device=DEV), e, e, e)) == 0
+
+
+def test_prepare_for_evaluation_sort_unique_and_grouping():
+    """detector.py:573-584 (range filter, sort by score descending, unique) and :366-380 (per-sweep groups) on the device
+    record stream vs the oracle's restatement over numpy columns.  Duplicated detections (the same rows appended twice,
+    plus rows that only differ in one field) exercise unique(); the survivors are compared as a SET (polars leaves their
+    order unspecified) and their score order is checked."""
+    from rv3d.math.ops.coding import build_records_device, group_by_sweep, prepare_for_evaluation
+    params, scores, cats, bidx = _detections(seed=5)
+    n = params.shape[0]
+    dup = torch.arange(0, n, 3, device=DEV)
+    near = params[dup].clone(); near[:, 3] += 1e-3                                   # same row but for one field: NOT a duplicate
+    P = torch.cat([params, params[dup], near]); S = torch.cat([scores, scores[dup], scores[dup]])
+    C = torch.cat([cats, cats[dup], cats[dup]]); Bi = torch.cat([bidx, bidx[dup], bidx[dup]])
+    stamps = [315969904359876000 + 100_000_000 * b for b in range(3)]
+    rec = prepare_for_evaluation(P, S, C, Bi, stamps, 40.0)
+    names, want = assign_oracle.prepare_for_evaluation_rows(P.cpu(), S.cpu(), C.cpu(), Bi.cpu(), stamps, 40.0)
+    got = {tuple(rec[k][i].item() for k in names) for i in range(len(rec))}
+    assert len(rec) == len(got) == len(want) and got == set(want)
+    assert len(rec) < P.shape[0] - dup.numel() + 1 and len(rec) > n // 2              # duplicates and far rows are gone
+    assert np.all(np.diff(rec["score"]) <= 0)                                        # score descending
+    # per-sweep groups of the unfiltered stream
+    r, cnt = build_records_device(params, scores, cats, bidx, stamps)
+    off = group_by_sweep(r, cnt, 3).cpu().numpy()
+    b = bidx.cpu().numpy().astype(int).reshape(-1)
+    assert off[0] == 0 and off[-1] == n and np.array_equal(off, np.searchsorted(b, np.arange(4)))
+    e = torch.empty((0,), device=DEV)
+    assert len(prepare_for_evaluation(torch.empty((0, 10), device=DEV), e, e, e, None, 10.0)) == 0
