@@ -1,6 +1,9 @@
 """Summarise an .ncu-rep (ncu --set full) into a small markdown table of the metrics DESIGN.md / bench.py cite.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.md
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--traffic profiles/traffic.json] > profiles/<name>.md
+
+--traffic: also write dram__bytes_read.sum + dram__bytes_write.sum of the FIRST launch of raster_scatter, raster_resolve and
+decode_compact (the roofline pair of bench.py) as {"shape", "batch", "bytes_per_step", "per_kernel", "source"}.
 """
 import csv
 import subprocess
@@ -40,5 +43,24 @@ def main(path):
         print(f"| `{r[kn][:60]}` | " + " | ".join(cells) + " |")
 
 
+def traffic(path, out):
+    import json
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[2:]:
+        for name in ("raster_scatter", "raster_resolve", "decode_compact"):
+            if name in r[kn] and name not in per:
+                per[name] = int(float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]])
+    json.dump({"shape": "waymo", "batch": 16, "bytes_per_step": sum(per.values()), "per_kernel": per,
+               "source": f"ncu --set full, {path.split('/')[-1]} (cold cache per kernel: ncu flushes L2 between kernels, so part of "
+                         "the stores is still in L2 when a kernel ends and is not counted)"}, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
     main(sys.argv[1])
+    if "--traffic" in sys.argv:
+        traffic(sys.argv[1], sys.argv[sys.argv.index("--traffic") + 1])
