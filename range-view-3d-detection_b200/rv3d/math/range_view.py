@@ -100,6 +100,20 @@ def _column(sweep, name: str) -> np.ndarray:
     return np.asarray(col)
 
 
+def _build_range_view_f64(xyz, intensity, laser, laser_mapping, lidar_offset, num_lasers: int, width: int, device) -> np.ndarray:
+    """math/range_view.py:23-44 on float64 columns with rv3d.math.numpy.conversions' device operators."""
+    from .numpy.conversions import build_range_view_coordinates, cart_to_sph, z_buffer
+    keep = np.asarray(laser) < num_lasers                                              # :23-26
+    xyz, intensity, laser = xyz[keep], np.asarray(intensity)[keep], np.asarray(laser)[keep].astype(np.int64)
+    cart = xyz - np.asarray(lidar_offset, dtype=np.float64)                            # :29
+    sph = cart_to_sph(cart, device)                                                    # :30
+    features = np.concatenate([sph, xyz, intensity.reshape(-1, 1).astype(np.float64)], axis=1).transpose(1, 0)   # :33 (before the rescale, H3)
+    hybrid = build_range_view_coordinates(cart, sph, laser, np.asarray(laser_mapping), n_inclination_bins=num_lasers,
+                                          device=device)                               # :34-40 (1800 azimuth bins, the reference's default)
+    indices = np.ascontiguousarray(hybrid[:, :2].transpose(1, 0).astype(int))          # :41
+    return z_buffer(indices, hybrid[:, 2], np.ascontiguousarray(features), height=num_lasers, width=width, device=device)   # :42-43
+
+
 def build_range_view(sweep, laser_mapping: np.ndarray, lidar_offset: np.ndarray, timestamp_ns: Optional[int] = None,
                      max_timestamp_ns: Optional[int] = None, num_lasers: int = 64, width: int = 1800,
                      device: Union[str, torch.device] = "cuda") -> np.ndarray:
@@ -112,8 +126,10 @@ def build_range_view(sweep, laser_mapping: np.ndarray, lidar_offset: np.ndarray,
     del timestamp_ns, max_timestamp_ns  # unused upstream as well (range_view.py:25)
     xyz = np.stack([_column(sweep, "x"), _column(sweep, "y"), _column(sweep, "z")], axis=1)
     if xyz.dtype == np.float64:
-        raise TypeError("build_range_view: x/y/z must be float32 (or float16) storage; the f64 "
-                        "arithmetic happens on the device")
+        # Float64 coordinate columns (the reference takes whatever dtype the frame holds, range_view.py:27-29): the fused
+        # kernel reads float32 points, so these go through the free-standing operators, statement by statement.
+        return _build_range_view_f64(xyz, _column(sweep, "intensity"), _column(sweep, "laser_number"), laser_mapping,
+                                     lidar_offset, num_lasers, width, device)
     laser = _column(sweep, "laser_number")
     if laser.max(initial=0) > 255:
         raise ValueError("laser_number must fit uint8")

@@ -48,9 +48,13 @@ class RangeDecoder:
     # The host work in front of a decode launch (partition struct, candidate counts, parameter structs) only depends on
     # the decoder's fields and the tensor shapes: it is built once per distinct key and reused, which keeps the launch
     # ahead of the rasterizer's ~77 us instead of leaving the GPU idle behind it.
+    def _parts_key(self) -> Tuple:
+        """The partition VALUES (cache keys must not depend on object identity: the fields are mutable)."""
+        return ("parts", bool(self.enable_sample_by_range), tuple(float(v) for v in self.lower_bounds),
+                tuple(float(v) for v in self.upper_bounds), tuple(int(v) for v in self.subsampling_rates))
+
     def _partitions(self) -> N.Partitions:
-        key = ("parts", bool(self.enable_sample_by_range), tuple(self.lower_bounds), tuple(self.upper_bounds),
-               tuple(self.subsampling_rates))
+        key = self._parts_key()
         parts = self._cache.get(key)
         if parts is None:
             if not self.enable_sample_by_range:
@@ -61,7 +65,7 @@ class RangeDecoder:
         return parts
 
     def _num_candidates(self, parts: N.Partitions, H: int, W: int) -> int:
-        key = ("k", id(parts), H, W)
+        key = ("k", self._parts_key(), H, W)
         k = self._cache.get(key)
         if k is None:
             k = self._cache[key] = int(N.lib().rv3d_num_candidates(parts, H, W))
@@ -98,7 +102,7 @@ class RangeDecoder:
             cart = cart_as(dt, ms["cart"])
             mask = _mask_u8(ms["mask"])
             require_cuda(logits, reg, cart, mask)
-            pkey = ("p", id(parts), B, logits.shape[1], H, W, dt, cart.dtype, bool(self.enable_azimuth_invariant_targets),
+            pkey = ("p", self._parts_key(), B, logits.shape[1], H, W, dt, cart.dtype, bool(self.enable_azimuth_invariant_targets),
                     task_offset, cand_offset, total_candidates, total_classes, cand.keys.numel(),
                     float(post_processing_config["min_confidence"]))
             p = self._cache.get(pkey)

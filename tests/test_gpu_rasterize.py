@@ -199,3 +199,20 @@ def test_config4_multi_resolution(W):
                                                    num_lasers=64, width=W, n_azimuth_bins=W, return_winner=True)
         assert np.array_equal(win[b].cpu().numpy(), ref_win)
         _check_image(img[b].cpu().numpy(), ref_img)
+
+
+def test_build_range_view_float64_columns():
+    """The reference takes whatever dtype the frame holds (math/range_view.py:27-29): float64 x / y / z go through the
+    free-standing device operators and match the oracle run on the same float64 values."""
+    from rv3d.math.range_view import build_range_view
+    H = 16
+    xyz, inten, laser = synth.make_points(20_000, H, 21, extra_laser_frac=0.02)
+    xyz64 = xyz.astype(np.float64) + 1e-9                                            # not representable in float32
+    sweep = {"x": xyz64[:, 0], "y": xyz64[:, 1], "z": xyz64[:, 2], "intensity": inten, "laser_number": laser}
+    got = build_range_view(sweep, np.arange(H), synth.LIDAR_OFFSET, num_lasers=H, width=1800)
+    keep = laser < H
+    ref = oracle.build_range_view(xyz64[keep], inten[keep], laser[keep], np.arange(H), synth.LIDAR_OFFSET, num_lasers=H,
+                                  width=1800, n_azimuth_bins=1800)
+    assert got.shape == ref.shape == (7, H, 1800) and got.dtype == np.float32
+    assert np.array_equal(got[2:], ref[2:])                                          # range, x, y, z, intensity: bit-exact
+    np.testing.assert_allclose(got[:2], ref[:2], rtol=0, atol=2.4e-7)               # az / inc: device vs host libm, 1 float32 ulp
