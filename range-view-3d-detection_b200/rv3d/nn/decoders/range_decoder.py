@@ -45,6 +45,9 @@ class RangeDecoder:
 
     _cache: dict = field(default_factory=dict, init=False, repr=False, compare=False)
 
+    # event recorded by decode_async behind the dense decode kernel (None before the first call)
+    dense_done: Any = field(default=None, init=False, repr=False, compare=False)
+
     # The host work in front of a decode launch (partition struct, candidate counts, parameter structs) only depends on
     # the decoder's fields and the tensor shapes: it is built once per distinct key and reused, which keeps the launch
     # ahead of the rasterizer's ~77 us instead of leaving the GPU idle behind it.
@@ -138,6 +141,10 @@ class RangeDecoder:
         if mode not in ("HARD", "WEIGHTED"):
             raise NotImplementedError(f"NMS Mode: {mode} is not implemented.")
         cand = self.candidates(multiscale_outputs, post_processing_config, task_config)
+        # The dense (whole-GPU) part of the step is enqueued; what follows is one CTA per (sweep, class) segment.  A caller
+        # with independent work for the idle SMs (the rasterizer of the next batch) makes its stream wait on this event.
+        self.dense_done = torch.cuda.Event()
+        self.dense_done.record()
         thr = float(post_processing_config["min_confidence"])
         score_range = (max(thr, 0.0), 1.0) if thr < 1.0 else (0.0, 0.0)     # sigmoid * mask lies in [0, 1]
         peer_kw = {}
