@@ -363,6 +363,20 @@ int rv3d_unmotion_compensate(const double *xyz, const int64_t *offset_ns, int64_
                              const double *target_translation, double *out_xyz, uint8_t *out_valid,
                              rv3d_stream_t stream);
 
+/* Table form of the same operator for the production shape (one log = one pose table, many sweeps).
+ * rv3d_pose_intervals: once per table -> intervals (M-1, 8) f64 device = per pose pair the normalised lower
+ * quaternion (4) and the rotation vector of q0^-1 q1 (3) + 1 pad, i.e. what scipy's Slerp.__init__ precomputes
+ * (utils.py:251-256 builds the Slerp once per call).  rv3d_unmotion_compensate_table: same result as
+ * rv3d_unmotion_compensate; first_ns / last_ns = pose_timestamps_ns[0] / [M-1] (host copies, the caller owns the
+ * table); *n_dropped (device i32, may be NULL, caller zeroes it) counts the rows the reference's filter removes, so
+ * the caller can skip the compaction when it is 0. */
+int rv3d_pose_intervals(const double *pose_quat_xyzw, int32_t n_poses, double *intervals, rv3d_stream_t stream);
+int rv3d_unmotion_compensate_table(const double *xyz, const int64_t *offset_ns, int64_t n, int64_t timestamp_ns,
+                                   const int64_t *pose_timestamps_ns, const double *pose_translation,
+                                   const double *intervals, int32_t n_poses, int64_t first_ns, int64_t last_ns,
+                                   const double *target_quat_xyzw, const double *target_translation,
+                                   double *out_xyz, uint8_t *out_valid, int32_t *n_dropped, rv3d_stream_t stream);
+
 /* Rigid transform of (N,3) f64 points: out = xyz @ R^T + t, or with `inverse` the transform of
  * SE3(R, t).inverse() (R^T, R^T.(-t)) as utils.py:54-57 builds sensor_SE3_egovehicle.
  * rotation (9, row-major) and translation (3): HOST doubles. */
@@ -389,6 +403,26 @@ int rv3d_correct_laser_numbers(const int64_t *laser_numbers, int64_t n, const in
 size_t rv3d_instance_topk_scratch_bytes(int64_t n);
 int rv3d_instance_topk(const float *affinity, const int32_t *segment, int64_t n, int32_t n_segments, int32_t k,
                        float *likelihood, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);
+
+/* compute_classification_targets as ONE call (math/ops/assignment.py:76-148), float32 tensors:
+ * input / target (B,8,H,W), labels (B,H,W) i64 in [0, n_classes] (n_classes = background_index), cart (B,3,H,W),
+ * mask (B,1,H,W) bool bytes, panoptics (B,H,W) i64 (0 = background) -> affinities (B,n_classes,H,W) f32,
+ * foreground (B,1,H,W) f32, background / reg_weights (B,1,H,W) bool bytes.  affinity_fn: 0 = BEV (aligned rotated
+ * IoU of the decoded boxes, clamped, :64-73), 1 = GAUSSIAN without normalisation (exp(-|centre distance| / sigma2),
+ * :151-161).  k: slots per instance (<= 64), 0 = nothing is foreground, RV3D_TOPK_ALL = every pixel of an instance is
+ * in its top-k (the production setting k = inf, conf/model/range_view.yaml:126).  id_capacity: instance ids per sweep
+ * the call can hold; *status (device i32, caller zeroes it) is set to 1 when an id >= id_capacity was met (the results
+ * are then incomplete and the caller must retry with a larger capacity).  Only foreground pixels are decoded; no
+ * dense intermediate is written. */
+#define RV3D_TOPK_ALL 0x7fffffff
+size_t rv3d_classification_targets_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t k,
+                                                 int32_t id_capacity);
+int rv3d_classification_targets(const float *input, const float *target, const int64_t *labels, const float *cart,
+                                const uint8_t *mask, const int64_t *panoptics, int32_t batch, int32_t n_classes,
+                                int32_t height, int32_t width, int32_t affinity_fn, int32_t az_inv_targets, int32_t k,
+                                float sigma2, int32_t id_capacity, float *affinities, float *foreground,
+                                uint8_t *background, uint8_t *reg_weights, int32_t *status, void *scratch,
+                                size_t scratch_bytes, rv3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * 6. Detection wire format

@@ -55,7 +55,7 @@ def compute_classification_targets(inp, target, labels, cart, cfg, mask, panopti
             d_i = pds[i][:, m].t()
             g_i = gts[i][:, m].t()
             a_i = fn(d_i, g_i, **cfg)
-            k = min(int(cfg["k"]), len(a_i))
+            k = min(cfg["k"], len(a_i))                          # :129 (k may be .inf: conf/model/range_view.yaml:126)
             val, idx = a_i.topk(k)
             like = torch.zeros_like(a_i).scatter(0, idx, val)
             aff[i, 0][m] = like.type_as(aff)

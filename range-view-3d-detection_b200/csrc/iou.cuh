@@ -98,7 +98,7 @@ __device__ __forceinline__ void hard_vertices(float xc, float yc, const HardRec 
   v[3].y = 2 * yc - v[1].y;
 }
 
-__device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b) {
+static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b) {
   const float area1 = a.w * a.h, area2 = b.w * b.h;
   if (static_cast<double>(area1) < 1e-14 || static_cast<double>(area2) < 1e-14) return 0.f;
   // shift both centres by their midpoint (computed in double upstream)
@@ -244,7 +244,7 @@ __device__ __forceinline__ bool in_box2d(const WRec &b, P2 p) {
   return rx > b.x1 - MARGIN && rx < b.x2 + MARGIN && ry > b.y1 - MARGIN && ry < b.y2 + MARGIN;
 }
 
-__device__ __noinline__ float bev_iou(const WRec &a, const WRec &b) {
+static __device__ __noinline__ float bev_iou(const WRec &a, const WRec &b) {
   P2 A[5], B[5];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { A[k] = P2{a.qx[k], a.qy[k]}; B[k] = P2{b.qx[k], b.qy[k]}; }

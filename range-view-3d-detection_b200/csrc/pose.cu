@@ -136,6 +136,96 @@ unmotion_kernel(UnmotionArgs a, const double *__restrict__ xyz, const long long 
   for (int k = 0; k < 3; ++k) out[3 * i + k] = R[k] * v[0] + R[3 + k] * v[1] + R[6 + k] * v[2];
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Table form (the production shape: one log = one pose table, many sweeps).  Everything about a Slerp step that
+// depends on the pose PAIR only -- the normalised lower quaternion and the rotation vector of q0^-1 q1 (scipy
+// Slerp.__init__ computes exactly this once per interval) -- is computed once per interval by pose_intervals_kernel
+// with the same device functions as above, so a point's work shrinks to: locate the interval (interpolation guess +
+// a short walk instead of two 12-step binary searches), blend, one sincos, one quaternion product, apply.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pose_intervals_kernel(int n_poses, const double *__restrict__ pose_quat, double *__restrict__ iv) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_poses - 1) return;
+  const Quat q0 = load_quat(pose_quat + 4 * k), q1 = load_quat(pose_quat + 4 * (k + 1));
+  double rv[3];
+  q_to_rotvec(q_normalized(q_mul(Quat{-q0.x, -q0.y, -q0.z, q0.w}, q1)), rv);
+  double *o = iv + 8 * static_cast<size_t>(k);
+  o[0] = q0.x; o[1] = q0.y; o[2] = q0.z; o[3] = q0.w; o[4] = rv[0]; o[5] = rv[1]; o[6] = rv[2]; o[7] = 0.0;
+}
+
+struct UnmotionTableArgs {
+  long long n;
+  long long timestamp_ns;
+  long long first_ns, last_ns;   // pose_ts[0], pose_ts[M - 1]
+  double guess_scale;            // (M - 1) / (last - first)
+  int n_poses;
+  double target_rot[9];
+  double target_t[3];
+};
+
+__global__ void __launch_bounds__(256)
+unmotion_table_kernel(UnmotionTableArgs a, const double *__restrict__ xyz, const long long *__restrict__ offset_ns,
+                      const long long *__restrict__ pose_ts, const double *__restrict__ pose_t,
+                      const double *__restrict__ iv, double *__restrict__ out, uint8_t *__restrict__ valid,
+                      int *__restrict__ n_dropped) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool live = i < a.n;
+  const long long t = live ? a.timestamp_ns + offset_ns[i] : 0;               // :236
+  const bool ok = live && t > a.first_ns && t < a.last_ns;                     // :237-240 (strict on both sides)
+  if (n_dropped) {                                                             // rows the reference's filter removes
+    const unsigned bad = __ballot_sync(0xffffffffu, live && !ok);
+    if (bad && (threadIdx.x & 31) == 0) atomicAdd(n_dropped, __popc(bad));
+  }
+  if (!live) return;
+  valid[i] = ok ? 1 : 0;
+  if (!ok) {
+    out[3 * i] = CUDART_NAN; out[3 * i + 1] = CUDART_NAN; out[3 * i + 2] = CUDART_NAN;
+    return;
+  }
+  const int M = a.n_poses;
+  // idx = first k with pose_ts[k] >= t (searchsorted side = "left", :244); ts[0] < t < ts[M-1] => 1 <= idx <= M-1.
+  // Pose tables are (nearly) uniform in time: start at the interpolated position and walk; a table that defeats the
+  // guess falls back to the binary search.
+  int idx = static_cast<int>(static_cast<double>(t - a.first_ns) * a.guess_scale) + 1;
+  idx = idx < 1 ? 1 : (idx > M - 1 ? M - 1 : idx);
+  int steps = 0;
+  while (steps < 6 && idx > 1 && pose_ts[idx - 1] >= t) { --idx; ++steps; }
+  while (steps < 6 && pose_ts[idx] < t) { ++idx; ++steps; }
+  if (steps >= 6) idx = lower_bound(M, t, [&](int k) { return pose_ts[k]; });
+  const long long ts_lo = pose_ts[idx - 1], ts_hi = pose_ts[idx];
+  const double alpha = static_cast<double>(t - ts_lo) / static_cast<double>(ts_hi - ts_lo);   // :275
+  double tp[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)   // :276 -- the weights are the reference's (alpha on the LOWER pose)
+    tp[k] = pose_t[3 * (idx - 1) + k] * alpha + (1.0 - alpha) * pose_t[3 * idx + k];
+
+  // scipy Slerp searches float64 timestamps.  The conversion is monotone, so its lower bound is idx unless earlier
+  // timestamps round to the same double as t (t within ~256 ns of a pose): walk down over those.
+  const double tf = static_cast<double>(t);
+  int lb = idx;
+  while (lb > 0 && static_cast<double>(pose_ts[lb - 1]) >= tf) --lb;
+  int ind = lb - 1;
+  if (tf == static_cast<double>(a.first_ns)) ind = 0;
+  ind = ind < 0 ? 0 : (ind > M - 2 ? M - 2 : ind);
+  const double t0 = static_cast<double>(pose_ts[ind]), t1 = static_cast<double>(pose_ts[ind + 1]);
+  const double beta = (tf - t0) / (t1 - t0);
+  const double *v8 = iv + 8 * static_cast<size_t>(ind);
+  const Quat q0{v8[0], v8[1], v8[2], v8[3]};
+  double rv[3] = {v8[4] * beta, v8[5] * beta, v8[6] * beta};
+  const Quat qp = q_normalized(q_mul(q0, q_from_rotvec(rv)));
+  double R[9];
+  q_to_matrix(qp, R);
+  const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  double v[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    v[k] = (a.target_rot[3 * k] * x + a.target_rot[3 * k + 1] * y + a.target_rot[3 * k + 2] * z) + (a.target_t[k] - tp[k]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[3 * i + k] = R[k] * v[0] + R[3 + k] * v[1] + R[6 + k] * v[2];
+}
+
 struct RigidArgs { double r[9]; double t[3]; };
 
 // out = p @ R^T + t  (av2 SE3.transform_point_cloud)
@@ -148,23 +238,37 @@ transform_kernel(RigidArgs a, const double *__restrict__ xyz, long long n, doubl
   for (int k = 0; k < 3; ++k) out[3 * i + k] = (a.r[3 * k] * x + a.r[3 * k + 1] * y + a.r[3 * k + 2] * z) + a.t[k];
 }
 
+// two rows per thread (16-byte loads / stores when the arrays are 16-byte aligned); the two small tables sit in shared memory
 __global__ void __launch_bounds__(256)
 laser_numbers_kernel(const long long *__restrict__ laser, long long n, const long long *__restrict__ laser_mapping,
                      const long long *__restrict__ row_mapping, int n_rows, long long *__restrict__ out,
-                     int *__restrict__ bad) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+                     int *__restrict__ bad, int vec_ok) {
+  __shared__ long long s_rows[256];
+  __shared__ long long s_map[32];
+  const int nr = n_rows < 256 ? n_rows : 256;
+  for (int k = threadIdx.x; k < nr; k += blockDim.x) s_rows[k] = row_mapping[k];
+  if (laser_mapping && threadIdx.x < 32) s_map[threadIdx.x] = laser_mapping[threadIdx.x];
+  __syncthreads();
+  auto one = [&](long long l) -> long long {
+    if (laser_mapping) {                        // :214-220 (log in LOG_IDS): upper and lower block of 32 beams
+      if (l >= 32 && l < 64) l = s_map[l - 32] + 32;
+      else if (l >= 0 && l < 32) l = s_map[l];
+    }
+    if (l < 0 || l >= n_rows) {                 // numpy would raise IndexError
+      if (bad) atomicExch(bad, 1);
+      return -1;
+    }
+    return l < 256 ? s_rows[l] : row_mapping[l];   // :222-226
+  };
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i >= n) return;
-  long long l = laser[i];
-  if (laser_mapping) {                          // :214-220 (log in LOG_IDS): upper and lower block of 32 beams
-    if (l >= 32 && l < 64) l = laser_mapping[l - 32] + 32;
-    else if (l >= 0 && l < 32) l = laser_mapping[l];
+  if (vec_ok && i + 1 < n) {
+    const longlong2 v = *reinterpret_cast<const longlong2 *>(laser + i);
+    *reinterpret_cast<longlong2 *>(out + i) = make_longlong2(one(v.x), one(v.y));
+  } else {
+    out[i] = one(laser[i]);
+    if (i + 1 < n) out[i + 1] = one(laser[i + 1]);
   }
-  if (l < 0 || l >= n_rows) {                   // numpy would raise IndexError
-    if (bad) atomicExch(bad, 1);
-    out[i] = -1;
-    return;
-  }
-  out[i] = row_mapping[l];                      // :222-226
 }
 
 }  // namespace rv3d
@@ -202,6 +306,37 @@ extern "C" int rv3d_unmotion_compensate(const double *xyz, const int64_t *offset
   return RV3D_OK;
 }
 
+
+extern "C" int rv3d_pose_intervals(const double *pose_quat_xyzw, int32_t n_poses, double *intervals, rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n_poses >= 2 && pose_quat_xyzw && intervals);
+  pose_intervals_kernel<<<ceil_div(n_poses - 1, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(n_poses, pose_quat_xyzw,
+                                                                                                 intervals);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
+extern "C" int rv3d_unmotion_compensate_table(const double *xyz, const int64_t *offset_ns, int64_t n, int64_t timestamp_ns,
+                                              const int64_t *pose_timestamps_ns, const double *pose_translation,
+                                              const double *intervals, int32_t n_poses, int64_t first_ns, int64_t last_ns,
+                                              const double *target_quat_xyzw, const double *target_translation,
+                                              double *out_xyz, uint8_t *out_valid, int32_t *n_dropped,
+                                              rv3d_stream_t stream) {
+  RV3D_CHECK_ARG(n >= 0 && n_poses >= 2 && pose_timestamps_ns && pose_translation && intervals && last_ns > first_ns);
+  RV3D_CHECK_ARG(target_quat_xyzw && target_translation);
+  if (n == 0) return RV3D_OK;
+  RV3D_CHECK_ARG(xyz && offset_ns && out_xyz && out_valid);
+  UnmotionTableArgs a;
+  a.n = n; a.timestamp_ns = timestamp_ns; a.n_poses = n_poses; a.first_ns = first_ns; a.last_ns = last_ns;
+  a.guess_scale = static_cast<double>(n_poses - 1) / static_cast<double>(last_ns - first_ns);
+  quat_to_matrix_host(target_quat_xyzw, a.target_rot);
+  for (int k = 0; k < 3; ++k) a.target_t[k] = target_translation[k];
+  unmotion_table_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, xyz, reinterpret_cast<const long long *>(offset_ns), reinterpret_cast<const long long *>(pose_timestamps_ns),
+      pose_translation, intervals, out_xyz, out_valid, n_dropped);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
+}
+
 extern "C" int rv3d_transform_points(const double *xyz, int64_t n, const double *rotation, const double *translation,
                                      int32_t inverse, double *out, rv3d_stream_t stream) {
   RV3D_CHECK_ARG(n >= 0 && rotation && translation);
@@ -228,9 +363,10 @@ extern "C" int rv3d_correct_laser_numbers(const int64_t *laser_numbers, int64_t 
   RV3D_CHECK_ARG(n >= 0 && row_mapping && n_rows > 0);
   if (n == 0) return RV3D_OK;
   RV3D_CHECK_ARG(laser_numbers && out);
-  laser_numbers_kernel<<<ceil_div(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int vec_ok = aligned(laser_numbers, 16) && aligned(out, 16);
+  laser_numbers_kernel<<<ceil_div(n, 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long *>(laser_numbers), n, reinterpret_cast<const long long *>(laser_mapping),
-      reinterpret_cast<const long long *>(row_mapping), n_rows, reinterpret_cast<long long *>(out), out_of_range);
+      reinterpret_cast<const long long *>(row_mapping), n_rows, reinterpret_cast<long long *>(out), out_of_range, vec_ok);
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }

@@ -95,6 +95,9 @@ _SIGNATURES = {
     "rv3d_pack_candidates_scratch_bytes": (_SZ, [_I32]),
     "rv3d_pack_candidates": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "rv3d_box_iou_rotated": (C.c_int, [_P, _I64, _P, _I64, _I32, _P, _P]),
+    "rv3d_classification_targets_scratch_bytes": (_SZ, [_I32, _I32, _I32, _I32, _I32]),
+    "rv3d_classification_targets": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32,
+                                              _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "rv3d_instance_topk_scratch_bytes": (_SZ, [_I64]),
     "rv3d_instance_topk": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "rv3d_detection_records_scratch_bytes": (_SZ, [_I64]),
@@ -103,6 +106,8 @@ _SIGNATURES = {
     "rv3d_records_sort_unique": (C.c_int, [_P, _P, _I64, _P, _P, _P, _SZ, _P]),
     "rv3d_records_group_offsets": (C.c_int, [_P, _P, _I32, _P, _P]),
     "rv3d_unmotion_compensate": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
+    "rv3d_pose_intervals": (C.c_int, [_P, _I32, _P, _P]),
+    "rv3d_unmotion_compensate_table": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _I32, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "rv3d_transform_points": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P]),
     "rv3d_correct_laser_numbers": (C.c_int, [_P, _I64, _P, _P, _I32, _P, _P, _P]),
 }

@@ -19,7 +19,7 @@ from ..._util import ptr, stream_ptr
 from ...constants import LASER_MAPPING, ROW_MAPPING_32, ROW_MAPPING_64
 from ...math.numpy.conversions import _back, _dev, _to_dev, build_range_view_coordinates, cart_to_sph, z_buffer
 
-__all__ = ["unmotion_compensate", "sensor_from_egovehicle", "correct_laser_numbers", "build_range_view"]
+__all__ = ["PoseTable", "unmotion_compensate", "sensor_from_egovehicle", "correct_laser_numbers", "build_range_view"]
 
 
 def _host_f64(x, shape) -> np.ndarray:
@@ -28,40 +28,80 @@ def _host_f64(x, shape) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(shape))
 
 
-def unmotion_compensate(xyz, offset_ns, timestamp_ns: int, pose_timestamps_ns, pose_quat_xyzw, pose_translation,
+class PoseTable:
+    """A log's ``city_SE3_egovehicle`` table, resident on the device (one upload per log instead of one per sweep) with
+    everything a Slerp step needs per pose pair precomputed (``rv3d_pose_intervals``; scipy's ``Slerp.__init__`` does
+    the same once per construction, utils.py:251-256).  Pass it to ``unmotion_compensate`` in place of the three arrays."""
+
+    def __init__(self, pose_timestamps_ns, pose_quat_xyzw, pose_translation, device=None):
+        dev = _dev(device)
+        ts_host = (pose_timestamps_ns.detach().cpu().numpy() if isinstance(pose_timestamps_ns, torch.Tensor)
+                   else np.asarray(pose_timestamps_ns)).astype(np.int64)
+        self.quat_host = _host_f64(pose_quat_xyzw, (-1, 4))
+        self.trans_host = _host_f64(pose_translation, (-1, 3))
+        m = ts_host.shape[0]
+        if m != self.quat_host.shape[0] or m != self.trans_host.shape[0] or m < 2:
+            raise ValueError("pose table: need >= 2 rows and equally long timestamp / quaternion / translation arrays")
+        self.ts_host, self.device, self.n_poses = ts_host, dev, m
+        self.first_ns, self.last_ns = int(ts_host[0]), int(ts_host[-1])
+        if self.last_ns <= self.first_ns:
+            raise ValueError("pose table: timestamps must be sorted and span a positive interval")
+        self._row_of = None
+        self.ts = torch.as_tensor(ts_host, device=dev)
+        self.trans = torch.as_tensor(self.trans_host, device=dev)
+        quat = torch.as_tensor(self.quat_host, device=dev)
+        self.intervals = torch.empty((m - 1, 8), dtype=torch.float64, device=dev)
+        N.check(N.lib().rv3d_pose_intervals(ptr(quat), m, ptr(self.intervals), stream_ptr(dev)), "rv3d_pose_intervals")
+
+    def row_at(self, timestamp_ns: int) -> int:
+        """Row of the pose stamped exactly ``timestamp_ns`` (utils.py:258-273); ValueError when there is none."""
+        if self._row_of is None:
+            self._row_of = {}
+            for k in range(self.n_poses - 1, -1, -1):      # the FIRST matching row wins, like the reference's filter()[0]
+                self._row_of[int(self.ts_host[k])] = k
+        try:
+            return self._row_of[int(timestamp_ns)]
+        except KeyError:
+            raise ValueError(f"no pose at the sweep's timestamp {timestamp_ns}") from None
+
+
+def unmotion_compensate(xyz, offset_ns, timestamp_ns: int, pose_timestamps_ns, pose_quat_xyzw=None, pose_translation=None,
                         device=None) -> Tuple:
     """utils.py:229-295 -> (xyz_p (N',3) float64, keep (N,) bool).
 
     ``xyz`` (N,3), ``offset_ns`` (N,) are the sweep's columns; the three pose arrays are the log's
     ``city_SE3_egovehicle`` table sorted by time (``timestamp_ns``, the ``(qx,qy,qz,qw)`` columns in that order,
-    ``(tx_m,ty_m,tz_m)``).  Rows whose time is not strictly inside the table are dropped like the reference's
-    ``filter`` (``keep`` marks the survivors so the caller can filter its other columns).  Raises ``ValueError``
-    when no pose carries the sweep's own ``timestamp_ns`` (the reference fails on the empty selection)."""
-    dev = _dev(device)
+    ``(tx_m,ty_m,tz_m)``) -- or ONE ``PoseTable`` built once per log in place of ``pose_timestamps_ns``.  Rows whose
+    time is not strictly inside the table are dropped like the reference's ``filter`` (``keep`` marks the survivors so
+    the caller can filter its other columns).  Raises ``ValueError`` when no pose carries the sweep's own
+    ``timestamp_ns`` (the reference fails on the empty selection)."""
+    table = pose_timestamps_ns if isinstance(pose_timestamps_ns, PoseTable) else None
+    dev = table.ts.device if (table is not None and device is None) else _dev(device)
+    if table is None:
+        ts_host = (pose_timestamps_ns.detach().cpu().numpy() if isinstance(pose_timestamps_ns, torch.Tensor)
+                   else np.asarray(pose_timestamps_ns)).astype(np.int64)
+        if not np.any(ts_host == int(timestamp_ns)):                 # fail before any device work, like the reference
+            raise ValueError(f"no pose at the sweep's timestamp {timestamp_ns}")
+        table = PoseTable(ts_host, pose_quat_xyzw, pose_translation, dev)
+    elif table.ts.device != _to_dev(np.zeros(0), torch.float64, dev).device:
+        raise ValueError("the PoseTable lives on another device")
+    row = table.row_at(timestamp_ns)
     pts = _to_dev(xyz, torch.float64, dev).reshape(-1, 3)
     off = _to_dev(offset_ns, torch.int64, dev).reshape(-1)
-    ts_host = (pose_timestamps_ns.detach().cpu().numpy() if isinstance(pose_timestamps_ns, torch.Tensor)
-               else np.asarray(pose_timestamps_ns)).astype(np.int64)
-    hit = np.nonzero(ts_host == int(timestamp_ns))[0]
-    if hit.size == 0:
-        raise ValueError(f"no pose at the sweep's timestamp {timestamp_ns}")
-    quat_host = _host_f64(pose_quat_xyzw, (-1, 4))
-    trans_host = _host_f64(pose_translation, (-1, 3))
-    if ts_host.shape[0] != quat_host.shape[0] or ts_host.shape[0] != trans_host.shape[0] or ts_host.shape[0] < 2:
-        raise ValueError("pose table: need >= 2 rows and equally long timestamp / quaternion / translation arrays")
     if pts.shape[0] != off.shape[0]:
         raise ValueError("xyz and offset_ns disagree in length")
-    ts = torch.as_tensor(ts_host, device=dev)
-    quat = torch.as_tensor(quat_host, device=dev)
-    trans = torch.as_tensor(trans_host, device=dev)
-    tq = np.ascontiguousarray(quat_host[hit[0]])
-    tt = np.ascontiguousarray(trans_host[hit[0]])
+    tq = np.ascontiguousarray(table.quat_host[row])
+    tt = np.ascontiguousarray(table.trans_host[row])
     out = torch.empty_like(pts)
     valid = torch.empty((pts.shape[0],), dtype=torch.uint8, device=dev)
-    N.check(N.lib().rv3d_unmotion_compensate(ptr(pts), ptr(off), pts.shape[0], int(timestamp_ns), ptr(ts), ptr(quat),
-                                             ptr(trans), ts.shape[0], tq.ctypes.data, tt.ctypes.data, ptr(out),
-                                             ptr(valid), stream_ptr(dev)), "rv3d_unmotion_compensate")
-    keep = valid.bool()
+    dropped = torch.zeros(1, dtype=torch.int32, device=dev)
+    N.check(N.lib().rv3d_unmotion_compensate_table(ptr(pts), ptr(off), pts.shape[0], int(timestamp_ns), ptr(table.ts),
+                                                   ptr(table.trans), ptr(table.intervals), table.n_poses, table.first_ns,
+                                                   table.last_ns, tq.ctypes.data, tt.ctypes.data, ptr(out), ptr(valid),
+                                                   ptr(dropped), stream_ptr(dev)), "rv3d_unmotion_compensate_table")
+    keep = valid.view(torch.bool)
+    if int(dropped.item()) == 0:          # the usual case (a sweep inside its log's pose table): nothing to compact
+        return _back(out, xyz), _back(keep, xyz)
     return _back(out[keep], xyz), _back(keep, xyz)
 
 
@@ -78,21 +118,35 @@ def sensor_from_egovehicle(xyz, rotation, translation, device=None):
     return _back(out, xyz)
 
 
+_LASER_TABLES = {}
+
+
+def _laser_tables(dev, height: int, remap: bool):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), int(height) == 32, bool(remap))
+    t = _LASER_TABLES.get(key)
+    if t is None:
+        rows = torch.as_tensor((ROW_MAPPING_32 if height == 32 else ROW_MAPPING_64).astype(np.int64), device=dev)
+        mapping = torch.as_tensor(LASER_MAPPING.astype(np.int64), device=dev) if remap else None
+        t = _LASER_TABLES[key] = (rows, mapping)
+    return t
+
+
 def correct_laser_numbers(laser_numbers, log_id: str, height: int, log_ids: Optional[Collection[str]] = None,
-                          device=None):
+                          device=None, validate: bool = True):
     """utils.py:211-226 -> row-mapped laser numbers (int64).  ``log_ids`` is the reference's ``LOG_IDS`` table
     (``datasets/argoverse/constants.py:269``: the logs recorded with the other beam ordering); it is dataset
-    metadata, not arithmetic, and stays with the caller.  Out-of-table laser numbers raise ``IndexError`` like numpy."""
+    metadata, not arithmetic, and stays with the caller.  Out-of-table laser numbers raise ``IndexError`` like numpy;
+    that check is the call's only host read -- ``validate=False`` skips it (out-of-table rows come back as -1) for
+    callers that keep the stream asynchronous."""
     dev = _dev(device)
     las = _to_dev(laser_numbers, torch.int64, dev).reshape(-1)
     remap = log_ids is not None and log_id in log_ids
-    mapping = torch.as_tensor(LASER_MAPPING.astype(np.int64), device=dev) if remap else None
-    rows = torch.as_tensor((ROW_MAPPING_32 if height == 32 else ROW_MAPPING_64).astype(np.int64), device=dev)
+    rows, mapping = _laser_tables(dev, height, remap)
     out = torch.empty_like(las)
-    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if validate else None
     N.check(N.lib().rv3d_correct_laser_numbers(ptr(las), las.shape[0], ptr(mapping), ptr(rows), rows.shape[0], ptr(out),
                                                ptr(bad), stream_ptr(dev)), "rv3d_correct_laser_numbers")
-    if int(bad.item()):
+    if validate and int(bad.item()):
         raise IndexError("laser number outside the mapping tables")
     return _back(out, laser_numbers)
 

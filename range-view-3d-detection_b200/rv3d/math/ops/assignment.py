@@ -3,6 +3,7 @@ SURVEY 8f row 4).  Same names, arguments and results; the per-instance Python lo
 ``compute_classification_targets`` (:121-139) becomes one segmented top-k on the device."""
 from __future__ import annotations
 
+import math
 from typing import Any, Mapping, Tuple
 
 import torch
@@ -57,16 +58,73 @@ def _segment_min(values: Tensor, seg: Tensor, n_seg: int) -> Tensor:
     return out.scatter_reduce(0, seg.long(), values, reduce="amin")
 
 
+TOPK_ALL = 0x7FFFFFFF      # include/rv3d.h RV3D_TOPK_ALL
+
+
+def _k_slots(k) -> int:
+    """targets_config.k -> slots per instance: the production value is ``.inf`` (conf/model/range_view.yaml:126:
+    ``min(k, len)`` then keeps every pixel of the instance)."""
+    if isinstance(k, float) and (math.isinf(k) or k >= TOPK_ALL):
+        return TOPK_ALL
+    return min(int(k), TOPK_ALL)
+
+
 def compute_classification_targets(input: Tensor, target: Tensor, classification_labels: Tensor, cart: Tensor,
                                    targets_config: Mapping[str, Any], mask: Tensor, panoptics: Tensor,
-                                   background_index: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                                   background_index: int, max_instances: int = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Drop-in for assignment.py:76-148 -> (affinities (B,C,H,W), foreground_mask (B,1,H,W),
-    background_mask (B,1,H,W) bool, regression_weights (B,1,H,W) bool)."""
+    background_mask (B,1,H,W) bool, regression_weights (B,1,H,W) bool).
+
+    float32 tensors with k <= 64 (or k = inf, the production setting) run as ONE fused call
+    (``rv3d_classification_targets``: only foreground pixels are decoded, per-instance top-k through atomic slot lists,
+    no dense intermediates).  ``max_instances`` (an upper bound on the panoptic ids, exclusive) lets the caller skip the
+    one host read the fused form needs to size its slot table; without it the largest id is read back.  Other dtypes,
+    larger finite k and GAUSSIAN + normalize_affinities take the composed form below."""
     dev = require_cuda(input, target, cart)
     cfg = dict(targets_config)
     name = str(cfg["affinity_fn"]).upper()
     if name not in ("BEV", "GAUSSIAN"):
         raise NotImplementedError("This affinity function is not implemented.")
+    k = _k_slots(cfg["k"])
+    fused = (input.dtype == target.dtype == cart.dtype == torch.float32 and (k <= 64 or k == TOPK_ALL) and k >= 0
+             and not (name == "GAUSSIAN" and cfg["normalize_affinities"]) and panoptics.numel() > 0)
+    if not fused:
+        return _compute_classification_targets_composed(input, target, classification_labels, cart, cfg, mask, panoptics,
+                                                        background_index, name, k)
+    if name == "BEV" and cfg["normalize_affinities"]:      # the reference's own failure mode (:71)
+        if bool((panoptics > 0).any()):
+            raise UnboundLocalError("cannot access local variable 'object_ious' where it is not associated with a value")
+    B, _, H, W = target.shape
+    C = int(background_index)
+    cap = int(max_instances) if max_instances is not None else int(panoptics.max()) + 1
+    cap = max(cap, 1)
+    lib = N.lib()
+    inp, tgt, crt = input.detach().contiguous(), target.contiguous(), cart.contiguous()
+    lab = classification_labels.reshape(B, H, W).to(torch.int64).contiguous()
+    pan = panoptics.reshape(B, H, W).to(torch.int64).contiguous()
+    msk = mask.reshape(B, H, W).to(torch.bool).contiguous()
+    affinities = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    foreground = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    background = torch.empty((B, 1, H, W), dtype=torch.bool, device=dev)
+    reg_w = torch.empty((B, 1, H, W), dtype=torch.bool, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    work = scratch(lib.rv3d_classification_targets_scratch_bytes(B, H, W, k, cap), dev)
+    sigma2 = float(cfg.get("sigma", 1.0)) ** 2 if name == "GAUSSIAN" else 1.0
+    N.check(lib.rv3d_classification_targets(ptr(inp), ptr(tgt), ptr(lab), ptr(crt), ptr(msk), ptr(pan), B, C, H, W,
+                                            1 if name == "GAUSSIAN" else 0, int(bool(cfg["enable_azimuth_invariant_targets"])),
+                                            k, sigma2, cap, ptr(affinities), ptr(foreground), ptr(background), ptr(reg_w),
+                                            ptr(status), ptr(work), work.numel(), stream_ptr(dev)),
+            "rv3d_classification_targets")
+    if max_instances is not None:      # the caller's promise, checked without a host read (a violated promise traps)
+        torch._assert_async(status[0] == 0)
+    return affinities, foreground, background, reg_w
+
+
+def _compute_classification_targets_composed(input, target, classification_labels, cart, cfg, mask, panoptics,
+                                             background_index, name, k):
+    """The same function composed from the free-standing operators (dense decodes, gathers, segmented top-k by one
+    stable sort): any floating dtype, any k."""
+    dev = input.device
     all_foreground = F.one_hot(classification_labels, background_index + 1).permute(0, 3, 1, 2)[:, :-1].float()   # :91-95
     pds = decode_range_view(input.detach(), cart, True)                                                           # :105-109
     gts = decode_range_view(target, cart, bool(cfg["enable_azimuth_invariant_targets"]))                          # :110-114
@@ -92,7 +150,7 @@ def compute_classification_targets(input: Tensor, target: Tensor, classification
         like = torch.empty_like(aff)
         lib = N.lib()
         work = scratch(lib.rv3d_instance_topk_scratch_bytes(aff.numel()), dev)
-        N.check(lib.rv3d_instance_topk(ptr(aff), ptr(seg), aff.numel(), B * n_ids, int(cfg["k"]), ptr(like), ptr(work),
+        N.check(lib.rv3d_instance_topk(ptr(aff), ptr(seg), aff.numel(), B * n_ids, k, ptr(like), ptr(work),
                                        work.numel(), stream_ptr(dev)), "rv3d_instance_topk")
         affinities[b_idx, 0, h_idx, w_idx] = like.type_as(affinities)                                            # :134-136
         foreground_mask[b_idx, 0, h_idx, w_idx] = like.bool().type_as(affinities)                                # :137-139

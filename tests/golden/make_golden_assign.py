@@ -38,6 +38,10 @@ def main():
         "bev": Cfg(affinity_fn="bev", enable_azimuth_invariant_targets=True, k=5, normalize_affinities=False, sigma=1.0),
         "gauss": Cfg(affinity_fn="gaussian", enable_azimuth_invariant_targets=True, k=3, normalize_affinities=True, sigma=0.7),
         "gauss_raw": Cfg(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=False, k=100, normalize_affinities=False, sigma=1.5),
+        # the production setting (conf/model/range_view.yaml:126 k = .inf, baseline.yaml:43-45 GAUSSIAN, sigma 0.75)
+        "gauss_inf": Cfg(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=True, k=float("inf"), normalize_affinities=False, sigma=0.75),
+        "gauss_k4": Cfg(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=True, k=4, normalize_affinities=False, sigma=0.75),
+        "bev_k1": Cfg(affinity_fn="BEV", enable_azimuth_invariant_targets=False, k=1, normalize_affinities=False, sigma=1.0),
     }.items():
         res = ref.compute_classification_targets(d["input"].clone(), d["target"].clone(), d["labels"], d["cart"], cfg, d["mask"],
                                                  d["panoptics"], 3)

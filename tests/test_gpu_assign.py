@@ -48,6 +48,38 @@ def test_compute_classification_targets_full_size_vs_oracle():
     assert int(ref[1].sum()) > 200
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(affinity_fn="bev", enable_azimuth_invariant_targets=True, k=8, normalize_affinities=False, sigma=1.0),
+    dict(affinity_fn="bev", enable_azimuth_invariant_targets=False, k=1, normalize_affinities=False, sigma=1.0),
+    dict(affinity_fn="gaussian", enable_azimuth_invariant_targets=True, k=3, normalize_affinities=False, sigma=0.75),
+    dict(affinity_fn="gaussian", enable_azimuth_invariant_targets=True, k=float("inf"), normalize_affinities=False, sigma=0.75),
+    dict(affinity_fn="gaussian", enable_azimuth_invariant_targets=True, k=64, normalize_affinities=False, sigma=0.75),
+])
+def test_fused_targets_equal_composed(cfg):
+    """The fused call (foreground-only decode, atomic top-k slot lists) against the same function composed from the
+    free-standing operators (dense decodes + one stable sort): masks identical, affinities to float32 rounding of the
+    Gaussian (the BEV IoU is the same routine: bit-equal).  Large instances (hundreds of pixels >> k) contend for the slots."""
+    from rv3d.math.ops import assignment as A
+    d = synth.make_assignment_inputs(3, 3, 64, 512, seed=11, n_instances=40)
+    pan = d["panoptics"]
+    pan[0, 0, 10:40, 100:160] = 41                        # one 1800-pixel instance
+    pan[~d["mask"]] = 0
+    dv = {k: v.to(DEV) for k, v in d.items()}
+    args = (dv["input"], dv["target"], dv["labels"], dv["cart"], cfg, dv["mask"], dv["panoptics"], 3)
+    fused = A.compute_classification_targets(*args)
+    hinted = A.compute_classification_targets(*args, max_instances=64)
+    comp = A._compute_classification_targets_composed(*args[:4], dict(cfg), *args[5:], str(cfg["affinity_fn"]).upper(), A._k_slots(cfg["k"]))
+    for f, h in zip(fused, hinted):
+        assert torch.equal(f, h)
+    for f, c in zip(fused[1:], comp[1:]):
+        assert f.dtype == c.dtype and torch.equal(f, c)
+    if str(cfg["affinity_fn"]).upper() == "BEV":
+        assert torch.equal(fused[0], comp[0])
+    else:
+        torch.testing.assert_close(fused[0], comp[0], rtol=2e-6, atol=1e-7)
+    assert int(fused[1].sum()) > 100
+
+
 def test_compute_classification_targets_edges():
     d = synth.make_assignment_inputs(1, 2, 8, 64, seed=6, n_instances=4)
     cfg = dict(affinity_fn="bev", enable_azimuth_invariant_targets=True, k=4, normalize_affinities=False, sigma=1.0)

@@ -45,6 +45,34 @@ def test_unmotion_compensate_full_size_vs_oracle():
     assert np.abs(ref - xyz[keep_ref]).max() > 0.05
 
 
+def test_unmotion_compensate_pose_table_and_irregular_poses():
+    """One resident PoseTable serves many sweeps; a table with very uneven spacing defeats the interpolation guess and
+    takes the binary-search fallback; both against the oracle (and the per-call form)."""
+    from rv3d.converters.av2.utils import PoseTable, unmotion_compensate
+    ts, quat, trans = synth.make_pose_table(600, seed=21)
+    rng = np.random.default_rng(3)
+    keep_rows = np.sort(rng.choice(np.arange(1, 599), size=120, replace=False))
+    keep_rows = np.concatenate([[0], keep_rows[keep_rows < 80], keep_rows[keep_rows > 400], [599]])   # a 3 s hole + jitter
+    for sel in (slice(None), keep_rows):
+        t_s, q_s, p_s = ts[sel], quat[sel], trans[sel]
+        table = PoseTable(t_s, q_s, p_s, device=DEV)
+        for row in (5, len(t_s) // 2, len(t_s) - 4):
+            t0 = int(t_s[row])
+            xyz, off, *_ = synth.make_raw_sweep(20_000, seed=30 + row)
+            off = off.copy()
+            off[:50] = rng.integers(-(t0 - int(t_s[0])) - 5, int(t_s[-1]) - t0 + 5, size=50)    # anywhere in (and just outside) the table
+            if row != 5:                                  # rows the reference's filter drops: the compaction branch
+                off[50], off[51] = int(t_s[0]) - t0, int(t_s[-1]) - t0 + 3
+            ref, keep_ref = av2_prep.unmotion_compensate(xyz, off, t0, t_s, q_s, p_s)
+            out, keep = unmotion_compensate(xyz, off, t0, table)
+            assert np.array_equal(keep, keep_ref) and (row == 5 or not keep[50:52].any())
+            np.testing.assert_allclose(out, ref, rtol=0, atol=ATOL)
+            out2, keep2 = unmotion_compensate(xyz, off, t0, t_s, q_s, p_s, device=DEV)
+            assert np.array_equal(out, out2) and np.array_equal(keep, keep2)
+    with pytest.raises(ValueError):
+        unmotion_compensate(xyz, off, int(ts[7]) + 3, PoseTable(ts, quat, trans, device=DEV))
+
+
 def test_unmotion_compensate_edges():
     from rv3d.converters.av2.utils import unmotion_compensate
     ts, quat, trans = synth.make_pose_table(16, seed=2)
@@ -86,6 +114,11 @@ def test_correct_laser_numbers_golden(g):
     assert np.array_equal(correct_laser_numbers(g["laser64"].astype(np.int64), "x", 64, device=DEV), g["rows64_plain"])
     with pytest.raises(IndexError):                      # a 64-beam number against the 32-row table, like numpy
         correct_laser_numbers(np.array([3, 40]), "x", 32, device=DEV)
+    lazy = correct_laser_numbers(np.array([3, 40, 7]), "x", 32, device=DEV, validate=False)    # no host read: -1 marks the row
+    assert lazy[1] == -1 and np.array_equal(lazy[[0, 2]], correct_laser_numbers(np.array([3, 7]), "x", 32, device=DEV))
+    odd = g["laser64"].astype(np.int64)[1:-2]            # odd length, 8-byte-aligned start: the scalar tail / unaligned form
+    assert np.array_equal(correct_laser_numbers(torch.from_numpy(g["laser64"].astype(np.int64)).to(DEV)[1:-2], "x", 64).cpu().numpy(),
+                          g["rows64_plain"][1:-2]) and len(odd) > 10
 
 
 @pytest.mark.parametrize("uniform", [False, True])

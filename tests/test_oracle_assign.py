@@ -11,6 +11,10 @@ CFGS = {
     "bev": dict(affinity_fn="bev", enable_azimuth_invariant_targets=True, k=5, normalize_affinities=False, sigma=1.0),
     "gauss": dict(affinity_fn="gaussian", enable_azimuth_invariant_targets=True, k=3, normalize_affinities=True, sigma=0.7),
     "gauss_raw": dict(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=False, k=100, normalize_affinities=False, sigma=1.5),
+    # the production setting (conf/model/range_view.yaml:126 k = .inf, baseline.yaml:43-45 GAUSSIAN, sigma 0.75)
+    "gauss_inf": dict(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=True, k=float("inf"), normalize_affinities=False, sigma=0.75),
+    "gauss_k4": dict(affinity_fn="GAUSSIAN", enable_azimuth_invariant_targets=True, k=4, normalize_affinities=False, sigma=0.75),
+    "bev_k1": dict(affinity_fn="BEV", enable_azimuth_invariant_targets=False, k=1, normalize_affinities=False, sigma=1.0),
 }
 
 

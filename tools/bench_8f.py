@@ -99,10 +99,15 @@ def main():
     xyz, off, *_ = synth.make_raw_sweep(n, seed=10)
     dx, do = torch.from_numpy(xyz).to(DEV), torch.from_numpy(off).to(DEV)
     t0n = int(ts[1500])
-    ms = timed(lambda: cu.unmotion_compensate(dx, do, t0n, ts, quat, trans))
     s = 180_000
     t0 = time.perf_counter(); av2_prep.unmotion_compensate(xyz[:s], off[:s], t0n, ts, quat, trans); cpu = time.perf_counter() - t0
-    report("unmotion_compensate", ms, n * (32 + 25), n, "points", cpu, s, "row 2: includes the mirror's table upload + boolean compaction (torch)")
+    ms = timed(lambda: cu.unmotion_compensate(dx, do, t0n, ts, quat, trans))
+    report("unmotion_compensate (per-call table)", ms, n * (32 + 25), n, "points", cpu, s,
+           "row 2: the reference's signature: pose table uploaded and its Slerp intervals prepared on every call, one host read (dropped-row count)")
+    table = cu.PoseTable(ts, quat, trans, device=DEV)
+    ms = timed(lambda: cu.unmotion_compensate(dx, do, t0n, table))
+    report("unmotion_compensate (resident PoseTable)", ms, n * (32 + 25), n, "points", cpu, s,
+           "row 2: one PoseTable per log; fp64-issue-bound (~330 fp64 instructions per point), one host read (dropped-row count)")
     rot = av2_prep.quat_to_matrix(np.array([0.0012, -0.0031, 0.0052, 0.99998]))
     tr = np.array([1.35, 0.0, 1.64])
     ms = timed(lambda: cu.sensor_from_egovehicle(dx, rot, tr))
@@ -112,7 +117,9 @@ def main():
     ms = timed(lambda: cu.correct_laser_numbers(las, "a", 64, log_ids=("a",)))
     ln = las[:s].cpu().numpy()
     t0 = time.perf_counter(); av2_prep.correct_laser_numbers(ln, True, 64); cpu = time.perf_counter() - t0
-    report("correct_laser_numbers", ms, n * 16, n, "points", cpu, s, "row 2: includes the out-of-range flag read (host sync)")
+    report("correct_laser_numbers", ms, n * 16, n, "points", cpu, s, "row 2: includes the out-of-range flag read (host sync, numpy's IndexError)")
+    ms = timed(lambda: cu.correct_laser_numbers(las, "a", 64, log_ids=("a",), validate=False))
+    report("correct_laser_numbers(validate=False)", ms, n * 16, n, "points", cpu, s, "row 2: no host read (out-of-table rows come back as -1)")
 
     # ---- row 4: training-time callers --------------------------------------------------------
     head = synth.make_head_outputs(B, 3, H, W, seed=1, n_objects=32)
@@ -129,11 +136,21 @@ def main():
     d = synth.make_assignment_inputs(4, 3, H, W, seed=5, n_instances=150)
     dv = {k: v.to(DEV) for k, v in d.items()}
     cfg = dict(affinity_fn="bev", enable_azimuth_invariant_targets=True, k=8, normalize_affinities=False, sigma=1.0)
-    ms = timed(lambda: compute_classification_targets(dv["input"], dv["target"], dv["labels"], dv["cart"], cfg, dv["mask"], dv["panoptics"], 3), iters=10)
     d1 = {k: v[:1] for k, v in d.items()}
-    t0 = time.perf_counter(); assign_oracle.compute_classification_targets(d1["input"], d1["target"], d1["labels"], d1["cart"], cfg, d1["mask"], d1["panoptics"], 3); cpu = time.perf_counter() - t0
-    report("compute_classification_targets", ms, 4 * H * W * (2 * (11 * 4 + 7 * 4) + 8 + 8 + 4 * 3 + 4 + 2), 4, "sweeps", cpu, 1,
-           "row 4: whole mirror function (2 dense decodes, torch gathers, IoU, segmented top-k, scatters)")
+    from rv3d.math.ops import assignment as A
+    io_bytes = 4 * H * W * ((8 + 8 + 3) * 4 + 8 + 8 + 1 + (3 + 1) * 4 + 2)      # every input once + every output once
+    for tag, c in (("BEV k=8", cfg), ("GAUSSIAN k=inf (production config)", dict(cfg, affinity_fn="gaussian", k=float("inf"), sigma=0.75))):
+        t0 = time.perf_counter(); assign_oracle.compute_classification_targets(d1["input"], d1["target"], d1["labels"], d1["cart"], c, d1["mask"], d1["panoptics"], 3); cpu = time.perf_counter() - t0
+        args = (dv["input"], dv["target"], dv["labels"], dv["cart"], c, dv["mask"], dv["panoptics"], 3)
+        ms = timed(lambda: A._compute_classification_targets_composed(*args[:4], dict(c), *args[5:], str(c["affinity_fn"]).upper(), A._k_slots(c["k"])), iters=10)
+        report(f"compute_classification_targets composed, {tag}", ms, io_bytes, 4, "sweeps", cpu, 1,
+               "row 4: round-1 form (2 dense decodes, torch gathers, IoU, one stable sort, scatters)")
+        ms = timed(lambda: compute_classification_targets(*args), iters=10)
+        report(f"compute_classification_targets fused, {tag}", ms, io_bytes, 4, "sweeps", cpu, 1,
+               "row 4: ONE call (foreground-only decode, atomic top-k slots) + one host read of the largest instance id")
+        ms = timed(lambda: compute_classification_targets(*args, max_instances=256), iters=10)
+        report(f"compute_classification_targets fused, max_instances given, {tag}", ms, io_bytes, 4, "sweeps", cpu, 1,
+               "row 4: ONE call, no host read")
 
 
 if __name__ == "__main__":
