@@ -412,7 +412,8 @@ int rv3d_instance_topk(const float *affinity, const int32_t *segment, int64_t n,
  * :151-161).  k: slots per instance (<= 64), 0 = nothing is foreground, RV3D_TOPK_ALL = every pixel of an instance is
  * in its top-k (the production setting k = inf, conf/model/range_view.yaml:126).  id_capacity: instance ids per sweep
  * the call can hold; *status (device i32, caller zeroes it) is set to 1 when an id >= id_capacity was met (the results
- * are then incomplete and the caller must retry with a larger capacity).  Only foreground pixels are decoded; no
+ * are then incomplete and the caller must retry with a larger capacity); with status = NULL such an id traps the kernel
+ * (a sticky launch failure: loud, and no host read on the good path).  Only foreground pixels are decoded; no
  * dense intermediate is written. */
 #define RV3D_TOPK_ALL 0x7fffffff
 size_t rv3d_classification_targets_scratch_bytes(int32_t batch, int32_t height, int32_t width, int32_t k,

@@ -80,7 +80,10 @@ targets_affinity_kernel(TargetsArgs a, const T *__restrict__ input, const T *__r
   const size_t gp = static_cast<size_t>(b) * a.HW + p;
   const long long id = panoptics[gp];
   if (id <= 0) return;                                   // one_hot(panoptics)[:, 1:]: id 0 is background (:118)
-  if (id >= a.id_cap) { atomicExch(status, 1); return; }
+  if (id >= a.id_cap) {                                  // the caller's capacity promise is broken: flag it, or fail loudly
+    if (status) atomicExch(status, 1); else __trap();
+    return;
+  }
   float ri[8], rt[8], c[3];
 #pragma unroll
   for (int k = 0; k < 8; ++k) ri[k] = Ld<T>::one(input + (static_cast<size_t>(b) * 8 + k) * a.HW + p);
@@ -218,7 +221,7 @@ extern "C" int rv3d_classification_targets(const float *input, const float *targ
   RV3D_CHECK_ARG(k == kKeepAll || k <= 64);
   RV3D_CHECK_ARG(static_cast<int64_t>(height) * width < (int64_t(1) << 31));
   if (batch == 0) return RV3D_OK;
-  RV3D_CHECK_ARG(input && target && labels && cart && mask && panoptics && affinities && foreground && background && reg_weights && status && scratch);
+  RV3D_CHECK_ARG(input && target && labels && cart && mask && panoptics && affinities && foreground && background && reg_weights && scratch);
   if (!aligned(scratch, 256)) return RV3D_ERR_ALIGN;
   if (scratch_bytes < rv3d_classification_targets_scratch_bytes(batch, height, width, k, id_capacity)) return RV3D_ERR_SCRATCH;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

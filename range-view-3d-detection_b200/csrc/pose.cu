@@ -14,6 +14,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace rv3d {
 
@@ -144,6 +145,64 @@ unmotion_kernel(UnmotionArgs a, const double *__restrict__ xyz, const long long 
 // with the same device functions as above, so a point's work shrinks to: locate the interval (interpolation guess +
 // a short walk instead of two 12-step binary searches), blend, one sincos, one quaternion product, apply.
 // ------------------------------------------------------------------------------------------
+
+// ---- the per-point arithmetic of the table form: same formulas, cheaper primitives (all within ~2 fp64 ulps of the IEEE /
+// libm forms above, far below the 1e-9 m the parity tests allow; everything outside the guarded ranges takes the forms
+// above).  An IEEE fp64 division is ~20 instructions with a slow-path branch, libm's sin + cos ~80: a point has 7 of the
+// former and one pair of the latter. ----
+__device__ __forceinline__ double fast_rcp(double x) {      // 2^-500 < |x| < 2^500 (callers guard)
+  double r = rcp_seed(x);
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ bool rcp_ok(double x) {
+  return (static_cast<uint32_t>(__double2hiint(x)) >> 20 & 0x7ffu) - 523u < 1000u;
+}
+// sin / cos of a small angle (|x| <= 0.5: a Slerp step between neighbouring poses is milliradians): Taylor to x^15 / x^16
+__device__ __forceinline__ void sincos_small(double x, double &s, double &c) {
+  const double x2 = x * x;
+  double ps = fma(x2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+  ps = fma(x2, ps, -1.0 / 39916800.0);
+  ps = fma(x2, ps, 1.0 / 362880.0);
+  ps = fma(x2, ps, -1.0 / 5040.0);
+  ps = fma(x2, ps, 1.0 / 120.0);
+  ps = fma(x2, ps, -1.0 / 6.0);
+  s = fma(x * x2, ps, x);
+  double pc = fma(x2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
+  pc = fma(x2, pc, 1.0 / 479001600.0);
+  pc = fma(x2, pc, -1.0 / 3628800.0);
+  pc = fma(x2, pc, 1.0 / 40320.0);
+  pc = fma(x2, pc, -1.0 / 720.0);
+  pc = fma(x2, pc, 1.0 / 24.0);
+  pc = fma(x2, pc, -0.5);
+  c = fma(x2, pc, 1.0);
+}
+__device__ __forceinline__ Quat q_normalized_fast(Quat q) {
+  const double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+  if (!(n2 > 0x1p-200 && n2 < 0x1p200)) return q_normalized(q);
+  const double y = rsqrt_seed(n2);                         // 1 / sqrt(n2): seed + coupled Newton steps (fast_sqrt's core)
+  double g = n2 * y, h = 0.5 * y;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g); h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  h = fma(h, e, h);
+  const double r = 2.0 * h;
+  return Quat{q.x * r, q.y * r, q.z * r, q.w * r};
+}
+__device__ __forceinline__ Quat q_from_rotvec_fast(const double (&rv)[3]) {
+  const double n2 = rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2];
+  if (!(n2 > 1e-6 && n2 <= 1.0)) return q_from_rotvec(rv);    // n <= 1e-3 takes scipy's series, n > 1 the library sincos
+  const double n = fast_sqrt(n2);
+  double sn, cs;
+  sincos_small(0.5 * n, sn, cs);
+  const double scale = sn * fast_rcp(n);
+  return Quat{scale * rv[0], scale * rv[1], scale * rv[2], cs};
+}
+
 __global__ void __launch_bounds__(128)
 pose_intervals_kernel(int n_poses, const double *__restrict__ pose_quat, double *__restrict__ iv) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,7 +254,9 @@ unmotion_table_kernel(UnmotionTableArgs a, const double *__restrict__ xyz, const
   while (steps < 6 && pose_ts[idx] < t) { ++idx; ++steps; }
   if (steps >= 6) idx = lower_bound(M, t, [&](int k) { return pose_ts[k]; });
   const long long ts_lo = pose_ts[idx - 1], ts_hi = pose_ts[idx];
-  const double alpha = static_cast<double>(t - ts_lo) / static_cast<double>(ts_hi - ts_lo);   // :275
+  const double span = static_cast<double>(ts_hi - ts_lo);
+  const double alpha = rcp_ok(span) ? static_cast<double>(t - ts_lo) * fast_rcp(span)                // :275
+                                    : static_cast<double>(t - ts_lo) / span;
   double tp[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k)   // :276 -- the weights are the reference's (alpha on the LOWER pose)
@@ -210,11 +271,11 @@ unmotion_table_kernel(UnmotionTableArgs a, const double *__restrict__ xyz, const
   if (tf == static_cast<double>(a.first_ns)) ind = 0;
   ind = ind < 0 ? 0 : (ind > M - 2 ? M - 2 : ind);
   const double t0 = static_cast<double>(pose_ts[ind]), t1 = static_cast<double>(pose_ts[ind + 1]);
-  const double beta = (tf - t0) / (t1 - t0);
+  const double beta = rcp_ok(t1 - t0) ? (tf - t0) * fast_rcp(t1 - t0) : (tf - t0) / (t1 - t0);
   const double *v8 = iv + 8 * static_cast<size_t>(ind);
   const Quat q0{v8[0], v8[1], v8[2], v8[3]};
   double rv[3] = {v8[4] * beta, v8[5] * beta, v8[6] * beta};
-  const Quat qp = q_normalized(q_mul(q0, q_from_rotvec(rv)));
+  const Quat qp = q_normalized_fast(q_mul(q0, q_from_rotvec_fast(rv)));
   double R[9];
   q_to_matrix(qp, R);
   const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];

@@ -46,7 +46,7 @@ class PoseTable:
         self.first_ns, self.last_ns = int(ts_host[0]), int(ts_host[-1])
         if self.last_ns <= self.first_ns:
             raise ValueError("pose table: timestamps must be sorted and span a positive interval")
-        self._row_of = None
+        self._sorted = bool(np.all(ts_host[1:] >= ts_host[:-1]))
         self.ts = torch.as_tensor(ts_host, device=dev)
         self.trans = torch.as_tensor(self.trans_host, device=dev)
         quat = torch.as_tensor(self.quat_host, device=dev)
@@ -54,15 +54,18 @@ class PoseTable:
         N.check(N.lib().rv3d_pose_intervals(ptr(quat), m, ptr(self.intervals), stream_ptr(dev)), "rv3d_pose_intervals")
 
     def row_at(self, timestamp_ns: int) -> int:
-        """Row of the pose stamped exactly ``timestamp_ns`` (utils.py:258-273); ValueError when there is none."""
-        if self._row_of is None:
-            self._row_of = {}
-            for k in range(self.n_poses - 1, -1, -1):      # the FIRST matching row wins, like the reference's filter()[0]
-                self._row_of[int(self.ts_host[k])] = k
-        try:
-            return self._row_of[int(timestamp_ns)]
-        except KeyError:
-            raise ValueError(f"no pose at the sweep's timestamp {timestamp_ns}") from None
+        """Row of the pose stamped exactly ``timestamp_ns`` (utils.py:258-273; the first one, like the reference's
+        ``filter(...)[0]``); ValueError when there is none."""
+        t = int(timestamp_ns)
+        if self._sorted:
+            k = int(np.searchsorted(self.ts_host, t, side="left"))
+            if k < self.n_poses and int(self.ts_host[k]) == t:
+                return k
+        else:
+            hit = np.nonzero(self.ts_host == t)[0]
+            if hit.size:
+                return int(hit[0])
+        raise ValueError(f"no pose at the sweep's timestamp {timestamp_ns}")
 
 
 def unmotion_compensate(xyz, offset_ns, timestamp_ns: int, pose_timestamps_ns, pose_quat_xyzw=None, pose_translation=None,
