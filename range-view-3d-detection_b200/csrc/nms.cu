@@ -259,7 +259,17 @@ scatter_records_kernel(const unsigned long long *__restrict__ keys, Builder buil
 // ------------------------------------------------------------------------------------------
 // the suppression kernel
 // ------------------------------------------------------------------------------------------
+// Weighted mode, hand-over from the per-segment scan to the grid-wide tail pass (wnms_tail_kernel): once a segment has
+// kept num_post_nms boxes, every candidate behind the scan position still owes the kept boxes its merge contribution.
+// The scan publishes the record range [pos_lo, pos_hi) that is left (whole score bins inside the num_pre_nms cut), the
+// number of kept boxes and the geometry of its kept-box grid; the grid itself is in global memory by then.
+struct TailInfo {
+  int pos_lo, pos_hi, kept, nos;
+  float inv_cell, r_cap;
+};
+
 struct NmsArgs {
+  TailInfo *tail;                 // [seg], zeroed per call; null: the scan kernel does the tail itself
   const void *recs;               // HardRec / WRec, grouped by (segment, score bin)
   unsigned long long *skey;       // [pos] low key bits (score desc | candidate), the fine sort key
   uint32_t *gorder;               // scratch for bins larger than a window (sorted through global memory)
@@ -1124,16 +1134,52 @@ nms_pull_kernel(NmsArgs a) {
     rank_base += wn;
   }
   if (kWeighted && done) {
-    // ... and so do all candidates behind this window: one pull each against every kept box, merges only
-    while (rank_base < n_use) {
-      const int wn = next_window(false);
-      if (wn <= 0) break;
-      for (int t = tid; t < wn; t += kNmsThreads) surv_a[t] = static_cast<uint16_t>(t);
-      __syncthreads();
-      lap(0);
-      pull(surv_a, wn, 0, true);
-      rank_base += wn;
+    // ... and so do all candidates behind this window: one pull each against every kept box, merges only.
+    auto tail_windows = [&](bool chunk_only) {
+      while (rank_base < n_use && (!chunk_only || chunk_hi > chunk_lo)) {
+        const int wn = next_window(false);
+        if (wn <= 0) break;
+        for (int t = tid; t < wn; t += kNmsThreads) surv_a[t] = static_cast<uint16_t>(t);
+        __syncthreads();
+        lap(0);
+        pull(surv_a, wn, 0, true);
+        rank_base += wn;
+      }
+    };
+    if (a.tail) {
+      // One CTA doing this for a long tail is the whole call's critical path (200 k candidates: 39 ms), while the
+      // candidates are independent of each other now: the keep-set is final.  What is left in whole score bins inside
+      // the num_pre_nms cut goes to the grid-wide wnms_tail_kernel; this CTA only finishes a giant bin it is in the
+      // middle of, and afterwards the one bin the cut falls into (whose members need their exact rank).
+      tail_windows(true);
+      if (rank_base < n_use) {
+        int pos_lo, pos_hi, b_cut = 0;
+        if (a.presorted) {
+          pos_lo = rank_base; pos_hi = n_use;
+        } else {
+          int lo = bin_cur, hi = a.nb;             // largest b with s_bins[b] <= n_use (every thread, same result)
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_bins[mid] <= n_use) lo = mid; else hi = mid - 1;
+          }
+          b_cut = lo; pos_lo = s_bins[bin_cur]; pos_hi = s_bins[b_cut];
+        }
+        if (pos_hi > pos_lo) {
+          if (kSm) {                                 // the kept-box grid leaves shared memory
+            for (int i = tid; i < kept; i += kNmsThreads) a.kxyr_g[kbase + i] = kxyr[i];
+            int *hg = a.heads_g + static_cast<size_t>(seg) * kBucketsSmem;
+            for (int i = tid; i < kBucketsSmem; i += kNmsThreads) hg[i] = heads[i];
+            const int nos = s_nos;
+            for (int i = tid; i < nos; i += kNmsThreads) a.kos[kbase + i] = kos[i];
+          }
+          if (tid == 0) a.tail[seg] = TailInfo{pos_lo, pos_hi, kept, s_nos, inv_cell, r_cap};
+          if (!a.presorted) bin_cur = b_cut;
+          rank_base += pos_hi - pos_lo;
+          __syncthreads();
+        }
+      }
     }
+    tail_windows(false);
   }
 
   if (tid == 0) a.kept_count[seg] = kept;
@@ -1161,6 +1207,243 @@ nms_pull_kernel(NmsArgs a) {
         for (int k = 0; k < 6; ++k) a.stats[12 + k] = static_cast<unsigned long long>(ph[k]);
       atomicMax(a.stats + 11, static_cast<unsigned long long>(n_seg));   // largest segment (candidates)
       atomicAdd(a.stats + 20, static_cast<unsigned long long>(min(rank_base, n_use)));   // candidates consumed by the scan
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weighted mode: merge contributions of the candidates behind the scan, grid-wide
+// ------------------------------------------------------------------------------------------
+// One thread per record of a published tail range (TailInfo).  The keep-set is final, so the candidates are independent:
+// each walks its segment's kept-box grid (the same padded-circle test and upper bound as the scan kernel, the same
+// bit-exact IoU with the kept box as box 1), finds its FIRST suppressor fs = the lowest kept index with iou > thr, and
+// adds its score-weighted row to every kept box k <= fs with iou > merge_thr -- exactly what pull(.., merges_only) does
+// for a window, without the window.  Accumulation is the same fp64 atomicAdd into NmsArgs::acc.
+// kSm: the grid was copied out of the scan kernel's shared memory in its packed form ((next + 1) << 20 | position in w).
+constexpr int kTailThreads = 128;
+constexpr int kTailPairs = 768;      // per-warp buffer of (candidate, kept) pairs: circle hits, then the ones the bound lets through
+
+template <bool kSm>
+__global__ void __launch_bounds__(kTailThreads)
+wnms_tail_kernel(NmsArgs a, int S) {
+  // A warp works on 32 candidates at a time in three converged steps, so that the bit-exact IoU routine (a few thousand
+  // instructions, called out of line) and the upper bound in front of it always run on dense lanes: (1) every lane walks
+  // its candidate's grid window with the padded-circle test only and appends the hits to the warp's buffer; (1b) the
+  // buffer is filtered by the upper bound on the IoU, one pair per lane, and compacted in place; (2) the survivors are
+  // evaluated one pair per lane: flags + each candidate's first suppressor (shared-memory atomicMin); (3) the buffer is
+  // walked again, one pair per lane, for the merges up to and including the first suppressor.  (ncu, first form with the
+  // bound inside the walk: walk 45 %, bound 26 %, exact routine 26 % of 430 M warp instructions at ~20 % lane use.)
+  __shared__ uint32_t s_pair[kTailThreads / 32][kTailPairs];     // lane << 20 | kept index
+  __shared__ uint8_t s_flag[kTailThreads / 32][kTailPairs];
+  __shared__ int s_fs[kTailThreads / 32][32];
+  __shared__ int s_cnt[kTailThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t *pairs = s_pair[wid];
+  uint8_t *flags = s_flag[wid];
+  int *fsw = s_fs[wid];
+  const int n_total = a.seg_begin[S - 1] + a.seg_count[S - 1];
+  const float thr_any = fminf(a.thr, a.mthr);
+  const bool prune = a.prune != 0;
+  unsigned long long st_iou = 0, st_circle = 0, st_bound = 0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int g0 = blockIdx.x * blockDim.x + wid * 32; g0 < n_total; g0 += stride) {   // warp-uniform trip count
+    const int g = g0 + lane;
+    bool live = g < n_total;
+    int seg = 0, beg = 0, pos = 0, kbase = 0;
+    TailInfo ti{};
+    if (live) {
+      int lo = 0, hi = S - 1;                     // largest seg with seg_begin[seg] <= g (empty segments share a begin)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.seg_begin[mid] <= g) lo = mid; else hi = mid - 1;
+      }
+      seg = lo;
+      beg = a.seg_begin[seg];
+      pos = g - beg;
+      ti = a.tail[seg];
+      live = pos >= ti.pos_lo && pos < ti.pos_hi;
+      kbase = a.kept_stride > 0 ? seg * a.kept_stride : beg;
+    }
+    if (!__any_sync(0xffffffffu, live)) continue;
+    if (lane == 0) s_cnt[wid] = 0;
+    fsw[lane] = 0x7fffffff;
+    __syncwarp();
+    const WRec *recs = static_cast<const WRec *>(a.recs) + beg;
+    const float4 *kxyr = a.kxyr_g + kbase;
+    const int *knext = kSm ? nullptr : a.knext_g + kbase;
+    const int n_buckets = kSm ? kBucketsSmem : a.n_buckets_g;
+    const int *heads = a.heads_g + static_cast<size_t>(seg) * n_buckets;
+    const uint32_t bmask = static_cast<uint32_t>(n_buckets - 1);
+    const int *kos = a.kos + kbase;
+    auto position_of = [&](float w) -> int {
+      const uint32_t u = __float_as_uint(w);
+      return static_cast<int>(kSm ? (u & 0xfffffu) : u);
+    };
+    auto exact = [&](const WRec &rk, const WRec &rj, bool &above, bool &above_m) {
+      const float iou = pair_iou(rk, rj);          // the kept box ranks higher: box 1 of the routine
+      ++st_iou;
+      above = iou > a.thr;
+      above_m = iou > a.mthr;
+    };
+    auto accumulate = [&](int kb, int k, int row_index) {
+      const float *row = a.data + static_cast<size_t>(row_index) * a.D;
+      float v[kMaxD];
+#pragma unroll
+      for (int c = 0; c < kMaxD; ++c) v[c] = c < a.D ? row[c] : 0.f;
+      const double sj = row[a.D - 1];
+      double *acc = a.acc + static_cast<size_t>(kb + k) * a.D;
+#pragma unroll
+      for (int c = 0; c < kMaxD; ++c)
+        if (c < a.D - 1) atomicAdd(acc + c, sj * static_cast<double>(v[c]));
+      atomicAdd(acc + a.D - 1, sj);
+      atomicAdd(a.merge_count + kb + k, 1);
+    };
+    // ---- (1) cheap tests; survivors go to the warp's buffer.  A pair that finds the buffer full is evaluated in place
+    // and, because its candidate's first suppressor is not final yet, remembered in `late` for step (3).
+    WRec rj{};
+    int late_n = 0;
+    if (live) {
+      rj = recs[pos];
+      const float x = rec_cx(rj), y = rec_cy(rj), r = rj.r;
+      const float inv_cell = ti.inv_cell, r_cap = ti.r_cap;
+      auto cell_of = [&](float v) -> int { return static_cast<int>(fminf(fmaxf(floorf(v * inv_cell), -32768.f), 32767.f)); };
+      auto bucket_of = [&](int ix, int iy) -> uint32_t {
+        return (static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u);
+      };
+      auto touches = [&](float qx, float qy, float qr) -> bool {
+        const float dx = qx - x, dy = qy - y, rr = qr + r;
+        return dx * dx + dy * dy <= rr * rr;
+      };
+      auto offer = [&](int k, int kpos) {
+        const int slot = atomicAdd(&s_cnt[wid], 1);
+        if (slot < kTailPairs) { pairs[slot] = (static_cast<uint32_t>(lane) << 20) | static_cast<uint32_t>(k); return; }
+        ++st_bound;                                  // buffer full (32 candidates inside a very dense cluster of kept boxes)
+        if (prune && !iou_may_exceed(recs[kpos], rj, thr_any)) return;
+        bool above, above_m;
+        exact(recs[kpos], rj, above, above_m);
+        if (above) atomicMin(&fsw[lane], k);
+        if (above_m) ++late_n;
+      };
+      bool scan_all = !prune, skip = false;
+      int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
+      if (prune) {
+        if (!(x == x) || !(y == y) || !(r == r)) skip = true;            // NaN boxes never interact
+        const float reach = r + r_cap;
+        if (!(reach <= kPosCap) || !(fabsf(x) <= kPosCap) || !(fabsf(y) <= kPosCap)) scan_all = true;
+        else {
+          ix0 = cell_of(x - reach); ix1 = cell_of(x + reach); iy0 = cell_of(y - reach); iy1 = cell_of(y + reach);
+          scan_all = (ix1 - ix0 + 1) * (iy1 - iy0 + 1) > kMaxCellsPerQuery;
+        }
+      }
+      if (skip) {
+      } else if (scan_all) {
+        for (int k = 0; k < ti.kept; ++k) {
+          const float4 q = kxyr[k];
+          ++st_circle;
+          if (!prune || touches(q.x, q.y, q.z)) offer(k, position_of(q.w));
+        }
+      } else {
+        for (int iy = iy0; iy <= iy1; ++iy)
+          for (int ix = ix0; ix <= ix1; ++ix) {
+            int k = heads[bucket_of(ix, iy) & bmask];
+            while (k >= 0) {
+              const float4 q = kxyr[k];
+              const int next = kSm ? static_cast<int>(__float_as_uint(q.w) >> 20) - 1 : knext[k];
+              ++st_circle;
+              if (touches(q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) offer(k, position_of(q.w));
+              k = next;
+            }
+          }
+        for (int o = 0; o < ti.nos; ++o) {
+          const int k = kos[o];
+          const float4 q = kxyr[k];
+          ++st_circle;
+          if (touches(q.x, q.y, q.z)) offer(k, position_of(q.w));
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (1b) the upper bound, one pair per lane; survivors move to the front of the buffer (order is irrelevant)
+    int nq = min(s_cnt[wid], kTailPairs);
+    if (prune) {
+      int kept_pairs = 0;                            // warp-uniform
+      for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int q = q0 + lane;
+        const uint32_t e = q < nq ? pairs[q] : 0u;
+        const int l = static_cast<int>(e >> 20), k = static_cast<int>(e & 0xfffffu);
+        const int c_beg = __shfl_sync(0xffffffffu, beg, l), c_pos = __shfl_sync(0xffffffffu, pos, l);
+        const int c_kbase = __shfl_sync(0xffffffffu, kbase, l);
+        bool pass = false;
+        if (q < nq) {
+          const WRec *rs = static_cast<const WRec *>(a.recs) + c_beg;
+          ++st_bound;
+          pass = iou_may_exceed(rs[position_of((a.kxyr_g + c_kbase)[k].w)], rs[c_pos], thr_any);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        __syncwarp();                                // every lane has read its entry before any slot of this round is reused
+        if (pass) pairs[kept_pairs + __popc(m & ((1u << lane) - 1u))] = e;   // kept_pairs + rank <= q: never ahead of the reads
+        kept_pairs += __popc(m);
+      }
+      nq = kept_pairs;
+      __syncwarp();
+    }
+    // ---- (2) exact routine, one pair per lane.  The pair's candidate belongs to lane l: its segment data comes by shuffle.
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+      const int q = q0 + lane;
+      const uint32_t e = q < nq ? pairs[q] : 0u;
+      const int l = static_cast<int>(e >> 20), k = static_cast<int>(e & 0xfffffu);
+      const int c_beg = __shfl_sync(0xffffffffu, beg, l), c_pos = __shfl_sync(0xffffffffu, pos, l);
+      const int c_kbase = __shfl_sync(0xffffffffu, kbase, l);
+      if (q < nq) {
+        const WRec *rs = static_cast<const WRec *>(a.recs) + c_beg;
+        const int kpos = position_of((a.kxyr_g + c_kbase)[k].w);
+        bool above, above_m;
+        exact(rs[kpos], rs[c_pos], above, above_m);
+        flags[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
+        if (above) atomicMin(&fsw[l], k);
+      }
+    }
+    __syncwarp();
+    // ---- (3) merges up to and including the first suppressor
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+      const int q = q0 + lane;
+      const uint32_t e = q < nq ? pairs[q] : 0u;
+      const int l = static_cast<int>(e >> 20), k = static_cast<int>(e & 0xfffffu);
+      const int c_beg = __shfl_sync(0xffffffffu, beg, l), c_pos = __shfl_sync(0xffffffffu, pos, l);
+      const int c_kbase = __shfl_sync(0xffffffffu, kbase, l);
+      if (q < nq && (flags[q] & 2u) && k <= fsw[l]) accumulate(c_kbase, k, c_beg + c_pos);
+    }
+    if (late_n > 0) {
+      // the pairs this lane evaluated in place: walk again, now that its first suppressor is final, skipping the buffered ones
+      const int fs = fsw[lane];
+      const float x = rec_cx(rj), y = rec_cy(rj), r = rj.r;
+      for (int k = 0; k < ti.kept; ++k) {            // (rare: > 256 bound-passing pairs in one warp) plain scan over the kept boxes
+        if (k > fs) break;
+        const float4 q = kxyr[k];
+        const float dx = q.x - x, dy = q.y - y, rr = q.z + r;
+        if (prune && !(dx * dx + dy * dy <= rr * rr)) continue;
+        bool buffered = false;
+        for (int t = 0; t < nq; ++t) buffered |= pairs[t] == ((static_cast<uint32_t>(lane) << 20) | static_cast<uint32_t>(k));
+        if (buffered) continue;
+        const int kpos = position_of(q.w);
+        if (prune && !iou_may_exceed(recs[kpos], rj, thr_any)) continue;
+        bool above, above_m;
+        exact(recs[kpos], rj, above, above_m);
+        if (above_m) accumulate(kbase, k, beg + pos);
+      }
+    }
+    __syncwarp();
+  }
+  if (a.stats) {
+    for (int o = 16; o; o >>= 1) {
+      st_iou += __shfl_xor_sync(0xffffffffu, st_iou, o);
+      st_circle += __shfl_xor_sync(0xffffffffu, st_circle, o);
+      st_bound += __shfl_xor_sync(0xffffffffu, st_bound, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, st_iou);
+      atomicAdd(a.stats + 3, st_circle);
+      atomicAdd(a.stats + 19, st_bound);
     }
   }
 }
@@ -1391,6 +1674,7 @@ struct Carver {
 struct NmsPlan {
   int cap, S, nb, kc, kept_stride, kept_rows, n_buckets_g;
   bool weighted, kept_in_smem;
+  bool tail_pass;    // weighted: the candidates behind the scan are merged by the grid-wide tail kernel
   int D;
 };
 
@@ -1412,6 +1696,8 @@ static NmsPlan make_plan(int cap, int S, int per_segment_max, int num_pre, int n
   if (static_cast<int64_t>(S) * kc <= pl.cap) { pl.kept_stride = kc; pl.kept_rows = S * kc; }
   else { pl.kept_stride = 0; pl.kept_rows = pl.cap; }
   pl.kept_in_smem = kc <= kKeptSmem;
+  // (a copy of every segment's 16 KB bucket array: not for calls with tens of thousands of segments)
+  pl.tail_pass = weighted && (!pl.kept_in_smem || static_cast<int64_t>(S) * kBucketsSmem * 4 <= (int64_t(256) << 20));
   pl.n_buckets_g = 0;
   if (!pl.kept_in_smem) {
     int64_t nbk = pow2_ceil(2 * static_cast<int64_t>(kc));
@@ -1428,6 +1714,7 @@ struct NmsLayout {
   int *hist, *ticket, *kept_count;
   double *acc;
   int *merge_count;
+  TailInfo *tail;
   size_t zero_bytes;
   uint32_t *minmax;      // [2] + BinMap
   BinMap *binmap;
@@ -1449,9 +1736,11 @@ static NmsLayout nms_layout(void *scratch, const NmsPlan &pl, bool own_keys, boo
   L.ticket = c.take<int>(4);
   L.kept_count = c.take<int>(S);
   L.acc = nullptr; L.merge_count = nullptr;
+  L.tail = nullptr;
   if (pl.weighted) {
     L.acc = c.take<double>(kr * pl.D);
     L.merge_count = c.take<int>(kr);
+    if (pl.tail_pass) L.tail = c.take<TailInfo>(S);
   }
   L.zero_bytes = align_up(c.used, 256);
   L.minmax = c.take<uint32_t>(2);
@@ -1475,6 +1764,10 @@ static NmsLayout nms_layout(void *scratch, const NmsPlan &pl, bool own_keys, boo
     L.knext_g = c.take<int>(kr);
     L.heads_bytes = sizeof(int) * S * static_cast<size_t>(pl.n_buckets_g);
     L.heads_g = c.take<int>(S * static_cast<size_t>(pl.n_buckets_g));
+  } else if (pl.tail_pass) {
+    // the scan kernel's shared-memory grid is copied here (packed form) when it hands its tail to wnms_tail_kernel
+    L.kxyr_g = c.take<float4>(kr);
+    L.heads_g = c.take<int>(S * static_cast<size_t>(kBucketsSmem));   // written in full by the scan kernel: no memset
   }
   L.total = align_up(c.used, 256);
   return L;
@@ -1507,9 +1800,17 @@ static int launch_nms_kernel(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s
   RV3D_CHECK_LAUNCH();
   return RV3D_OK;
 }
+static int sm_count();
 template <typename Rec, bool kWeighted>
 static int launch_nms_segments(const NmsArgs &a, const NmsPlan &pl, cudaStream_t s) {
-  return pl.kept_in_smem ? launch_nms_kernel<Rec, kWeighted, true>(a, pl, s) : launch_nms_kernel<Rec, kWeighted, false>(a, pl, s);
+  const int rc = pl.kept_in_smem ? launch_nms_kernel<Rec, kWeighted, true>(a, pl, s) : launch_nms_kernel<Rec, kWeighted, false>(a, pl, s);
+  if (rc != RV3D_OK || !kWeighted || !a.tail) return rc;
+  const int want = ceil_div(pl.cap, kTailThreads), most = sm_count() * 8;
+  const int grid = want < most ? want : most;
+  if (pl.kept_in_smem) wnms_tail_kernel<true><<<grid, kTailThreads, 0, s>>>(a, pl.S);
+  else wnms_tail_kernel<false><<<grid, kTailThreads, 0, s>>>(a, pl.S);
+  RV3D_CHECK_LAUNCH();
+  return RV3D_OK;
 }
 
 // hist -> bin_scan -> (caller's scatter) : shared front of every sorted entry point
@@ -1552,6 +1853,8 @@ static NmsArgs base_args(const NmsPlan &pl, const NmsLayout &L, int num_pre, int
   (void)flags;
   a.kept_stride = pl.kept_stride; a.kept_pos = L.kept_pos; a.kept_count = L.kept_count;
   a.kxyr_g = L.kxyr_g; a.knext_g = L.knext_g; a.heads_g = L.heads_g; a.n_buckets_g = pl.n_buckets_g; a.kos = L.kos;
+  a.tail = L.tail;
+  if (const char *e = getenv("RV3D_NMS_NO_TAIL")) { if (atoi(e)) a.tail = nullptr; }   // experiments / A-B tests only
   a.data = L.data; a.D = pl.D; a.acc = L.acc; a.merge_count = L.merge_count;
   a.stats = reinterpret_cast<unsigned long long *>(stats);
   a.rcap_mult = 2.0f; a.cell_mult = 3.0f;   // measured sweep (profiles/r02_nms_geometry.md): r_cap 2, cell 3 mean radii

@@ -92,8 +92,11 @@ def test_batched_nms_golden(mode):
 @pytest.mark.parametrize("mode", ["HARD", "WEIGHTED"])
 # the last case has 24 x 26 = 624 (sweep, class) segments: above 512 the output offsets come from the scan kernel,
 # below from the pack kernel itself
+# (1, 40000, 1, 3000, 30000, 2200): more than 2048 kept boxes per segment -> the kept-box grid lives in global memory;
+# in WEIGHTED mode the candidates behind the scan go to the grid-wide tail kernel in both forms, with the num_pre_nms
+# cut inside the tail (cases 2 and 5)
 @pytest.mark.parametrize("cfg", [(3, 20000, 5, 40, 50000, 1000), (2, 30000, 2, 25, 4000, 50), (1, 6000, 26, 30, 50000, 7),
-                                 (24, 1500, 26, 20, 50000, 5)])
+                                 (24, 1500, 26, 20, 50000, 5), (1, 40000, 1, 3000, 30000, 2200)])
 def test_batched_nms_vs_oracle(mode, cfg):
     from rv3d.math.ops.nms import batched_multiclass_nms
     B, K, C, M, pre, post = cfg

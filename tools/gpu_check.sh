@@ -1,5 +1,5 @@
 timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -30
-timeout 500 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err
+timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err
 tail -c 2000 gpurun_out/bench_b.err
 python - <<EOF
 import json
