@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(256)
 scatter_records_kernel(const unsigned long long *__restrict__ keys, Builder build, const int32_t *__restrict__ n_ptr,
                        int capacity, KeyGeom g, BinMapArg bma, int n_segments, int *__restrict__ cursor,
                        const int *__restrict__ bin_start, const int *__restrict__ seg_begin, void *__restrict__ recs,
-                       unsigned long long *__restrict__ skey, uint32_t *__restrict__ src, float *__restrict__ data) {
+                       unsigned long long *__restrict__ skey, uint32_t *__restrict__ src, float *__restrict__ data,
+                       int lazy_records = 0) {
   const int n = live_count(n_ptr, capacity);
   const BinMap bm = bma.get();
   const uint32_t smask = g.score_bits >= 32 ? 0xffffffffu : ((1u << g.score_bits) - 1u);
@@ -241,9 +242,14 @@ scatter_records_kernel(const unsigned long long *__restrict__ keys, Builder buil
     skey[pos] = k & lowmask;
     src[pos] = static_cast<uint32_t>(i);
     if (!kWeighted) {
-      HardRec r;
-      build.hard(i, r);
-      static_cast<HardRec *>(recs)[pos] = r;
+      // lazy_records: the suppression kernel builds the records of the windows it actually consumes (a hard scan stops
+      // at num_post_nms kept boxes: 12 % of the candidates at the bench workload) from `src` -- this pass then neither
+      // reads the 32-byte box rows nor writes the 32-byte records
+      if (!lazy_records) {
+        HardRec r;
+        build.hard(i, r);
+        static_cast<HardRec *>(recs)[pos] = r;
+      }
     } else {
       WRec r;
       float d[9];
@@ -270,6 +276,8 @@ struct TailInfo {
 
 struct NmsArgs {
   TailInfo *tail;                 // [seg], zeroed per call; null: the scan kernel does the tail itself
+  const float *lazy_boxes;        // hard mode, non-null: records are built per window from these (n, 8) rows via src[pos]
+  const uint32_t *src;            // [pos] source row of a record
   const void *recs;               // HardRec / WRec, grouped by (segment, score bin)
   unsigned long long *skey;       // [pos] low key bits (score desc | candidate), the fine sort key
   uint32_t *gorder;               // scratch for bins larger than a window (sorted through global memory)
@@ -869,6 +877,18 @@ nms_pull_kernel(NmsArgs a) {
   while (rank_base < n_use && !done) {
     const int wn = next_window(true);
     if (wn <= 0) break;
+    if (!kWeighted && a.lazy_boxes) {
+      // records of this window, built here instead of by the bucketing pass for every candidate of the segment
+      HardRec *recs_w = const_cast<HardRec *>(reinterpret_cast<const HardRec *>(recs));
+      const RecFromBoxes8 build{a.lazy_boxes};
+      for (int t = tid; t < wn; t += kNmsThreads) {
+        const uint32_t pos = wpos[t];
+        HardRec r;
+        build.hard(static_cast<int>(a.src[beg + pos]), r);
+        recs_w[pos] = r;
+      }
+      __syncthreads();
+    }
     if (!geom_set) {
       // cell size of the grids from the padded radii of the first (top-scored) window
       float sr = 0.f, sc = 0.f;
@@ -1925,11 +1945,12 @@ extern "C" int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys_in, const
                                                                     L.seg_begin, L.recs, L.skey, L.src, L.data);
   else
     scatter_records_kernel<false><<<stride_grid(pl.cap), 256, 0, s>>>(keys, build, n_candidates, pl.cap, g, bma, S, L.hist, L.bin_start,
-                                                                     L.seg_begin, L.recs, L.skey, L.src, nullptr);
+                                                                     L.seg_begin, L.recs, L.skey, L.src, nullptr, 1);
   RV3D_CHECK_LAUNCH();
 
   // K4 / K5
-  const NmsArgs a = base_args(pl, L, p->num_pre_nms, p->num_post_nms, p->iou_threshold, p->merge_threshold, weighted, p->flags, stats);
+  NmsArgs a = base_args(pl, L, p->num_pre_nms, p->num_post_nms, p->iou_threshold, p->merge_threshold, weighted, p->flags, stats);
+  if (!weighted) { a.lazy_boxes = boxes; a.src = L.src; }
   rc = weighted ? launch_nms_segments<WRec, true>(a, pl, s) : launch_nms_segments<HardRec, false>(a, pl, s);
   if (rc != RV3D_OK) return rc;
 
