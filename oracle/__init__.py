@@ -12,8 +12,10 @@ Pinning status (see DESIGN.md "Oracle"):
   * rotated IoU (detectron2 / mmcv), weighted-NMS IoU + merge (TorchEx), and
     ``quaternion_from_euler`` (kornia): third-party code that is NOT in the
     reference tree and is not installed here -> restated from the published
-    algorithms => **parity unpinned** for those four; geometry cross-checked against
-    an independent fp64 polygon clip and OpenCV (tests/test_oracle_iou.py).
+    algorithms => **parity unpinned** (float32 bits) for those four; values anchored on
+    detectron2's and mmcv's own published unit-test vectors (restated in
+    tests/test_oracle_iou.py: they pin mmcv's rotation direction, which differs from
+    detectron2's), an independent fp64 polygon clip and OpenCV.
 """
 from .build import lib, build  # noqa: F401
 from .rv_oracle import *  # noqa: F401,F403

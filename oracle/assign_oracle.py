@@ -1,14 +1,15 @@
 """CPU restatement of the training-time callers.  TEST INFRASTRUCTURE ONLY.
 
 math/ops/assignment.py (paths relative to /root/reference) with mmcv's box_iou_rotated replaced by the oracle's C
-routine (orc_rot_iou, radians) -> the IoU arithmetic itself stays "parity unpinned" (un-vendored mmcv), the control
+routine (orc_rot_iou_aligned_mmcv: radians, mmcv's rotation direction, pinned by mmcv's published unit-test vector
+to 1e-4; un-vendored, so its float32 bits stay unpinned), the control
 flow is pinned by tests/golden/assign.npz (verbatim reference module, same substitution)."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from .rv_oracle import decode_range_view, rot_iou_pairs
+from .rv_oracle import decode_range_view, mmcv_iou_pairs
 
 XYLWA = [0, 1, 3, 4, 6]
 
@@ -16,11 +17,11 @@ XYLWA = [0, 1, 3, 4, 6]
 def box_iou_rotated(a: torch.Tensor, b: torch.Tensor, aligned: bool = False) -> torch.Tensor:
     a, b = a.float().numpy(), b.float().numpy()
     if aligned:
-        return torch.from_numpy(rot_iou_pairs(a, b, 1.0))
+        return torch.from_numpy(mmcv_iou_pairs(a, b))
     n, m = len(a), len(b)
     if n == 0 or m == 0:
         return torch.zeros((n, m))
-    return torch.from_numpy(rot_iou_pairs(np.repeat(a, m, axis=0), np.tile(b, (n, 1)), 1.0).reshape(n, m))
+    return torch.from_numpy(mmcv_iou_pairs(np.repeat(a, m, axis=0), np.tile(b, (n, 1))).reshape(n, m))
 
 
 def iou_2d_axis_aligned(a, b, **kw):                                   # :64-73

@@ -35,6 +35,8 @@ def lib() -> ctypes.CDLL:
         _lib.orc_rot_iou.argtypes = [c.c_void_p, c.c_void_p, c.c_double]
         _lib.orc_rot_iou_aligned.restype = None
         _lib.orc_rot_iou_aligned.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_double, c.c_void_p]
+        _lib.orc_rot_iou_aligned_mmcv.restype = None
+        _lib.orc_rot_iou_aligned_mmcv.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p]
         _lib.orc_nms_rotated.restype = c.c_int64
         _lib.orc_nms_rotated.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_double, c.c_double,
                                          c.c_void_p, c.c_void_p, c.c_int64]

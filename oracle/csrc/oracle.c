@@ -81,15 +81,26 @@ static inline float cross2(pt a, pt b) { return a.x * b.y - b.x * a.y; }
 static inline float dot2(pt a, pt b) { return a.x * b.x + a.y * b.y; }
 static inline pt sub(pt a, pt b) { pt r = {a.x - b.x, a.y - b.y}; return r; }
 
-/* vertices of a box (xc,yc,w,h,theta[rad as double]) */
+/* vertices of a box (xc,yc,w,h,theta[rad as double]).
+ * detectron2 (box_iou_rotated_utils.h get_rotated_vertices): the w-axis points along (cos, -sin).
+ * mmcv (ops/csrc/common/box_iou_rotated_utils.hpp, "y: top --> down; x: left --> right", its default
+ * clockwise=True): the same routine with the OTHER rotation direction, w-axis along (cos, +sin), and its own
+ * vertex order.  mmcv's published unit-test vector (tests/test_oracle_iou.py) tells the two apart. */
 static void rot_vertices(float xc, float yc, float w, float h, double theta,
-                         pt v[4]) {
+                         int mmcv, pt v[4]) {
   float c2 = (float)cos(theta) * 0.5f;
   float s2 = (float)sin(theta) * 0.5f;
-  v[0].x = xc + s2 * h + c2 * w;
-  v[0].y = yc + c2 * h - s2 * w;
-  v[1].x = xc - s2 * h + c2 * w;
-  v[1].y = yc - c2 * h - s2 * w;
+  if (mmcv) {
+    v[0].x = xc - s2 * h - c2 * w;
+    v[0].y = yc + c2 * h - s2 * w;
+    v[1].x = xc + s2 * h - c2 * w;
+    v[1].y = yc - c2 * h - s2 * w;
+  } else {
+    v[0].x = xc + s2 * h + c2 * w;
+    v[0].y = yc + c2 * h - s2 * w;
+    v[1].x = xc - s2 * h + c2 * w;
+    v[1].y = yc - c2 * h - s2 * w;
+  }
   v[2].x = 2 * xc - v[0].x;
   v[2].y = 2 * yc - v[0].y;
   v[3].x = 2 * xc - v[1].x;
@@ -188,7 +199,7 @@ static float poly_area(const pt q[24], int m) {
 
 /* box = (xc, yc, w, h, angle); angle_scale converts the stored angle to
  * radians in double: detectron2 uses 0.01745329251 (degrees in), mmcv uses 1. */
-float orc_rot_iou(const float *b1, const float *b2, double angle_scale) {
+static float rot_iou_flavour(const float *b1, const float *b2, double angle_scale, int mmcv) {
   float sx = (float)((double)(b1[0] + b2[0]) / 2.0);
   float sy = (float)((double)(b1[1] + b2[1]) / 2.0);
   float x1 = (float)((double)b1[0] - (double)sx), y1 = (float)((double)b1[1] - (double)sy);
@@ -196,8 +207,8 @@ float orc_rot_iou(const float *b1, const float *b2, double angle_scale) {
   float area1 = b1[2] * b1[3], area2 = b2[2] * b2[3];
   if (area1 < 1e-14 || area2 < 1e-14) return 0.f;
   pt p1[4], p2[4], ip[24], hp[24];
-  rot_vertices(x1, y1, b1[2], b1[3], (double)b1[4] * angle_scale, p1);
-  rot_vertices(x2, y2, b2[2], b2[3], (double)b2[4] * angle_scale, p2);
+  rot_vertices(x1, y1, b1[2], b1[3], (double)b1[4] * angle_scale, mmcv, p1);
+  rot_vertices(x2, y2, b2[2], b2[3], (double)b2[4] * angle_scale, mmcv, p2);
   int n = isect_points(p1, p2, ip);
   float inter = 0.f;
   if (n > 2) {
@@ -207,9 +218,18 @@ float orc_rot_iou(const float *b1, const float *b2, double angle_scale) {
   return inter / (area1 + area2 - inter);
 }
 
+float orc_rot_iou(const float *b1, const float *b2, double angle_scale) {   /* detectron2 */
+  return rot_iou_flavour(b1, b2, angle_scale, 0);
+}
+
 void orc_rot_iou_aligned(const float *a, const float *b, int64_t n,
                          double angle_scale, float *out) {
   for (int64_t i = 0; i < n; ++i) out[i] = orc_rot_iou(a + 5 * i, b + 5 * i, angle_scale);
+}
+
+/* mmcv.ops.box_iou_rotated(aligned=True, clockwise=True): angles in radians */
+void orc_rot_iou_aligned_mmcv(const float *a, const float *b, int64_t n, float *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = rot_iou_flavour(a + 5 * i, b + 5 * i, 1.0, 1);
 }
 
 /* order[] must hold the indices sorted by score descending (ties: index

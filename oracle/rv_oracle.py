@@ -29,7 +29,7 @@ __all__ = [
     "ROW_MAPPING_64", "cart_to_sph", "build_range_view_coordinates",
     "build_range_view_coordinates_converter", "z_buffer", "build_range_view",
     "decode_range_view", "sample_by_range", "bchw_to_bkc", "yaw_to_quat",
-    "rot_iou_pairs", "nms_rotated", "iou_bev_pairs", "weighted_nms",
+    "rot_iou_pairs", "mmcv_iou_pairs", "nms_rotated", "iou_bev_pairs", "weighted_nms",
     "hard_multiclass_nms", "weighted_multiclass_nms", "batched_multiclass_nms",
     "range_decoder_decode", "iou_3d_axis_aligned", "subsample_range_view",
 ]
@@ -197,12 +197,23 @@ def yaw_to_quat(yaw: torch.Tensor) -> torch.Tensor:
 # IoU / NMS kernels (C)                                                        #
 # --------------------------------------------------------------------------- #
 def rot_iou_pairs(a: np.ndarray, b: np.ndarray, angle_scale: float) -> np.ndarray:
-    """Aligned rotated IoU of (n,5) f32 (xc,yc,w,h,angle) boxes.
-    angle_scale = 0.01745329251 for detectron2 (degrees), 1.0 for mmcv (radians)."""
+    """Aligned rotated IoU of (n,5) f32 (xc,yc,w,h,angle) boxes, detectron2's routine and rotation direction (w-axis
+    along (cos, -sin)); angle_scale = 0.01745329251 for degrees in (detectron2's own unit), 1.0 for radians."""
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
     out = np.empty(a.shape[0], dtype=np.float32)
     lib().orc_rot_iou_aligned(_p(a), _p(b), a.shape[0], float(angle_scale), _p(out))
+    return out
+
+
+def mmcv_iou_pairs(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """mmcv.ops.box_iou_rotated(a, b, aligned=True) with its default clockwise=True: angles in radians, w-axis along
+    (cos, +sin) -- the same routine as detectron2's with the other rotation direction (pinned by mmcv's published
+    unit-test vector, tests/test_oracle_iou.py::test_mmcv_published_vectors)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    out = np.empty(a.shape[0], dtype=np.float32)
+    lib().orc_rot_iou_aligned_mmcv(_p(a), _p(b), a.shape[0], _p(out))
     return out
 
 
@@ -362,9 +373,9 @@ def range_decoder_decode(multiscale_outputs: Dict, post_processing_config: Dict,
 # aligned 3D IoU                                                               #
 # --------------------------------------------------------------------------- #
 def iou_3d_axis_aligned(a: torch.Tensor, b: torch.Tensor):
-    """math/ops/iou.py:11-47 with mmcv box_iou_rotated(aligned=True) -> orc_rot_iou (radians)."""
+    """math/ops/iou.py:11-47 with mmcv box_iou_rotated(aligned=True) -> orc_rot_iou_aligned_mmcv."""
     idx = [0, 1, 3, 4, 6]
-    iou_bev = torch.from_numpy(rot_iou_pairs(a[:, idx].float().numpy(), b[:, idx].float().numpy(), 1.0))
+    iou_bev = torch.from_numpy(mmcv_iou_pairs(a[:, idx].float().numpy(), b[:, idx].float().numpy()))
     iou_bev = iou_bev.clamp(0.0, 1.0).nan_to_num(nan=0.0)
     area_a, area_b = a[:, [3, 4]].prod(-1), b[:, [3, 4]].prod(-1)
     ov_bev = iou_bev * (area_a + area_b) / (1.0 + iou_bev)

@@ -107,7 +107,7 @@ targets_affinity_kernel(TargetsArgs a, const T *__restrict__ input, const T *__r
     aff = expf(-d / a.sigma2);
   } else {
     // XYLWA_INDICES = (0, 1, 3, 4, 6); mmcv box_iou_rotated: angle in radians; .clamp(0, 1) keeps NaN
-    const float v = rot_iou(make_hard_rec(pd[0], pd[1], pd[3], pd[4], pd[6], 1.0), make_hard_rec(gt[0], gt[1], gt[3], gt[4], gt[6], 1.0));
+    const float v = rot_iou(make_hard_rec(pd[0], pd[1], pd[3], pd[4], pd[6], 1.0, true), make_hard_rec(gt[0], gt[1], gt[3], gt[4], gt[6], 1.0, true));
     aff = v != v ? v : fminf(fmaxf(v, 0.0f), 1.0f);
   }
   aff_px[gp] = aff;

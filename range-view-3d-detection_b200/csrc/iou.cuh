@@ -25,9 +25,9 @@ __device__ __forceinline__ P2 sub2(P2 a, P2 b) { return P2{a.x - b.x, a.y - b.y}
 // ------------------------------------------------------------------------------------------
 struct __align__(16) HardRec {  // 32 B
   float x, y, w, h;             // centre, extent along the box axis / across it
-  float c2, s2;                 // (float)cos(theta) * 0.5f, (float)sin(theta) * 0.5f
+  float c2, s2;                 // (float)cos(theta) * 0.5f, (float)sin(theta) * 0.5f (mmcv flavour: -sin, see make_hard_rec)
   float r;                      // padded circumscribed radius (pruning only)
-  float pad;
+  float wv;                     // w as the vertex formula sees it: w (detectron2) or -w (mmcv)
 };
 
 struct __align__(16) WRec {     // 64 B
@@ -50,15 +50,23 @@ __device__ __forceinline__ float padded_radius(float w, float h) {
   return r * 1.002f + 1e-3f + 2e-5f / fminf(fabsf(w), fabsf(h));
 }
 
+// mmcv = false: detectron2's get_rotated_vertices (the w-axis points along (cos, -sin); nms_rotated, degrees in).
+// mmcv = true: mmcv.ops.box_iou_rotated with its default clockwise=True (radians): the same routine with the OTHER rotation
+// direction and its own vertex order,
+//     v0 = (xc - s2 h - c2 w, yc + c2 h - s2 w),  v1 = (xc + s2 h - c2 w, yc - c2 h - s2 w),
+// which is detectron2's formula evaluated with s2 -> -s2 and w -> -w: sign changes are exact in floating point, so storing
+// the record that way reproduces mmcv's arithmetic bit for bit with ONE vertex routine (area and pruning keep the true w).
+// Which direction mmcv uses is pinned by its published unit-test vector (tests/test_oracle_iou.py::test_mmcv_published_vectors).
 __device__ __forceinline__ HardRec make_hard_rec(float xc, float yc, float w, float h, float angle,
-                                                 double angle_scale) {
+                                                 double angle_scale, bool mmcv = false) {
   HardRec r;
   const double theta = static_cast<double>(angle) * angle_scale;
   r.x = xc; r.y = yc; r.w = w; r.h = h;
   r.c2 = static_cast<float>(cos(theta)) * 0.5f;
-  r.s2 = static_cast<float>(sin(theta)) * 0.5f;
+  const float s2 = static_cast<float>(sin(theta)) * 0.5f;
+  r.s2 = mmcv ? -s2 : s2;
   r.r = padded_radius(w, h);
-  r.pad = 0.f;
+  r.wv = mmcv ? -w : w;
   return r;
 }
 
@@ -88,10 +96,10 @@ __device__ __forceinline__ float rec_cy(const WRec &r) { return (r.y1 + r.y2) * 
 // detectron2-style rotated IoU.  a = higher-ranked box (box1), b = lower-ranked (box2).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void hard_vertices(float xc, float yc, const HardRec &b, P2 (&v)[4]) {
-  v[0].x = xc + b.s2 * b.h + b.c2 * b.w;
-  v[0].y = yc + b.c2 * b.h - b.s2 * b.w;
-  v[1].x = xc - b.s2 * b.h + b.c2 * b.w;
-  v[1].y = yc - b.c2 * b.h - b.s2 * b.w;
+  v[0].x = xc + b.s2 * b.h + b.c2 * b.wv;
+  v[0].y = yc + b.c2 * b.h - b.s2 * b.wv;
+  v[1].x = xc - b.s2 * b.h + b.c2 * b.wv;
+  v[1].y = yc - b.c2 * b.h - b.s2 * b.wv;
   v[2].x = 2 * xc - v[0].x;
   v[2].y = 2 * yc - v[0].y;
   v[3].x = 2 * xc - v[1].x;

@@ -2053,8 +2053,8 @@ iou3d_aligned_kernel(const float *__restrict__ A, const float *__restrict__ B, i
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float *a = A + i * 7, *b = B + i * 7;
-  const HardRec ra = make_hard_rec(a[0], a[1], a[3], a[4], a[6], 1.0);  // mmcv: angle in radians
-  const HardRec rb = make_hard_rec(b[0], b[1], b[3], b[4], b[6], 1.0);
+  const HardRec ra = make_hard_rec(a[0], a[1], a[3], a[4], a[6], 1.0, true);  // mmcv: angle in radians, its rotation direction
+  const HardRec rb = make_hard_rec(b[0], b[1], b[3], b[4], b[6], 1.0, true);
   float bev = rot_iou(ra, rb);
   bev = (bev != bev) ? bev : fminf(fmaxf(bev, 0.0f), 1.0f);  // clamp keeps NaN
   bev = nan_to_num_f(bev);
@@ -2087,7 +2087,7 @@ box_iou_rotated_kernel(const float *__restrict__ A, int64_t n, const float *__re
   if (t >= total) return;
   const int64_t i = aligned ? t : t / m, j = aligned ? t : t - i * m;
   const float *a = A + i * 5, *b = B + j * 5;
-  out[t] = rot_iou(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 1.0), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 1.0));
+  out[t] = rot_iou(make_hard_rec(a[0], a[1], a[2], a[3], a[4], 1.0, true), make_hard_rec(b[0], b[1], b[2], b[3], b[4], 1.0, true));
 }
 
 // The pruning decision of the NMS kernels, exposed for tests/test_gpu_iou_decisions.py: aligned pairs.

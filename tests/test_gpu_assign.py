@@ -102,6 +102,17 @@ def test_pair_affinities_golden(g):
     np.testing.assert_allclose(iou_3d_axis_aligned(a, b, normalize_affinities=True).cpu().numpy(), g["pair_iou3d_norm"], rtol=1e-6, atol=1e-7)
 
 
+def test_box_iou_rotated_mmcv_published_vector():
+    """mmcv's own unit-test vector for box_iou_rotated (upstream tests/test_ops/test_box_iou_rotated.py, atol 1e-4) through
+    the device operator: pins the stand-in's rotation direction (see tests/test_oracle_iou.py::test_mmcv_published_vectors)."""
+    from rv3d.math.ops.assignment import box_iou_rotated
+    b1 = torch.tensor([[1.0, 1.0, 3.0, 4.0, 0.5], [2.0, 2.0, 3.0, 4.0, 0.6], [7.0, 7.0, 8.0, 8.0, 0.4]], device=DEV)
+    b2 = torch.tensor([[0.0, 2.0, 2.0, 5.0, 0.3], [2.0, 1.0, 3.0, 3.0, 0.5], [5.0, 5.0, 6.0, 7.0, 0.4]], device=DEV)
+    want = np.array([[0.3708, 0.4351, 0.0000], [0.1104, 0.4487, 0.0424], [0.0000, 0.0000, 0.3622]], np.float32)
+    assert np.allclose(box_iou_rotated(b1, b2).cpu().numpy(), want, atol=1e-4)
+    assert np.allclose(box_iou_rotated(b1, b2, aligned=True).cpu().numpy(), np.diag(want), atol=1e-4)
+
+
 def test_box_iou_rotated_all_pairs_and_collision_test():
     from rv3d.math.ops.assignment import box_iou_rotated
     from rv3d.prototype.loader import intersection_test

@@ -274,10 +274,12 @@ def test_bench_workload_properties_full_size(fp_rate):
     seg_out = bc * C + cc
     counts = np.bincount(seg_out, minlength=B * C)
     assert counts.max() <= pp["num_post_nms"]
-    # kept boxes as (x, y, l, w, angle): detectron2's convention is angle = -yaw (nms.py:40); the radian routine sees
-    # -yaw too.  The float32 degree round trip differs by ~1e-7 rad, so comparisons carry a 1e-4 IoU margin.
+    # kept boxes as (x, y, l, w, angle): detectron2 gets angle = -rad2deg(yaw) (nms.py:40); the radian routine checked with
+    # here is mmcv's, whose rotation direction is the opposite one, so it sees +yaw for the same geometry.  The float32
+    # degree round trip differs by ~1e-7 rad and the two flavours enumerate the vertices differently, so comparisons
+    # carry a 1e-4 IoU margin.
     cand_boxes = torch.from_numpy(u["boxes"]).to(DEV)
-    cand5 = torch.stack([cand_boxes[:, 0], cand_boxes[:, 1], cand_boxes[:, 3], cand_boxes[:, 4], -cand_boxes[:, 6]], 1)
+    cand5 = torch.stack([cand_boxes[:, 0], cand_boxes[:, 1], cand_boxes[:, 3], cand_boxes[:, 4], cand_boxes[:, 6]], 1)
     cand_seg = u["sweep"] * C + u["category"]
     thr = 0.3
     # map kept rows back to candidates through (segment, score, position): scores are distinct per sweep in this generator

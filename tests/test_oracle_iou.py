@@ -71,12 +71,42 @@ def _random_boxes(n, seed):
 
 
 def test_rot_iou_matches_fp64_clip_radians():
-    """mmcv convention: angle in radians, w-axis along (cos a, -sin a)  => equals a CCW box at -a."""
+    """detectron2's routine fed radians: w-axis along (cos a, -sin a)  => equals a CCW box at -a.
+    mmcv's flavour (its default clockwise=True): w-axis along (cos a, +sin a) => the CCW box at +a."""
     a, b = _random_boxes(3000, 0)
     got = oracle.rot_iou_pairs(a, b, 1.0)
     ref = np.array([_iou64((x[0], x[1], x[2], x[3], -x[4]), (y[0], y[1], y[2], y[3], -y[4])) for x, y in zip(a.astype(float), b.astype(float))])
     assert np.abs(got - ref).max() < 2e-4
     assert (ref > 0.3).mean() > 0.3
+    got_m = oracle.mmcv_iou_pairs(a, b)
+    ref_m = np.array([_iou64(tuple(x), tuple(y)) for x, y in zip(a.astype(float), b.astype(float))])
+    assert np.abs(got_m - ref_m).max() < 2e-4
+    assert np.abs(got_m - got).max() > 0.05          # the two directions are different functions of the same rows
+
+
+def test_mmcv_published_vectors():
+    """mmcv's own unit test for box_iou_rotated (upstream tests/test_ops/test_box_iou_rotated.py; mmcv is not vendored
+    under /root/reference and not installable here, so the vector is restated from the published file): three boxes
+    against three, all pairs and aligned, default clockwise=True, and the same boxes with negated angles under
+    clockwise=False (which negates them back).  Upstream tolerance: atol 1e-4.  The configuration is asymmetric, so it
+    pins the ROTATION DIRECTION of the stand-in (detectron2's direction gives 0.2881 / 0.0109 / 0.0948 / 0.3760 where
+    mmcv expects 0.3708 / 0.0000 / 0.0424 / 0.3622), which is what the reference's call sites rely on when they hand
+    mmcv a plain yaw (math/ops/assignment.py:24,68, math/ops/iou.py:15, prototype/loader.py:785) and detectron2
+    -rad2deg(yaw) (math/ops/nms.py:40)."""
+    from oracle import assign_oracle
+    b1 = torch.tensor([[1.0, 1.0, 3.0, 4.0, 0.5], [2.0, 2.0, 3.0, 4.0, 0.6], [7.0, 7.0, 8.0, 8.0, 0.4]])
+    b2 = torch.tensor([[0.0, 2.0, 2.0, 5.0, 0.3], [2.0, 1.0, 3.0, 3.0, 0.5], [5.0, 5.0, 6.0, 7.0, 0.4]])
+    want = np.array([[0.3708, 0.4351, 0.0000], [0.1104, 0.4487, 0.0424], [0.0000, 0.0000, 0.3622]], np.float32)
+    want_aligned = np.array([0.3708, 0.4487, 0.3622], np.float32)
+    assert np.allclose(assign_oracle.box_iou_rotated(b1, b2).numpy(), want, atol=1e-4)
+    assert np.allclose(assign_oracle.box_iou_rotated(b1, b2, aligned=True).numpy(), want_aligned, atol=1e-4)
+    # the detectron2 direction on the same rows does NOT reproduce it
+    d2 = oracle.rot_iou_pairs(b1.numpy(), b2.numpy(), 1.0)
+    assert abs(float(d2[0]) - 0.3708) > 0.05
+    # ... and is what mmcv computes for the negated angles (its clockwise=False path flips the sign and runs the same kernel)
+    n1, n2 = b1.clone(), b2.clone()
+    n1[:, 4] *= -1; n2[:, 4] *= -1
+    assert np.allclose(oracle.rot_iou_pairs(n1.numpy(), n2.numpy(), 1.0), want_aligned, atol=1e-4)
 
 
 def test_rot_iou_degrees_matches_negated_yaw():
@@ -113,6 +143,45 @@ def test_rot_iou_known_answers():
     assert iou([0, 0, 2, 2, 0], [1, 0, 2, 2, 0]) == pytest.approx(1 / 3, abs=1e-6)        # half shift
     assert iou([0, 0, 1e-8, 1e-8, 0], [0, 0, 1, 1, 0]) == 0.0                            # area < 1e-14
     assert iou([0, 0, 4, 2, 90], [0, 0, 2, 4, 0], 0.01745329251) == pytest.approx(1.0, abs=1e-6)   # degrees
+
+
+def test_rot_iou_detectron2_published_vectors():
+    """Known-answer vectors of detectron2's own unit tests for box_iou_rotated (upstream
+    tests/structures/test_rotated_boxes.py: test_iou_half_overlap, test_iou_precision, test_iou_issue_2154,
+    test_iou_issue_2167, test_iou_extreme, test_pairwise_iou_0_degree / _45_degrees / _orthogonal / _large_close_boxes,
+    test_pairwise_iou_issue1207_simplified).  detectron2 is not vendored under /root/reference and not installable here,
+    so the vectors are restated from the published test file; upstream checks them with numpy.allclose defaults.  They
+    pin the restatement's area / intersection arithmetic and its precision corner cases (near-identical boxes, huge
+    coordinates); being symmetric configurations they do not pin the rotation direction, which
+    test_rot_iou_degrees_matches_negated_yaw anchors on the reference's own call site (nms.py:40)."""
+    deg = 0.01745329251
+    s2 = math.sqrt(2.0)
+
+    def iou(a, b):
+        return float(oracle.rot_iou_pairs(np.array([a], np.float32), np.array([b], np.float32), deg)[0])
+
+    unit = [0.5, 0.5, 1.0, 1.0, 0.0]
+    cases = [
+        (unit, [0.25, 0.5, 0.5, 1.0, 0.0], 0.5),                                          # test_iou_half_overlap
+        ([565, 565, 10, 10.0, 0], [565, 565, 10, 8.3, 0], 8.3 / 10.0),                     # test_iou_precision
+        ([296.6620178222656, 458.73883056640625, 23.515729904174805, 47.677001953125, 0.08795166015625],
+         [296.66201, 458.73882000000003, 23.51573, 47.67702, 0.087951], 1.0),              # test_iou_issue_2154
+        ([2563.74462890625, 1436.7901611328125, 2174.703369140625, 214.09500122070312, 115.11834716796875],
+         [2563.74462890625, 1436.7901611328125, 2174.703369140625, 214.09500122070312, 115.11834716796875], 1.0),   # issue_2167
+        (unit, unit, 1.0), (unit, [0.5, 0.25, 1.0, 0.5, 0.0], 0.5), (unit, [0.25, 0.25, 0.5, 0.5, 0.0], 0.25),       # 0_degree
+        (unit, [0.75, 0.75, 0.5, 0.5, 0.0], 0.25), (unit, [1.0, 1.0, 1.0, 1.0, 0.0], 0.25 / (2 - 0.25)),
+        ([1, 1, s2, s2, 45], [1, 1, 2, 2, 0], 0.5), ([1, 1, 2 * s2, 2 * s2, -45], [1, 1, 2, 2, 0], 0.5),             # 45_degrees
+        ([5, 5, 10.0, 6.0, 55], [5, 5, 10.0, 6.0, -35], (6.0 * 6.0) / (2 * 60.0 - 36.0)),                              # orthogonal
+        ([299.5, 417.370422, 600.0, 364.259186, 27.1828], [299.5, 417.370422, 600.0, 364.259155, 27.1828],
+         364.259155 / 364.259186),                                                                                     # large_close_boxes
+        ([3, 3, 8, 2, -45.0], [6, 0, 8, 2, -45.0], 0.0),                                                               # issue1207_simplified
+    ]
+    for a, b, want in cases:
+        assert np.allclose(iou(a, b), want), (a, b, iou(a, b), want)
+        assert np.allclose(iou(b, a), want), (b, a, iou(b, a), want)
+    extreme = iou([160.0, 153.0, 230.0, 23.0, -37.0],                                      # test_iou_extreme: finite and >= 0
+                  [-1.117407639806935e17, 1.3858420478349148e18, 1000.0000610351562, 1000.0000610351562, 1612.0])
+    assert extreme >= 0.0 and math.isfinite(extreme)
 
 
 def test_iou_bev_matches_fp64_clip():
