@@ -26,6 +26,7 @@ COMMON = [
     # Every float op on this path must round exactly once so results are bit-identical to the
     # CPU oracle (gcc -ffp-contract=off): no FMA contraction, IEEE div/sqrt, no flush-to-zero.
     "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+    *os.environ.get("RV3D_NVCC_DEFS", "").split(),      # experiments only, e.g. -DRV3D_NMS_THREADS=1024
 ]
 
 

@@ -39,7 +39,10 @@
 
 namespace rv3d {
 
-constexpr int kNmsThreads = 512;
+#ifndef RV3D_NMS_THREADS
+#define RV3D_NMS_THREADS 512
+#endif
+constexpr int kNmsThreads = RV3D_NMS_THREADS;
 constexpr int kNmsWarps = kNmsThreads / 32;
 // frontier size: 512 boxes per round in hard mode (one 32 KB bit-matrix), 256 in weighted mode (two matrices,
 // 64-byte records)
