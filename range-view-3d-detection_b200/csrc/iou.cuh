@@ -106,16 +106,34 @@ __device__ __forceinline__ void hard_vertices(float xc, float yc, const HardRec 
   v[3].y = 2 * yc - v[1].y;
 }
 
+// The upstream routine compares float32 values with double constants (1e-5, 1e-14, 1e-6, 1e-8) and halves / subtracts
+// through double.  On sm_100 every float <-> double conversion is an XU-pipe instruction (16 lanes per SM): the literal
+// form spent 85 F2F + 134 DSETP per call, on the suppression kernel's critical path.  Each of those operations has an
+// exactly equivalent float32 form:
+//   (double)t > D  <=>  t > FL(D),  FL(D) = the largest float32 <= D;      (double)t < D  <=>  t < FC(D),  FC(D) = the
+//   smallest float32 >= D   (no float32 lies strictly between D and its float32 neighbour);  a bound computed at run time
+//   in double, (double)u + 1e-5, becomes its round-up conversion;  halving is exact in either type;  the difference of two
+//   float32 values rounded through double equals their float32 difference (the double difference is exact unless the
+//   operands are > 2^29 apart, where both forms return the larger one).
+// The CPU oracle keeps the literal form; tests/test_gpu_nms.py and tests/test_gpu_iou_decisions.py compare bit for bit.
+constexpr float kNegEpsLE = -0x1.4f8b5ap-17f;      // FL(-1e-5)
+constexpr float kOnePlusEpsGE = 0x1.0000a8p+0f;    // FC(1 + 1e-5)
+constexpr float kDetLE = 0x1.6849b8p-47f;          // FL(1e-14)
+constexpr float kAreaGE = 0x1.6849bap-47f;         // FC(1e-14)
+constexpr float kNegCpGE = -0x1.0c6f7ap-20f;       // FC(-1e-6)
+constexpr float kCpGE = 0x1.0c6f7cp-20f;           // FC(1e-6)
+constexpr float kDistLE = 0x1.5798eep-27f;         // FL(1e-8)
+
 static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b) {
   const float area1 = a.w * a.h, area2 = b.w * b.h;
-  if (static_cast<double>(area1) < 1e-14 || static_cast<double>(area2) < 1e-14) return 0.f;
+  if (area1 < kAreaGE || area2 < kAreaGE) return 0.f;
   // shift both centres by their midpoint (computed in double upstream)
-  const float sx = static_cast<float>(static_cast<double>(a.x + b.x) / 2.0);
-  const float sy = static_cast<float>(static_cast<double>(a.y + b.y) / 2.0);
-  const float ax = static_cast<float>(static_cast<double>(a.x) - static_cast<double>(sx));
-  const float ay = static_cast<float>(static_cast<double>(a.y) - static_cast<double>(sy));
-  const float bx = static_cast<float>(static_cast<double>(b.x) - static_cast<double>(sx));
-  const float by = static_cast<float>(static_cast<double>(b.y) - static_cast<double>(sy));
+  const float sx = (a.x + b.x) * 0.5f;
+  const float sy = (a.y + b.y) * 0.5f;
+  const float ax = a.x - sx;
+  const float ay = a.y - sy;
+  const float bx = b.x - sx;
+  const float by = b.y - sy;
   P2 p1[4], p2[4];
   hard_vertices(ax, ay, a, p1);
   hard_vertices(bx, by, b, p2);
@@ -134,11 +152,11 @@ static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float det = cross2(v2[j], v1[i]);
-      if (fabs(static_cast<double>(det)) <= 1e-14) continue;
+      if (fabsf(det) <= kDetLE) continue;
       const P2 v12 = sub2(p2[j], p1[i]);
       const float t1 = cross2(v2[j], v12) / det;
       const float t2 = cross2(v1[i], v12) / det;
-      if (t1 > -EPS && t1 < 1.0f + EPS && t2 > -EPS && t2 < 1.0f + EPS) {
+      if (t1 > kNegEpsLE && t1 < kOnePlusEpsGE && t2 > kNegEpsLE && t2 < kOnePlusEpsGE) {
         ip[n].x = p1[i].x + v1[i].x * t1;
         ip[n].y = p1[i].y + v1[i].y * t1;
         ++n;
@@ -147,24 +165,26 @@ static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b)
   }
   {
     const P2 AB = v2[0], DA = v2[3];
-    const float ABdotAB = dot2(AB, AB), ADdotAD = dot2(DA, DA);
+    const float ubAB = __double2float_ru(static_cast<double>(dot2(AB, AB)) + EPS);   // FC(ABdotAB + EPS)
+    const float ubAD = __double2float_ru(static_cast<double>(dot2(DA, DA)) + EPS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const P2 AP = sub2(p1[i], p2[0]);
       const float APdotAB = dot2(AP, AB);
       const float APdotAD = -dot2(AP, DA);
-      if (APdotAB > -EPS && APdotAD > -EPS && APdotAB < ABdotAB + EPS && APdotAD < ADdotAD + EPS) ip[n++] = p1[i];
+      if (APdotAB > kNegEpsLE && APdotAD > kNegEpsLE && APdotAB < ubAB && APdotAD < ubAD) ip[n++] = p1[i];
     }
   }
   {
     const P2 AB = v1[0], DA = v1[3];
-    const float ABdotAB = dot2(AB, AB), ADdotAD = dot2(DA, DA);
+    const float ubAB = __double2float_ru(static_cast<double>(dot2(AB, AB)) + EPS);
+    const float ubAD = __double2float_ru(static_cast<double>(dot2(DA, DA)) + EPS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const P2 AP = sub2(p2[i], p1[0]);
       const float APdotAB = dot2(AP, AB);
       const float APdotAD = -dot2(AP, DA);
-      if (APdotAB > -EPS && APdotAD > -EPS && APdotAB < ABdotAB + EPS && APdotAD < ADdotAD + EPS) ip[n++] = p2[i];
+      if (APdotAB > kNegEpsLE && APdotAD > kNegEpsLE && APdotAB < ubAB && APdotAD < ubAD) ip[n++] = p2[i];
     }
   }
   float inter = 0.f;
@@ -182,15 +202,14 @@ static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b)
     for (int i = 1; i < n - 1; ++i)
       for (int j = i + 1; j < n; ++j) {
         const float cp = cross2(q[i], q[j]);
-        if ((static_cast<double>(cp) < -1e-6) ||
-            (fabs(static_cast<double>(cp)) < 1e-6 && dist[i] > dist[j])) {
+        if (cp < kNegCpGE || (fabsf(cp) < kCpGE && dist[i] > dist[j])) {
           const P2 qt = q[i]; q[i] = q[j]; q[j] = qt;
           const float dt = dist[i]; dist[i] = dist[j]; dist[j] = dt;
         }
       }
     int k = 1;
     for (; k < n; ++k)
-      if (static_cast<double>(dist[k]) > 1e-8) break;
+      if (dist[k] > kDistLE) break;
     int m = 1;
     if (k < n) {
       q[1] = q[k];
@@ -206,7 +225,7 @@ static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b)
     if (m > 2) {
       float area = 0.f;
       for (int i = 1; i < m - 1; ++i) area += fabsf(cross2(sub2(q[i], q[0]), sub2(q[i + 1], q[0])));
-      inter = static_cast<float>(static_cast<double>(area) / 2.0);
+      inter = area * 0.5f;
     }
   }
   return inter / (area1 + area2 - inter);
