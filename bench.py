@@ -822,6 +822,8 @@ def run_ours(args):
                     "pairs_above_thr_per_step": st[18],
                     # cycles summed over the segments' CTAs per phase: window sort, pull walk, pull IoU, frontier pairs, greedy, publish
                     "phase_mcycles_per_step": [round(x / 1e6, 3) for x in st[4:10]],
+                    "sub_phase_mcycles_per_step": {"frontier_walk": round(st[21] / 1e6, 3), "frontier_eval": round(st[22] / 1e6, 3),
+                                                   "pull_walk_scan": round(st[23] / 1e6, 3)},
                     "slowest_segment_mcycles": round(float(hp.stats[10].item()) / 1e6, 3),
                     "largest_segment": int(hp.stats[11].item()),
                     "slowest_segment_phase_kcycles": [int(x) // 1000 for x in hp.stats[12:18].tolist()]},

@@ -277,7 +277,8 @@ size_t rv3d_nms_scratch_bytes(const rv3d_nms_params *p);
  * stats (device, 24 x i64, may be NULL): [0] exact rotated-IoU evaluations, [1] kept, [2] frontier rounds,
  * [3] circle tests, [4..9] SM cycles summed over segments per phase (window sort, pull walk, pull IoU, frontier
  * pairs, greedy, publish), [10] slowest segment (cycles), [11] largest segment, [12..17] its phases, [18] pairs
- * above the threshold, [19] approximate-IoU evaluations, [20] candidates consumed by the scan. */
+ * above the threshold, [19] upper-bound tests, [20] candidates consumed by the scan, [21..23] sub-phases (frontier walk,
+ * frontier evaluation, pull walk + scan; subsets of [7], [7], [5]). */
 int rv3d_nms(const rv3d_nms_params *p, const uint64_t *keys, const float *boxes, const int32_t *n_candidates,
              float *out_params, float *out_scores, float *out_categories, float *out_batch, int32_t *out_count,
              int64_t *stats, void *scratch, size_t scratch_bytes, rv3d_stream_t stream);

@@ -357,7 +357,6 @@ __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   b += sizeof(uint32_t) * kWin;                                    // wpos
   b += sizeof(uint16_t) * kWin * 2;                                // survivor lists (double buffer)
   b += kWin;                                                       // walive
-  b += sizeof(uint16_t) * kNmsThreads;                             // batch slot -> window index
   b += sizeof(Rec) * kF;                                           // frec
   b += sizeof(float4) * kF;                                        // fq
   b += sizeof(int) * kFrontBuckets + sizeof(uint16_t) * kF;        // fheads, fos
@@ -471,7 +470,6 @@ nms_pull_kernel(NmsArgs a) {
   uint16_t *surv_a = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kWin;
   uint16_t *surv_b = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kWin;
   uint8_t *walive = reinterpret_cast<uint8_t *>(p); p += kWin;
-  uint16_t *s_bj = reinterpret_cast<uint16_t *>(p); p += sizeof(uint16_t) * kNmsThreads;
   Rec *frec = reinterpret_cast<Rec *>(p); p += sizeof(Rec) * kF;
   float4 *fq = reinterpret_cast<float4 *>(p); p += sizeof(float4) * kF;            // frontier (x, y, padded radius, next in chain)
   int *fheads = reinterpret_cast<int *>(p); p += sizeof(int) * kFrontBuckets;
@@ -513,11 +511,14 @@ nms_pull_kernel(NmsArgs a) {
   if (tid == 0) { s_nos = 0; s_qn = 0; }
   __syncthreads();
 
-  unsigned long long st_iou = 0, st_circle = 0, st_hit = 0, st_bound = 0;   // exact IoUs, circle tests, pairs above thr, upper-bound tests
+  uint32_t st_iou = 0, st_circle = 0, st_hit = 0, st_bound = 0;   // per thread: exact IoUs, circle tests, pairs above thr, upper-bound tests
   // per-phase cycle counters (thread 0, only when stats are requested):
   // [0] window assembly + sort, [1] pull: grid walks, [2] pull: IoU, [3] frontier pairs, [4] greedy, [5] publish (+ weighted merges)
   long long ph[6] = {0, 0, 0, 0, 0, 0};
   long long t_mark = clock64();
+  long long sub[3] = {0, 0, 0}, t_sub = 0;   // [0] frontier walk, [1] frontier evaluation, [2] pull walk + scan (subsets of ph[3], ph[3], ph[1])
+  auto sub_begin = [&]() { if (a.stats && tid == 0) t_sub = clock64(); };
+  auto sub_end = [&](int k) { if (a.stats && tid == 0) { const long long t = clock64(); sub[k] += t - t_sub; t_sub = t; } };
   auto lap = [&](int k) {
     if (a.stats && tid == 0) { const long long t = clock64(); ph[k] += t - t_mark; t_mark = t; }
   };
@@ -680,7 +681,47 @@ nms_pull_kernel(NmsArgs a) {
   auto pull = [&](const uint16_t *list, int ns, int since, bool merges_only) {
     if (since >= kept || ns <= 0) return;
     int bi = 0;
+    int base = 0;   // pairs waiting in the queue (uniform).  Entries are (window index << 20 | kept index).
+    // The batches of a pull only ENQUEUE; the queue is evaluated once at the end (or when it is full): the bit-exact
+    // routine is a ~2000-instruction dependent chain, so every evaluation costs its latency once however few pairs it
+    // has -- one evaluation per pull instead of one per batch of kNmsThreads candidates, on fuller warps.
+    auto flush = [&]() {
+      const int qn = base;
+      auto get = [&](int q, Rec &ra, Rec &rb) {
+        const uint32_t e = queue2[q];
+        ra = recs[kept_position(static_cast<int>(e & 0xfffffu))];   // the kept box ranks higher: box1 of the routine
+        rb = recs[wpos[e >> 20]];
+      };
+      if (!kWeighted) {
+        eval_queue(qn, get, [&](int q, bool above, bool) {
+          if (above) { ++st_hit; walive[queue2[q] >> 20] = 0; }
+        });
+        __syncthreads();
+      } else {
+        for (int q = tid; q < qn; q += kNmsThreads) qflag[q] = 0;
+        __syncthreads();
+        // pass 1: the two comparisons of every queued pair; each candidate's FIRST suppressor
+        eval_queue(qn, get, [&](int q, bool above, bool above_m) {
+          qflag[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
+          if (above) atomicMin(&wfs[queue2[q] >> 20], static_cast<int>(queue2[q] & 0xfffffu));
+        });
+        __syncthreads();
+        // pass 2: merges up to and including the first suppressor; a suppressed candidate leaves the window
+        for (int q = tid; q < qn; q += kNmsThreads) {
+          const uint32_t e = queue2[q];
+          const int jj = static_cast<int>(e >> 20), k = static_cast<int>(e & 0xfffffu);
+          const int fs = wfs[jj];
+          if (k > fs) continue;
+          if (qflag[q] & 2u) accumulate(k, static_cast<int>(wpos[jj]));
+          if (k == fs && !merges_only) walive[jj] = 0;
+        }
+        __syncthreads();
+      }
+      lap(2);
+      base = 0;
+    };
     while (bi < ns) {
+      sub_begin();
       const int t = bi + tid;
       const bool active = t < ns;
       int j = 0, pos = 0, cnt = 0;
@@ -698,12 +739,12 @@ nms_pull_kernel(NmsArgs a) {
         });
       }
       int total;
-      const int off = block_exclusive_scan(cnt, s_warp, total);
+      const int off = base + block_exclusive_scan(cnt, s_warp, total);
+      sub_end(2);
       const bool ok = active && (off + cnt <= kQ2Cap);
-      int m = __syncthreads_count(ok);
-      if (tid == 0) s_qn = 0;
-      __syncthreads();
+      const int m = __syncthreads_count(ok);   // the offsets are a prefix sum: the threads that fit are exactly tid < m
       if (m == 0) {
+        if (base > 0) { flush(); continue; }   // retry the batch against an empty queue
         // the first candidate alone overflows the queue: thread 0 evaluates its pairs in place
         if (tid == 0) {
           const Rec rj = recs[pos];
@@ -729,9 +770,8 @@ nms_pull_kernel(NmsArgs a) {
         continue;
       }
       if (ok) {
-        s_bj[tid] = static_cast<uint16_t>(j);
         if (kWeighted) wfs[j] = 0x7fffffff;
-        const uint32_t tag = static_cast<uint32_t>(tid) << 20;
+        const uint32_t tag = static_cast<uint32_t>(j) << 20;
         if (cnt <= kPullCache) {
 #pragma unroll
           for (int c = 0; c < kPullCache; ++c)
@@ -740,44 +780,16 @@ nms_pull_kernel(NmsArgs a) {
           int w = off;
           for_each_near(x, y, r, since, [&](int k) { queue2[w++] = tag | static_cast<uint32_t>(k); });
         }
-        if (tid == m - 1) s_qn = off + cnt;   // ok threads are exactly tid < m
+        if (tid == m - 1) s_qn = off + cnt;
       }
       __syncthreads();
       lap(1);
-      const int qn = s_qn;
-      auto get = [&](int q, Rec &ra, Rec &rb) {
-        const uint32_t e = queue2[q];
-        ra = recs[kept_position(static_cast<int>(e & 0xfffffu))];   // the kept box ranks higher: box1 of the routine
-        rb = recs[wpos[s_bj[e >> 20]]];
-      };
-      if (!kWeighted) {
-        eval_queue(qn, get, [&](int q, bool above, bool) {
-          if (above) { ++st_hit; walive[s_bj[queue2[q] >> 20]] = 0; }
-        });
-        __syncthreads();
-      } else {
-        for (int q = tid; q < qn; q += kNmsThreads) qflag[q] = 0;
-        __syncthreads();
-        // pass 1: the two comparisons of every queued pair; each candidate's FIRST suppressor
-        eval_queue(qn, get, [&](int q, bool above, bool above_m) {
-          qflag[q] = static_cast<uint8_t>((above ? 1u : 0u) | (above_m ? 2u : 0u));
-          if (above) atomicMin(&wfs[s_bj[queue2[q] >> 20]], static_cast<int>(queue2[q] & 0xfffffu));
-        });
-        __syncthreads();
-        // pass 2: merges up to and including the first suppressor; a suppressed candidate leaves the window
-        for (int q = tid; q < qn; q += kNmsThreads) {
-          const uint32_t e = queue2[q];
-          const int jj = s_bj[e >> 20], k = static_cast<int>(e & 0xfffffu);
-          const int fs = wfs[jj];
-          if (k > fs) continue;
-          if (qflag[q] & 2u) accumulate(k, static_cast<int>(wpos[jj]));
-          if (k == fs && !merges_only) walive[jj] = 0;
-        }
-        __syncthreads();
-      }
-      lap(2);
+      base = s_qn;
+      const bool cut = m < min(kNmsThreads, ns - bi);   // a candidate of this batch did not fit: evaluate, then go on with it
       bi += m;
+      if (cut) flush();
     }
+    if (base > 0) flush();
   };
 
   // order-preserving compaction of a survivor list by walive
@@ -963,6 +975,7 @@ nms_pull_kernel(NmsArgs a) {
           if (above) { ++st_hit; atomicOr(&sup[i * kFW + (j >> 5)], 1u << (j & 31)); }
           if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
         };
+        sub_begin();
         // thread i collects the frontier boxes j > i whose circles touch its own: the cells around it, plus the
         // frontier's oversize list; (i, j) goes to the work queue (in place if the queue is full: marking is
         // order-independent)
@@ -1007,12 +1020,14 @@ nms_pull_kernel(NmsArgs a) {
           }
         }
         __syncthreads();
+        sub_end(0);
         eval_queue(min(s_qn, kQ2Cap),
                    [&](int q, Rec &ra, Rec &rb) { ra = frec[queue2[q] >> 10]; rb = frec[queue2[q] & 1023]; },
                    [&](int q, bool above, bool above_m) {
                      mark(static_cast<int>(queue2[q] >> 10), static_cast<int>(queue2[q] & 1023), above, above_m);
                    });
         __syncthreads();
+        sub_end(1);
       }
       lap(3);
       // ================= greedy resolution of the frontier =================
@@ -1207,18 +1222,19 @@ nms_pull_kernel(NmsArgs a) {
 
   if (tid == 0) a.kept_count[seg] = kept;
   if (a.stats) {
-    // warp-reduce then one atomic per warp
+    // warp-reduce (widened: the per-thread counters are 32-bit to keep the inner loops at one IADD) then one atomic per warp
+    unsigned long long w_iou = st_iou, w_circle = st_circle, w_hit = st_hit, w_bound = st_bound;
     for (int o = 16; o; o >>= 1) {
-      st_iou += __shfl_xor_sync(0xffffffffu, st_iou, o);
-      st_circle += __shfl_xor_sync(0xffffffffu, st_circle, o);
-      st_hit += __shfl_xor_sync(0xffffffffu, st_hit, o);
-      st_bound += __shfl_xor_sync(0xffffffffu, st_bound, o);
+      w_iou += __shfl_xor_sync(0xffffffffu, w_iou, o);
+      w_circle += __shfl_xor_sync(0xffffffffu, w_circle, o);
+      w_hit += __shfl_xor_sync(0xffffffffu, w_hit, o);
+      w_bound += __shfl_xor_sync(0xffffffffu, w_bound, o);
     }
     if (lane == 0) {
-      atomicAdd(a.stats + 0, st_iou);
-      atomicAdd(a.stats + 3, st_circle);
-      atomicAdd(a.stats + 18, st_hit);
-      atomicAdd(a.stats + 19, st_bound);
+      atomicAdd(a.stats + 0, w_iou);
+      atomicAdd(a.stats + 3, w_circle);
+      atomicAdd(a.stats + 18, w_hit);
+      atomicAdd(a.stats + 19, w_bound);
     }
     if (tid == 0) {
       atomicAdd(a.stats + 1, static_cast<unsigned long long>(kept));
@@ -1230,6 +1246,7 @@ nms_pull_kernel(NmsArgs a) {
         for (int k = 0; k < 6; ++k) a.stats[12 + k] = static_cast<unsigned long long>(ph[k]);
       atomicMax(a.stats + 11, static_cast<unsigned long long>(n_seg));   // largest segment (candidates)
       atomicAdd(a.stats + 20, static_cast<unsigned long long>(min(rank_base, n_use)));   // candidates consumed by the scan
+      for (int k = 0; k < 3; ++k) atomicAdd(a.stats + 21 + k, static_cast<unsigned long long>(sub[k]));
     }
   }
 }
