@@ -37,6 +37,8 @@
 #include "common.cuh"
 #include "iou.cuh"
 
+#include <cstdio>
+#include <type_traits>
 namespace rv3d {
 
 #ifndef RV3D_NMS_THREADS
@@ -52,6 +54,7 @@ constexpr int kWin = 2048;           // window: candidates sorted and pulled tog
 constexpr int kMaxBins = 2048;       // coarse score bins per segment (bin offsets live in shared memory)
 constexpr int kQ2Cap = 8192;         // IoU work queue (pairs that passed the circle test)
 constexpr int kWBuf = 64;            // per-warp buffer of pairs waiting for the exact routine
+constexpr int kHitCap = 12;          // per-thread buffer (shared memory) of the hits of one grid walk; longer lists walk twice
 constexpr int kKeptSmem = 2048;      // kept boxes tracked in shared memory when num_post_nms <= this, else in global memory
 constexpr int kBucketsSmem = 4096;   // hash buckets of the kept-box grid (shared-memory form)
 constexpr float kPosCap = 1.0e6f;
@@ -364,6 +367,7 @@ __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
   b += sizeof(uint32_t) * kQ2Cap;                                  // queue2 (the window sort's keys + indices alias it)
   b += sizeof(uint32_t) * kNmsWarps * kWBuf;                       // per-warp exact-IoU buffers
+  b += (kept_in_smem ? sizeof(uint16_t) : sizeof(uint32_t)) * kNmsThreads * kHitCap;   // hitbuf
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
   if (kWeighted) b += sizeof(int) * kWin + kQ2Cap + sizeof(int) * kF; // wfs, qflag, killer
   if (kept_in_smem) b += sizeof(float4) * kKeptSmem + sizeof(int) * kBucketsSmem + sizeof(int) * kKeptSmem;
@@ -482,6 +486,9 @@ nms_pull_kernel(NmsArgs a) {
   unsigned long long *wkey = reinterpret_cast<unsigned long long *>(queue2);        // window sort only
   uint16_t *widx = reinterpret_cast<uint16_t *>(wkey + kWin);
   uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * kNmsWarps * kWBuf;
+  // hits of the walk a thread is doing, [c * kNmsThreads + tid] (conflict-free); kept indices fit 16 bits in the kSm form
+  using Hit = typename std::conditional<kSm, uint16_t, uint32_t>::type;
+  Hit *hitbuf = reinterpret_cast<Hit *>(p) + tid; p += sizeof(Hit) * kNmsThreads * kHitCap;
   uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
   int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
   p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
@@ -672,12 +679,11 @@ nms_pull_kernel(NmsArgs a) {
   };
 
   // ---- PULL: the candidates list[0, ns) (window indices, rank order) against the kept boxes [since, kept).
-  // One candidate per thread: walk the grid once (the first kPullCache hits stay in registers), block scan of the hit
+  // One candidate per thread: walk the grid once (the first kHitCap hits go to the thread's slots of hitbuf), block scan of the hit
   // counts, write the (candidate, kept) pairs to the queue at the scanned offsets, evaluate the queue on dense lanes.
   // A batch whose pairs do not fit the queue is cut at the last thread that fits (the offsets are a prefix sum, so the
   // threads that fit form a prefix of the batch).
   // merges_only: the scan is over (weighted, num_post_nms reached) -- candidates only contribute to merge sets.
-  constexpr int kPullCache = 4;
   // The list has two zones: entries [0, n_a) have met the kept boxes below since_a already, the entries behind them
   // none of the kept boxes (lazy pulls, see the round loop).
   auto pull = [&](const uint16_t *list, int ns, int n_a, int since_a, bool merges_only) {
@@ -728,7 +734,6 @@ nms_pull_kernel(NmsArgs a) {
       const bool active = t < ns;
       const int since = t < n_a ? since_a : 0;
       int j = 0, pos = 0, cnt = 0;
-      int hk[kPullCache];
       float x = 0.f, y = 0.f, r = 0.f;
       if (active) {
         j = list[t];
@@ -736,9 +741,7 @@ nms_pull_kernel(NmsArgs a) {
         x = rec_cx(recs[pos]); y = rec_cy(recs[pos]); r = recs[pos].r;
         if (since < kept)
           for_each_near(x, y, r, since, [&](int k) {
-#pragma unroll
-            for (int c = 0; c < kPullCache; ++c)
-              if (cnt == c) hk[c] = k;
+            if (cnt < kHitCap) hitbuf[cnt * kNmsThreads] = static_cast<Hit>(k);
             ++cnt;
           });
       }
@@ -776,10 +779,8 @@ nms_pull_kernel(NmsArgs a) {
       if (ok) {
         if (kWeighted) wfs[j] = 0x7fffffff;
         const uint32_t tag = static_cast<uint32_t>(j) << 20;
-        if (cnt <= kPullCache) {
-#pragma unroll
-          for (int c = 0; c < kPullCache; ++c)
-            if (c < cnt) queue2[off + c] = tag | static_cast<uint32_t>(hk[c]);
+        if (cnt <= kHitCap) {
+          for (int c = 0; c < cnt; ++c) queue2[off + c] = tag | static_cast<uint32_t>(hitbuf[c * kNmsThreads]);
         } else {
           int w = off;
           for_each_near(x, y, r, since, [&](int k) { queue2[w++] = tag | static_cast<uint32_t>(k); });
@@ -998,11 +999,10 @@ nms_pull_kernel(NmsArgs a) {
         };
         sub_begin();
         // Thread i collects the frontier boxes j > i whose circles touch its own: the cells around it, plus the
-        // frontier's oversize list.  Count first (the first kFrontCache hits stay in registers), block scan, write the
+        // frontier's oversize list.  Count first (the first kHitCap hits go to hitbuf), block scan, write the
         // (i, j) pairs at the scanned offsets: the queue is ordered by i, so the evaluation's loads of frec[i] are
         // warp-uniform (with one shared slot counter the pairs arrived in random order: evaluation 5.0 -> 3.5 Mcycles
         // per step, greedy resolution 1.26 -> 0.68).
-        constexpr int kFrontCache = 6;
         static_assert(kQ2Cap >= kF, "one frontier box's pairs always fit the queue");
         auto walk_front = [&](int i, auto &&fn) {
           int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
@@ -1040,12 +1040,9 @@ nms_pull_kernel(NmsArgs a) {
         while (f0 < nf) {
           const bool active = tid >= f0 && tid < nf;
           int cnt = 0;
-          int hj[kFrontCache];
           if (active)
             walk_front(tid, [&](int j) {
-#pragma unroll
-              for (int c = 0; c < kFrontCache; ++c)
-                if (cnt == c) hj[c] = j;
+              if (cnt < kHitCap) hitbuf[cnt * kNmsThreads] = static_cast<Hit>(j);
               ++cnt;
             });
           int total;
@@ -1054,10 +1051,8 @@ nms_pull_kernel(NmsArgs a) {
           const int m = __syncthreads_count(ok);   // prefix sum: the threads that fit are exactly f0 <= tid < f0 + m, m >= 1
           if (ok) {
             const uint32_t tag = static_cast<uint32_t>(tid) << 10;
-            if (cnt <= kFrontCache) {
-#pragma unroll
-              for (int c = 0; c < kFrontCache; ++c)
-                if (c < cnt) queue2[off + c] = tag | static_cast<uint32_t>(hj[c]);
+            if (cnt <= kHitCap) {
+              for (int c = 0; c < cnt; ++c) queue2[off + c] = tag | static_cast<uint32_t>(hitbuf[c * kNmsThreads]);
             } else {
               int w = off;
               walk_front(tid, [&](int j) { queue2[w++] = tag | static_cast<uint32_t>(j); });
@@ -1269,6 +1264,11 @@ nms_pull_kernel(NmsArgs a) {
   }
 
   if (tid == 0) a.kept_count[seg] = kept;
+#ifdef RV3D_NMS_DEBUG_PRINT   // per-segment figures for tools/dev_nms_segments.py (RV3D_NVCC_DEFS=-DRV3D_NMS_DEBUG_PRINT)
+  if (tid == 0 && a.stats)
+    printf("seg %d n %d consumed %d kept %d rounds %d cycles %lld ph %lld %lld %lld %lld %lld sub %lld %lld %lld\n", seg, n_seg, rank_base, kept, rounds,
+           ph[0] + ph[1] + ph[2] + ph[3] + ph[4] + ph[5], ph[0], ph[1], ph[2], ph[3], ph[4], sub[0], sub[1], sub[2]);
+#endif
   if (a.stats) {
     // warp-reduce (widened: the per-thread counters are 32-bit to keep the inner loops at one IADD) then one atomic per warp
     unsigned long long w_iou = st_iou, w_circle = st_circle, w_hit = st_hit, w_bound = st_bound;
