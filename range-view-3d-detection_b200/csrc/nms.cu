@@ -998,30 +998,52 @@ nms_pull_kernel(NmsArgs a) {
           if (kWeighted && above_m) atomicOr(&mrg[i * kFW + (j >> 5)], 1u << (j & 31));
         };
         sub_begin();
-        // Thread i collects the frontier boxes j > i whose circles touch its own: the cells around it, plus the
-        // frontier's oversize list.  Count first (the first kHitCap hits go to hitbuf), block scan, write the
-        // (i, j) pairs at the scanned offsets: the queue is ordered by i, so the evaluation's loads of frec[i] are
-        // warp-uniform (with one shared slot counter the pairs arrived in random order: evaluation 5.0 -> 3.5 Mcycles
-        // per step, greedy resolution 1.26 -> 0.68).
+        // Thread i collects the touching pairs it owns: the cells around it, plus the frontier's oversize list.  Count
+        // first (the first kHitCap hits go to hitbuf), block scan, write the pairs at the scanned offsets: the queue is
+        // ordered by the enumerating box, so the evaluation's record loads are mostly warp-uniform (with one shared
+        // slot counter the pairs arrived in random order: evaluation 5.0 -> 3.5 Mcycles per step, greedy 1.26 -> 0.68).
         static_assert(kQ2Cap >= kF, "one frontier box's pairs always fit the queue");
+        // Every touching pair is enumerated by exactly ONE of its two boxes, its owner: for two boxes that are both in
+        // the grid, the one in the lexicographically smaller cell (row, column; same cell: the smaller slot) -- so a
+        // box only walks its own cell and the cells AFTER it in its window (5 - 6 of 9 instead of all 9, and half the
+        // entries); if either box is on the oversize list, the smaller slot.  A touching in-grid partner's cell always
+        // lies inside the owner's window (reach = r + r_cap >= r + r_partner).
         auto walk_front = [&](int i, auto &&fn) {
           int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
           bool skip;
+          const bool gridded = prune && in_grid(mx, my, mrad);
+          const int cix = cell_of(mx), ciy = cell_of(my);
           if (!query_cells(mx, my, mrad, ix0, ix1, iy0, iy1, skip)) {
-            if (!skip)
+            if (skip) return;
+            if (!gridded) {
               for (int j = i + 1; j < nf; ++j) {
                 const float4 q = fq[j];
                 ++st_circle;
                 if (!prune || touches(mx, my, mrad, q.x, q.y, q.z)) fn(j);
               }
+            } else {   // (window larger than kMaxCellsPerQuery: only with an unusual grid geometry) same ownership rule, linear scan
+              for (int j = 0; j < nf; ++j) {
+                if (j == i) continue;
+                const float4 q = fq[j];
+                ++st_circle;
+                if (!touches(mx, my, mrad, q.x, q.y, q.z)) continue;
+                bool own = j > i;
+                if (in_grid(q.x, q.y, q.z)) {
+                  const int cjx = cell_of(q.x), cjy = cell_of(q.y);
+                  own = cjy > ciy || (cjy == ciy && (cjx > cix || (cjx == cix && j > i)));
+                }
+                if (own) fn(j);
+              }
+            }
           } else {
-            for (int iy = iy0; iy <= iy1; ++iy)
-              for (int ix = ix0; ix <= ix1; ++ix) {
+            for (int iy = gridded ? ciy : iy0; iy <= iy1; ++iy)
+              for (int ix = (gridded && iy == ciy) ? cix : ix0; ix <= ix1; ++ix) {
+                const int jmin = (!gridded || (iy == ciy && ix == cix)) ? i : -1;   // own cell (or an oversize walker): larger slots only
                 int j = fheads[bucket_of(ix, iy) & (kFrontBuckets - 1)];
                 while (j >= 0) {
                   const float4 q = fq[j];
                   ++st_circle;
-                  if (j > i && touches(mx, my, mrad, q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) fn(j);
+                  if (j > jmin && touches(mx, my, mrad, q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) fn(j);
                   j = __float_as_int(q.w);
                 }
               }
@@ -1050,12 +1072,14 @@ nms_pull_kernel(NmsArgs a) {
           const bool ok = active && (off + cnt <= kQ2Cap);
           const int m = __syncthreads_count(ok);   // prefix sum: the threads that fit are exactly f0 <= tid < f0 + m, m >= 1
           if (ok) {
-            const uint32_t tag = static_cast<uint32_t>(tid) << 10;
+            auto entry = [&](int j) -> uint32_t {   // (higher-ranked slot << 10) | lower-ranked slot
+              return static_cast<uint32_t>(j > tid ? ((tid << 10) | j) : ((j << 10) | tid));
+            };
             if (cnt <= kHitCap) {
-              for (int c = 0; c < cnt; ++c) queue2[off + c] = tag | static_cast<uint32_t>(hitbuf[c * kNmsThreads]);
+              for (int c = 0; c < cnt; ++c) queue2[off + c] = entry(static_cast<int>(hitbuf[c * kNmsThreads]));
             } else {
               int w = off;
-              walk_front(tid, [&](int j) { queue2[w++] = tag | static_cast<uint32_t>(j); });
+              walk_front(tid, [&](int j) { queue2[w++] = entry(j); });
             }
             if (tid == f0 + m - 1) s_qn = off + cnt;
           }
