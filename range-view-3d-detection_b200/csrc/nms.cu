@@ -947,7 +947,10 @@ nms_pull_kernel(NmsArgs a) {
       const int nf_want = min(kF, room + (room >> 2) + 16);   // a later round tops up if fewer than `room` are kept
       // ================= a / c. pull against the kept boxes, drop the suppressed =================
       if (kept > 0) {
-        const int np = min(ns, max(n_a, nf_want + (nf_want >> 2) + 32));
+        // chunk: what the frontier wants plus the share the kept boxes usually suppress -- but not a second, mostly idle
+        // batch of the pull (one candidate per thread)
+        const int want = min(nf_want + (nf_want >> 2) + 32, max(nf_want, kNmsThreads));
+        const int np = min(ns, max(n_a, want));
         pull(list, np, n_a, since_a, false);
         const int ns2 = compact(list, np, other);
         for (int t = np + tid; t < ns; t += kNmsThreads) other[ns2 + t - np] = list[t];   // zone B moves up behind the survivors
