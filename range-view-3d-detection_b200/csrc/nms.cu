@@ -531,6 +531,7 @@ nms_pull_kernel(NmsArgs a) {
   };
 
   int kept = 0;          // boxes kept so far (uniform)
+  float surv_rate = 1.f; // share of the last pulled chunk that survived (uniform; sizes the next chunk)
   int rounds = 0;
   float inv_cell = 0.f, r_cap = 0.f;
   bool geom_set = false;
@@ -947,12 +948,16 @@ nms_pull_kernel(NmsArgs a) {
       const int nf_want = min(kF, room + (room >> 2) + 16);   // a later round tops up if fewer than `room` are kept
       // ================= a / c. pull against the kept boxes, drop the suppressed =================
       if (kept > 0) {
-        // chunk: what the frontier wants plus the share the kept boxes usually suppress -- but not a second, mostly idle
-        // batch of the pull (one candidate per thread)
-        const int want = min(nf_want + (nf_want >> 2) + 32, max(nf_want, kNmsThreads));
+        // chunk: what the frontier wants, scaled by the share of the previous chunk that survived its pull (dense scenes
+        // lose most of a chunk to the kept boxes: an under-filled frontier means more rounds) -- but not a second,
+        // mostly idle batch of the pull (one candidate per thread) for a few more candidates
+        int want = static_cast<int>(static_cast<float>(nf_want) * 1.1f / surv_rate) + 32;
+        if (want <= kNmsThreads + kNmsThreads / 2) want = min(want, max(nf_want, kNmsThreads));
+        want = min(want, kWin);
         const int np = min(ns, max(n_a, want));
         pull(list, np, n_a, since_a, false);
         const int ns2 = compact(list, np, other);
+        if (np >= 64) surv_rate = fmaxf(static_cast<float>(ns2) / static_cast<float>(np), 0.05f);
         for (int t = np + tid; t < ns; t += kNmsThreads) other[ns2 + t - np] = list[t];   // zone B moves up behind the survivors
         __syncthreads();
         uint16_t *tmp = list; list = other; other = tmp;
