@@ -275,6 +275,19 @@ scatter_records_kernel(const unsigned long long *__restrict__ keys, Builder buil
 // kept num_post_nms boxes, every candidate behind the scan position still owes the kept boxes its merge contribution.
 // The scan publishes the record range [pos_lo, pos_hi) that is left (whole score bins inside the num_pre_nms cut), the
 // number of kept boxes and the geometry of its kept-box grid; the grid itself is in global memory by then.
+// Buckets of the spatial grids: a TORUS of the cell grid, bucket = (iy mod 2^by) << bx | (ix mod 2^bx), both dimensions
+// >= 32 cells.  A query window spans at most kMaxCellsPerQuery (25) cells per axis, so (1) its cells map to distinct
+// buckets -- an entry is met at most once per query -- and (2) an entry that aliases into a visited bucket from another
+// cell lies >= 32 - 12 - 1 = 19 cells away from the query while the query's reach is < 13 cells: it fails the circle
+// test.  The circle test alone therefore decides, exactly; the walks need no "does this entry belong to the cell I am
+// visiting" check (two float -> int conversions per hit with a multiplicative hash, where cells of one window could
+// share a bucket).
+__device__ __forceinline__ uint32_t torus_bucket(int ix, int iy, int bx, uint32_t bmask) {
+  return ((static_cast<uint32_t>(iy) << bx) | (static_cast<uint32_t>(ix) & ((1u << bx) - 1u))) & bmask;
+}
+__device__ __forceinline__ int torus_bits_x(int n_buckets) { return (31 - __clz(n_buckets)) >> 1; }
+static_assert(kMaxCellsPerQuery < 32 && kFrontBuckets == 1024 && kBucketsSmem == 4096, "torus dimensions (32 x 32, 64 x 64, >= 64 x 64)");
+
 struct TailInfo {
   int pos_lo, pos_hi, kept, nos;
   float inv_cell, r_cap;
@@ -537,9 +550,9 @@ nms_pull_kernel(NmsArgs a) {
   bool geom_set = false;
 
   auto cell_of = [&](float v) -> int { return static_cast<int>(fminf(fmaxf(floorf(v * inv_cell), -32768.f), 32767.f)); };
-  auto bucket_of = [&](int ix, int iy) -> uint32_t {
-    return (static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u);
-  };
+  const int kbx = kSm ? 6 : torus_bits_x(a.n_buckets_g);
+  auto kept_bucket = [&](int ix, int iy) -> uint32_t { return torus_bucket(ix, iy, kbx, bmask); };
+  auto front_bucket = [&](int ix, int iy) -> uint32_t { return torus_bucket(ix, iy, 5, kFrontBuckets - 1); };
   auto in_grid = [&](float x, float y, float r) -> bool {
     return (r <= r_cap) && (fabsf(x) <= kPosCap) && (fabsf(y) <= kPosCap);   // false for NaN
   };
@@ -572,9 +585,8 @@ nms_pull_kernel(NmsArgs a) {
   };
 
   // Every kept box k >= since whose padded circle touches (x, y, r): fn(k).  Chains are newest-first (insertion
-  // prepends, kept indices only grow), so a walk stops at the first index below `since`.  The circle test comes
-  // first; only a hit pays for the check that the entry really belongs to the queried cell (cells share buckets, and a
-  // box visited through two cells of the window must not count twice).
+  // prepends, kept indices only grow), so a walk stops at the first index below `since`.  The circle test alone decides
+  // (torus_bucket: the cells of one window never share a bucket, aliases from other cells are too far away to touch).
   auto for_each_near = [&](float x, float y, float r, int since, auto &&fn) {
     int ix0 = 0, ix1 = 0, iy0 = 0, iy1 = 0;
     bool skip;
@@ -589,12 +601,12 @@ nms_pull_kernel(NmsArgs a) {
     }
     for (int iy = iy0; iy <= iy1; ++iy)
       for (int ix = ix0; ix <= ix1; ++ix) {
-        int k = heads[bucket_of(ix, iy) & bmask];
+        int k = heads[kept_bucket(ix, iy)];
         while (k >= since) {
           float qx, qy, qr; int next;
           kept_entry(k, qx, qy, qr, next);
           ++st_circle;
-          if (touches(x, y, r, qx, qy, qr) && cell_of(qx) == ix && cell_of(qy) == iy) fn(k);
+          if (touches(x, y, r, qx, qy, qr)) fn(k);
           k = next;
         }
       }
@@ -994,7 +1006,7 @@ nms_pull_kernel(NmsArgs a) {
       if (tid < nf) {
         int next = -1;
         if (prune) {
-          if (in_grid(mx, my, mrad)) next = atomicExch(&fheads[bucket_of(cell_of(mx), cell_of(my)) & (kFrontBuckets - 1)], tid);
+          if (in_grid(mx, my, mrad)) next = atomicExch(&fheads[front_bucket(cell_of(mx), cell_of(my))], tid);
           else fos[atomicAdd(&s_nfos, 1)] = static_cast<uint16_t>(tid);
         }
         fq[tid] = make_float4(mx, my, mrad, __int_as_float(next));
@@ -1047,11 +1059,11 @@ nms_pull_kernel(NmsArgs a) {
             for (int iy = gridded ? ciy : iy0; iy <= iy1; ++iy)
               for (int ix = (gridded && iy == ciy) ? cix : ix0; ix <= ix1; ++ix) {
                 const int jmin = (!gridded || (iy == ciy && ix == cix)) ? i : -1;   // own cell (or an oversize walker): larger slots only
-                int j = fheads[bucket_of(ix, iy) & (kFrontBuckets - 1)];
+                int j = fheads[front_bucket(ix, iy)];
                 while (j >= 0) {
                   const float4 q = fq[j];
                   ++st_circle;
-                  if (j > jmin && touches(mx, my, mrad, q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) fn(j);
+                  if (j > jmin && touches(mx, my, mrad, q.x, q.y, q.z)) fn(j);
                   j = __float_as_int(q.w);
                 }
               }
@@ -1185,7 +1197,7 @@ nms_pull_kernel(NmsArgs a) {
         kept_pos[k] = pos;
         const float4 q = fq[fi];
         int next = -1;
-        if (in_grid(q.x, q.y, q.z)) next = atomicExch(&heads[bucket_of(cell_of(q.x), cell_of(q.y)) & bmask], k);
+        if (in_grid(q.x, q.y, q.z)) next = atomicExch(&heads[kept_bucket(cell_of(q.x), cell_of(q.y))], k);
         else kos[atomicAdd(&s_nos, 1)] = k;
         if (kSm) {
           kxyr[k] = make_float4(q.x, q.y, q.z, __uint_as_float((static_cast<uint32_t>(next + 1) << 20) | static_cast<uint32_t>(pos)));
@@ -1427,9 +1439,7 @@ wnms_tail_kernel(NmsArgs a, int S) {
       const float x = rec_cx(rj), y = rec_cy(rj), r = rj.r;
       const float inv_cell = ti.inv_cell, r_cap = ti.r_cap;
       auto cell_of = [&](float v) -> int { return static_cast<int>(fminf(fmaxf(floorf(v * inv_cell), -32768.f), 32767.f)); };
-      auto bucket_of = [&](int ix, int iy) -> uint32_t {
-        return (static_cast<uint32_t>(ix) * 73856093u) ^ (static_cast<uint32_t>(iy) * 19349663u);
-      };
+      const int kbx = torus_bits_x(n_buckets);
       auto touches = [&](float qx, float qy, float qr) -> bool {
         const float dx = qx - x, dy = qy - y, rr = qr + r;
         return dx * dx + dy * dy <= rr * rr;
@@ -1465,12 +1475,12 @@ wnms_tail_kernel(NmsArgs a, int S) {
       } else {
         for (int iy = iy0; iy <= iy1; ++iy)
           for (int ix = ix0; ix <= ix1; ++ix) {
-            int k = heads[bucket_of(ix, iy) & bmask];
+            int k = heads[torus_bucket(ix, iy, kbx, bmask)];
             while (k >= 0) {
               const float4 q = kxyr[k];
               const int next = kSm ? static_cast<int>(__float_as_uint(q.w) >> 20) - 1 : knext[k];
               ++st_circle;
-              if (touches(q.x, q.y, q.z) && cell_of(q.x) == ix && cell_of(q.y) == iy) offer(k, position_of(q.w));
+              if (touches(q.x, q.y, q.z)) offer(k, position_of(q.w));
               k = next;
             }
           }

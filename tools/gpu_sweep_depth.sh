@@ -1,4 +1,4 @@
-for d in 3 4 5 6 8; do
+for d in ${DEPTHS:-3 4 5 6 8}; do
   timeout 300 python bench.py --steps 24 --warmup 3 --no-extras --no-cpu-baseline --pipeline-depth $d > gpurun_out/pd.json 2> gpurun_out/pd.err
   tail -c 600 gpurun_out/pd.err
   python - <<EOF
