@@ -53,7 +53,6 @@ constexpr int kMaxD = 16;            // max data columns of the weighted merge
 constexpr int kWin = 2048;           // window: candidates sorted and pulled together
 constexpr int kMaxBins = 2048;       // coarse score bins per segment (bin offsets live in shared memory)
 constexpr int kQ2Cap = 8192;         // IoU work queue (pairs that passed the circle test)
-constexpr int kWBuf = 64;            // per-warp buffer of pairs waiting for the exact routine
 constexpr int kHitCap = 12;          // per-thread buffer (shared memory) of the hits of one grid walk; longer lists walk twice
 constexpr int kKeptSmem = 2048;      // kept boxes tracked in shared memory when num_post_nms <= this, else in global memory
 constexpr int kBucketsSmem = 4096;   // hash buckets of the kept-box grid (shared-memory form)
@@ -379,7 +378,6 @@ __host__ __device__ inline size_t nms_smem_bytes(bool kept_in_smem) {
   b += sizeof(uint16_t) * kF;                                      // front_w
   b += sizeof(uint32_t) * kF * kFW * (kWeighted ? 2 : 1);          // sup (+ mrg)
   b += sizeof(uint32_t) * kQ2Cap;                                  // queue2 (the window sort's keys + indices alias it)
-  b += sizeof(uint32_t) * kNmsWarps * kWBuf;                       // per-warp exact-IoU buffers
   b += (kept_in_smem ? sizeof(uint16_t) : sizeof(uint32_t)) * kNmsThreads * kHitCap;   // hitbuf
   b += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);  // keptf, keptrank
   if (kWeighted) b += sizeof(int) * kWin + kQ2Cap + sizeof(int) * kF; // wfs, qflag, killer
@@ -458,7 +456,7 @@ nms_pull_kernel(NmsArgs a) {
   static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0 && kF <= kNmsThreads, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsWarps + 1];
-  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_nfos;
+  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_nfos, s_xn;
   __shared__ float s_red[kNmsWarps * 2];
   __shared__ float s_cell[2];   // inv_cell, r_cap
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
@@ -498,10 +496,11 @@ nms_pull_kernel(NmsArgs a) {
   uint32_t *queue2 = reinterpret_cast<uint32_t *>(p); p += sizeof(uint32_t) * kQ2Cap;
   unsigned long long *wkey = reinterpret_cast<unsigned long long *>(queue2);        // window sort only
   uint16_t *widx = reinterpret_cast<uint16_t *>(wkey + kWin);
-  uint32_t *wbuf = reinterpret_cast<uint32_t *>(p) + wid * kWBuf; p += sizeof(uint32_t) * kNmsWarps * kWBuf;
   // hits of the walk a thread is doing, [c * kNmsThreads + tid] (conflict-free); kept indices fit 16 bits in the kSm form
   using Hit = typename std::conditional<kSm, uint16_t, uint32_t>::type;
-  Hit *hitbuf = reinterpret_cast<Hit *>(p) + tid; p += sizeof(Hit) * kNmsThreads * kHitCap;
+  Hit *hitbuf = reinterpret_cast<Hit *>(p) + tid;
+  uint16_t *xq = reinterpret_cast<uint16_t *>(p);   // eval_queue's list of pairs for the exact routine: the walks' hits are in the queue by then
+  p += sizeof(Hit) * kNmsThreads * kHitCap;
   uint16_t *keptf = reinterpret_cast<uint16_t *>(p);
   int16_t *keptrank = reinterpret_cast<int16_t *>(keptf + kF);
   p += align_up_c(sizeof(uint16_t) * kF + sizeof(int16_t) * kF, 16);
@@ -644,51 +643,49 @@ nms_pull_kernel(NmsArgs a) {
     above_m = kWeighted && iou > a.mthr;
   };
 
-  // Evaluation of a queue of pairs, warp-converged: every lane tests its pair against the cheap upper bound; the
-  // pairs that may exceed a threshold are compacted per warp (wbuf) so that the bit-exact routine always runs on
-  // (nearly) full warps.  get(q, ra, rb) loads the pair, emit(q, above_thr, above_mthr) consumes the two comparisons
-  // (only called for pairs that reach the exact routine: a pair stopped by the bound is below both thresholds).
+  // Evaluation of a queue of pairs.  Phase 1: every lane tests its pair against the cheap upper bound; the pairs that may
+  // exceed a threshold go to a CTA-wide list (xq, warp-aggregated reservation).  Phase 2: the bit-exact routine runs over
+  // that list on dense lanes, 32 pairs per warp.  The routine is a ~2000-instruction dependent chain, so what an
+  // evaluation costs is the number of times the busiest warp has to run it: ceil(pending / (32 * warps)) with the shared
+  // list -- once for up to 512 pairs -- where per-warp lists ran it twice as soon as one warp's share exceeded 32.
+  // get(q, ra, rb) loads the pair, emit(q, above_thr, above_mthr) consumes the two comparisons (only called for pairs that
+  // reach the exact routine: a pair stopped by the bound is below both thresholds).  Callers sync before and after.
+  constexpr int kXq = kNmsThreads * kHitCap;   // uint16 entries that fit the hit buffer in either form
+  static_assert(kXq % 32 == 0 && kQ2Cap <= 65536, "queue slices are whole warps; queue indices fit 16 bits");
   auto eval_queue = [&](int qn, auto &&get, auto &&emit) {
-    int nbuf = 0;   // warp-uniform
-    auto exact32 = [&](int count) {
-      __syncwarp();
-      if (lane < count) {
-        const int q = static_cast<int>(wbuf[lane]);
+    for (int q_lo = 0; q_lo < qn; q_lo += kXq) {   // (one slice unless more than kXq pairs are queued)
+      const int q_hi = min(qn, q_lo + kXq);
+      if (tid == 0) s_xn = 0;
+      __syncthreads();
+      const int q_pad = q_lo + ((q_hi - q_lo + 31) & ~31);
+      for (int q = q_lo + tid; q < q_pad; q += kNmsThreads) {   // warp-uniform trip count
+        bool pending = q < q_hi;
+        if (pending && prune) {
+          Rec ra, rb;
+          get(q, ra, rb);
+          ++st_bound;
+          pending = iou_may_exceed(ra, rb, thr_any);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, pending);
+        if (m) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(&s_xn, __popc(m));
+          at = __shfl_sync(0xffffffffu, at, 0);
+          if (pending) xq[at + __popc(m & ((1u << lane) - 1u))] = static_cast<uint16_t>(q);
+        }
+      }
+      __syncthreads();
+      const int xn = s_xn;
+      for (int x = tid; x < xn; x += kNmsThreads) {
+        const int q = static_cast<int>(xq[x]);
         Rec ra, rb;
         get(q, ra, rb);
         const float iou = pair_iou(ra, rb);
         ++st_iou;
         emit(q, iou > a.thr, kWeighted && iou > a.mthr);
       }
-      __syncwarp();
-    };
-    const int qn_pad = (qn + 31) & ~31;
-    for (int q0 = wid * 32; q0 < qn_pad; q0 += kNmsThreads) {   // each warp owns 32 consecutive entries per pass
-      __syncwarp();
-      const int q = q0 + lane;
-      bool pending = false;
-      if (q < qn) {
-        pending = true;
-        if (prune) {
-          Rec ra, rb;
-          get(q, ra, rb);
-          ++st_bound;
-          pending = iou_may_exceed(ra, rb, thr_any);
-        }
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, pending);
-      if (m) {
-        if (pending) wbuf[nbuf + __popc(m & ((1u << lane) - 1u))] = static_cast<uint32_t>(q);
-        nbuf += __popc(m);
-        if (nbuf >= 32) {
-          exact32(32);
-          if (lane < nbuf - 32) wbuf[lane] = wbuf[32 + lane];
-          nbuf -= 32;
-          __syncwarp();
-        }
-      }
+      if (q_hi < qn) __syncthreads();   // the next slice reuses xq and the counter
     }
-    if (nbuf > 0) exact32(nbuf);
   };
 
   // ---- PULL: the candidates list[0, ns) (window indices, rank order) against the kept boxes [since, kept).
