@@ -17,16 +17,18 @@
 //   K4  nms_pull_kernel, one CTA per segment, "pull" form of the greedy scan:
 //         repeat: take the next window (<= 2048 candidates = whole score bins), sort it exactly in shared
 //                 memory by (score desc, candidate asc);
-//           a. PULL: every window candidate looks up the boxes KEPT so far in a spatial hash of kept boxes
-//              (circle pre-test -> work queue -> IoU upper bound -> bit-exact IoU on dense lanes) and dies if suppressed;
-//           b. the first kF survivors form a frontier: all pairs inside it -> suppression bit-matrix ->
-//              greedy resolution in rank order -> newly kept boxes join the hash;
-//           c. the remaining survivors pull again, against the NEW kept boxes only; back to b.
+//           a. PULL (lazy): the candidates the next frontier needs -- the leftovers of the previous chunk against the
+//              NEW kept boxes, the next chunk of the window against ALL kept boxes -- look up the kept boxes in a
+//              spatial grid (circle pre-test -> work queue -> IoU upper bound -> bit-exact IoU on dense lanes) and die
+//              if suppressed;
+//           b. the first nf survivors form a frontier (nf <= kF, and no more than the room under num_post_nms can
+//              use): all touching pairs inside it -> suppression bit-matrix -> greedy resolution in rank order ->
+//              newly kept boxes join the grid; back to a.
 //         until num_post_nms boxes are kept or the candidates run out.
-//       A candidate is only ever tested against kept boxes, candidates behind the last consumed window are never
+//       A candidate is only ever tested against kept boxes, candidates behind the last pulled chunk are never
 //       touched in hard mode, and nothing is tested twice.  The result equals the sequential greedy scan: a
-//       candidate reaches a frontier only if no earlier kept box suppressed it, frontiers are resolved in rank
-//       order, pruned pairs have IoU exactly 0 (iou.cuh padded_radius).
+//       candidate reaches a frontier only after it has met every kept box that ranks above it, frontiers are
+//       resolved in rank order, pruned pairs have IoU exactly 0 (iou.cuh padded_radius).
 //   K5  weighted mode: the same scan, every (candidate, kept) comparison also feeds the merge sets; after the
 //       last kept box the candidates behind it are pulled once more for their merge contributions only.
 #include <cstdlib>
@@ -456,7 +458,7 @@ nms_pull_kernel(NmsArgs a) {
   static_assert(kF <= 1024 && kFW <= 32 && kNmsThreads % kFW == 0 && kF <= kNmsThreads, "frontier size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_warp[kNmsWarps + 1];
-  __shared__ int s_qn, s_qvalid, s_nk, s_nos, s_nfos, s_xn;
+  __shared__ int s_qn, s_nk, s_nos, s_nfos, s_xn;
   __shared__ float s_red[kNmsWarps * 2];
   __shared__ float s_cell[2];   // inv_cell, r_cap
   __shared__ uint32_t s_haspred[kFW], s_removed[kFW];
