@@ -190,23 +190,43 @@ static __device__ __noinline__ float rot_iou(const HardRec &a, const HardRec &b)
   float inter = 0.f;
   if (n > 2) {
     // Graham scan (shift_to_zero variant), CUDA flavour of the angular sort
+    // (ip / q / dist are indexed dynamically and live in local memory: the loops below keep the element they work on
+    // in registers, so the exchange sort loads one element per step instead of re-reading q[i] and both distances --
+    // the same operations in the same order as upstream)
     int t = 0;
-    for (int i = 1; i < n; ++i)
-      if (ip[i].y < ip[t].y || (ip[i].y == ip[t].y && ip[i].x < ip[t].x)) t = i;
-    const P2 start = ip[t];
+    P2 start = ip[0];
+    for (int i = 1; i < n; ++i) {
+      const P2 c = ip[i];
+      if (c.y < start.y || (c.y == start.y && c.x < start.x)) { t = i; start = c; }
+    }
     P2 q[24];
     float dist[24];
-    for (int i = 0; i < n; ++i) q[i] = sub2(ip[i], start);
-    { const P2 tmp = q[0]; q[0] = q[t]; q[t] = tmp; }
-    for (int i = 0; i < n; ++i) dist[i] = dot2(q[i], q[i]);
-    for (int i = 1; i < n - 1; ++i)
+    for (int i = 0; i < n; ++i) {
+      const P2 d = sub2(ip[i], start);
+      q[i] = d;
+      dist[i] = dot2(d, d);
+    }
+    {
+      const P2 tmp = q[0]; q[0] = q[t]; q[t] = tmp;
+      const float dt = dist[0]; dist[0] = dist[t]; dist[t] = dt;
+    }
+    for (int i = 1; i < n - 1; ++i) {
+      P2 qi = q[i];
+      float di = dist[i];
       for (int j = i + 1; j < n; ++j) {
-        const float cp = cross2(q[i], q[j]);
-        if (cp < kNegCpGE || (fabsf(cp) < kCpGE && dist[i] > dist[j])) {
-          const P2 qt = q[i]; q[i] = q[j]; q[j] = qt;
-          const float dt = dist[i]; dist[i] = dist[j]; dist[j] = dt;
+        const P2 qj = q[j];
+        const float cp = cross2(qi, qj);
+        bool exchange = cp < kNegCpGE;
+        if (!exchange && fabsf(cp) < kCpGE) exchange = di > dist[j];
+        if (exchange) {
+          const float dj = dist[j];
+          q[j] = qi; dist[j] = di;
+          qi = qj; di = dj;
         }
       }
+      q[i] = qi;
+      dist[i] = di;
+    }
     int k = 1;
     for (; k < n; ++k)
       if (dist[k] > kDistLE) break;
