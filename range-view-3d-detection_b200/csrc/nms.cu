@@ -512,7 +512,7 @@ nms_pull_kernel(NmsArgs a) {
     qflag = reinterpret_cast<uint8_t *>(p); p += kQ2Cap;             // per queued pair: bit0 iou > thr, bit1 iou > merge_thr
     killer = reinterpret_cast<int *>(p); p += sizeof(int) * kF;      // frontier box -> rank of its first suppressor
   }
-  // Kept boxes: a spatial hash with chaining.  Shared-memory form (kSm, num_post_nms <= kKeptSmem): ONE 16-byte entry
+  // Kept boxes: a spatial grid (torus_bucket) with chaining.  Shared-memory form (kSm, num_post_nms <= kKeptSmem): ONE 16-byte entry
   // per kept box, (x, y, padded radius, next + 1 << 20 | position in the segment), so a chain step is a single LDS.128.
   // Global form: (x, y, r, position) + a separate next array, for calls that may keep more than kKeptSmem boxes.
   float4 *kxyr; int *knext = nullptr, *heads, *kos; uint32_t bmask;
